@@ -1,0 +1,212 @@
+"""Minimal stand-in for the un-vendored third-party graph packages so that the
+UNMODIFIED reference model files import and run on CPU.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Restates, from their published semantics (versions unpinned by the reference:
+no requirements/lock file; PyG 2.0.x-2.1.x inferred from the private
+`__check_input__/__collect__` API used at pose_gnn.py:163-181):
+
+  torch_geometric.nn.MessagePassing  -> exactly what `propagate` touches
+                                        (pose_gnn.py:134-196, clr_att_gnn.py:238-300)
+  torch_geometric.nn.GATConv         -> SURVEY.md §A.6  (pose_gnn.py:55, clr_att_gnn.py:93)
+  torch_geometric.nn.knn_graph       -> SURVEY.md §A.5  (pose_gnn.py:78, clr_att_gnn.py:182)
+  torch_scatter.scatter              -> SURVEY.md §A.4  (pose_gnn.py:240, clr_att_gnn.py:344)
+
+`install()` pre-populates sys.modules; `load_reference()` then imports the
+reference modules from /root/reference (only possible in the build container).
+"""
+import inspect
+import math
+import sys
+import types
+
+import torch
+from torch import nn
+
+
+# --------------------------------------------------------------------------- scatter
+def scatter(src, index, dim=0, out=None, dim_size=None, reduce="sum"):
+    """torch_scatter.scatter for reduce in {'add','sum'} along dim 0 (A.4):
+    out = zeros(dim_size, C); out.scatter_add_(0, index[:,None].expand_as(src), src).
+    CPU scatter_add_ is sequential in edge order == index_add_."""
+    assert reduce in ("add", "sum") and dim in (0, -2)
+    if dim_size is None:
+        dim_size = int(index.max()) + 1 if index.numel() else 0
+    res = src.new_zeros((dim_size,) + tuple(src.shape[1:]))
+    return res.index_add_(0, index, src)
+
+
+# --------------------------------------------------------------------------- knn_graph
+def knn_graph(x, k, batch=None, loop=False, flow="source_to_target", **_):
+    """A.5 with the build's tie-break spec: squared L2 accumulated in fp32 in
+    ascending feature order, order by (distance, neighbour index), self
+    excluded by index, k_eff = min(k, n-1). Returns [2, n*k_eff] int64 with
+    row 0 = neighbour (source), row 1 = query (target), grouped by query."""
+    assert batch is None and not loop and flow == "source_to_target"
+    n = x.size(0)
+    if n <= 1:
+        return torch.zeros((2, 0), dtype=torch.long, device=x.device)
+    xd = x.detach().to(torch.float32)
+    d = torch.zeros((n, n), dtype=torch.float32)
+    for c in range(xd.size(1)):  # ascending d, separate mul and add (no FMA)
+        diff = xd[:, c].unsqueeze(1) - xd[:, c].unsqueeze(0)
+        d = d + diff * diff
+    d.fill_diagonal_(float("inf"))
+    keff = min(k, n - 1)
+    # stable sort on distance == (distance, index) order
+    order = torch.sort(d, dim=1, stable=True).indices[:, :keff]
+    row = order.reshape(-1)
+    col = torch.arange(n).unsqueeze(1).expand(n, keff).reshape(-1)
+    return torch.stack([row, col], dim=0)
+
+
+# --------------------------------------------------------------------------- GATConv
+def _glorot(t):
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        t.uniform_(-a, a)
+
+
+class GATConv(nn.Module):
+    """A.6: heads=1, concat=True, negative_slope=0.2, dropout=0, bias=True.
+    Parameter names follow PyG 2.0.x (`lin_src`, shared with lin_dst)."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2,
+                 dropout=0.0, add_self_loops=True, bias=True, **_):
+        super().__init__()
+        assert heads == 1 and not add_self_loops
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.negative_slope = negative_slope
+        self.lin_src = nn.Linear(in_channels, out_channels, bias=False)
+        self.lin_dst = self.lin_src
+        self.att_src = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        _glorot(self.lin_src.weight)
+        _glorot(self.att_src)
+        _glorot(self.att_dst)
+
+    def forward(self, x, edge_index):
+        n = x.size(0)
+        h = self.lin_src(x)
+        a_s = (h * self.att_src.view(1, -1)).sum(-1)
+        a_d = (h * self.att_dst.view(1, -1)).sum(-1)
+        s, t = edge_index[0], edge_index[1]
+        z = torch.nn.functional.leaky_relu(a_s[s] + a_d[t], self.negative_slope)
+        zmax = torch.full((n,), float("-inf"), dtype=z.dtype)
+        zmax = zmax.scatter_reduce(0, t, z, reduce="amax", include_self=True)
+        ez = torch.exp(z - zmax[t])
+        den = torch.zeros(n, dtype=z.dtype).index_add_(0, t, ez)
+        alpha = ez / (den[t] + 1e-16)
+        out = torch.zeros_like(h).index_add_(0, t, alpha.unsqueeze(1) * h[s])
+        return out + self.bias
+
+
+# --------------------------------------------------------------------------- MessagePassing
+class _Inspector:
+    def __init__(self, owner):
+        self.owner = owner
+
+    def params(self, name, pop_first=False):
+        p = list(inspect.signature(getattr(self.owner, name)).parameters)
+        return p[1:] if pop_first else p
+
+    def distribute(self, name, d):
+        return {k: d[k] for k in self.params(name, pop_first=(name != "message")) if k in d}
+
+
+class MessagePassing(nn.Module):
+    """Only what the reference's overridden `propagate` uses (A.3)."""
+    special_args = {"edge_index", "adj_t", "edge_index_i", "edge_index_j", "size", "size_i",
+                    "size_j", "ptr", "index", "dim_size"}
+
+    def __init__(self, aggr="add", flow="source_to_target", node_dim=-2):
+        super().__init__()
+        assert flow == "source_to_target"
+        self.aggr, self.flow, self.node_dim = aggr, flow, node_dim
+        self.inspector = _Inspector(self)
+        self.fuse = False
+        self.__explain__ = False
+        user = set(self.inspector.params("message")) | set(self.inspector.params("aggregate", True)) \
+            | set(self.inspector.params("update", True))
+        self.__user_args__ = user - self.special_args
+        self.__fused_user_args__ = set()
+
+    def __check_input__(self, edge_index, size):
+        assert isinstance(edge_index, torch.Tensor) and edge_index.dtype == torch.long
+        assert edge_index.dim() == 2 and edge_index.size(0) == 2
+        the_size = [None, None]
+        if size is not None:
+            the_size[0], the_size[1] = size[0], size[1]
+        return the_size
+
+    def __collect__(self, args, edge_index, size, kwargs):
+        i, j = 1, 0  # source_to_target
+        out = {}
+        for arg in args:
+            if arg[-2:] not in ("_i", "_j"):
+                out[arg] = kwargs.get(arg, inspect.Parameter.empty)
+            else:
+                dim = j if arg[-2:] == "_j" else i
+                data = kwargs.get(arg[:-2], inspect.Parameter.empty)
+                if isinstance(data, torch.Tensor):
+                    data = data.index_select(self.node_dim, edge_index[dim])
+                out[arg] = data
+        out["edge_index"] = edge_index
+        out["index"] = edge_index[i]
+        out["size"] = size
+        out["dim_size"] = size[1]
+        return out
+
+
+# --------------------------------------------------------------------------- install
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def install():
+    """Pre-populate sys.modules with the stand-ins (idempotent)."""
+    if "torch_geometric" in sys.modules and getattr(sys.modules["torch_geometric"], "_b3d_shim", False):
+        return
+    from typing import Optional, Tuple
+    typing_mod = _mod("torch_geometric.typing", Adj=torch.Tensor, Size=Optional[Tuple[int, int]])
+    nn_mod = _mod("torch_geometric.nn", MessagePassing=MessagePassing, GATConv=GATConv,
+                  knn_graph=knn_graph, Sequential=nn.Sequential)
+    tg = _mod("torch_geometric", nn=nn_mod, typing=typing_mod, _b3d_shim=True)
+    tg.__path__ = []
+    _mod("torch_scatter", scatter=scatter, gather_csr=None, segment_csr=None)
+    _mod("torch_sparse", SparseTensor=type("SparseTensor", (), {}))
+    mpl = _mod("matplotlib", pyplot=None)
+    mpl.__path__ = []
+    mpl.pyplot = _mod("matplotlib.pyplot")
+
+
+def load_reference(root="/root/reference"):
+    """Import the unmodified reference model modules. Build-container only."""
+    import importlib
+    import os
+    if not os.path.isdir(root):
+        raise RuntimeError(f"reference tree {root} not present (it never is on the GPU box)")
+    install()
+    # A product-side `batch_3dmot` re-export package may already be imported; drop it.
+    for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
+        del sys.modules[k]
+    sys.path.insert(0, root)
+    try:
+        pkg = importlib.import_module("batch_3dmot.models")
+        for missing in ("heterolinear", "message_passing", "attention_message_passing"):
+            m = _mod(f"batch_3dmot.models.{missing}", HeteroLinear=None, Linear=None)
+            setattr(pkg, missing, m)
+        pose = importlib.import_module("batch_3dmot.models.pose_gnn")
+        clr = importlib.import_module("batch_3dmot.models.clr_att_gnn")
+    finally:
+        sys.path.remove(root)
+    # leave no trace of the reference package for later product imports
+    for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
+        del sys.modules[k]
+    return pose, clr
