@@ -1,0 +1,116 @@
+"""ctypes binding of libb3d.so (include/b3d.h). The product path has NO fallback: if the
+library is missing or a call fails, this raises."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb3d.so")
+
+MASK_NONE, MASK_RELU, MASK_SIGMOID = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+FLAG_ACCUMULATE = 1
+MAX_SEGS = 8
+
+
+class Seg(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("idx", C.c_void_p), ("mask", C.c_void_p), ("width", C.c_int32),
+                ("ld", C.c_int32), ("ldmask", C.c_int32), ("mask_mode", C.c_int32)]
+
+
+_SIGS = {
+    "b3d_last_error": (C.c_char_p, []),
+    "b3d_launch_count": (C.c_int64, []),
+    "b3d_reset_launch_count": (None, []),
+    "b3d_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "b3d_csr_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 6 +
+                      [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "b3d_segment_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                  C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "b3d_gather_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                  C.c_int32, C.c_void_p]),
+    "b3d_linear": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                             C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                             C.c_int32, C.c_void_p, C.c_void_p]),
+    "b3d_wgrad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "b3d_wgrad": (C.c_int, [C.POINTER(Seg), C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                            C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b3d_knn_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b3d_gat_aggregate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b3d_row_nonzero": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b3d_bce_partials": (C.c_int64, [C.c_int64]),
+    "b3d_bce_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b3d_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int32, C.c_float,
+                                                                                  C.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names declared in include/b3d.h (used by the CPU test that checks the .so exports them)."""
+    return sorted(_SIGS)
+
+
+def lib():
+    """Load libb3d.so (once). Raises if it has not been built: there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m batch3dmot_b200.build` "
+                               "(the product path has no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            f = getattr(l, name)
+            f.restype, f.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"libb3d {what} failed (rc={rc}): {lib().b3d_last_error().decode()}")
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _check_f32_rows(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1, \
+        f"expected a CUDA fp32 row-major matrix, got {t.dtype} {tuple(t.shape)} {t.stride()}"
+
+
+def make_segs(items):
+    """items: list of (tensor[rows,width], idx int32 or None, mask tensor or None, mask_mode)."""
+    assert 1 <= len(items) <= MAX_SEGS
+    arr = (Seg * len(items))()
+    for s, (t, idx, mask, mode) in zip(arr, items):
+        _check_f32_rows(t)
+        s.ptr, s.width, s.ld = t.data_ptr(), t.size(1), t.stride(0)
+        s.idx = idx.data_ptr() if idx is not None else None
+        if idx is not None:
+            assert idx.dtype == torch.int32 and idx.is_contiguous()
+        if mask is not None:
+            _check_f32_rows(mask)
+            s.mask, s.ldmask, s.mask_mode = mask.data_ptr(), mask.stride(0), mode
+        else:
+            s.mask, s.ldmask, s.mask_mode = None, 0, MASK_NONE
+    return arr
+
+
+def launch_count():
+    return int(lib().b3d_launch_count())
+
+
+def reset_launch_count():
+    lib().b3d_reset_launch_count()

@@ -1,0 +1,214 @@
+// Frame-local brute-force k-NN with warp-level top-k selection, and the GATConv
+// softmax-aggregate over the resulting padded neighbour table.
+#include <limits.h>
+#include <math.h>
+
+#include "b3d_common.cuh"
+
+namespace b3d {
+
+constexpr int KNN_QB = 32;      // queries per block
+constexpr int KNN_WARPS = 8;    // one warp owns KNN_QPW queries
+constexpr int KNN_QPW = KNN_QB / KNN_WARPS;
+constexpr int KNN_CT = 64;      // candidates staged per tile
+
+__global__ void k_knn_blockptr(const int32_t* __restrict__ frame_ptr, int F, int32_t* __restrict__ blk_ptr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    blk_ptr[0] = 0;
+    for (int f = 0; f < F; ++f) {
+      int n = frame_ptr[f + 1] - frame_ptr[f];
+      acc += (n + KNN_QB - 1) / KNN_QB;
+      blk_ptr[f + 1] = acc;
+    }
+  }
+}
+
+__device__ __forceinline__ bool pair_less(float d0, int i0, float d1, int i1) {
+  return d0 < d1 || (d0 == d1 && i0 < i1);
+}
+
+// stride: floats per staged row, >= round_up(D,4), == 4 (mod 8) -> conflict-free LDS.128
+__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_frames(
+    const float* __restrict__ x, int ldx, int D, int stride, const int32_t* __restrict__ frame_ptr, int F,
+    const int32_t* __restrict__ blk_ptr, int k, int64_t* __restrict__ idx_out) {
+  extern __shared__ __align__(16) float sm[];
+  float* q_s = sm;                      // [KNN_QB][stride]
+  float* c_s = sm + KNN_QB * stride;    // [KNN_CT][stride]
+  const int b = blockIdx.x;
+  if (b >= __ldg(blk_ptr + F)) return;
+  int lo = 0, hi = F;  // find frame f: blk_ptr[f] <= b < blk_ptr[f+1]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(blk_ptr + mid) <= b) lo = mid; else hi = mid;
+  }
+  const int f = lo;
+  const int fs = __ldg(frame_ptr + f), fe = __ldg(frame_ptr + f + 1);
+  const int q0 = fs + (b - __ldg(blk_ptr + f)) * KNN_QB;
+  const int nq = min(KNN_QB, fe - q0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D4 = (D + 3) & ~3;
+
+  for (int i = tid; i < KNN_QB * D4; i += KNN_WARPS * 32) {
+    int r = i / D4, d = i - r * D4;
+    q_s[r * stride + d] = (r < nq && d < D) ? __ldg(x + (long long)(q0 + r) * ldx + d) : 0.f;
+  }
+  float bd[KNN_QPW];
+  int bi[KNN_QPW];
+#pragma unroll
+  for (int qq = 0; qq < KNN_QPW; ++qq) { bd[qq] = INFINITY; bi[qq] = INT_MAX; }
+
+  for (int c0 = fs; c0 < fe; c0 += KNN_CT) {
+    const int nc = min(KNN_CT, fe - c0);
+    __syncthreads();  // previous tile fully consumed (and q_s visible on first pass)
+    for (int i = tid; i < KNN_CT * D4; i += KNN_WARPS * 32) {
+      int r = i / D4, d = i - r * D4;
+      c_s[r * stride + d] = (r < nc && d < D) ? __ldg(x + (long long)(c0 + r) * ldx + d) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int half = 0; half < KNN_CT / 32; ++half) {
+      const int j = half * 32 + lane;
+      const int cand = c0 + j;
+      const bool cvalid = j < nc;
+      float dist[KNN_QPW];
+#pragma unroll
+      for (int qq = 0; qq < KNN_QPW; ++qq) dist[qq] = 0.f;
+      const float4* cp = reinterpret_cast<const float4*>(c_s + j * stride);
+      for (int d4 = 0; d4 < D4 / 4; ++d4) {
+        const float4 cv = cp[d4];
+#pragma unroll
+        for (int qq = 0; qq < KNN_QPW; ++qq) {
+          const float4 qv = reinterpret_cast<const float4*>(q_s + (warp * KNN_QPW + qq) * stride)[d4];
+          float t;
+          // ascending feature order, separate multiply and add (no FMA): the A.5 spec
+          t = __fsub_rn(qv.x, cv.x); dist[qq] = __fadd_rn(dist[qq], __fmul_rn(t, t));
+          t = __fsub_rn(qv.y, cv.y); dist[qq] = __fadd_rn(dist[qq], __fmul_rn(t, t));
+          t = __fsub_rn(qv.z, cv.z); dist[qq] = __fadd_rn(dist[qq], __fmul_rn(t, t));
+          t = __fsub_rn(qv.w, cv.w); dist[qq] = __fadd_rn(dist[qq], __fmul_rn(t, t));
+        }
+      }
+#pragma unroll
+      for (int qq = 0; qq < KNN_QPW; ++qq) {
+        const int q = q0 + warp * KNN_QPW + qq;
+        if (warp * KNN_QPW + qq >= nq) continue;  // warp-uniform
+        const float kd = __shfl_sync(0xffffffffu, bd[qq], k - 1);
+        const int ki = __shfl_sync(0xffffffffu, bi[qq], k - 1);
+        const bool beats = cvalid && cand != q && pair_less(dist[qq], cand, kd, ki);
+        unsigned m = __ballot_sync(0xffffffffu, beats);
+        while (m) {
+          const int srcl = __ffs(m) - 1;
+          m &= m - 1;
+          const float cd = __shfl_sync(0xffffffffu, dist[qq], srcl);
+          const int ci = __shfl_sync(0xffffffffu, cand, srcl);
+          const int pos = __popc(__ballot_sync(0xffffffffu, pair_less(bd[qq], bi[qq], cd, ci)));
+          const float ud = __shfl_up_sync(0xffffffffu, bd[qq], 1);
+          const int ui = __shfl_up_sync(0xffffffffu, bi[qq], 1);
+          if (pos < k) {
+            if (lane > pos) { bd[qq] = ud; bi[qq] = ui; }
+            else if (lane == pos) { bd[qq] = cd; bi[qq] = ci; }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int qq = 0; qq < KNN_QPW; ++qq) {
+    if (warp * KNN_QPW + qq >= nq) continue;
+    const long long q = q0 + warp * KNN_QPW + qq;
+    if (lane < k) idx_out[q * k + lane] = (bi[qq] == INT_MAX) ? (int64_t)-1 : (int64_t)bi[qq];
+  }
+}
+
+// ------------------------------------------------------------------ GAT
+__global__ void __launch_bounds__(256) k_gat_scores(const float* __restrict__ h, int ldh, int D,
+                                                    const float* __restrict__ att_src,
+                                                    const float* __restrict__ att_dst, long long N,
+                                                    float* __restrict__ a_s, float* __restrict__ a_d) {
+  const int lane = threadIdx.x & 31;
+  const long long n = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float s = 0.f, d = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    float v = __ldg(h + n * ldh + c);
+    s = fmaf(v, __ldg(att_src + c), s);
+    d = fmaf(v, __ldg(att_dst + c), d);
+  }
+  s = warp_sum(s); d = warp_sum(d);
+  if (lane == 0) { a_s[n] = s; a_d[n] = d; }
+}
+
+__global__ void __launch_bounds__(256) k_gat_aggregate(
+    const float* __restrict__ h, int ldh, int D, const float* __restrict__ a_s, const float* __restrict__ a_d,
+    const float* __restrict__ bias, const int64_t* __restrict__ nbr, int k, long long N, float slope,
+    float* __restrict__ out, int ldo, float* __restrict__ alpha_out) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= N) return;
+  long long nb = (lane < k) ? nbr[t * k + lane] : -1;
+  const bool valid = nb >= 0;
+  float z = -INFINITY;
+  if (valid) {
+    z = __ldg(a_s + nb) + __ldg(a_d + t);
+    z = z > 0.f ? z : slope * z;
+  }
+  const float zmax = warp_max(z);
+  const float ez = valid ? expf(z - zmax) : 0.f;
+  const float den = warp_sum(ez);
+  const float alpha = valid ? ez / (den + 1e-16f) : 0.f;
+  if (alpha_out && lane < k) alpha_out[t * k + lane] = alpha;
+  for (int c = lane; c < D; c += 32) {
+    float acc = 0.f;
+    for (int l = 0; l < k; ++l) {
+      const float al = __shfl_sync(0xffffffffu, alpha, l);
+      const long long nl = __shfl_sync(0xffffffffu, nb, l);
+      if (nl >= 0) acc = __fadd_rn(acc, __fmul_rn(al, __ldg(h + nl * ldh + c)));
+    }
+    out[t * ldo + c] = acc + (bias ? __ldg(bias + c) : 0.f);
+  }
+}
+
+}  // namespace b3d
+
+using namespace b3d;
+
+extern "C" int b3d_knn_frames(const float* x, int32_t ldx, int32_t D, const int32_t* frame_ptr, int32_t F,
+                              int64_t N, int32_t k, int64_t* idx_out, int32_t* scratch, void* stream) {
+  if (!x || !frame_ptr || !idx_out || !scratch) return bad_arg("b3d_knn_frames: null pointer");
+  if (k < 1 || k > 32) return bad_arg("b3d_knn_frames: k must be in [1,32]");
+  if (D < 1 || D > 256) return bad_arg("b3d_knn_frames: D must be in [1,256]");
+  if (N == 0 || F == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int stride = (D + 3) & ~3;
+  while ((stride & 7) != 4) stride += 4;
+  size_t smem = sizeof(float) * (size_t)(KNN_QB + KNN_CT) * stride;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_knn_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail("knn smem attr", e);
+    smem_set = smem;
+  }
+  k_knn_blockptr<<<1, 32, 0, st>>>(frame_ptr, F, scratch);
+  B3D_LAUNCH_CHECK("k_knn_blockptr");
+  unsigned grid = (unsigned)(ceil_div(N, KNN_QB) + F);
+  k_knn_frames<<<grid, KNN_WARPS * 32, smem, st>>>(x, ldx, D, stride, frame_ptr, F, scratch, k, idx_out);
+  B3D_LAUNCH_CHECK("k_knn_frames");
+  return 0;
+}
+
+extern "C" int b3d_gat_aggregate(const float* h, int32_t ldh, int32_t D, const float* att_src,
+                                 const float* att_dst, const float* bias, const int64_t* nbr, int32_t k,
+                                 int64_t N, float slope, float* out, int32_t ldo, float* alpha_out,
+                                 float* scratch, void* stream) {
+  if (!h || !att_src || !att_dst || !nbr || !out || !scratch) return bad_arg("b3d_gat_aggregate: null pointer");
+  if (k < 1 || k > 32) return bad_arg("b3d_gat_aggregate: k must be in [1,32]");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* a_s = scratch;
+  float* a_d = scratch + N;
+  k_gat_scores<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(h, ldh, D, att_src, att_dst, N, a_s, a_d);
+  B3D_LAUNCH_CHECK("k_gat_scores");
+  k_gat_aggregate<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(h, ldh, D, a_s, a_d, bias, nbr, k, N, slope, out, ldo, alpha_out);
+  B3D_LAUNCH_CHECK("k_gat_aggregate");
+  return 0;
+}

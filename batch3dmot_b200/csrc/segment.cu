@@ -1,0 +1,123 @@
+// Deterministic warp-per-node segmented reduction (replaces torch_scatter atomics),
+// row gather (its backward) and the modality-present row predicate.
+#include "b3d_common.cuh"
+
+namespace b3d {
+
+constexpr int SEG_WARPS = 8;
+
+// One warp per node; lanes cover columns (float4 when aligned); edges summed in ascending
+// k = the order sequential CPU scatter_add_ uses, so results match index_add_ bit-for-bit.
+template <bool VEC>
+__global__ void __launch_bounds__(SEG_WARPS * 32) k_segment_sum(
+    const float* __restrict__ src, int ld, const int32_t* __restrict__ perm,
+    const int32_t* __restrict__ rowptr, long long N, int C, float* __restrict__ out, int ldo, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long node = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int beg = __ldg(rowptr + node), end = __ldg(rowptr + node + 1);
+  if (VEC) {
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int k = beg;
+      for (; k + 4 <= end; k += 4) {  // 4 independent loads in flight, summed in order
+        long long e0 = perm ? __ldg(perm + k) : k, e1 = perm ? __ldg(perm + k + 1) : k + 1;
+        long long e2 = perm ? __ldg(perm + k + 2) : k + 2, e3 = perm ? __ldg(perm + k + 3) : k + 3;
+        float4 v0 = __ldg(reinterpret_cast<const float4*>(src + e0 * ld + c));
+        float4 v1 = __ldg(reinterpret_cast<const float4*>(src + e1 * ld + c));
+        float4 v2 = __ldg(reinterpret_cast<const float4*>(src + e2 * ld + c));
+        float4 v3 = __ldg(reinterpret_cast<const float4*>(src + e3 * ld + c));
+        acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+        acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+        acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+        acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+      }
+      for (; k < end; ++k) {
+        long long e = perm ? __ldg(perm + k) : k;
+        float4 v = __ldg(reinterpret_cast<const float4*>(src + e * ld + c));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      float4* o = reinterpret_cast<float4*>(out + node * ldo + c);
+      if (accumulate) { float4 p = *o; acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w; }
+      *o = acc;
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) {
+      float acc = 0.f;
+      for (int k = beg; k < end; ++k) {
+        long long e = perm ? __ldg(perm + k) : k;
+        acc += __ldg(src + e * ld + c);
+      }
+      float* o = out + node * ldo + c;
+      *o = accumulate ? *o + acc : acc;
+    }
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows(
+    const float* __restrict__ src, int ld, const int32_t* __restrict__ idx, long long M, int C,
+    float* __restrict__ out, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
+  if (r >= M) return;
+  const long long g = __ldg(idx + r);
+  if (VEC) {
+    for (int c = lane * 4; c < C; c += 128)
+      *reinterpret_cast<float4*>(out + r * ldo + c) = __ldg(reinterpret_cast<const float4*>(src + g * ld + c));
+  } else {
+    for (int c = lane; c < C; c += 32) out[r * ldo + c] = __ldg(src + g * ld + c);
+  }
+}
+
+__global__ void __launch_bounds__(SEG_WARPS * 32) k_row_nonzero(const float* __restrict__ f, long long row_len,
+                                                               long long N, uint8_t* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
+  if (r >= N) return;
+  const float* p = f + r * row_len;
+  float s = 0.f;
+  for (long long c = lane; c < row_len; c += 32) s += __ldg(p + c);
+  s = warp_sum(s);
+  if (lane == 0) mask[r] = (s != 0.f) ? 1 : 0;
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace b3d
+
+using namespace b3d;
+
+extern "C" int b3d_segment_sum(const float* src, int32_t ld_src, const int32_t* perm,
+                               const int32_t* rowptr, int64_t N, int32_t C, float* out, int32_t ld_out,
+                               int32_t flags, void* stream) {
+  if (!src || !rowptr || !out || C <= 0 || N < 0) return bad_arg("b3d_segment_sum");
+  if (N == 0) return 0;
+  bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
+  unsigned grid = (unsigned)ceil_div(N, SEG_WARPS);
+  int acc = (flags & B3D_FLAG_ACCUMULATE) ? 1 : 0;
+  if (vec) k_segment_sum<true><<<grid, SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(src, ld_src, perm, rowptr, N, C, out, ld_out, acc);
+  else k_segment_sum<false><<<grid, SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(src, ld_src, perm, rowptr, N, C, out, ld_out, acc);
+  B3D_LAUNCH_CHECK("k_segment_sum");
+  return 0;
+}
+
+extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
+                               float* out, int32_t ld_out, void* stream) {
+  if (!src || !idx || !out || C <= 0 || M < 0) return bad_arg("b3d_gather_rows");
+  if (M == 0) return 0;
+  bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
+  unsigned grid = (unsigned)ceil_div(M, SEG_WARPS);
+  if (vec) k_gather_rows<true><<<grid, SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(src, ld_src, idx, M, C, out, ld_out);
+  else k_gather_rows<false><<<grid, SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(src, ld_src, idx, M, C, out, ld_out);
+  B3D_LAUNCH_CHECK("k_gather_rows");
+  return 0;
+}
+
+extern "C" int b3d_row_nonzero(const float* feats, int64_t row_len, int64_t N, uint8_t* mask, void* stream) {
+  if (!feats || !mask || row_len <= 0 || N < 0) return bad_arg("b3d_row_nonzero");
+  if (N == 0) return 0;
+  k_row_nonzero<<<(unsigned)ceil_div(N, SEG_WARPS), SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(feats, row_len, N, mask);
+  B3D_LAUNCH_CHECK("k_row_nonzero");
+  return 0;
+}

@@ -1,0 +1,283 @@
+"""Host-side operators over the libb3d C ABI: thin wrappers plus torch.autograd.Functions so
+the drop-in layers train with the reference's own `loss.backward(); optimizer.step()`
+(train.py:157-160). Every FLOP on this path runs in a libb3d kernel; torch provides device
+memory, streams and autograd bookkeeping only."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+# ----------------------------------------------------------------------------- graph tables
+class NodeIndex:
+    """One endpoint of the edge list: int32 ids per edge plus the CSR that groups edges by
+    that endpoint (rowptr [n+1], stable perm [E])."""
+    __slots__ = ("idx", "rowptr", "perm", "n", "sorted")
+
+    def __init__(self, idx, rowptr, perm, n, is_sorted=False):
+        self.idx, self.rowptr, self.perm, self.n, self.sorted = idx, rowptr, perm, n, is_sorted
+
+
+class Graph:
+    """CSC (by target) + CSR (by source) of an edge_index, built once on device by the radix
+    sort in csr.cu (replaces the per-call atomics of torch_scatter, pose_gnn.py:190-191)."""
+
+    def __init__(self, edge_index, num_nodes, check=False):
+        assert edge_index.is_cuda and edge_index.dtype == torch.int64 and edge_index.dim() == 2 \
+            and edge_index.size(0) == 2, "edge_index must be a CUDA int64 [2,E] tensor"  # __check_input__
+        ei = edge_index.contiguous()
+        dev = ei.device
+        E, N = ei.size(1), int(num_nodes)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.E, self.N = E, N
+        self.src32, self.dst32 = torch.empty(E, **i32), torch.empty(E, **i32)
+        self.rowptr_dst, self.perm_dst = torch.empty(N + 1, **i32), torch.empty(E, **i32)
+        self.rowptr_src, self.perm_src = torch.empty(N + 1, **i32), torch.empty(E, **i32)
+        self.status = torch.zeros(1, **i32)
+        lib = L.lib()
+        wsb = lib.b3d_csr_workspace_bytes(E, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        L.check(lib.b3d_csr_build(L.ptr(ei), E, N, L.ptr(self.src32), L.ptr(self.dst32),
+                                  L.ptr(self.rowptr_dst), L.ptr(self.perm_dst), L.ptr(self.rowptr_src),
+                                  L.ptr(self.perm_src), L.ptr(ws), wsb, L.ptr(self.status), L.stream()),
+                "b3d_csr_build")
+        if check and int(self.status.item()) != 0:   # optional (syncs)
+            raise IndexError("edge_index holds node ids outside [0, num_nodes)")
+        self.by_dst = NodeIndex(self.dst32, self.rowptr_dst, self.perm_dst, N)
+        self.by_src = NodeIndex(self.src32, self.rowptr_src, self.perm_src, N)
+
+
+_graph_cache = {}
+
+
+def graph_of(edge_index, num_nodes):
+    """Cache keyed by the edge_index storage, so the sort really is one-time per graph."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes))
+    g = _graph_cache.get(key)
+    if g is None:
+        if len(_graph_cache) > 64:
+            _graph_cache.clear()
+        g = _graph_cache[key] = Graph(edge_index, num_nodes)
+        g._keepalive = edge_index
+    return g
+
+
+# ----------------------------------------------------------------------------- raw wrappers
+def _rows(t):
+    if t.dim() == 1:
+        t = t.unsqueeze(1)
+    if t.stride(1) != 1 or t.dtype != torch.float32:
+        t = t.contiguous().float()
+    return t
+
+
+def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accumulate=False,
+               out_mask=None, row_mask=None, n_out=None):
+    """items: [(tensor, idx32|None, mask|None, mode)]. Returns Y [M, n_out]."""
+    segs = L.make_segs(items)
+    if n_out is None:
+        n_out = W.size(1) if trans_w else W.size(0)
+    assert W.dtype == torch.float32 and W.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float32, device=W.device)
+    if bias is not None:
+        assert bias.is_contiguous() and bias.numel() == n_out
+    L.check(L.lib().b3d_linear(segs, len(items), L.ptr(W), W.stride(0), int(trans_w), L.ptr(bias),
+                               L.ptr(out), out.stride(0), M, n_out, act,
+                               L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(out_mask),
+                               out_mask.stride(0) if out_mask is not None else 0, L.ptr(row_mask),
+                               L.stream()), "b3d_linear")
+    return out
+
+
+def wgrad_raw(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=False, want_bias=True):
+    dev = dy_item[0].device
+    if dW is None:
+        dW = torch.empty((n_out, K), dtype=torch.float32, device=dev)
+    if db is None and want_bias:
+        db = torch.empty(n_out, dtype=torch.float32, device=dev)
+    lib = L.lib()
+    wsb = lib.b3d_wgrad_workspace_bytes(M, n_out, K)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    L.check(lib.b3d_wgrad(L.make_segs([dy_item]), L.make_segs(items), len(items), L.ptr(dW), dW.stride(0),
+                          L.ptr(db), M, n_out, L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(ws), wsb,
+                          L.stream()), "b3d_wgrad")
+    return dW, db
+
+
+def segment_sum_raw(src, nidx, out=None, accumulate=False):
+    src = _rows(src)
+    C_ = src.size(1)
+    if out is None:
+        out = torch.empty((nidx.n, C_), dtype=torch.float32, device=src.device)
+    perm = None if nidx.sorted else nidx.perm
+    L.check(L.lib().b3d_segment_sum(L.ptr(src), src.stride(0), L.ptr(perm), L.ptr(nidx.rowptr), nidx.n, C_,
+                                    L.ptr(out), out.stride(0), L.FLAG_ACCUMULATE if accumulate else 0,
+                                    L.stream()), "b3d_segment_sum")
+    return out
+
+
+def gather_rows_raw(src, idx32):
+    src = _rows(src)
+    M = idx32.numel()
+    out = torch.empty((M, src.size(1)), dtype=torch.float32, device=src.device)
+    L.check(L.lib().b3d_gather_rows(L.ptr(src), src.stride(0), L.ptr(idx32), M, src.size(1), L.ptr(out),
+                                    out.stride(0), L.stream()), "b3d_gather_rows")
+    return out
+
+
+def row_nonzero(feats):
+    """bool [N]: sum(feats[n]) != 0 — the modality-present predicate (clr_att_gnn.py:111-121)."""
+    f = feats.reshape(feats.size(0), -1).contiguous().float()
+    mask = torch.empty(f.size(0), dtype=torch.uint8, device=f.device)
+    L.check(L.lib().b3d_row_nonzero(L.ptr(f), f.size(1), f.size(0), L.ptr(mask), L.stream()), "b3d_row_nonzero")
+    return mask.bool()
+
+
+def knn_frames(x, frame_ptr, k):
+    """[N,k] int64 neighbour table (global ids, -1 padded), SURVEY A.5 order."""
+    x = _rows(x.detach())
+    N, D = x.shape
+    fp = frame_ptr.to(device=x.device, dtype=torch.int32).contiguous()
+    F = fp.numel() - 1
+    out = torch.empty((N, k), dtype=torch.int64, device=x.device)
+    scratch = torch.empty(F + 1, dtype=torch.int32, device=x.device)
+    L.check(L.lib().b3d_knn_frames(L.ptr(x), x.stride(0), D, L.ptr(fp), F, N, k, L.ptr(out), L.ptr(scratch),
+                                   L.stream()), "b3d_knn_frames")
+    return out
+
+
+def gat_aggregate(h, att_src, att_dst, bias, nbr, slope=0.2):
+    h = _rows(h)
+    N, D = h.shape
+    out = torch.empty((N, D), dtype=torch.float32, device=h.device)
+    scratch = torch.empty(2 * N, dtype=torch.float32, device=h.device)
+    L.check(L.lib().b3d_gat_aggregate(L.ptr(h), h.stride(0), D, L.ptr(att_src.reshape(-1).contiguous()),
+                                      L.ptr(att_dst.reshape(-1).contiguous()), L.ptr(bias), L.ptr(nbr),
+                                      nbr.size(1), N, slope, L.ptr(out), out.stride(0), None, L.ptr(scratch),
+                                      L.stream()), "b3d_gat_aggregate")
+    return out
+
+
+def adam_step(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale=1.0):
+    """In-place Adam on flat fp32 buffers (train.py:106-109)."""
+    L.check(L.lib().b3d_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, betas[0], betas[1],
+                                  eps, weight_decay, step, grad_scale, L.stream()), "b3d_adam_step")
+
+
+# ----------------------------------------------------------------------------- autograd
+_ACT = {None: L.ACT_NONE, "relu": L.ACT_RELU, "sigmoid": L.ACT_SIGMOID}
+_MASK = {None: L.MASK_NONE, "relu": L.MASK_RELU, "sigmoid": L.MASK_SIGMOID}
+
+
+class _FusedLinear(torch.autograd.Function):
+    """y = act(cat_s(gather(x_s, idx_s)) W^T + b) [rows zeroed by row_mask].
+    Backward: dW/db by the deterministic split-row wgrad, dX by the transposed GEMM, gathered
+    segments reduced back to nodes with the CSR segmented sum (no atomics)."""
+
+    @staticmethod
+    def forward(ctx, W, bias, act, row_mask, nidx, *xs):
+        xs = [_rows(x) for x in xs]
+        M = nidx[0].idx.numel() if nidx[0] is not None else xs[0].size(0)
+        for x, ni in zip(xs, nidx):
+            assert (ni.idx.numel() if ni is not None else x.size(0)) == M, "segment row counts differ"
+        W = W if W.stride(1) == 1 else W.contiguous()
+        assert sum(x.size(1) for x in xs) == W.size(1), "concatenated width != weight in_features"
+        items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
+        rm = row_mask.to(torch.uint8).contiguous() if row_mask is not None else None
+        y = linear_raw(items, W, bias.contiguous() if bias is not None else None, M, _ACT[act], row_mask=rm)
+        ctx.act, ctx.nidx, ctx.M, ctx.has_bias = act, nidx, M, bias is not None
+        ctx.rm = rm
+        ctx.save_for_backward(W, y if act is not None else None, *xs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        W, y, *xs = ctx.saved_tensors
+        nidx, M = ctx.nidx, ctx.M
+        dy = _rows(dy)
+        if ctx.rm is not None:
+            dy = dy * ctx.rm.unsqueeze(1)
+        dy_item = (dy, None, y, _MASK[ctx.act])
+        n_out, K = W.shape
+        dW = db = None
+        if ctx.needs_input_grad[0]:
+            items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
+            dW, db = wgrad_raw(dy_item, items, M, n_out, K, want_bias=ctx.has_bias)
+        need = ctx.needs_input_grad[5:]
+        dxs = [None] * len(xs)
+        if any(need):
+            dA = linear_raw([dy_item], W, None, M, trans_w=True)      # [M, K]
+            off = 0
+            for s, (x, ni) in enumerate(zip(xs, nidx)):
+                w = x.size(1)
+                if need[s]:
+                    sl = dA[:, off:off + w]
+                    dxs[s] = segment_sum_raw(sl, ni) if ni is not None else sl
+                off += w
+        return (dW, db if ctx.has_bias else None, None, None, None, *dxs)
+
+
+def fused_linear(inputs, weight, bias=None, act=None, row_mask=None):
+    """inputs: list of (tensor [rows,w], NodeIndex|None). The concatenation order defines the
+    weight's input-column layout."""
+    xs = [t for t, _ in inputs]
+    nidx = tuple(ni for _, ni in inputs)
+    return _FusedLinear.apply(weight, bias, act, row_mask, nidx, *xs)
+
+
+def run_mlp(seq, inputs, final_act=None, row_mask=None):
+    """Run an nn.Sequential of Linear/ReLU(/Sigmoid) parameter containers through fused_linear."""
+    linears = [m for m in seq if isinstance(m, torch.nn.Linear)]
+    x = None
+    for n, lin in enumerate(linears):
+        last = n == len(linears) - 1
+        act = final_act if last else "relu"
+        x = fused_linear(inputs if n == 0 else [(x, None)], lin.weight, lin.bias, act,
+                         row_mask=row_mask if last else None)
+    return x
+
+
+class _SegmentSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, nidx):
+        ctx.nidx = nidx
+        return segment_sum_raw(src, nidx)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return gather_rows_raw(dout, ctx.nidx.idx), None
+
+
+def segment_sum(src, nidx):
+    """out[n] = sum of src rows whose endpoint is n (torch_scatter.scatter(reduce='add'))."""
+    return _SegmentSum.apply(src, nidx)
+
+
+class _BCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, y, w, scale, from_logits):
+        x = inp.reshape(-1).contiguous().float()
+        E = x.numel()
+        lib = L.lib()
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x)
+        part = torch.empty(int(lib.b3d_bce_partials(E)), dtype=torch.float32, device=x.device)
+        yy = y.reshape(-1).to(torch.int64).contiguous()
+        ww = w.reshape(-1).contiguous().float() if w is not None else None
+        L.check(lib.b3d_bce_fwd_bwd(L.ptr(x), L.ptr(yy), L.ptr(ww), E, float(scale), int(from_logits),
+                                    L.ptr(loss), L.ptr(grad), L.ptr(part), L.stream()), "b3d_bce_fwd_bwd")
+        ctx.save_for_backward(grad)
+        ctx.shape = inp.shape
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dl):
+        (grad,) = ctx.saved_tensors
+        return (grad * dl).reshape(ctx.shape), None, None, None, None
+
+
+def bce_loss(out, y, weight=None, batch_size=1, from_logits=False):
+    """BCELoss(weight)(out, y) / batch_size (train.py:136-141); from_logits for PoseGNN (C11)."""
+    return _BCE.apply(out, y, weight, 1.0 / batch_size, from_logits)

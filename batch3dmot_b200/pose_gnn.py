@@ -1,0 +1,81 @@
+"""Poses-only tracking GNN on libb3d kernels — drop-in for the reference
+batch_3dmot/models/pose_gnn.py (PoseGNN :24-86, CausalMessagePassing :89-252): same
+constructor arguments, forward(data) inputs/outputs and state_dict keys.
+
+The nn.Sequential members are parameter CONTAINERS only (so keys, shapes and default
+initialisation order equal the reference's); compute goes through ops.fused_linear /
+ops.segment_sum, i.e. the gather + concat + Linear + ReLU chains and the two scatter-adds run
+as libb3d kernels."""
+import torch
+from torch import nn
+
+from . import ops
+from .gat import GATConv, knn_attention_conv
+
+
+def _mlp(*dims, inplace=False):
+    mods = []
+    for i in range(len(dims) - 1):
+        mods.append(nn.Linear(dims[i], dims[i + 1]))
+        if i + 2 < len(dims):
+            mods.append(nn.ReLU(inplace=inplace))
+    return nn.Sequential(*mods)
+
+
+class CausalMessagePassing(nn.Module):
+    """Time-aware message passing (pose_gnn.py:89-252). Weights are shared by all iterations.
+    edge_index[0] = source j (earlier node), edge_index[1] = target i (later node)."""
+    node_width, edge_width = 48, 32
+
+    def __init__(self):
+        super().__init__()
+        self.aggr, self.node_dim = "add", 0
+        self.edge_update = _mlp(128, 96, 64, 32)
+        self.create_past_msgs = _mlp(128, 96, 64)
+        self.create_future_msgs = _mlp(128, 96, 64)
+        self.combine_future_past = _mlp(128, 96, 64, 48)
+
+    def forward(self, x, edge_index, edge_attr, initial_x, att_edge_attr=None):
+        g = ops.graph_of(edge_index, x.size(0))
+        return self.forward_graph(x, g, edge_attr, initial_x, att_edge_attr)
+
+    def forward_graph(self, x, g, e, x0, att=None):
+        dst, src = g.by_dst, g.by_src
+        feats = [(x, dst), (x, src), (e, None)] + ([(att, None)] if att is not None else [])  # :210
+        e_new = ops.run_mlp(self.edge_update, feats)
+        fut = ops.run_mlp(self.create_future_msgs, [(x, dst), (e_new, None), (x0, dst)])       # :215
+        past = ops.run_mlp(self.create_past_msgs, [(x, src), (e_new, None), (x0, src)])        # :222
+        m_past = ops.segment_sum(past, dst)     # :190 messages from the past into the later node
+        m_fut = ops.segment_sum(fut, src)       # :191 messages from the future into the earlier node
+        x_new = ops.run_mlp(self.combine_future_past, [(m_past, None), (m_fut, None)])         # :193-196
+        return x_new, e_new
+
+
+class PoseGNN(nn.Module):
+    """forward(data) -> (edge_logits [E,1], x_enc [N,48]) (pose_gnn.py:58-86).
+    edge_dim / node_dim / mp_type are accepted and ignored like the reference (C5).
+    apply_knn_update=False reproduces the shipped behaviour where the k-NN attention conv result
+    is discarded (C1) — the dead compute is skipped; True applies the intended update."""
+
+    def __init__(self, gnn_depth=6, edge_dim=16, node_dim=19, mp_type: str = "attention",
+                 apply_knn_update=False):
+        super().__init__()
+        self.depth = gnn_depth
+        self.apply_knn_update = apply_knn_update
+        self.edge_encoder = _mlp(4, 8, 16, 32, inplace=True)
+        self.node_encoder = _mlp(19, 24, 36, 48)
+        self.edge_classifier = _mlp(32, 16, 8, 4, 1)
+        self.knn_conv = GATConv(48, 48, add_self_loops=False)
+        self.message_passing = CausalMessagePassing()
+
+    def forward(self, data):
+        pose, ei = data.pose_feats, data.edge_index
+        g = getattr(data, "_b3d_graph", None) or ops.graph_of(ei, pose.size(0))
+        e = ops.run_mlp(self.edge_encoder, [(data.edge_attr.float(), None)])         # :67
+        x0 = ops.run_mlp(self.node_encoder, [(pose, None)])                          # :68 (C6: once)
+        x, x_enc = x0, x0
+        for i in range(self.depth):
+            if i % 2 == 0 and self.apply_knn_update:
+                x = knn_attention_conv(self.knn_conv, x, data.node_timestamps)
+            x, e = self.message_passing.forward_graph(x, g, e, x0)                   # :83
+        return ops.run_mlp(self.edge_classifier, [(e, None)]), x_enc                 # :86

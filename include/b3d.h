@@ -1,0 +1,160 @@
+/*
+ * b3d.h — C ABI of libb3d.so: the B200 (sm_100a) kernels behind the Batch3DMOT
+ * tracking-graph GNN hot path.
+ *
+ * The reference (robot-learning-freiburg/Batch3DMOT) has no FFI layer for this
+ * path: its boundary is the Python layer API in batch_3dmot/models/pose_gnn.py
+ * and clr_att_gnn.py, which reaches device code only through PyTorch /
+ * torch_geometric / torch_scatter / torch_cluster calls. Each entry point below
+ * names the reference call site(s) it replaces (file:line relative to the
+ * reference tree). The host-side binding is batch3dmot_b200/_lib.py (ctypes);
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     stated otherwise; matrices are row-major fp32 with an explicit leading
+ *     dimension (in elements);
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*),
+ *     never allocates, never synchronises; scratch memory is passed in by the
+ *     caller and sized by the *_workspace_bytes functions;
+ *   - return value 0 = success, otherwise a cudaError_t (or -1 for an argument
+ *     error); b3d_last_error() returns a static description;
+ *   - results are deterministic: no floating-point atomics anywhere.
+ */
+#ifndef B3D_H_
+#define B3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B3D_MAX_SEGS 8
+
+/* Operand modifiers for b3d_seg_t.mask_mode / epilogue activations. */
+enum { B3D_MASK_NONE = 0, B3D_MASK_RELU = 1, B3D_MASK_SIGMOID = 2 };
+enum { B3D_ACT_NONE = 0, B3D_ACT_RELU = 1, B3D_ACT_SIGMOID = 2 };
+enum { B3D_FLAG_ACCUMULATE = 1 };   /* out += result instead of out = result */
+
+/* One column block of a (virtually) concatenated, optionally row-gathered
+ * operand: rows r = 0..M-1 read ptr[(idx ? idx[r] : r) * ld + 0..width-1].
+ * Replaces torch.cat([...], dim=1) of index_select'ed tensors
+ * (pose_gnn.py:210,215,222; clr_att_gnn.py:161-163,314,319,326) and PyG's
+ * MessagePassing.__collect__ gathers (pose_gnn.py:180).
+ * mask (optional, same row addressing as ptr but leading dimension ldmask)
+ * turns the value v into  v * (mask > 0)            for B3D_MASK_RELU,
+ *                         v * mask * (1 - mask)     for B3D_MASK_SIGMOID,
+ * which is how the backward pass of ReLU / Sigmoid is folded into the GEMMs. */
+typedef struct {
+  const float* ptr;
+  const int32_t* idx;
+  const float* mask;
+  int32_t width;
+  int32_t ld;
+  int32_t ldmask;
+  int32_t mask_mode;
+} b3d_seg_t;
+
+const char* b3d_last_error(void);
+/* Number of kernels launched by this library since the last reset (host counter). */
+int64_t b3d_launch_count(void);
+void b3d_reset_launch_count(void);
+
+/* ---- graph plumbing ------------------------------------------------------
+ * One-time stable LSD radix sort of edge_index into CSC (by target,
+ * edge_index[1]) and CSR (by source, edge_index[0]). Replaces the atomics of
+ * torch_scatter.scatter(reduce='add') (pose_gnn.py:240, :190-191;
+ * clr_att_gnn.py:344, :293-294) by segment tables. Bit-exact spec:
+ * perm == torch.argsort(index, stable=True), rowptr == cumsum(bincount).
+ * edge_index: int64 [2,E] contiguous. src32/dst32: int32 [E] copies.
+ * status: int32[1], set non-zero if an index is outside [0,N). */
+size_t b3d_csr_workspace_bytes(int64_t E, int64_t N);
+int b3d_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
+                  int32_t* src32, int32_t* dst32,
+                  int32_t* rowptr_dst, int32_t* perm_dst,
+                  int32_t* rowptr_src, int32_t* perm_src,
+                  void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+
+/* out[n, 0:C] (+)= sum_{k in [rowptr[n], rowptr[n+1])} src[(perm ? perm[k] : k), 0:C]
+ * summed in ascending k (== edge order within the node, as sequential CPU
+ * scatter_add_ does). Warp-per-node segmented reduction.
+ * Replaces torch_scatter.scatter(reduce='add') pose_gnn.py:190-191,240. */
+int b3d_segment_sum(const float* src, int32_t ld_src, const int32_t* perm, const int32_t* rowptr,
+                    int64_t N, int32_t C, float* out, int32_t ld_out, int32_t flags, void* stream);
+
+/* out[r, 0:C] = src[idx[r], 0:C]  (index_select; backward of segment_sum). */
+int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
+                    float* out, int32_t ld_out, void* stream);
+
+/* ---- dense layers with fused gather / concat / activation ------------------
+ * Y[M,Nout] (+)= act( cat_s(A_s)[M,K] * op(W) + bias ) [* (out_mask > 0)] [row_mask]
+ *   trans_w == 0: W is [Nout,K] row-major (nn.Linear.weight), Y = A W^T   (forward)
+ *   trans_w == 1: W is [K,Nout] row-major,                   Y = A W     (input gradient)
+ * Replaces nn.Linear/addmm + torch.cat + index_select + ReLU/Sigmoid chains
+ * (pose_gnn.py:29-53,94-120,210-223; clr_att_gnn.py:35-91,196-222,314-327).
+ * out_mask (optional [M,Nout], ld ldm): multiply result by (out_mask > 0) (ReLU backward
+ * of the producing layer). row_mask (optional uint8[M]): rows with 0 are written as 0
+ * (clr_att_gnn.py:132-133,140-141 zero-fill of missing modalities). */
+int b3d_linear(const b3d_seg_t* segs /*host*/, int32_t nseg, const float* W, int32_t ldw,
+               int32_t trans_w, const float* bias, float* Y, int32_t ldy, int64_t M, int32_t Nout,
+               int32_t act, int32_t flags, const float* out_mask, int32_t ldm,
+               const uint8_t* row_mask, void* stream);
+
+/* dW[Nout,K] (+)= dY^T cat_s(A_s),  db[Nout] (+)= colsum(dY)   (weight gradient)
+ * dy: a single segment (may carry a ReLU/Sigmoid mask). Deterministic split over rows
+ * with a fixed-order second pass; workspace from b3d_wgrad_workspace_bytes. */
+size_t b3d_wgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
+int b3d_wgrad(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, int32_t nseg,
+              float* dW, int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- frame-wise k-NN + attention-weighted convolution ----------------------
+ * Brute-force frame-local k-NN with warp-level top-k selection. Replaces
+ * torch_geometric.nn.knn_graph(x_t, k=20, loop=False) per timestamp
+ * (pose_gnn.py:76-78, clr_att_gnn.py:180-182). Spec: squared L2
+ * accumulated in fp32 in ascending feature order with separate multiply and
+ * add, ordered by (distance, neighbour id), self excluded by id,
+ * k_eff = min(k, n_frame-1). Nodes must be grouped by frame; frame_ptr int32
+ * [F+1]. idx_out: int64 [N,k] global neighbour ids, -1 padded. k <= 32.
+ * scratch: int32 [F+1]. */
+int b3d_knn_frames(const float* x, int32_t ldx, int32_t D, const int32_t* frame_ptr, int32_t F,
+                   int64_t N, int32_t k, int64_t* idx_out, int32_t* scratch, void* stream);
+
+/* GATConv(D,D,heads=1,add_self_loops=False) aggregation over a padded
+ * neighbour table (pose_gnn.py:55,79; clr_att_gnn.py:93,183):
+ * given h = x W^T [N,D] (b3d_linear), a_s = h.att_src, a_d = h.att_dst,
+ * z = leaky_relu(a_s[nbr] + a_d[t], slope), alpha = softmax_t(z) with PyG's +1e-16,
+ * out[t] = sum alpha h[nbr] + bias. alpha_out (optional [N,k]) saves alpha for backward.
+ * scratch: float [2N] (a_s, a_d). */
+int b3d_gat_aggregate(const float* h, int32_t ldh, int32_t D, const float* att_src,
+                      const float* att_dst, const float* bias, const int64_t* nbr, int32_t k,
+                      int64_t N, float slope, float* out, int32_t ldo, float* alpha_out,
+                      float* scratch, void* stream);
+
+/* ---- multimodal front end ---------------------------------------------------
+ * mask[n] = (sum(feats[n, 0:row_len]) != 0): modality-present predicate
+ * (clr_att_gnn.py:107-121, 2N host syncs in the reference). */
+int b3d_row_nonzero(const float* feats, int64_t row_len, int64_t N, uint8_t* mask, void* stream);
+
+/* ---- loss and optimiser ------------------------------------------------------
+ * Weighted BCE (train.py:111,136-141): loss = scale * mean_e w_e * bce(p_e, y_e).
+ * from_logits=1 for PoseGNN (returns logits, pose_gnn.py:86), 0 for GNN (Sigmoid,
+ * clr_att_gnn.py:57). y int64 [E]; w optional. loss_out: float[1]; grad_out [E] =
+ * d loss / d input. partials: float scratch [b3d_bce_partials(E)]. */
+int64_t b3d_bce_partials(int64_t E);
+int b3d_bce_fwd_bwd(const float* input, const int64_t* y, const float* w, int64_t E, float scale,
+                    int32_t from_logits, float* loss_out, float* grad_out, float* partials,
+                    void* stream);
+
+/* torch.optim.Adam step on flat buffers (train.py:106-109,160): L2 weight decay,
+ * bias correction by `step` (1-based). grad_scale multiplies g first (1/world for DP). */
+int b3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B3D_H_ */

@@ -196,16 +196,17 @@ def load_reference(root="/root/reference"):
     # A product-side `batch_3dmot` re-export package may already be imported; drop it.
     for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
         del sys.modules[k]
-    sys.path.insert(0, root)
-    try:
-        pkg = importlib.import_module("batch_3dmot.models")
-        for missing in ("heterolinear", "message_passing", "attention_message_passing"):
-            m = _mod(f"batch_3dmot.models.{missing}", HeteroLinear=None, Linear=None)
-            setattr(pkg, missing, m)
-        pose = importlib.import_module("batch_3dmot.models.pose_gnn")
-        clr = importlib.import_module("batch_3dmot.models.clr_att_gnn")
-    finally:
-        sys.path.remove(root)
+    # The reference's batch_3dmot/ has no __init__.py (namespace package), so a regular package of
+    # the same name elsewhere on sys.path would shadow it: pin the package path explicitly.
+    top = types.ModuleType("batch_3dmot")
+    top.__path__ = [os.path.join(root, "batch_3dmot")]
+    sys.modules["batch_3dmot"] = top
+    pkg = importlib.import_module("batch_3dmot.models")
+    for missing in ("heterolinear", "message_passing", "attention_message_passing"):
+        m = _mod(f"batch_3dmot.models.{missing}", HeteroLinear=None, Linear=None)
+        setattr(pkg, missing, m)
+    pose = importlib.import_module("batch_3dmot.models.pose_gnn")
+    clr = importlib.import_module("batch_3dmot.models.clr_att_gnn")
     # leave no trace of the reference package for later product imports
     for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
         del sys.modules[k]

@@ -1,0 +1,118 @@
+"""CPU tests of the host logic: C-ABI exports, drop-in module surface (constructor args,
+state_dict keys / shapes / default-init parity with the reference), generators."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from batch3dmot_b200 import _lib, synth
+from .conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    hdr = open(os.path.join(ROOT, "include", "b3d.h")).read()
+    declared = sorted(set(re.findall(r"\b(b3d_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == _lib.exported_symbols(), "ctypes table and include/b3d.h disagree"
+    so = ctypes.CDLL(lib_built)
+    for name in declared:
+        assert hasattr(so, name), f"{name} not exported by libb3d.so"
+    # host-only entry points are callable without a GPU
+    so.b3d_csr_workspace_bytes.restype = ctypes.c_size_t
+    so.b3d_csr_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64]
+    assert so.b3d_csr_workspace_bytes(1000, 100) > 0
+    so.b3d_last_error.restype = ctypes.c_char_p
+    assert isinstance(so.b3d_last_error(), bytes)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_pose_gnn_dropin_surface():
+    from batch_3dmot.models.pose_gnn import PoseGNN, CausalMessagePassing   # reference import path
+    g = load_golden("pose_small.pt")
+    torch.manual_seed(5621)
+    m = PoseGNN(gnn_depth=6, edge_dim=16, node_dim=19, mp_type="attention")
+    sd = m.state_dict()
+    ref = g["state_dict"]
+    assert set(sd) | {"knn_conv.lin_dst.weight"} == set(ref) | {"knn_conv.lin_dst.weight"}
+    for k in sd:
+        assert sd[k].shape == ref[k].shape, k
+        assert torch.equal(sd[k], ref[k]), f"default init differs from the reference at {k}"
+    m.load_state_dict(ref, strict=True)       # PyG 2.0.x checkpoints carry lin_dst.weight too
+    assert isinstance(m.message_passing, CausalMessagePassing)
+    assert sum(p.numel() for p in m.parameters()) == 86605
+
+
+def test_mm_gnn_dropin_surface():
+    from batch_3dmot.models.clr_att_gnn import GNN
+    g = load_golden("mm_small.pt")
+    d = g["data"]
+    enc = [synth.EmbeddingEncoder(d[k]) for k in ("x_img", "pointnet_out", "radarnet_out")]
+    torch.manual_seed(5621)
+    m = GNN(*enc, use_attention=True, gnn_depth=6, edge_dim=64, node_dim=179)
+    sd, ref = m.state_dict(), g["state_dict"]
+    assert set(sd) | {"knn_conv.lin_dst.weight"} == set(ref) | {"knn_conv.lin_dst.weight"}
+    for k in sd:
+        assert torch.equal(sd[k], ref[k]), f"default init differs from the reference at {k}"
+    m.load_state_dict(ref, strict=True)
+    trainable = sum(p.numel() for n, p in m.named_parameters() if p.requires_grad)
+    assert trainable == 1319697
+    with pytest.raises(NotImplementedError):
+        GNN(*enc, use_attention=False)
+
+
+def test_newer_pyg_gat_key_spelling_loads():
+    from batch3dmot_b200.gat import GATConv
+    c = GATConv(48, 48)
+    sd = c.state_dict()
+    sd["lin.weight"] = sd.pop("lin_src.weight") + 1
+    c.load_state_dict(sd, strict=True)
+    assert torch.equal(c.lin_src.weight, sd["lin.weight"])
+
+
+def test_scene_graph_properties():
+    g = synth.scene_graph(seed=5621, T=10, nodes_per_frame=20, k=40)
+    src, dst = g.edge_index
+    assert g.pose_feats.shape == (200, 19) and g.edge_attr.dtype == torch.float64
+    assert bool((src < dst).all()) and bool((dst[1:] >= dst[:-1]).all())
+    assert bool((g.node_classes[src] == g.node_classes[dst]).all())          # category-disjoint
+    dt = g.node_timestamps[dst] - g.node_timestamps[src]
+    assert int(dt.min()) >= 1 and int(dt.max()) <= 4
+    assert torch.equal(g.edge_attr[:, 3], dt.double())
+    assert int(torch.bincount(dst).max()) <= 40
+    g2 = synth.scene_graph(seed=5621, T=10, nodes_per_frame=20, k=40)
+    assert torch.equal(g.edge_index, g2.edge_index) and torch.equal(g.pose_feats, g2.pose_feats)
+
+
+def test_config1_shape():
+    g = synth.scene_graph(seed=5621)          # T=40, 50 nodes/frame
+    assert g.num_nodes == 2000 and 50000 < g.edge_index.size(1) < 70000
+
+
+def test_collate_and_windows():
+    a = synth.add_labels(synth.add_modalities(synth.scene_graph(seed=1, T=7, nodes_per_frame=6, k=5), 1), 1)
+    b = synth.add_labels(synth.add_modalities(synth.scene_graph(seed=2, T=6, nodes_per_frame=4, k=5), 2), 2)
+    c = synth.collate([a, b])
+    assert c.num_nodes == a.num_nodes + b.num_nodes
+    assert torch.equal(c.edge_index[:, a.edge_index.size(1):], b.edge_index + a.num_nodes)
+    assert torch.equal(c.batch, torch.cat([torch.zeros(a.num_nodes), torch.ones(b.num_nodes)]).long())
+    assert c.lidar_feats.shape == (c.num_nodes, 128, 3)
+    ws = synth.windows(a, 5)
+    assert len(ws) == 3
+    for w in ws:
+        assert int(w.node_timestamps.max() - w.node_timestamps.min()) <= 4
+        s, d = w.edge_index
+        assert bool((a.edge_index[:, w.global_edge_id] == torch.stack([w.global_node_id[s], w.global_node_id[d]])).all())
+
+
+def test_cb_weights_match_reference_formula():
+    # graph_data.py:126-138 evaluated by hand for 'car' (class id 3)
+    beta, n = 0.8, 5 * synth.REL_FREQ_TRAIN["car"]
+    w = synth.cb_weights(torch.tensor([3.0]))
+    assert abs(float(w) - (1 - beta) / (1 - beta ** n)) < 1e-7
