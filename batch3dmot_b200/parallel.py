@@ -1,0 +1,97 @@
+"""Scene-sharded data parallelism. Scenes / window graphs are independent
+disjoint graphs (predict.py:172-190 builds one Data per window; the graph construction only links
+same-category nodes inside a window), so:
+  * inference shards graphs across ranks with NO data-path collective;
+  * training has exactly one exchange step: a SUM all-reduce of one flat fp32 gradient buffer
+    (1,319,697 floats = 5.28 MB for the multimodal model), then the same Adam step on every rank.
+The reference trains the GNN on a single device (train.py:45); its only DDP precedent is the
+encoder trainer (training/train_resnet_ae_ddp.py:125-175)."""
+import torch
+import torch.distributed as dist
+
+
+def lpt_partition(costs, world_size):
+    """Longest-processing-time bin packing: returns `world_size` lists of item ids, balancing
+    the summed cost (edge counts vary ~10x between scenes). Deterministic: ties by id."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0] * world_size
+    bins = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda j: (loads[j], j))
+        bins[r].append(i)
+        loads[r] += costs[i]
+    for b in bins:
+        b.sort()
+    return bins
+
+
+class FlatParams:
+    """Re-homes a module's trainable parameters (and their .grad) as views of two flat fp32
+    buffers, so weight-gradient kernels accumulate straight into ONE contiguous all-reduce
+    payload and the optimiser is one kernel."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+        self.numel = n
+
+    def zero_grad(self):
+        self.grad.zero_()
+        off = 0
+        for p in self.params:      # re-attach in case autograd replaced .grad
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.grad[off:off + k].data_ptr():
+                p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+
+
+def allreduce_sum_(flat_grad):
+    """The single training collective: NCCL SUM all-reduce over NVLink (gloo in CPU tests)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    return flat_grad
+
+
+class Trainer:
+    """fwd + weighted BCE + bwd + gradient all-reduce + Adam, mirroring train.py:126-160
+    (Adam lr 1e-4, weight_decay 1e-4, betas .9/.999; loss / batch_size)."""
+
+    def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, batch_size=2,
+                 from_logits=False):
+        from . import ops
+        self.ops = ops
+        self.model = model
+        self.fp = FlatParams(model)
+        self.m = torch.zeros_like(self.fp.flat)
+        self.v = torch.zeros_like(self.fp.flat)
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.batch_size, self.from_logits = batch_size, from_logits
+        self.step_no = 0
+
+    def step(self, data, global_edges=None, **fwd_kwargs):
+        """One optimisation step on this rank's shard. With `global_edges` (sum of E over ranks)
+        the local mean loss is re-weighted so that the SUM all-reduce yields exactly the gradient
+        of the mean loss over the union batch."""
+        ops = self.ops
+        self.fp.zero_grad()
+        out, _ = self.model(data, **fwd_kwargs)
+        loss = ops.bce_loss(out, data.y, getattr(data, "edge_weights", None), batch_size=self.batch_size,
+                            from_logits=self.from_logits)
+        if global_edges is not None:
+            loss = loss * (out.size(0) / float(global_edges))
+        loss.backward()
+        allreduce_sum_(self.fp.grad)
+        self.step_no += 1
+        ops.adam_step(self.fp.flat, self.fp.grad, self.m, self.v, self.lr, self.betas, self.eps, self.wd,
+                      self.step_no)
+        return loss.detach()

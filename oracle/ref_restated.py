@@ -223,3 +223,27 @@ def csr_build(index, n):
     rowptr = torch.zeros(n + 1, dtype=torch.long)
     rowptr[1:] = torch.bincount(index, minlength=n).cumsum(0)
     return rowptr, perm
+
+
+# ----------------------------------------------------------------------------- CPU baseline driver
+def build_mha(params):
+    """The three nn.MultiheadAttention modules of clr_att_gnn.py:77-79 loaded from `params`, for
+    the op-faithful (reference-timing) variant of mm_gnn_forward."""
+    out = {}
+    for name, D in (("c2c_att", 96), ("l2l_att", 128), ("r2r_att", 64)):
+        m = torch.nn.MultiheadAttention(embed_dim=D, num_heads=2, kdim=D, vdim=D, batch_first=True)
+        m.load_state_dict({k[len(name) + 1:]: v.detach() for k, v in params.items() if k.startswith(name + ".")})
+        out[name] = m
+    return out
+
+
+def cpu_train_step(params, data, mha=None, batch_size=2):
+    """One reference-style CPU step on `data`: faithful forward (dead k-NN/GAT, six per-edge MHA
+    calls, torch.cat + Linear chains, sequential index_add_ scatters) + BCELoss(weight) + backward
+    (train.py:133-159). Used as the timed CPU baseline; returns the loss value."""
+    for p in params.values():
+        p.grad = None
+    out, _ = mm_gnn_forward(params, data, faithful=mha is not None, mha_modules=mha)
+    loss = bce_loss(out, data.y, getattr(data, "edge_weights", None), batch_size=batch_size)
+    loss.backward()
+    return float(loss.item())

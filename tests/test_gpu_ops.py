@@ -1,0 +1,248 @@
+"""GPU parity tests of the individual libb3d entry points (called through the C ABI via
+ctypes) against the CPU oracle. Integer / index work is bit-exact; fp32 work uses the
+tolerance stated in each test (north_star: 1e-4 relative for the fp32 path)."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import ref_restated as R
+from batch3dmot_b200 import _lib as L, ops, synth
+from .conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------ CSR / radix sort (bit-exact)
+@pytest.mark.parametrize("E,N", [(0, 5), (1, 1), (1000, 50), (60489, 2000), (300000, 70000), (5000, 3)])
+def test_csr_build_bit_exact(E, N):
+    g = torch.Generator().manual_seed(E + N)
+    ei = torch.randint(0, N, (2, E), generator=g)
+    G = ops.Graph(ei.to(DEV), N, check=True)
+    for idx, rowptr, perm in ((ei[1], G.rowptr_dst, G.perm_dst), (ei[0], G.rowptr_src, G.perm_src)):
+        rp, pm = R.csr_build(idx, N)
+        assert torch.equal(rowptr.cpu().long(), rp)
+        assert torch.equal(perm.cpu().long(), pm)
+    assert torch.equal(G.src32.cpu().long(), ei[0]) and torch.equal(G.dst32.cpu().long(), ei[1])
+
+
+def test_csr_reference_ordering_and_bad_index():
+    g = synth.scene_graph(seed=5621)
+    G = ops.Graph(g.edge_index.to(DEV), g.num_nodes, check=True)
+    # reference edge order is target-sorted -> the CSC permutation is the identity
+    assert torch.equal(G.perm_dst.cpu().long(), torch.arange(G.E))
+    bad = g.edge_index.clone(); bad[0, 7] = g.num_nodes
+    with pytest.raises(IndexError):
+        ops.Graph(bad.to(DEV), g.num_nodes, check=True)
+
+
+def test_csr_large_full_size_properties():
+    """BASELINE-sized batch (32 scenes): sortedness + permutation properties instead of the oracle."""
+    scenes = [synth.scene_graph(seed=100 + i) for i in range(8)]
+    c = synth.collate(scenes)
+    ei = c.edge_index.to(DEV)
+    G = ops.Graph(ei, c.num_nodes, check=True)
+    for key, perm, rowptr in ((ei[0], G.perm_src, G.rowptr_src), (ei[1], G.perm_dst, G.rowptr_dst)):
+        p = perm.long()
+        assert torch.equal(torch.sort(p).values, torch.arange(G.E, device=DEV))       # a permutation
+        ks = key[p]
+        assert bool((ks[1:] >= ks[:-1]).all())                                         # sorted
+        same = ks[1:] == ks[:-1]
+        assert bool((p[1:][same] > p[:-1][same]).all())                                # stable
+        assert torch.equal(rowptr.long()[1:] - rowptr.long()[:-1], torch.bincount(key, minlength=c.num_nodes))
+
+
+# ------------------------------------------------------------------ segmented sum (bit-exact vs index_add_)
+@pytest.mark.parametrize("C", [64, 128, 192, 48, 5])
+def test_segment_sum_bit_exact(C):
+    g = synth.scene_graph(seed=7, T=12, nodes_per_frame=30)
+    ei, N = g.edge_index, g.num_nodes
+    G = ops.Graph(ei.to(DEV), N)
+    src = torch.randn(ei.size(1), C)
+    for nidx, index in ((G.by_dst, ei[1]), (G.by_src, ei[0])):
+        got = ops.segment_sum_raw(src.to(DEV), nidx)
+        ref = R.scatter_add(src, index, N)          # sequential CPU order
+        assert torch.equal(got.cpu(), ref)
+    # strided source (column slice) + accumulate
+    wide = torch.randn(ei.size(1), C + 8).to(DEV)
+    out = torch.ones(N, C, device=DEV)
+    ops.segment_sum_raw(wide[:, 4:4 + C], G.by_src, out=out, accumulate=True)
+    ref = 1 + R.scatter_add(wide[:, 4:4 + C].cpu(), ei[0], N)
+    assert rel_err(out, ref) < 1e-6
+
+
+def test_segment_sum_empty_and_isolated():
+    ei = torch.tensor([[0, 0, 3], [5, 5, 5]])
+    G = ops.Graph(ei.to(DEV), 8)
+    src = torch.randn(3, 64)
+    got = ops.segment_sum_raw(src.to(DEV), G.by_dst).cpu()
+    assert torch.equal(got[5], (src[0] + src[1]) + src[2]) and float(got[[0, 1, 2, 3, 4, 6, 7]].abs().max()) == 0
+    assert torch.equal(ops.gather_rows_raw(got.to(DEV), G.dst32).cpu(), got[ei[1]])
+
+
+# ------------------------------------------------------------------ dense layers
+@pytest.mark.parametrize("widths,n_out,gather", [((48, 48, 32), 96, True), ((96, 96, 64, 64), 256, True),
+                                                ((19,), 24, False), ((4,), 8, False), ((64,), 1, False),
+                                                ((64, 128, 96, 64, 128, 96, 64), 512, True)])
+def test_linear_forward(widths, n_out, gather):
+    torch.manual_seed(sum(widths) + n_out)
+    N, M = 300, 1111
+    idx = torch.randint(0, N, (len(widths), M))
+    xs = [torch.randn(N if gather and s % 3 != 2 else M, w) for s, w in enumerate(widths)]
+    W, b = torch.randn(n_out, sum(widths)) * 0.1, torch.randn(n_out)
+    cat = torch.cat([x[idx[s]] if x.size(0) == N and gather else x for s, x in enumerate(xs)], 1)
+    items = [(x.to(DEV), idx[s].int().to(DEV) if (x.size(0) == N and gather) else None, None, 0)
+             for s, x in enumerate(xs)]
+    for act, fn in ((L.ACT_NONE, lambda t: t), (L.ACT_RELU, torch.relu), (L.ACT_SIGMOID, torch.sigmoid)):
+        y = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, act)
+        ref = fn(cat.double() @ W.double().t() + b.double())
+        assert rel_err(y, ref) < 2e-6          # fp32 FMA accumulation vs float64 reference
+    # transposed weight (input gradient) + output ReLU mask + accumulate
+    dy = torch.randn(M, n_out)
+    hmask = torch.randn(M, sum(widths))
+    out = torch.full((M, sum(widths)), 0.5, device=DEV)
+    ops.linear_raw([(dy.to(DEV), None, None, 0)], W.to(DEV), None, M, trans_w=True, out=out, accumulate=True,
+                   out_mask=hmask.to(DEV))
+    ref = 0.5 + (dy.double() @ W.double()) * (hmask > 0)
+    assert rel_err(out, ref) < 2e-6
+
+
+def test_linear_row_mask_and_operand_masks():
+    torch.manual_seed(3)
+    M, K, n_out = 500, 40, 24
+    x, W = torch.randn(M, K), torch.randn(n_out, K)
+    rm = (torch.rand(M) < 0.7)
+    y = ops.linear_raw([(x.to(DEV), None, None, 0)], W.to(DEV), None, M, row_mask=rm.to(torch.uint8).to(DEV))
+    assert rel_err(y, (x @ W.t()) * rm[:, None]) < 2e-6
+    act = torch.rand(M, K) - 0.3
+    y = ops.linear_raw([(x.to(DEV), None, act.to(DEV), L.MASK_RELU)], W.to(DEV), None, M)
+    assert rel_err(y, ((x * (act > 0)).double() @ W.double().t())) < 2e-6
+    sg = torch.sigmoid(act)
+    y = ops.linear_raw([(x.to(DEV), None, sg.to(DEV), L.MASK_SIGMOID)], W.to(DEV), None, M)
+    assert rel_err(y, ((x * sg * (1 - sg)).double() @ W.double().t())) < 2e-6
+
+
+@pytest.mark.parametrize("widths,n_out,M", [((48, 48, 32), 96, 3000), ((19,), 24, 700), ((96, 64, 96), 192, 20000),
+                                            ((4,), 1, 10), ((96, 96, 64, 64), 256, 70000)])
+def test_wgrad(widths, n_out, M):
+    torch.manual_seed(M)
+    N = 257
+    idx = torch.randint(0, N, (len(widths), M))
+    xs = [torch.randn(N if s % 2 == 0 else M, w) for s, w in enumerate(widths)]
+    cat = torch.cat([x[idx[s]] if x.size(0) == N else x for s, x in enumerate(xs)], 1).double()
+    dy, y = torch.randn(M, n_out), torch.randn(M, n_out)
+    items = [(x.to(DEV), idx[s].int().to(DEV) if x.size(0) == N else None, None, 0) for s, x in enumerate(xs)]
+    dW, db = ops.wgrad_raw((dy.to(DEV), None, y.to(DEV), L.MASK_RELU), items, M, n_out, sum(widths))
+    dym = (dy * (y > 0)).double()
+    assert rel_err(dW, dym.t() @ cat) < 1e-5 and rel_err(db, dym.sum(0)) < 1e-5
+    # accumulate + determinism
+    dW2, db2 = ops.wgrad_raw((dy.to(DEV), None, y.to(DEV), L.MASK_RELU), items, M, n_out, sum(widths),
+                             dW=dW.clone(), db=db.clone(), accumulate=True)
+    assert rel_err(dW2, 2 * (dym.t() @ cat)) < 1e-5
+    dW3, _ = ops.wgrad_raw((dy.to(DEV), None, y.to(DEV), L.MASK_RELU), items, M, n_out, sum(widths))
+    assert torch.equal(dW3, dW)
+
+
+def test_fused_linear_autograd_matches_torch():
+    torch.manual_seed(5)
+    g = synth.scene_graph(seed=9, T=8, nodes_per_frame=15, k=8)
+    G = ops.Graph(g.edge_index.to(DEV), g.num_nodes)
+    N, E = g.num_nodes, g.edge_index.size(1)
+    x = torch.randn(N, 48, requires_grad=True); e = torch.randn(E, 32, requires_grad=True)
+    W = (torch.randn(96, 128) * 0.1).requires_grad_(True); b = torch.randn(96, requires_grad=True)
+    ref = torch.relu(torch.cat([x[g.edge_index[1]], x[g.edge_index[0]], e], 1) @ W.t() + b)
+    m_ref = R.scatter_add(ref, g.edge_index[0], N)
+    (m_ref ** 2).sum().backward()
+    xc, ec, Wc, bc = [t.detach().to(DEV).requires_grad_(True) for t in (x, e, W, b)]
+    y = ops.fused_linear([(xc, G.by_dst), (xc, G.by_src), (ec, None)], Wc, bc, "relu")
+    m = ops.segment_sum(y, G.by_src)
+    (m ** 2).sum().backward()
+    assert rel_err(m, m_ref) < 1e-5
+    for a, r in ((xc, x), (ec, e), (Wc, W), (bc, b)):
+        assert rel_err(a.grad, r.grad) < 1e-4
+
+
+# ------------------------------------------------------------------ k-NN (bit-exact) + GAT
+def test_knn_golden_and_gat():
+    g = load_golden("knn_gat_small.pt")
+    idx = ops.knn_frames(g["x"].to(DEV), g["frame_ptr"], g["k"])
+    assert torch.equal(idx.cpu(), g["idx"])
+    sd = g["gat_state_dict"]
+    h = ops.linear_raw([(g["x"].to(DEV), None, None, 0)], sd["knn_conv.lin_src.weight"].to(DEV), None, g["x"].size(0))
+    out = ops.gat_aggregate(h, sd["knn_conv.att_src"].to(DEV), sd["knn_conv.att_dst"].to(DEV),
+                            sd["knn_conv.bias"].to(DEV), idx)
+    assert rel_err(out, g["gat_out"]) < 1e-5
+
+
+@pytest.mark.parametrize("N,frame,D,k,skewed", [(2000, 250, 48, 8, False), (3000, 250, 96, 16, False),
+                                                (2500, 100, 48, 20, True), (600, 7, 96, 20, False),
+                                                (1500, 300, 19, 32, False)])
+def test_knn_grid_features_bit_exact(N, frame, D, k, skewed):
+    """B.3: grid features make every distance exact in fp32; ties are frequent -> tests the
+    (distance, index) tie-break, frames smaller than k, frames of one node."""
+    x, ptr = synth.knn_stress(N + k, N, frame=frame, D=D, skewed=skewed)
+    idx = ops.knn_frames(x.to(DEV), ptr, k)
+    assert torch.equal(idx.cpu(), R.knn_frames(x, ptr, k))
+
+
+def test_knn_continuous_features():
+    x, ptr = synth.knn_stress(77, 2000, frame=200, D=48, continuous=True)
+    idx = ops.knn_frames(x.to(DEV), ptr, 20).cpu()
+    ref = R.knn_frames(x, ptr, 20)
+    assert torch.equal(idx, ref)   # same op order (sub, mul, add in ascending d, no FMA) -> identical
+
+
+def test_knn_large_properties():
+    """Config-3 size (200k nodes): compare a sampled subset of queries with the oracle."""
+    x, ptr = synth.knn_stress(5, 200000, frame=250, D=48)
+    idx = ops.knn_frames(x.to(DEV), ptr, 16).cpu()
+    assert int(idx.min()) >= 0
+    fr = torch.arange(200000) // 250
+    assert bool((fr[idx] == fr[:, None]).all())                       # frame-local
+    assert bool((idx != torch.arange(200000)[:, None]).all())        # self excluded
+    sub = slice(250 * 11, 250 * 13)
+    assert torch.equal(idx[sub], R.knn_frames(x[sub], torch.tensor([0, 250, 500]), 16) + 250 * 11)
+
+
+# ------------------------------------------------------------------ masks, loss, optimiser
+def test_row_nonzero():
+    f = torch.zeros(100, 128, 3)
+    present = torch.rand(100) < 0.6
+    f[present] = torch.randn(int(present.sum()), 128, 3)
+    f[3] = 0; f[3, 5, 1] = 1e-30; present[3] = True
+    assert torch.equal(ops.row_nonzero(f.to(DEV)).cpu(), present)
+
+
+@pytest.mark.parametrize("from_logits", [False, True])
+def test_bce(from_logits):
+    torch.manual_seed(0)
+    E = 10007
+    z = torch.randn(E) * 3
+    y = (torch.rand(E) < 0.1).long()
+    w = torch.rand(E) + 0.5
+    inp = (z if from_logits else torch.sigmoid(z)).requires_grad_(True)
+    ref = (R.bce_logits_loss if from_logits else R.bce_loss)(inp, y, w, batch_size=2)
+    ref.backward()
+    ic = inp.detach().to(DEV).requires_grad_(True)
+    loss = ops.bce_loss(ic, y.to(DEV), w.to(DEV), batch_size=2, from_logits=from_logits)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel_err(ic.grad, inp.grad) < 1e-5
+
+
+def test_adam_matches_torch():
+    torch.manual_seed(1)
+    p = torch.randn(5000, requires_grad=True)
+    opt = torch.optim.Adam([p], lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999))
+    pc = p.detach().clone().to(DEV); m = torch.zeros_like(pc); v = torch.zeros_like(pc)
+    for step in range(1, 4):
+        g = torch.randn(5000)
+        p.grad = g.clone()
+        opt.step()
+        ops.adam_step(pc, g.to(DEV), m, v, 1e-4, (0.9, 0.999), 1e-8, 1e-4, step)
+    assert float((pc.cpu() - p.detach()).abs().max()) < 1e-7
