@@ -157,14 +157,15 @@ __global__ void __launch_bounds__(256) k_gat_aggregate(
   const float den = warp_sum(ez);
   const float alpha = valid ? ez / (den + 1e-16f) : 0.f;
   if (alpha_out && lane < k) alpha_out[t * k + lane] = alpha;
-  for (int c = lane; c < D; c += 32) {
+  for (int c0 = 0; c0 < D; c0 += 32) {   // uniform trip count: the shuffles below need all lanes
+    const int c = c0 + lane;
     float acc = 0.f;
     for (int l = 0; l < k; ++l) {
       const float al = __shfl_sync(0xffffffffu, alpha, l);
       const long long nl = __shfl_sync(0xffffffffu, nb, l);
-      if (nl >= 0) acc = __fadd_rn(acc, __fmul_rn(al, __ldg(h + nl * ldh + c)));
+      if (nl >= 0 && c < D) acc = __fadd_rn(acc, __fmul_rn(al, __ldg(h + nl * ldh + c)));
     }
-    out[t * ldo + c] = acc + (bias ? __ldg(bias + c) : 0.f);
+    if (c < D) out[t * ldo + c] = acc + (bias ? __ldg(bias + c) : 0.f);
   }
 }
 

@@ -357,9 +357,9 @@ extern "C" int b3d_linear(const b3d_seg_t* segs, int32_t nseg, const float* W, i
                           int32_t Nout, int32_t act, int32_t flags, const float* out_mask, int32_t ldm,
                           const uint8_t* row_mask, void* stream) {
   LinArgs a;
+  if (M == 0) return 0;
   if (to_dev(segs, nseg, a.seg)) return bad_arg("b3d_linear segments");
   if (!W || !Y || Nout <= 0 || M < 0) return bad_arg("b3d_linear W/Y/Nout/M");
-  if (M == 0) return 0;
   a.nseg = nseg; a.W = W; a.ldw = ldw; a.trans_w = trans_w; a.bias = bias; a.Y = Y; a.ldy = ldy;
   a.M = M; a.Nout = Nout; a.act = act; a.flags = flags; a.out_mask = out_mask; a.ldm = ldm;
   a.row_mask = row_mask;
@@ -379,12 +379,15 @@ extern "C" int b3d_wgrad(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t nse
                          int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,
                          void* workspace, size_t workspace_bytes, void* stream) {
   WgArgs a;
-  if (to_dev(segs, nseg, a.seg) || to_dev(dy, 1, &a.dy)) return bad_arg("b3d_wgrad segments");
-  if (a.dy.idx) return bad_arg("b3d_wgrad: dy must not be gathered");
-  if (a.dy.width != Nout) return bad_arg("b3d_wgrad: dy.width != Nout");
-  int K = 0;
-  for (int s = 0; s < nseg; ++s) K += a.seg[s].width;
   cudaStream_t st = (cudaStream_t)stream;
+  int K = 0;
+  if (nseg < 1 || nseg > B3D_MAX_SEGS) return bad_arg("b3d_wgrad nseg");
+  for (int s = 0; s < nseg; ++s) K += segs[s].width;
+  if (M > 0) {
+    if (to_dev(segs, nseg, a.seg) || to_dev(dy, 1, &a.dy)) return bad_arg("b3d_wgrad segments");
+    if (a.dy.idx) return bad_arg("b3d_wgrad: dy must not be gathered");
+    if (a.dy.width != Nout) return bad_arg("b3d_wgrad: dy.width != Nout");
+  }
   if (M <= 0) {
     if (!(flags & B3D_FLAG_ACCUMULATE)) {
       for (int n = 0; n < Nout; ++n) cudaMemsetAsync(dW + (size_t)n * lddw, 0, sizeof(float) * K, st);

@@ -91,7 +91,7 @@ using namespace b3d;
 extern "C" int b3d_segment_sum(const float* src, int32_t ld_src, const int32_t* perm,
                                const int32_t* rowptr, int64_t N, int32_t C, float* out, int32_t ld_out,
                                int32_t flags, void* stream) {
-  if (!src || !rowptr || !out || C <= 0 || N < 0) return bad_arg("b3d_segment_sum");
+  if (!rowptr || !out || C <= 0 || N < 0) return bad_arg("b3d_segment_sum");  // src may be NULL when E == 0
   if (N == 0) return 0;
   bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
   unsigned grid = (unsigned)ceil_div(N, SEG_WARPS);
@@ -104,8 +104,8 @@ extern "C" int b3d_segment_sum(const float* src, int32_t ld_src, const int32_t* 
 
 extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
                                float* out, int32_t ld_out, void* stream) {
-  if (!src || !idx || !out || C <= 0 || M < 0) return bad_arg("b3d_gather_rows");
   if (M == 0) return 0;
+  if (!src || !idx || !out || C <= 0 || M < 0) return bad_arg("b3d_gather_rows");
   bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
   unsigned grid = (unsigned)ceil_div(M, SEG_WARPS);
   if (vec) k_gather_rows<true><<<grid, SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(src, ld_src, idx, M, C, out, ld_out);

@@ -24,7 +24,7 @@ def to_dev(ns):
 
 def rel(a, b):
     b = b.double().cpu()
-    return float((a.double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    return float((a.detach().double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
 def check_grads(model, ref_grads, tol=GRAD_TOL, skip_prefix=("knn_conv",)):
