@@ -6,23 +6,6 @@
 
 namespace b3d {
 
-struct SegDev {
-  const float* ptr;
-  const int32_t* idx;
-  const float* mask;
-  int width, ld, ldmask, mask_mode;
-};
-
-static int to_dev(const b3d_seg_t* in, int nseg, SegDev* out) {
-  if (nseg < 1 || nseg > B3D_MAX_SEGS) return -1;
-  for (int s = 0; s < nseg; ++s) {
-    if (!in[s].ptr || in[s].width <= 0 || in[s].ld < in[s].width) return -1;
-    out[s] = SegDev{in[s].ptr, in[s].idx, in[s].mask, in[s].width, in[s].ld,
-                    in[s].mask ? in[s].ldmask : 0, in[s].mask ? in[s].mask_mode : B3D_MASK_NONE};
-  }
-  return 0;
-}
-
 // ------------------------------------------------------------------ forward / dgrad GEMM
 constexpr int BM = 128, BN = 64, BK = 16, LIN_THREADS = 256;
 

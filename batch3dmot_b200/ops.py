@@ -63,6 +63,58 @@ def graph_of(edge_index, num_nodes):
     return g
 
 
+# ----------------------------------------------------------------------------- precision mode
+_PRECISION = "fp32"      # "fp32": FFMA kernels, 1e-4 parity mode; "bf16": tcgen05 tiles, 2e-2 mode
+_TC_MIN_ROWS = 256
+_packed = {}
+
+
+def set_precision(p):
+    """Select the arithmetic of the dense layers: 'fp32' (exact mode) or 'bf16' (tensor-core tiles
+    with fp32 accumulation; layers whose shapes do not fit the tile constraints stay fp32)."""
+    global _PRECISION
+    assert p in ("fp32", "bf16")
+    _PRECISION = p
+
+
+def get_precision():
+    return _PRECISION
+
+
+def invalidate_weight_cache():
+    """Packed bf16 weights are cached per (storage, version); call after updating weights through
+    raw pointers (b3d_adam_step does not bump torch's version counter)."""
+    _packed.clear()
+
+
+def _packed_weight(W, transpose):
+    key = (W.data_ptr(), W._version, tuple(W.shape), W.stride(0), bool(transpose))
+    wp = _packed.get(key)
+    if wp is None:
+        if len(_packed) > 256:
+            _packed.clear()
+        n_log, k_log = (W.size(1), W.size(0)) if transpose else (W.size(0), W.size(1))
+        lib = L.lib()
+        wp = torch.empty(lib.b3d_tc_packed_bytes(n_log, k_log), dtype=torch.uint8, device=W.device)
+        L.check(lib.b3d_tc_pack_weights(L.ptr(W), W.stride(0), n_log, k_log, int(transpose), L.ptr(wp),
+                                        L.stream()), "b3d_tc_pack_weights")
+        _packed[key] = wp
+    return wp
+
+
+def _al16(t):
+    return t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0
+
+
+def _tc_ok(items, M, n_out, K):
+    if _PRECISION != "bf16" or M < _TC_MIN_ROWS or n_out < 16 or K < 32:
+        return False
+    for t, _, mask, _ in items:
+        if t.size(1) % 8 or not _al16(t) or (mask is not None and not _al16(mask)):
+            return False
+    return True
+
+
 # ----------------------------------------------------------------------------- raw wrappers
 def _rows(t):
     if t.dim() == 1:
@@ -83,6 +135,14 @@ def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accum
         out = torch.empty((M, n_out), dtype=torch.float32, device=W.device)
     if bias is not None:
         assert bias.is_contiguous() and bias.numel() == n_out
+    K = sum(t.size(1) for t, _, _, _ in items)
+    if M > 0 and _tc_ok(items, M, n_out, K) and (out_mask is None or _al16(out_mask)):
+        wp = _packed_weight(W, trans_w)
+        L.check(L.lib().b3d_linear_tc(segs, len(items), L.ptr(wp), n_out, K, L.ptr(bias), L.ptr(out),
+                                      out.stride(0), M, act, L.FLAG_ACCUMULATE if accumulate else 0,
+                                      L.ptr(out_mask), out_mask.stride(0) if out_mask is not None else 0,
+                                      L.ptr(row_mask), L.stream()), "b3d_linear_tc")
+        return out
     L.check(L.lib().b3d_linear(segs, len(items), L.ptr(W), W.stride(0), int(trans_w), L.ptr(bias),
                                L.ptr(out), out.stride(0), M, n_out, act,
                                L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(out_mask),
@@ -98,6 +158,14 @@ def wgrad_raw(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=False, w
     if db is None and want_bias:
         db = torch.empty(n_out, dtype=torch.float32, device=dev)
     lib = L.lib()
+    if M > 0 and _tc_ok(items, M, max(n_out, 16), K) and _al16(dy_item[0]) and \
+            (dy_item[2] is None or _al16(dy_item[2])) and n_out * K >= 2048:
+        wsb = lib.b3d_wgrad_tc_workspace_bytes(M, n_out, K)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        L.check(lib.b3d_wgrad_tc(L.make_segs([dy_item]), L.make_segs(items), len(items), L.ptr(dW), dW.stride(0),
+                                 L.ptr(db), M, n_out, L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(ws), wsb,
+                                 L.stream()), "b3d_wgrad_tc")
+        return dW, db
     wsb = lib.b3d_wgrad_workspace_bytes(M, n_out, K)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     L.check(lib.b3d_wgrad(L.make_segs([dy_item]), L.make_segs(items), len(items), L.ptr(dW), dW.stride(0),

@@ -94,4 +94,5 @@ class Trainer:
         self.step_no += 1
         ops.adam_step(self.fp.flat, self.fp.grad, self.m, self.v, self.lr, self.betas, self.eps, self.wd,
                       self.step_no)
+        ops.invalidate_weight_cache()      # raw-pointer update: packed bf16 copies are stale
         return loss.detach()

@@ -171,8 +171,7 @@ def main():
 
     torch.manual_seed(SEED)
     model = GNN(None, None, None).to(dev)
-    if hasattr(model, "set_precision"):
-        model.set_precision(a.precision)
+    ops.set_precision(a.precision)
     trainer = Trainer(model, batch_size=2)
 
     def fwd_kwargs(d):

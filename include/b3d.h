@@ -110,6 +110,24 @@ int b3d_wgrad(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, int3
               float* dW, int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,
               void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- bf16 tensor-core variants (tcgen05.mma, fp32 accumulate in TMEM; 2e-2 tolerance mode) ----
+ * Same semantics as b3d_linear / b3d_wgrad; operands are rounded to bf16 while staged into shared
+ * memory. Requirements: every segment width is a multiple of 8 and rows are 16-byte aligned
+ * (ld % 4 == 0); otherwise -1 is returned and the caller uses the fp32 entry point.
+ * Weights are packed once per weight version into bf16 K-major slabs:
+ *   transpose == 0: B[n][k] = W[n*ldw + k]  (forward,  n_logical = out_features, k_logical = in_features)
+ *   transpose == 1: B[n][k] = W[k*ldw + n]  (input gradient, n_logical = in_features, k_logical = out_features) */
+size_t b3d_tc_packed_bytes(int32_t n_logical, int32_t k_logical);
+int b3d_tc_pack_weights(const float* W, int32_t ldw, int32_t n_logical, int32_t k_logical,
+                        int32_t transpose, void* Wp, void* stream);
+int b3d_linear_tc(const b3d_seg_t* segs /*host*/, int32_t nseg, const void* Wp, int32_t n_logical,
+                  int32_t k_logical, const float* bias, float* Y, int32_t ldy, int64_t M, int32_t act,
+                  int32_t flags, const float* out_mask, int32_t ldm, const uint8_t* row_mask, void* stream);
+size_t b3d_wgrad_tc_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
+int b3d_wgrad_tc(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, int32_t nseg,
+                 float* dW, int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- frame-wise k-NN + attention-weighted convolution ----------------------
  * Brute-force frame-local k-NN with warp-level top-k selection. Replaces
  * torch_geometric.nn.knn_graph(x_t, k=20, loop=False) per timestamp

@@ -1,0 +1,139 @@
+"""GPU parity of the bf16 tensor-core mode (tcgen05 tiles, fp32 accumulation in TMEM).
+Kernel-level: against a float64 reference on bf16-rounded operands (tight: only the accumulation
+order differs). Model-level: against the fp32 CPU oracle within the 2e-2 tolerance north_star
+states for bf16 MLP tiles."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import ref_restated as R
+from batch3dmot_b200 import _lib as L, ops, synth
+from batch3dmot_b200.pose_gnn import PoseGNN
+from batch3dmot_b200.clr_att_gnn import GNN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(autouse=True)
+def bf16_mode():
+    ops.set_precision("bf16")
+    ops.invalidate_weight_cache()
+    yield
+    ops.set_precision("fp32")
+    ops.invalidate_weight_cache()
+
+
+def bf(t):
+    return t.to(torch.bfloat16).to(torch.float64)
+
+
+def rel(a, b):
+    b = b.double().cpu()
+    return float((a.detach().double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _operands(M, widths, N=777):
+    xs = [torch.randn(N if s % 2 == 0 else M, w) for s, w in enumerate(widths)]
+    idx = torch.randint(0, N, (len(widths), M))
+    cat = torch.cat([x[idx[s]] if x.size(0) == N else x for s, x in enumerate(xs)], 1)
+    items = [(x.to(DEV), idx[s].int().to(DEV) if x.size(0) == N else None, None, 0) for s, x in enumerate(xs)]
+    return cat, items
+
+
+@pytest.mark.parametrize("M,widths,n_out", [(1024, (64,), 64), (3000, (48, 48, 32), 96), (5000, (96, 96, 64, 64), 256),
+                                            (2000, (64, 128, 96, 64, 128, 96, 64), 512), (1500, (256,), 128),
+                                            (700, (128,), 48), (300, (192,), 128), (129, (32,), 16)])
+def test_linear_tc(M, widths, n_out):
+    torch.manual_seed(M + n_out)
+    cat, items = _operands(M, widths)
+    W, b = torch.randn(n_out, sum(widths)) * 0.1, torch.randn(n_out)
+    launches = L.launch_count()
+    y = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, L.ACT_RELU)
+    assert M < 256 or L.launch_count() - launches == 2          # pack + k_linear_tc really ran
+    ref = torch.relu(bf(cat) @ bf(W).t() + b.double())
+    assert rel(y, ref) < (1e-5 if M >= 256 else 1e-2)
+    # input gradient form (transposed pack) with the ReLU mask folded into the A operand + accumulate
+    dy, ymask = torch.randn(M, n_out), torch.randn(M, n_out)
+    out = torch.full((M, sum(widths)), 0.25, device=DEV)
+    ops.linear_raw([(dy.to(DEV), None, ymask.to(DEV), L.MASK_RELU)], W.to(DEV), None, M, trans_w=True, out=out,
+                   accumulate=True)
+    if n_out % 8 == 0 and M >= 256 and n_out >= 32:
+        ref = 0.25 + bf(dy * (ymask > 0)) @ bf(W)
+        assert rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,widths,n_out", [(4096, (64,), 64), (3000, (48, 48, 32), 96), (70000, (96, 96, 64, 64), 256),
+                                            (9000, (96, 64, 96), 192), (5000, (128,), 64), (20000, (640,), 512),
+                                            (777, (64,), 32)])
+def test_wgrad_tc(M, widths, n_out):
+    torch.manual_seed(M)
+    cat, items = _operands(M, widths, N=333)
+    dy, y = torch.randn(M, n_out), torch.randn(M, n_out)
+    dW, db = ops.wgrad_raw((dy.to(DEV), None, y.to(DEV), L.MASK_RELU), items, M, n_out, sum(widths))
+    dym = dy * (y > 0)
+    assert rel(dW, bf(dym).t() @ bf(cat)) < 1e-5 and rel(db, bf(dym).sum(0)) < 1e-5
+    dW2, _ = ops.wgrad_raw((dy.to(DEV), None, y.to(DEV), L.MASK_RELU), items, M, n_out, sum(widths))
+    assert torch.equal(dW, dW2)                                   # deterministic
+    dW3, db3 = ops.wgrad_raw((dy.to(DEV), None, y.to(DEV), L.MASK_RELU), items, M, n_out, sum(widths),
+                             dW=dW.clone(), db=db.clone(), accumulate=True)
+    assert rel(dW3, 2 * dW) < 1e-6 and rel(db3, 2 * db) < 1e-6
+
+
+def to_dev(ns):
+    return SimpleNamespace(**{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in vars(ns).items()})
+
+
+def _grad_check(model, gref, tol):
+    worst = 0.0
+    for k, p in model.named_parameters():
+        if k.startswith("knn_conv") or k not in gref:
+            continue
+        got, ref = p.grad, gref[k]
+        if "in_proj" in k:
+            D = ref.size(0) // 3
+            got, ref = got[2 * D:], ref[2 * D:]
+        worst = max(worst, rel(got, ref))
+        assert rel(got, ref) < tol, (k, rel(got, ref))
+    return worst
+
+
+def test_pose_gnn_bf16_vs_oracle():
+    data = synth.add_labels(synth.scene_graph(seed=5621), 5621)
+    torch.manual_seed(5621)
+    m = PoseGNN()
+    params = {k: v.clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    out_ref, _ = R.pose_gnn_forward(params, data)
+    loss_ref = R.bce_logits_loss(out_ref, data.y, data.edge_weights)
+    loss_ref.backward()
+    m = m.to(DEV)
+    d = to_dev(data)
+    launches = L.launch_count()
+    out, _ = m(d)
+    loss = ops.bce_loss(out, d.y, d.edge_weights, from_logits=True)
+    loss.backward()
+    assert L.launch_count() > launches
+    assert rel(out, out_ref) < BF16_TOL
+    assert abs(loss.item() - loss_ref.item()) < BF16_TOL * abs(loss_ref.item())
+    _grad_check(m, {k: v.grad for k, v in params.items() if v.grad is not None}, 5e-2)
+
+
+def test_mm_gnn_bf16_vs_oracle():
+    data = synth.add_labels(synth.add_modalities(synth.scene_graph(seed=5621), 5621, raw=False), 5621)
+    torch.manual_seed(5621)
+    m = GNN(None, None, None)
+    params = {k: v.clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    out_ref, _ = R.mm_gnn_forward(params, data)
+    loss_ref = R.bce_loss(out_ref, data.y, data.edge_weights, batch_size=2)
+    loss_ref.backward()
+    m = m.to(DEV)
+    d = to_dev(data)
+    out, x_sens = m(d, x_img=d.x_img, pointnet_out=d.pointnet_out, radarnet_out=d.radarnet_out, lidar_mask=d.m_lidar,
+                    radar_mask=d.m_radar)
+    loss = ops.bce_loss(out, d.y, d.edge_weights, batch_size=2)
+    loss.backward()
+    assert rel(out, out_ref) < BF16_TOL
+    assert abs(loss.item() - loss_ref.item()) < BF16_TOL * abs(loss_ref.item())
+    _grad_check(m, {k: v.grad for k, v in params.items() if v.grad is not None}, 5e-2)
