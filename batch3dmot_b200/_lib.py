@@ -11,12 +11,13 @@ LIB_PATH = os.path.join(_HERE, "libb3d.so")
 MASK_NONE, MASK_RELU, MASK_SIGMOID = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 FLAG_ACCUMULATE = 1
+F32, BF16 = 0, 1
 MAX_SEGS = 8
 
 
 class Seg(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("idx", C.c_void_p), ("mask", C.c_void_p), ("width", C.c_int32),
-                ("ld", C.c_int32), ("ldmask", C.c_int32), ("mask_mode", C.c_int32)]
+                ("ld", C.c_int32), ("ldmask", C.c_int32), ("mask_mode", C.c_int32), ("dtype", C.c_int32)]
 
 
 _SIGS = {
@@ -40,8 +41,8 @@ _SIGS = {
     "b3d_tc_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p]),
     "b3d_linear_tc": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
-                                C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
-                                C.c_void_p, C.c_void_p]),
+                                C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "b3d_wgrad_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "b3d_wgrad_tc": (C.c_int, [C.POINTER(Seg), C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -94,8 +95,9 @@ def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _check_f32_rows(t):
-    assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1, \
+def _check_f32_rows(t, allow_bf16=False):
+    ok = (torch.float32, torch.bfloat16) if allow_bf16 else (torch.float32,)
+    assert t.is_cuda and t.dtype in ok and t.dim() == 2 and t.stride(1) == 1, \
         f"expected a CUDA fp32 row-major matrix, got {t.dtype} {tuple(t.shape)} {t.stride()}"
 
 
@@ -104,8 +106,9 @@ def make_segs(items):
     assert 1 <= len(items) <= MAX_SEGS
     arr = (Seg * len(items))()
     for s, (t, idx, mask, mode) in zip(arr, items):
-        _check_f32_rows(t)
+        _check_f32_rows(t, allow_bf16=True)
         s.ptr, s.width, s.ld = t.data_ptr(), t.size(1), t.stride(0)
+        s.dtype = BF16 if t.dtype == torch.bfloat16 else F32
         s.idx = idx.data_ptr() if idx is not None else None
         if idx is not None:
             assert idx.dtype == torch.int32 and idx.is_contiguous()

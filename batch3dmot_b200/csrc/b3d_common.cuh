@@ -50,7 +50,7 @@ struct SegDev {
   const float* ptr;
   const int32_t* idx;
   const float* mask;
-  int width, ld, ldmask, mask_mode;
+  int width, ld, ldmask, mask_mode, dtype;
 };
 
 inline int to_dev(const b3d_seg_t* in, int nseg, SegDev* out) {
@@ -58,9 +58,14 @@ inline int to_dev(const b3d_seg_t* in, int nseg, SegDev* out) {
   for (int s = 0; s < nseg; ++s) {
     if (!in[s].ptr || in[s].width <= 0 || in[s].ld < in[s].width) return -1;
     out[s] = SegDev{in[s].ptr, in[s].idx, in[s].mask, in[s].width, in[s].ld,
-                    in[s].mask ? in[s].ldmask : 0, in[s].mask ? in[s].mask_mode : B3D_MASK_NONE};
+                    in[s].mask ? in[s].ldmask : 0, in[s].mask ? in[s].mask_mode : B3D_MASK_NONE, in[s].dtype};
   }
   return 0;
+}
+inline bool all_f32(const SegDev* seg, int nseg) {
+  for (int s = 0; s < nseg; ++s)
+    if (seg[s].dtype != B3D_F32) return false;
+  return true;
 }
 
 }  // namespace b3d

@@ -341,7 +341,7 @@ extern "C" int b3d_linear(const b3d_seg_t* segs, int32_t nseg, const float* W, i
                           const uint8_t* row_mask, void* stream) {
   LinArgs a;
   if (M == 0) return 0;
-  if (to_dev(segs, nseg, a.seg)) return bad_arg("b3d_linear segments");
+  if (to_dev(segs, nseg, a.seg) || !all_f32(a.seg, nseg)) return bad_arg("b3d_linear segments (fp32 only)");
   if (!W || !Y || Nout <= 0 || M < 0) return bad_arg("b3d_linear W/Y/Nout/M");
   a.nseg = nseg; a.W = W; a.ldw = ldw; a.trans_w = trans_w; a.bias = bias; a.Y = Y; a.ldy = ldy;
   a.M = M; a.Nout = Nout; a.act = act; a.flags = flags; a.out_mask = out_mask; a.ldm = ldm;
@@ -367,7 +367,8 @@ extern "C" int b3d_wgrad(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t nse
   if (nseg < 1 || nseg > B3D_MAX_SEGS) return bad_arg("b3d_wgrad nseg");
   for (int s = 0; s < nseg; ++s) K += segs[s].width;
   if (M > 0) {
-    if (to_dev(segs, nseg, a.seg) || to_dev(dy, 1, &a.dy)) return bad_arg("b3d_wgrad segments");
+    if (to_dev(segs, nseg, a.seg) || to_dev(dy, 1, &a.dy) || !all_f32(a.seg, nseg) || !all_f32(&a.dy, 1))
+      return bad_arg("b3d_wgrad segments (fp32 only)");
     if (a.dy.idx) return bad_arg("b3d_wgrad: dy must not be gathered");
     if (a.dy.width != Nout) return bad_arg("b3d_wgrad: dy.width != Nout");
   }

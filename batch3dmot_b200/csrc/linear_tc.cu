@@ -1,26 +1,27 @@
 // bf16 tensor-core ("2e-2 mode") dense layers for sm_100a: tcgen05.mma with fp32 accumulators
 // in TMEM, operands staged in shared memory in the no-swizzle canonical UMMA layouts.
 //
-//   b3d_linear_tc : Y = act(cat_s(gather(A_s)) W^T + b)   (forward and, with a transposed pack,
-//                   the input gradient).  A: fp32 in HBM, converted to bf16 while staging
-//                   (K-major canonical layout); W: pre-packed bf16 slabs (b3d_tc_pack_weights).
-//   b3d_wgrad_tc  : dW = dY^T cat_s(A_s), db = colsum(dY).  Both operands are staged MN-major
-//                   (rows are the reduction dimension), rows split over CTAs, fixed-order reduce.
+//   b3d_linear_tc : Y = act(cat_s(gather(A_s)) W^T + b) [* (out_mask > 0)]  (forward and, with a
+//                   transposed pack, the input gradient). A segments: fp32 (converted to bf16
+//                   while staging) or bf16 (cp.async), K-major canonical layout; W: pre-packed
+//                   bf16 slabs (b3d_tc_pack_weights). Y: fp32 or bf16.
+//   b3d_wgrad_tc  : dW = dY^T cat_s(A_s), db = colsum(dY). Both operands staged MN-major (rows are
+//                   the reduction dimension), rows split over CTAs, fixed-order second pass.
 //
-// Pipeline (both kernels): 128 threads stage chunk c+1 while the tensor core works on chunk c
-// (tcgen05.mma is asynchronous; a tcgen05.commit -> mbarrier frees the stage). Two CTAs per SM
+// Pipeline (both kernels): 256 threads stage chunk c+1 while the tensor core works on chunk c
+// (tcgen05.mma is asynchronous; tcgen05.commit -> mbarrier frees the stage). Two CTAs per SM
 // overlap one CTA's epilogue with the other's main loop.
 #include "b3d_common.cuh"
 #include "tc_common.cuh"
 
 namespace b3d {
 
-
 constexpr int TC_BM = 128;      // rows per CTA (UMMA M)
 constexpr int TC_BK = 64;       // K elements staged per chunk (4 MMAs of K=16)
 constexpr int TC_NMAX = 256;    // max UMMA N per CTA
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;
 constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;  // 16 KB
+constexpr int TC_TAB = 256;     // max 8-column groups of a concatenated operand (K <= 2048)
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : 256u; }
@@ -44,6 +45,22 @@ __global__ void k_pack_weights(const float* __restrict__ W, int ldw, int n_log, 
   Wp[i] = __float2bfloat16_rn(v);
 }
 
+// (segment, offset) of every 8-column group of the concatenated operand; -1 past the end.
+__device__ __forceinline__ void build_group_table(const SegDev* seg, int nseg, int ngroups, int32_t* tab, int tid,
+                                                  int nthreads) {
+  for (int g = tid; g < ngroups; g += nthreads) {
+    int off = g * 8, sg = 0;
+    while (sg < nseg && off >= seg[sg].width) { off -= seg[sg].width; ++sg; }
+    tab[g] = (sg < nseg) ? ((sg << 24) | off) : -1;
+  }
+}
+
+__device__ __forceinline__ const void* seg_addr(const SegDev& S, long long row, int off) {
+  return S.dtype == B3D_BF16
+             ? static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + row * S.ld + off)
+             : static_cast<const void*>(S.ptr + row * S.ld + off);
+}
+
 // ------------------------------------------------------------------ forward / dgrad
 struct TcArgs {
   SegDev seg[B3D_MAX_SEGS];
@@ -51,28 +68,39 @@ struct TcArgs {
   const __nv_bfloat16* Wp;
   int Npad, Kpad;
   const float* bias;
-  float* Y;
-  int ldy;
+  void* Y;
+  int ldy, y_bf16;
   long long M;
   int Nout, act, flags;
-  const float* out_mask;
-  int ldm;
+  const void* out_mask;
+  int ldm, mask_bf16;
   const uint8_t* row_mask;
 };
 
+template <int ACT>
+__device__ __forceinline__ float activate(float v) {
+  if (ACT == B3D_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == B3D_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+template <int ACT>
 __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   using namespace tc;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * TC_BM;
   const int n0 = blockIdx.y * TC_NMAX;
   const int Nb = min(TC_NMAX, a.Npad - n0);
   const uint32_t b_stage = (uint32_t)Nb * (TC_BK * 2);   // Nb rows x 128 B
+  const uint32_t base_off = 2 * TC_A_STAGE + 2 * b_stage;
   const uint32_t sA = smem_u32(smem);
   const uint32_t sB = sA + 2 * TC_A_STAGE;
-  const uint32_t sBar = sB + 2 * b_stage;                // free[0], free[1], done, tmem ptr
-  int32_t* s_grow = reinterpret_cast<int32_t*>(smem + 2 * TC_A_STAGE + 2 * b_stage + 64);  // [nseg][128]
-  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + 2 * TC_A_STAGE + 2 * b_stage + 24);
+  const uint32_t sBar = sA + base_off;                    // free[0] @0, free[1] @8, done @16, tmem ptr @24
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + base_off + 24);
+  float* s_bias = reinterpret_cast<float*>(smem + base_off + 64);                       // [256]
+  int32_t* s_tab = reinterpret_cast<int32_t*>(smem + base_off + 64 + 1024);            // [TC_TAB]
+  int32_t* s_grow = reinterpret_cast<int32_t*>(smem + base_off + 64 + 1024 + 4 * TC_TAB);  // [nseg][128]
   const uint32_t ncols = tmem_cols_for(Nb);
 
   if (warp == 0) tmem_alloc(sBar + 24, ncols);
@@ -82,10 +110,14 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
     mbar_init(sBar + 16, 1);
     fence_mbar_init();
   }
-  const long long row = m0 + tid;
-  const bool row_ok = row < a.M;
-  for (int s = 0; s < a.nseg; ++s)
-    s_grow[s * TC_BM + tid] = row_ok ? (a.seg[s].idx ? __ldg(a.seg[s].idx + row) : (int32_t)row) : 0;
+  const int arow = tid & (TC_BM - 1), ahalf = tid >> 7;   // A staging role: row, which 4 of the 8 groups
+  const long long grow_row = m0 + arow;
+  const bool arow_ok = grow_row < a.M;
+  if (tid < TC_BM)
+    for (int s = 0; s < a.nseg; ++s)
+      s_grow[s * TC_BM + tid] = arow_ok ? (a.seg[s].idx ? __ldg(a.seg[s].idx + grow_row) : (int32_t)grow_row) : 0;
+  if (tid < Nb) s_bias[tid] = (a.bias && n0 + tid < a.Nout) ? __ldg(a.bias + n0 + tid) : 0.f;
+  build_group_table(a.seg, a.nseg, a.Kpad / 8, s_tab, tid, TC_THREADS);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -102,42 +134,43 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
     {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.Wp) + ((size_t)(c * 8) * a.Npad + n0) * 16;
       const uint32_t dst = sB + s * b_stage;
+      if (tid < Nb) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        for (int n = tid; n < Nb; n += TC_THREADS)
-          cp_async16(dst + (uint32_t)(g * Nb + n) * 16, wsrc + ((size_t)g * a.Npad + n) * 16);
+        for (int g = 0; g < 8; ++g)
+          cp_async16(dst + (uint32_t)(g * Nb + tid) * 16, wsrc + ((size_t)g * a.Npad + tid) * 16);
+      }
     }
-    // ---- A: one row per thread, 64 columns = 8 groups of 8 (gather + fp32->bf16)
+    // ---- A: thread = (row, half): 4 groups of 8 columns; bf16 sources by cp.async, fp32 via registers
     {
-      float4 v[16];
+      float4 v[8];
+      int ent[4];
+      const uint32_t dst0 = sA + s * TC_A_STAGE + arow * 16;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        int off = c * TC_BK + g * 8, sg = 0;
-        while (sg < a.nseg && off >= a.seg[sg].width) { off -= a.seg[sg].width; ++sg; }
-        if (row_ok && sg < a.nseg) {
-          const SegDev& S = a.seg[sg];
-          const long long gr = s_grow[sg * TC_BM + tid];
-          const float4* p = reinterpret_cast<const float4*>(S.ptr + gr * S.ld + off);
-          v[2 * g] = __ldg(p);
-          v[2 * g + 1] = __ldg(p + 1);
-          if (S.mask_mode != B3D_MASK_NONE) {
-            const float4* mp = reinterpret_cast<const float4*>(S.mask + gr * S.ldmask + off);
-            const float4 m0v = __ldg(mp), m1v = __ldg(mp + 1);
-            v[2 * g].x = apply_mask(v[2 * g].x, m0v.x, S.mask_mode); v[2 * g].y = apply_mask(v[2 * g].y, m0v.y, S.mask_mode);
-            v[2 * g].z = apply_mask(v[2 * g].z, m0v.z, S.mask_mode); v[2 * g].w = apply_mask(v[2 * g].w, m0v.w, S.mask_mode);
-            v[2 * g + 1].x = apply_mask(v[2 * g + 1].x, m1v.x, S.mask_mode); v[2 * g + 1].y = apply_mask(v[2 * g + 1].y, m1v.y, S.mask_mode);
-            v[2 * g + 1].z = apply_mask(v[2 * g + 1].z, m1v.z, S.mask_mode); v[2 * g + 1].w = apply_mask(v[2 * g + 1].w, m1v.w, S.mask_mode);
+      for (int j = 0; j < 4; ++j) {
+        const int g = ahalf * 4 + j;
+        ent[j] = arow_ok ? s_tab[c * 8 + g] : -1;
+        if (ent[j] >= 0) {
+          const SegDev& S = a.seg[ent[j] >> 24];
+          const long long gr = s_grow[(ent[j] >> 24) * TC_BM + arow];
+          const void* p = seg_addr(S, gr, ent[j] & 0xFFFFFF);
+          if (S.dtype == B3D_BF16) {
+            cp_async16(dst0 + g * (TC_BM * 16), p);
+            ent[j] = -2;   // done
+          } else {
+            v[2 * j] = __ldg(reinterpret_cast<const float4*>(p));
+            v[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
           }
-        } else {
-          v[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
-          v[2 * g + 1] = v[2 * g];
         }
       }
-      const uint32_t dst = sA + s * TC_A_STAGE + tid * 16;
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        st_shared_v4(dst + g * (TC_BM * 16), pack_bf16x2(v[2 * g].x, v[2 * g].y), pack_bf16x2(v[2 * g].z, v[2 * g].w),
-                     pack_bf16x2(v[2 * g + 1].x, v[2 * g + 1].y), pack_bf16x2(v[2 * g + 1].z, v[2 * g + 1].w));
+      for (int j = 0; j < 4; ++j) {
+        const int g = ahalf * 4 + j;
+        if (ent[j] >= 0)
+          st_shared_v4(dst0 + g * (TC_BM * 16), pack_bf16x2(v[2 * j].x, v[2 * j].y), pack_bf16x2(v[2 * j].z, v[2 * j].w),
+                       pack_bf16x2(v[2 * j + 1].x, v[2 * j + 1].y), pack_bf16x2(v[2 * j + 1].z, v[2 * j + 1].w));
+        else if (ent[j] == -1)
+          st_shared_v4(dst0 + g * (TC_BM * 16), 0u, 0u, 0u, 0u);
+      }
     }
     cp_async_wait_all();
     fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -146,10 +179,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
       tc_fence_after_sync();
 #pragma unroll
       for (int j = 0; j < TC_BK / 16; ++j) {
-        const uint32_t aaddr = sA + s * TC_A_STAGE + j * 2 * lbo_a;
-        const uint32_t baddr = sB + s * b_stage + j * 2 * lbo_b;
-        const uint64_t ad = make_smem_desc(aaddr, lbo_a, sbo);
-        const uint64_t bd = make_smem_desc(baddr, lbo_b, sbo);
+        const uint64_t ad = make_smem_desc(sA + s * TC_A_STAGE + j * 2 * lbo_a, lbo_a, sbo);
+        const uint64_t bd = make_smem_desc(sB + s * b_stage + j * 2 * lbo_b, lbo_b, sbo);
         mma_bf16_ss(tmem, ad, bd, idesc, (c | j) != 0);
       }
       mma_commit(sBar + 8 * s);
@@ -159,44 +190,101 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
   mbar_wait(sBar + 16, 0);
   tc_fence_after_sync();
 
-  // ---- epilogue: TMEM -> registers -> bias / activation / masks -> global (row per thread)
+  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column blocks (w/4), (w/4)+2, ...
+  const int lq = warp & 3;
+  const long long row = m0 + lq * 32 + lane;
+  const bool row_ok = row < a.M;
+  const bool plain = !a.out_mask && !a.row_mask && !(a.flags & B3D_FLAG_ACCUMULATE);
   const bool rz = row_ok && a.row_mask && a.row_mask[row] == 0;
-  const bool vec_ok = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0);
-  for (int col0 = 0; col0 < Nb; col0 += 32) {
+  for (int col0 = (warp >> 2) * 32; col0 < Nb; col0 += 64) {
     uint32_t r[32];
-    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)col0, r);
+    tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)col0, r);
     tmem_ld_wait();
     if (!row_ok) continue;
-    float* yrow = a.Y + row * a.ldy;
+    float o[32];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int cbase = n0 + col0 + 4 * q;
-      if (cbase >= a.Nout) break;
-      float o[4];
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * q);
+      o[4 * q + 0] = activate<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x);
+      o[4 * q + 1] = activate<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y);
+      o[4 * q + 2] = activate<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z);
+      o[4 * q + 3] = activate<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w);
+    }
+    const int cbase = n0 + col0;
+    if (!plain) {
+      if (a.out_mask) {   // ReLU backward of the producing layer: keep the gradient where its output was > 0
+        if (a.mask_bf16 && cbase + 31 < a.Nout && (a.ldm & 7) == 0) {
+          const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cc = cbase + j;
-        float val = __uint_as_float(r[4 * q + j]);
-        if (cc < a.Nout) {
-          if (a.bias) val += __ldg(a.bias + cc);
-          if (a.act == B3D_ACT_RELU) val = fmaxf(val, 0.f);
-          else if (a.act == B3D_ACT_SIGMOID) val = 1.f / (1.f + expf(-val));
-          if (a.out_mask) val = (__ldg(a.out_mask + row * a.ldm + cc) > 0.f) ? val : 0.f;
-          if (rz) val = 0.f;
-        }
-        o[j] = val;
-      }
-      if (vec_ok && cbase + 3 < a.Nout) {
-        float4* yp = reinterpret_cast<float4*>(yrow + cbase);
-        if (a.flags & B3D_FLAG_ACCUMULATE) { float4 p = *yp; o[0] += p.x; o[1] += p.y; o[2] += p.z; o[3] += p.w; }
-        *yp = make_float4(o[0], o[1], o[2], o[3]);
-      } else {
+          for (int q = 0; q < 4; ++q) {
+            const uint4 m = __ldg(mp + q);
+            const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (cbase + j < a.Nout) {
-            float* yp = yrow + cbase + j;
-            *yp = (a.flags & B3D_FLAG_ACCUMULATE) ? *yp + o[j] : o[j];
+            for (int j = 0; j < 4; ++j) {
+              if ((int16_t)(w[j] & 0xFFFFu) <= 0) o[8 * q + 2 * j] = 0.f;      // bf16 > 0  <=>  int16 bits > 0
+              if ((int16_t)(w[j] >> 16) <= 0) o[8 * q + 2 * j + 1] = 0.f;
+            }
           }
+        } else if (!a.mask_bf16 && cbase + 31 < a.Nout && (a.ldm & 3) == 0) {
+          const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.out_mask) + row * a.ldm + cbase);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 m = __ldg(mp + q);
+            if (!(m.x > 0.f)) o[4 * q] = 0.f;
+            if (!(m.y > 0.f)) o[4 * q + 1] = 0.f;
+            if (!(m.z > 0.f)) o[4 * q + 2] = 0.f;
+            if (!(m.w > 0.f)) o[4 * q + 3] = 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int cc = cbase + j;
+            if (cc < a.Nout) {
+              const float mv = a.mask_bf16
+                  ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.out_mask)[row * a.ldm + cc])
+                  : reinterpret_cast<const float*>(a.out_mask)[row * a.ldm + cc];
+              o[j] = mv > 0.f ? o[j] : 0.f;
+            }
+          }
+        }
+      }
+      if (rz) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = 0.f;
+      }
+      if ((a.flags & B3D_FLAG_ACCUMULATE) && !a.y_bf16) {
+        const float* yrow = reinterpret_cast<const float*>(a.Y) + row * a.ldy;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cbase + j < a.Nout) o[j] += yrow[cbase + j];
+      }
+    }
+    if (a.y_bf16) {
+      __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(a.Y) + row * a.ldy + cbase;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (cbase + 8 * q + 7 < a.Nout) {
+          uint4 pk = make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
+                                pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
+          *reinterpret_cast<uint4*>(yrow + 8 * q) = pk;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (cbase + 8 * q + j < a.Nout) yrow[8 * q + j] = __float2bfloat16_rn(o[8 * q + j]);
+        }
+      }
+    } else {
+      float* yrow = reinterpret_cast<float*>(a.Y) + row * a.ldy + cbase;
+      const bool vec_ok = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (vec_ok && cbase + 4 * q + 3 < a.Nout) {
+          *reinterpret_cast<float4*>(yrow + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (cbase + 4 * q + j < a.Nout) yrow[4 * q + j] = o[4 * q + j];
+        }
       }
     }
   }
@@ -217,20 +305,33 @@ struct WgTcArgs {
   float* part;                         // [S][Nout][Ktot+1]
 };
 
+// Stage one 8-element piece (row r, 8 consecutive columns at `p`) of an fp32/bf16 source.
+__device__ __forceinline__ void stage_piece(uint32_t dst, const void* p, int dtype) {
+  using namespace tc;
+  if (dtype == B3D_BF16) {
+    cp_async16(dst, p);
+  } else {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    st_shared_v4(dst, pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   using namespace tc;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x;
   const int nt = blockIdx.y / a.ktiles, kt = blockIdx.y % a.ktiles;
   const int n0 = nt * TC_BM, k0 = kt * TC_NMAX;
   const int Nk = min(TC_NMAX, a.Kp - k0);
   const uint32_t b_stage = (uint32_t)Nk * 128;
+  const uint32_t base_off = 2 * TC_A_STAGE + 2 * b_stage;
   const uint32_t sA = smem_u32(smem);
   const uint32_t sB = sA + 2 * TC_A_STAGE;
-  const uint32_t sBar = sB + 2 * b_stage;
-  int32_t* s_grow = reinterpret_cast<int32_t*>(smem + 2 * TC_A_STAGE + 2 * b_stage + 64);  // [nseg][64]
-  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + 2 * TC_A_STAGE + 2 * b_stage + 24);
+  const uint32_t sBar = sA + base_off;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + base_off + 24);
+  int32_t* s_tab = reinterpret_cast<int32_t*>(smem + base_off + 64);   // [TC_TAB]
   const uint32_t ncols = tmem_cols_for(Nk);
   if (warp == 0) tmem_alloc(sBar + 24, ncols);
   if (tid == 0) {
@@ -239,6 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
     mbar_init(sBar + 16, 1);
     fence_mbar_init();
   }
+  build_group_table(a.seg, a.nseg, a.Kp / 8 + 1, s_tab, tid, TC_THREADS);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -249,91 +351,63 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
   const int nchunks = (int)((r1 - r0 + TC_BK - 1) / TC_BK);
   const uint32_t idesc = make_idesc_bf16(TC_BM, (uint32_t)Nk, 1, 1);
   const int rl = tid & 7;        // row within an 8-row group
-  const int gq = tid >> 3;       // 0..15: which 8-wide MN group this thread starts at
+  const int gq = tid >> 3;       // 0..31
 
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
     const long long rbase = r0 + (long long)c * TC_BK;
     if (c >= 2) mbar_wait(sBar + 8 * s, ((c >> 1) - 1) & 1);
-    // gathered source rows of this chunk, per segment
-    __syncthreads();   // previous chunk's readers of s_grow are done
-    for (int i = tid; i < a.nseg * TC_BK; i += TC_THREADS) {
-      const int sg = i / TC_BK;
-      const long long r = rbase + (i % TC_BK);
-      s_grow[i] = (r < r1) ? (a.seg[sg].idx ? __ldg(a.seg[sg].idx + r) : (int32_t)r) : -1;
-    }
-    __syncthreads();
-    // ---- A' = dY^T chunk: [128 n][64 r]
+    // ---- A' = dY^T chunk: 16 n-groups x 64 rows; thread: n-group gq&15, r-groups (gq>>4)*4 .. +3
+    {
+      const int ng = gq & 15;
+      const int n = n0 + ng * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = i * 8 + rl;
-      const long long r = rbase + rr;
-      const int n = n0 + gq * 8;
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-      if (r < r1 && n < a.Nout) {
-        const float* p = a.dy.ptr + r * a.dy.ld + n;
-        if (n + 7 < a.Nout) {
-          v0 = __ldg(reinterpret_cast<const float4*>(p));
-          v1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-          if (a.dy.mask_mode != B3D_MASK_NONE) {
-            const float4* mp = reinterpret_cast<const float4*>(a.dy.mask + r * a.dy.ldmask + n);
-            const float4 m0v = __ldg(mp), m1v = __ldg(mp + 1);
-            v0.x = apply_mask(v0.x, m0v.x, a.dy.mask_mode); v0.y = apply_mask(v0.y, m0v.y, a.dy.mask_mode);
-            v0.z = apply_mask(v0.z, m0v.z, a.dy.mask_mode); v0.w = apply_mask(v0.w, m0v.w, a.dy.mask_mode);
-            v1.x = apply_mask(v1.x, m1v.x, a.dy.mask_mode); v1.y = apply_mask(v1.y, m1v.y, a.dy.mask_mode);
-            v1.z = apply_mask(v1.z, m1v.z, a.dy.mask_mode); v1.w = apply_mask(v1.w, m1v.w, a.dy.mask_mode);
-          }
-        } else {
+      for (int j = 0; j < 4; ++j) {
+        const int i = (gq >> 4) * 4 + j;
+        const long long r = rbase + i * 8 + rl;
+        const uint32_t dst = sA + s * TC_A_STAGE + ng * 1024 + i * 128 + rl * 16;
+        if (r < r1 && n + 7 < a.Nout) {
+          stage_piece(dst, seg_addr(a.dy, r, n), a.dy.dtype);
+        } else if (r < r1 && n < a.Nout) {   // ragged tail of Nout (not a multiple of 8): scalar
           float t[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            t[j] = 0.f;
-            if (n + j < a.Nout) {
-              t[j] = __ldg(p + j);
-              if (a.dy.mask_mode != B3D_MASK_NONE)
-                t[j] = apply_mask(t[j], __ldg(a.dy.mask + r * a.dy.ldmask + n + j), a.dy.mask_mode);
-            }
-          }
-          v0 = make_float4(t[0], t[1], t[2], t[3]); v1 = make_float4(t[4], t[5], t[6], t[7]);
+          for (int q = 0; q < 8; ++q)
+            t[q] = (n + q < a.Nout)
+                       ? (a.dy.dtype == B3D_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.dy.ptr)[r * a.dy.ld + n + q])
+                                                 : a.dy.ptr[r * a.dy.ld + n + q])
+                       : 0.f;
+          st_shared_v4(dst, pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+        } else {
+          st_shared_v4(dst, 0u, 0u, 0u, 0u);
         }
       }
-      st_shared_v4(sA + s * TC_A_STAGE + gq * 1024 + i * 128 + rl * 16, pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w),
-                   pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
     }
-    // ---- B' = Acat^T chunk: [Nk k][64 r]
-    for (int kg = gq; kg < Nk / 8; kg += 16) {
-      const int col = k0 + kg * 8;
-      int off = col, sg = 0;
-      while (sg < a.nseg && off >= a.seg[sg].width) { off -= a.seg[sg].width; ++sg; }
+    // ---- B' = Acat^T chunk: Nk/8 k-groups x 64 rows; thread: k-group gq, all 8 r-groups
+    if (gq < Nk / 8) {
+      const int ent = s_tab[k0 / 8 + gq];
+      const bool ones = (ent < 0) && (k0 + gq * 8 == a.Ktot);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int rr = i * 8 + rl;
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (sg < a.nseg) {
-          const int gr = s_grow[sg * TC_BK + rr];
-          if (gr >= 0) {
-            const SegDev& S = a.seg[sg];
-            const float4* p = reinterpret_cast<const float4*>(S.ptr + (long long)gr * S.ld + off);
-            v0 = __ldg(p);
-            v1 = __ldg(p + 1);
-          }
-        } else if (col == a.Ktot && rbase + rr < r1) {
-          v0.x = 1.f;   // virtual ones column -> bias gradient
+        const long long r = rbase + i * 8 + rl;
+        const uint32_t dst = sB + s * b_stage + gq * 1024 + i * 128 + rl * 16;
+        if (ent >= 0 && r < r1) {
+          const SegDev& S = a.seg[ent >> 24];
+          const long long gr = S.idx ? (long long)__ldg(S.idx + r) : r;
+          stage_piece(dst, seg_addr(S, gr, ent & 0xFFFFFF), S.dtype);
+        } else {
+          st_shared_v4(dst, (ones && r < r1) ? 0x00003F80u : 0u, 0u, 0u, 0u);   // bf16(1.0) in element 0
         }
-        st_shared_v4(sB + s * b_stage + kg * 1024 + i * 128 + rl * 16, pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w),
-                     pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
       }
     }
+    cp_async_wait_all();
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after_sync();
 #pragma unroll
       for (int j = 0; j < TC_BK / 16; ++j) {
-        const uint32_t aaddr = sA + s * TC_A_STAGE + j * 256;
-        const uint32_t baddr = sB + s * b_stage + j * 256;
-        const uint64_t ad = make_smem_desc(aaddr, 128, 1024);   // LBO: next 8-row K group, SBO: next 8-wide MN group
-        const uint64_t bd = make_smem_desc(baddr, 128, 1024);
+        const uint64_t ad = make_smem_desc(sA + s * TC_A_STAGE + j * 256, 128, 1024);   // LBO: next 8-row K group
+        const uint64_t bd = make_smem_desc(sB + s * b_stage + j * 256, 128, 1024);      // SBO: next 8-wide MN group
         mma_bf16_ss(tmem, ad, bd, idesc, (c | j) != 0);
       }
       mma_commit(sBar + 8 * s);
@@ -345,11 +419,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
     mbar_wait(sBar + 16, 0);
     tc_fence_after_sync();
   }
-  const int n = n0 + tid;   // TMEM lane == output row n
-  for (int col0 = 0; col0 < Nk; col0 += 32) {
+  const int lq = warp & 3;
+  const int n = n0 + lq * 32 + lane;   // TMEM lane == output row n
+  for (int col0 = (warp >> 2) * 32; col0 < Nk; col0 += 64) {
     uint32_t r[32];
     if (nchunks > 0) {
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)col0, r);
+      tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)col0, r);
       tmem_ld_wait();
     } else {
 #pragma unroll
@@ -399,12 +474,10 @@ static void wgrad_tc_plan(long long M, int Nout, int Ktot, int* S, long long* rp
   *rps = r;
 }
 
-static bool segs_tc_ok(const SegDev* seg, int nseg) {
-  for (int s = 0; s < nseg; ++s)
-    if ((seg[s].width & 7) || (seg[s].ld & 3) || (reinterpret_cast<uintptr_t>(seg[s].ptr) & 15) ||
-        (seg[s].mask_mode != B3D_MASK_NONE && ((seg[s].ldmask & 3) || (reinterpret_cast<uintptr_t>(seg[s].mask) & 15))))
-      return false;
-  return true;
+static bool seg_tc_ok(const SegDev& S) {
+  if (S.mask_mode != B3D_MASK_NONE || (S.width & 7)) return false;
+  if (reinterpret_cast<uintptr_t>(S.ptr) & 15) return false;
+  return S.dtype == B3D_BF16 ? (S.ld & 7) == 0 : (S.dtype == B3D_F32 && (S.ld & 3) == 0);
 }
 
 }  // namespace b3d
@@ -427,31 +500,41 @@ extern "C" int b3d_tc_pack_weights(const float* W, int32_t ldw, int32_t n_logica
 }
 
 extern "C" int b3d_linear_tc(const b3d_seg_t* segs, int32_t nseg, const void* Wp, int32_t n_logical,
-                             int32_t k_logical, const float* bias, float* Y, int32_t ldy, int64_t M, int32_t act,
-                             int32_t flags, const float* out_mask, int32_t ldm, const uint8_t* row_mask,
-                             void* stream) {
+                             int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype,
+                             int64_t M, int32_t act, int32_t flags, const void* out_mask, int32_t ldm,
+                             int32_t mask_dtype, const uint8_t* row_mask, void* stream) {
   if (M == 0) return 0;
   TcArgs a;
   if (to_dev(segs, nseg, a.seg)) return bad_arg("b3d_linear_tc segments");
-  if (!segs_tc_ok(a.seg, nseg)) return bad_arg("b3d_linear_tc: segment widths must be multiples of 8, 16-byte aligned");
   int K = 0;
-  for (int s = 0; s < nseg; ++s) K += a.seg[s].width;
+  for (int s = 0; s < nseg; ++s) {
+    if (!seg_tc_ok(a.seg[s])) return bad_arg("b3d_linear_tc: segment widths % 8, 16-byte aligned rows, no operand masks");
+    K += a.seg[s].width;
+  }
   if (K != k_logical) return bad_arg("b3d_linear_tc: sum of segment widths != k_logical");
   if (!Wp || !Y || n_logical <= 0 || M < 0) return bad_arg("b3d_linear_tc W/Y/N/M");
+  if (round_up(K, TC_BK) / 8 > TC_TAB) return bad_arg("b3d_linear_tc: K too large");
+  if (y_dtype == B3D_BF16 && ((ldy & 7) || (reinterpret_cast<uintptr_t>(Y) & 15) || (flags & B3D_FLAG_ACCUMULATE)))
+    return bad_arg("b3d_linear_tc: bf16 output needs ld % 8 == 0, 16-byte alignment, no accumulate");
   a.nseg = nseg; a.Ktot = K; a.Wp = reinterpret_cast<const __nv_bfloat16*>(Wp);
   a.Npad = round_up(n_logical, 16); a.Kpad = round_up(k_logical, TC_BK);
-  a.bias = bias; a.Y = Y; a.ldy = ldy; a.M = M; a.Nout = n_logical; a.act = act; a.flags = flags;
-  a.out_mask = out_mask; a.ldm = ldm; a.row_mask = row_mask;
+  a.bias = bias; a.Y = Y; a.ldy = ldy; a.y_bf16 = (y_dtype == B3D_BF16); a.M = M; a.Nout = n_logical; a.act = act;
+  a.flags = flags; a.out_mask = out_mask; a.ldm = ldm; a.mask_bf16 = (mask_dtype == B3D_BF16); a.row_mask = row_mask;
   int Nb = a.Npad < TC_NMAX ? a.Npad : TC_NMAX;
-  size_t smem = 2 * TC_A_STAGE + 2 * (size_t)Nb * 128 + 64 + sizeof(int32_t) * B3D_MAX_SEGS * TC_BM;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  size_t smem = 2 * TC_A_STAGE + 2 * (size_t)Nb * 128 + 64 + 1024 + 4 * TC_TAB + sizeof(int32_t) * B3D_MAX_SEGS * TC_BM;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_linear_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return fail("k_linear_tc smem attr", e);
-    smem_set = 112 * 1024;
+    attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(M, TC_BM), (unsigned)ceil_div(a.Npad, TC_NMAX));
-  k_linear_tc<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(a);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act == B3D_ACT_RELU) k_linear_tc<1><<<grid, TC_THREADS, smem, st>>>(a);
+  else if (act == B3D_ACT_SIGMOID) k_linear_tc<2><<<grid, TC_THREADS, smem, st>>>(a);
+  else k_linear_tc<0><<<grid, TC_THREADS, smem, st>>>(a);
   B3D_LAUNCH_CHECK("k_linear_tc");
   return 0;
 }
@@ -469,13 +552,17 @@ extern "C" int b3d_wgrad_tc(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t 
   WgTcArgs a;
   if (to_dev(segs, nseg, a.seg) || to_dev(dy, 1, &a.dy)) return bad_arg("b3d_wgrad_tc segments");
   if (a.dy.idx || a.dy.width != Nout) return bad_arg("b3d_wgrad_tc: dy");
-  for (int s = 0; s < nseg; ++s)
-    if (a.seg[s].mask_mode != B3D_MASK_NONE) return bad_arg("b3d_wgrad_tc: masked A segments unsupported");
-  if (!segs_tc_ok(a.seg, nseg) || (a.dy.ld & 3) || (reinterpret_cast<uintptr_t>(a.dy.ptr) & 15) ||
-      (a.dy.mask_mode != B3D_MASK_NONE && ((a.dy.ldmask & 3) || (reinterpret_cast<uintptr_t>(a.dy.mask) & 15))))
-    return bad_arg("b3d_wgrad_tc: alignment (widths % 8, 16-byte aligned rows)");
   int K = 0;
-  for (int s = 0; s < nseg; ++s) K += a.seg[s].width;
+  for (int s = 0; s < nseg; ++s) {
+    if (!seg_tc_ok(a.seg[s])) return bad_arg("b3d_wgrad_tc: segment widths % 8, 16-byte aligned rows, no masks");
+    K += a.seg[s].width;
+  }
+  {
+    SegDev d = a.dy;
+    d.width = 8;   // Nout itself may be ragged; only alignment / mask rules apply to dy
+    if (!seg_tc_ok(d)) return bad_arg("b3d_wgrad_tc: dy alignment / mask");
+  }
+  if (K / 8 + 2 > TC_TAB) return bad_arg("b3d_wgrad_tc: K too large");
   int S, ktiles, Kp; long long rps;
   wgrad_tc_plan(M, Nout, K, &S, &rps, &ktiles, &Kp);
   if (workspace_bytes < b3d_wgrad_tc_workspace_bytes(M, Nout, K)) return bad_arg("b3d_wgrad_tc workspace too small");
@@ -489,7 +576,7 @@ extern "C" int b3d_wgrad_tc(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t 
     attr_set = true;
   }
   int Nk = Kp < TC_NMAX ? Kp : TC_NMAX;
-  size_t smem = 2 * TC_A_STAGE + 2 * (size_t)Nk * 128 + 64 + sizeof(int32_t) * B3D_MAX_SEGS * TC_BK;
+  size_t smem = 2 * TC_A_STAGE + 2 * (size_t)Nk * 128 + 64 + 4 * TC_TAB;
   dim3 grid((unsigned)S, (unsigned)(ceil_div(Nout, TC_BM) * ktiles));
   k_wgrad_tc<<<grid, TC_THREADS, smem, st>>>(a);
   B3D_LAUNCH_CHECK("k_wgrad_tc");

@@ -103,14 +103,16 @@ def _packed_weight(W, transpose):
 
 
 def _al16(t):
-    return t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0
+    q = 8 if t.dtype == torch.bfloat16 else 4
+    return t.data_ptr() % 16 == 0 and t.stride(0) % q == 0
 
 
-def _tc_ok(items, M, n_out, K):
-    if _PRECISION != "bf16" or M < _TC_MIN_ROWS or n_out < 16 or K < 32:
+def _tc_shapes_ok(items, M, n_out, K):
+    """Tile constraints of the tcgen05 kernels (b3d.h): widths % 8, aligned rows, enough work."""
+    if M < _TC_MIN_ROWS or n_out < 16 or K < 32:
         return False
     for t, _, mask, _ in items:
-        if t.size(1) % 8 or not _al16(t) or (mask is not None and not _al16(mask)):
+        if t.size(1) % 8 or not _al16(t) or mask is not None:
             return False
     return True
 
@@ -119,30 +121,39 @@ def _tc_ok(items, M, n_out, K):
 def _rows(t):
     if t.dim() == 1:
         t = t.unsqueeze(1)
-    if t.stride(1) != 1 or t.dtype != torch.float32:
+    if t.stride(1) != 1 or t.dtype not in (torch.float32, torch.bfloat16):
         t = t.contiguous().float()
     return t
 
 
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
 def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accumulate=False,
-               out_mask=None, row_mask=None, n_out=None):
-    """items: [(tensor, idx32|None, mask|None, mode)]. Returns Y [M, n_out]."""
+               out_mask=None, row_mask=None, n_out=None, tc=None, out_dtype=torch.float32):
+    """items: [(tensor, idx32|None, mask|None, mode)]. Returns Y [M, n_out].
+    tc=None: use the tensor-core kernel iff the precision mode is bf16 and the shapes fit."""
     segs = L.make_segs(items)
     if n_out is None:
         n_out = W.size(1) if trans_w else W.size(0)
     assert W.dtype == torch.float32 and W.stride(1) == 1
+    K = sum(t.size(1) for t, _, _, _ in items)
+    if tc is None:
+        tc = _PRECISION == "bf16" and M > 0 and _tc_shapes_ok(items, M, n_out, K) and \
+            (out_mask is None or _al16(out_mask))
     if out is None:
-        out = torch.empty((M, n_out), dtype=torch.float32, device=W.device)
+        out = torch.empty((M, n_out), dtype=out_dtype if tc else torch.float32, device=W.device)
     if bias is not None:
         assert bias.is_contiguous() and bias.numel() == n_out
-    K = sum(t.size(1) for t, _, _, _ in items)
-    if M > 0 and _tc_ok(items, M, n_out, K) and (out_mask is None or _al16(out_mask)):
+    if tc:
         wp = _packed_weight(W, trans_w)
         L.check(L.lib().b3d_linear_tc(segs, len(items), L.ptr(wp), n_out, K, L.ptr(bias), L.ptr(out),
-                                      out.stride(0), M, act, L.FLAG_ACCUMULATE if accumulate else 0,
+                                      out.stride(0), _DT[out.dtype], M, act, L.FLAG_ACCUMULATE if accumulate else 0,
                                       L.ptr(out_mask), out_mask.stride(0) if out_mask is not None else 0,
-                                      L.ptr(row_mask), L.stream()), "b3d_linear_tc")
+                                      _DT[out_mask.dtype] if out_mask is not None else 0, L.ptr(row_mask),
+                                      L.stream()), "b3d_linear_tc")
         return out
+    assert out.dtype == torch.float32 and (out_mask is None or out_mask.dtype == torch.float32)
     L.check(L.lib().b3d_linear(segs, len(items), L.ptr(W), W.stride(0), int(trans_w), L.ptr(bias),
                                L.ptr(out), out.stride(0), M, n_out, act,
                                L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(out_mask),
@@ -151,15 +162,17 @@ def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accum
     return out
 
 
-def wgrad_raw(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=False, want_bias=True):
+def wgrad_raw(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=False, want_bias=True, tc=None):
     dev = dy_item[0].device
     if dW is None:
         dW = torch.empty((n_out, K), dtype=torch.float32, device=dev)
     if db is None and want_bias:
         db = torch.empty(n_out, dtype=torch.float32, device=dev)
     lib = L.lib()
-    if M > 0 and _tc_ok(items, M, max(n_out, 16), K) and _al16(dy_item[0]) and \
-            (dy_item[2] is None or _al16(dy_item[2])) and n_out * K >= 2048:
+    if tc is None:
+        tc = _PRECISION == "bf16" and M > 0 and _tc_shapes_ok(items, M, max(n_out, 16), K) and \
+            _al16(dy_item[0]) and dy_item[2] is None and n_out * K >= 2048
+    if tc:
         wsb = lib.b3d_wgrad_tc_workspace_bytes(M, n_out, K)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         L.check(lib.b3d_wgrad_tc(L.make_segs([dy_item]), L.make_segs(items), len(items), L.ptr(dW), dW.stride(0),
@@ -239,72 +252,104 @@ _ACT = {None: L.ACT_NONE, "relu": L.ACT_RELU, "sigmoid": L.ACT_SIGMOID}
 _MASK = {None: L.MASK_NONE, "relu": L.MASK_RELU, "sigmoid": L.MASK_SIGMOID}
 
 
-class _FusedLinear(torch.autograd.Function):
-    """y = act(cat_s(gather(x_s, idx_s)) W^T + b) [rows zeroed by row_mask].
-    Backward: dW/db by the deterministic split-row wgrad, dX by the transposed GEMM, gathered
-    segments reduced back to nodes with the CSR segmented sum (no atomics)."""
+class _FusedMLP(torch.autograd.Function):
+    """A whole nn.Sequential(Linear, ReLU, ..., Linear[, final act]) over a (virtually) concatenated,
+    optionally gathered input: y = MLP(cat_s(gather(x_s, idx_s))) [rows zeroed by row_mask].
+
+    Forward: one libb3d GEMM per layer with fused gather/concat/bias/activation. In bf16 mode the
+    hidden activations are stored in bf16 (they are rounded to bf16 by the next layer's tensor-core
+    tile anyway); the chain output stays fp32.
+    Backward, layer by layer: dW/db by the deterministic split-row wgrad; the input gradient of
+    layer l is produced by the transposed GEMM whose epilogue applies the ReLU mask of layer l-1
+    (so it IS the pre-activation gradient layer l-1 needs, no extra pass); gathered input segments
+    are reduced back to nodes with the CSR segmented sum (no atomics)."""
 
     @staticmethod
-    def forward(ctx, W, bias, act, row_mask, nidx, *xs):
-        xs = [_rows(x) for x in xs]
+    def forward(ctx, nl, final_act, row_mask, nidx, *tensors):
+        Ws = [w if w.stride(1) == 1 else w.contiguous() for w in tensors[0:2 * nl:2]]
+        bs = [b.contiguous() if b is not None else None for b in tensors[1:2 * nl:2]]
+        xs = [_rows(x) for x in tensors[2 * nl:]]
         M = nidx[0].idx.numel() if nidx[0] is not None else xs[0].size(0)
         for x, ni in zip(xs, nidx):
             assert (ni.idx.numel() if ni is not None else x.size(0)) == M, "segment row counts differ"
-        W = W if W.stride(1) == 1 else W.contiguous()
-        assert sum(x.size(1) for x in xs) == W.size(1), "concatenated width != weight in_features"
+        assert sum(x.size(1) for x in xs) == Ws[0].size(1), "concatenated width != weight in_features"
         items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
         rm = row_mask.to(torch.uint8).contiguous() if row_mask is not None else None
-        y = linear_raw(items, W, bias.contiguous() if bias is not None else None, M, _ACT[act], row_mask=rm)
-        ctx.act, ctx.nidx, ctx.M, ctx.has_bias = act, nidx, M, bias is not None
-        ctx.rm = rm
-        ctx.save_for_backward(W, y if act is not None else None, *xs)
-        return y
+        # the whole chain runs on tensor cores or not at all (keeps dtypes of saved activations uniform)
+        tc = _PRECISION == "bf16" and M > 0 and final_act is None and _tc_shapes_ok(items, M, Ws[0].size(0), Ws[0].size(1)) \
+            and all(w.size(0) % 8 == 0 and w.size(1) % 8 == 0 and w.size(0) >= 16 and w.size(1) >= 32 for w in Ws)
+        acts, cur = [], items
+        for l in range(nl):
+            last = l == nl - 1
+            y = linear_raw(cur, Ws[l], bs[l], M, _ACT[final_act] if last else L.ACT_RELU,
+                           row_mask=rm if last else None, tc=tc,
+                           out_dtype=torch.float32 if last else torch.bfloat16)
+            acts.append(y)
+            cur = [(y, None, None, 0)]
+        ctx.nl, ctx.final_act, ctx.rm, ctx.nidx, ctx.M, ctx.tc = nl, final_act, rm, nidx, M, tc
+        ctx.has_bias = [b is not None for b in bs]
+        ctx.save_for_backward(*Ws, *acts, *xs)
+        return acts[-1]
 
     @staticmethod
     def backward(ctx, dy):
-        W, y, *xs = ctx.saved_tensors
-        nidx, M = ctx.nidx, ctx.M
-        dy = _rows(dy)
+        nl, nidx, M, tc = ctx.nl, ctx.nidx, ctx.M, ctx.tc
+        saved = ctx.saved_tensors
+        Ws, acts, xs = saved[:nl], saved[nl:2 * nl], saved[2 * nl:]
+        dz = _rows(dy)
+        if dz.dtype != torch.float32:
+            dz = dz.float()
         if ctx.rm is not None:
-            dy = dy * ctx.rm.unsqueeze(1)
-        dy_item = (dy, None, y, _MASK[ctx.act])
-        n_out, K = W.shape
-        dW = db = None
-        if ctx.needs_input_grad[0]:
-            items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
-            dW, db = wgrad_raw(dy_item, items, M, n_out, K, want_bias=ctx.has_bias)
-        need = ctx.needs_input_grad[5:]
+            dz = dz * ctx.rm.unsqueeze(1)
+        # only a chain-final activation needs an operand mask (fp32 path; tc chains end linear)
+        dz_item = (dz, None, acts[-1] if ctx.final_act is not None else None, _MASK[ctx.final_act])
+        items0 = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
+        grads = [None] * (2 * nl)
+        need_x = ctx.needs_input_grad[4 + 2 * nl:]
         dxs = [None] * len(xs)
-        if any(need):
-            dA = linear_raw([dy_item], W, None, M, trans_w=True)      # [M, K]
-            off = 0
-            for s, (x, ni) in enumerate(zip(xs, nidx)):
-                w = x.size(1)
-                if need[s]:
-                    sl = dA[:, off:off + w]
-                    dxs[s] = segment_sum_raw(sl, ni) if ni is not None else sl
-                off += w
-        return (dW, db if ctx.has_bias else None, None, None, None, *dxs)
+        for l in range(nl - 1, -1, -1):
+            W = Ws[l]
+            n_out, K = W.shape
+            a_items = items0 if l == 0 else [(acts[l - 1], None, None, 0)]
+            if ctx.needs_input_grad[4 + 2 * l]:
+                dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc)
+                grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)
+            if l > 0:
+                dz = linear_raw([dz_item], W, None, M, trans_w=True, out_mask=acts[l - 1], tc=tc,
+                                out_dtype=torch.bfloat16)
+                dz_item = (dz, None, None, 0)
+            elif any(need_x):
+                dA = linear_raw([dz_item], W, None, M, trans_w=True, tc=tc)      # [M, K] fp32
+                off = 0
+                for s, (x, ni) in enumerate(zip(xs, nidx)):
+                    w = x.size(1)
+                    if need_x[s]:
+                        sl = dA[:, off:off + w]
+                        dxs[s] = segment_sum_raw(sl, ni) if ni is not None else sl
+                    off += w
+        return (None, None, None, None, *grads, *dxs)
+
+
+def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None):
+    """inputs: list of (tensor [rows,w], NodeIndex|None); the concatenation order defines the first
+    weight's input-column layout. weights/biases: per layer."""
+    xs = [t for t, _ in inputs]
+    nidx = tuple(ni for _, ni in inputs)
+    flat = []
+    for w, b in zip(weights, biases):
+        flat += [w, b]
+    return _FusedMLP.apply(len(weights), final_act, row_mask, nidx, *flat, *xs)
 
 
 def fused_linear(inputs, weight, bias=None, act=None, row_mask=None):
-    """inputs: list of (tensor [rows,w], NodeIndex|None). The concatenation order defines the
-    weight's input-column layout."""
-    xs = [t for t, _ in inputs]
-    nidx = tuple(ni for _, ni in inputs)
-    return _FusedLinear.apply(weight, bias, act, row_mask, nidx, *xs)
+    """Single layer: act(cat(inputs) W^T + b)."""
+    return fused_mlp(inputs, [weight], [bias], final_act=act, row_mask=row_mask)
 
 
 def run_mlp(seq, inputs, final_act=None, row_mask=None):
-    """Run an nn.Sequential of Linear/ReLU(/Sigmoid) parameter containers through fused_linear."""
+    """Run an nn.Sequential of Linear/ReLU(/Sigmoid) parameter containers as one fused chain."""
     linears = [m for m in seq if isinstance(m, torch.nn.Linear)]
-    x = None
-    for n, lin in enumerate(linears):
-        last = n == len(linears) - 1
-        act = final_act if last else "relu"
-        x = fused_linear(inputs if n == 0 else [(x, None)], lin.weight, lin.bias, act,
-                         row_mask=row_mask if last else None)
-    return x
+    return fused_mlp(inputs, [m.weight for m in linears], [m.bias for m in linears], final_act, row_mask)
 
 
 class _SegmentSum(torch.autograd.Function):

@@ -37,6 +37,7 @@ extern "C" {
 enum { B3D_MASK_NONE = 0, B3D_MASK_RELU = 1, B3D_MASK_SIGMOID = 2 };
 enum { B3D_ACT_NONE = 0, B3D_ACT_RELU = 1, B3D_ACT_SIGMOID = 2 };
 enum { B3D_FLAG_ACCUMULATE = 1 };   /* out += result instead of out = result */
+enum { B3D_F32 = 0, B3D_BF16 = 1 }; /* element type of a segment / output (bf16: tensor-core entry points only) */
 
 /* One column block of a (virtually) concatenated, optionally row-gathered
  * operand: rows r = 0..M-1 read ptr[(idx ? idx[r] : r) * ld + 0..width-1].
@@ -55,6 +56,7 @@ typedef struct {
   int32_t ld;
   int32_t ldmask;
   int32_t mask_mode;
+  int32_t dtype;   /* B3D_F32 (ptr is float*) or B3D_BF16 (ptr is really __nv_bfloat16*, ld in elements) */
 } b3d_seg_t;
 
 const char* b3d_last_error(void);
@@ -111,18 +113,22 @@ int b3d_wgrad(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, int3
               void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- bf16 tensor-core variants (tcgen05.mma, fp32 accumulate in TMEM; 2e-2 tolerance mode) ----
- * Same semantics as b3d_linear / b3d_wgrad; operands are rounded to bf16 while staged into shared
- * memory. Requirements: every segment width is a multiple of 8 and rows are 16-byte aligned
- * (ld % 4 == 0); otherwise -1 is returned and the caller uses the fp32 entry point.
+ * Same math as b3d_linear / b3d_wgrad with operands rounded to bf16. Segments may be fp32 (converted
+ * while staged into shared memory) or bf16 (copied with cp.async); operand masks are not supported
+ * (the backward pass pre-masks gradients in the producing kernel's epilogue via out_mask).
+ * Requirements: every segment width is a multiple of 8 and rows are 16-byte aligned; otherwise -1
+ * is returned and the caller uses the fp32 entry point.
  * Weights are packed once per weight version into bf16 K-major slabs:
- *   transpose == 0: B[n][k] = W[n*ldw + k]  (forward,  n_logical = out_features, k_logical = in_features)
- *   transpose == 1: B[n][k] = W[k*ldw + n]  (input gradient, n_logical = in_features, k_logical = out_features) */
+ *   transpose == 0: B[n][k] = W[n*ldw + k]  (forward;  n_logical = out_features, k_logical = in_features)
+ *   transpose == 1: B[n][k] = W[k*ldw + n]  (input gradient; n_logical = in_features, k_logical = out_features)
+ * Y / out_mask element types are given by y_dtype / mask_dtype (B3D_F32 or B3D_BF16). */
 size_t b3d_tc_packed_bytes(int32_t n_logical, int32_t k_logical);
 int b3d_tc_pack_weights(const float* W, int32_t ldw, int32_t n_logical, int32_t k_logical,
                         int32_t transpose, void* Wp, void* stream);
 int b3d_linear_tc(const b3d_seg_t* segs /*host*/, int32_t nseg, const void* Wp, int32_t n_logical,
-                  int32_t k_logical, const float* bias, float* Y, int32_t ldy, int64_t M, int32_t act,
-                  int32_t flags, const float* out_mask, int32_t ldm, const uint8_t* row_mask, void* stream);
+                  int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype, int64_t M,
+                  int32_t act, int32_t flags, const void* out_mask, int32_t ldm, int32_t mask_dtype,
+                  const uint8_t* row_mask, void* stream);
 size_t b3d_wgrad_tc_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
 int b3d_wgrad_tc(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, int32_t nseg,
                  float* dW, int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,

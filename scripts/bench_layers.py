@@ -44,11 +44,22 @@ def layer(name, items, n_out, act=1):
     print(f"fwd   {name:28s} M={M:7d} K={K:4d} N={n_out:4d}  {t*1e6:9.1f} us  {fl/t/1e12:7.1f} TFLOP/s  {by/t/1e9:7.0f} GB/s(alg)")
     dy = torch.randn(M, n_out, device=dev)
     dA = torch.empty(M, K, device=dev)
-    t = timeit(lambda: ops.linear_raw([(dy, None, out, L.MASK_RELU)], W, None, M, trans_w=True, out=dA))
+    hm = torch.randn(M, K, device=dev)
+    t = timeit(lambda: ops.linear_raw([(dy, None, None, 0)], W, None, M, trans_w=True, out=dA, out_mask=hm))
     print(f"dgrad {name:28s} {'':36s}{t*1e6:9.1f} us  {fl/t/1e12:7.1f} TFLOP/s")
     dW = torch.empty(n_out, K, device=dev); db = torch.empty(n_out, device=dev)
-    t = timeit(lambda: ops.wgrad_raw((dy, None, out, L.MASK_RELU), items, M, n_out, K, dW=dW, db=db))
+    t = timeit(lambda: ops.wgrad_raw((dy, None, None, 0), items, M, n_out, K, dW=dW, db=db))
     print(f"wgrad {name:28s} {'':36s}{t*1e6:9.1f} us  {fl/t/1e12:7.1f} TFLOP/s")
+    if prec == "bf16" and all(t_.size(1) % 8 == 0 for t_, _, _, _ in items):
+        it16 = [(t_.to(torch.bfloat16), i_, None, 0) for t_, i_, _, _ in items]
+        o16 = torch.empty(M, n_out, device=dev, dtype=torch.bfloat16)
+        t = timeit(lambda: ops.linear_raw(it16, W, b, M, act, out=o16, tc=True))
+        print(f"fwd16 {name:28s} {'':36s}{t*1e6:9.1f} us  {fl/t/1e12:7.1f} TFLOP/s  {2.0*M*(K+n_out)/t/1e9:7.0f} GB/s(alg)")
+        dy16 = dy.to(torch.bfloat16); hm16 = hm.to(torch.bfloat16); dA16 = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+        t = timeit(lambda: ops.linear_raw([(dy16, None, None, 0)], W, None, M, trans_w=True, out=dA16, out_mask=hm16, tc=True))
+        print(f"dgr16 {name:28s} {'':36s}{t*1e6:9.1f} us  {fl/t/1e12:7.1f} TFLOP/s")
+        t = timeit(lambda: ops.wgrad_raw((dy16, None, None, 0), it16, M, n_out, K, dW=dW, db=db, tc=True))
+        print(f"wgr16 {name:28s} {'':36s}{t*1e6:9.1f} us  {fl/t/1e12:7.1f} TFLOP/s")
 
 
 h1 = torch.randn(E, 256, device=dev); h2 = torch.randn(E, 128, device=dev); f1 = torch.randn(E, 192, device=dev)
