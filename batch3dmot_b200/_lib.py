@@ -27,13 +27,13 @@ _SIGS = {
     "b3d_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "b3d_csr_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 6 +
                       [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
-    "b3d_segment_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+    "b3d_segment_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_gather_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                   C.c_int32, C.c_void_p]),
     "b3d_linear": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                              C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
-                             C.c_int32, C.c_void_p, C.c_void_p]),
+                             C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p]),
     "b3d_wgrad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "b3d_wgrad": (C.c_int, [C.POINTER(Seg), C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                             C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -42,7 +42,7 @@ _SIGS = {
                                       C.c_void_p]),
     "b3d_linear_tc": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
-                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+                                C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p]),
     "b3d_wgrad_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "b3d_wgrad_tc": (C.c_int, [C.POINTER(Seg), C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),

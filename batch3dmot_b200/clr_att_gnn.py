@@ -14,16 +14,16 @@ from torch import nn
 
 from . import ops
 from .gat import GATConv, knn_attention_conv
-from .pose_gnn import _mlp
+from .pose_gnn import _mlp, CausalMessagePassing as _PoseCausalMessagePassing
 
 
-class CausalMessagePassing(nn.Module):
+class CausalMessagePassing(_PoseCausalMessagePassing):
     """Wider time-aware message passing with the attention edge feature as a fourth input
     block of edge_update (clr_att_gnn.py:191-356)."""
     node_width, edge_width = 96, 64
 
     def __init__(self):
-        super().__init__()
+        nn.Module.__init__(self)
         self.aggr, self.node_dim = "add", -2
         self.edge_update = _mlp(320, 256, 128, 64)
         self.create_past_msgs = _mlp(256, 192, 128)
@@ -33,16 +33,6 @@ class CausalMessagePassing(nn.Module):
     def forward(self, x, edge_index, edge_attr, initial_x, att_edge_attr):
         g = ops.graph_of(edge_index, x.size(0))
         return self.forward_graph(x, g, edge_attr, initial_x, att_edge_attr)
-
-    def forward_graph(self, x, g, e, x0, att):
-        dst, src = g.by_dst, g.by_src
-        e_new = ops.run_mlp(self.edge_update, [(x, dst), (x, src), (e, None), (att, None)])   # :314
-        fut = ops.run_mlp(self.create_future_msgs, [(x, dst), (e_new, None), (x0, dst)])      # :319
-        past = ops.run_mlp(self.create_past_msgs, [(x, src), (e_new, None), (x0, src)])       # :326
-        m_past = ops.segment_sum(past, dst)                                                   # :293
-        m_fut = ops.segment_sum(fut, src)                                                     # :294
-        x_new = ops.run_mlp(self.combine_future_past, [(m_past, None), (m_fut, None)])        # :296-300
-        return x_new, e_new
 
 
 class GNN(nn.Module):
@@ -117,15 +107,25 @@ class GNN(nn.Module):
         a_img = self._affine_attention(self.c2c_att, x_img)        # :148-149
         a_lid = self._affine_attention(self.l2l_att, x_lidar)      # :151-152
         a_rad = self._affine_attention(self.r2r_att, x_radar)      # :154-155
-        att_in = [(a_rad, dst), (a_lid, dst), (a_img, dst),        # x_sens_i :161
-                  (a_rad, src), (a_lid, src), (a_img, src),        # x_sens_j
-                  (e0, None)]                                      # :163
-        att = ops.run_mlp(self.att_edge_encoder, att_in)           # :164
+        if ops.get_precision() == "bf16":
+            # pre-projected form: the two 288-wide node-side blocks of att_edge_encoder.0 applied per node
+            ae = [m for m in self.att_edge_encoder if isinstance(m, nn.Linear)]
+            w0, sens = ae[0].weight, [(a_rad, None), (a_lid, None), (a_img, None)]
+            p_i = ops.fused_linear(sens, w0[:, :288], ae[0].bias)                  # [N,512]
+            p_j = ops.fused_linear(sens, w0[:, 288:576])
+            att = ops.fused_mlp([(e0, None)], [w0[:, 576:]] + [m.weight for m in ae[1:]],
+                                [None] + [m.bias for m in ae[1:]], adds=[(p_i, dst), (p_j, src)])
+        else:
+            att_in = [(a_rad, dst), (a_lid, dst), (a_img, dst),    # x_sens_i :161
+                      (a_rad, src), (a_lid, src), (a_img, src),    # x_sens_j
+                      (e0, None)]                                  # :163
+            att = ops.run_mlp(self.att_edge_encoder, att_in)       # :164
         x_sens = torch.cat([x_img, x_lidar, x_radar], dim=1)       # :172 (C7)
         x0 = ops.run_mlp(self.node_encoder, [(pose, None)])        # :174-176
         x, e = x0, e0
+        inv = self.message_passing.project_invariants(x0) if ops.get_precision() == "bf16" else None
         for i in range(self.depth):
             if i % 2 == 0 and self.apply_knn_update:
                 x = knn_attention_conv(self.knn_conv, x, data.node_timestamps)
-            x, e = self.message_passing.forward_graph(x, g, e, x0, att)                         # :186
+            x, e = self.message_passing.forward_graph(x, g, e, x0, att, inv)                    # :186
         return ops.run_mlp(self.edge_classifier, [(e, None)], final_act="sigmoid"), x_sens     # :188

@@ -22,6 +22,8 @@ struct LinArgs {
   const float* out_mask;
   int ldm;
   const uint8_t* row_mask;
+  SegDev add[2];
+  int nadd;
 };
 
 __global__ void __launch_bounds__(LIN_THREADS) k_linear(const LinArgs a) {
@@ -153,11 +155,16 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear(const LinArgs a) {
     long long r = m0 + ty * 8 + i;
     if (r >= a.M) continue;
     const bool rz = a.row_mask && a.row_mask[r] == 0;
+    const float* addp[2] = {nullptr, nullptr};
+    for (int q = 0; q < a.nadd; ++q)
+      addp[q] = a.add[q].ptr + (long long)(a.add[q].idx ? __ldg(a.add[q].idx + r) : r) * a.add[q].ld;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int c = n0 + tx * 4 + j;
       if (c >= a.Nout) continue;
       float v = acc[i][j] + bv[j];
+      if (addp[0]) v += __ldg(addp[0] + c);
+      if (addp[1]) v += __ldg(addp[1] + c);
       if (a.act == B3D_ACT_RELU) v = fmaxf(v, 0.f);
       else if (a.act == B3D_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
       if (a.out_mask) v = (__ldg(a.out_mask + r * a.ldm + c) > 0.f) ? v : 0.f;
@@ -338,9 +345,14 @@ using namespace b3d;
 extern "C" int b3d_linear(const b3d_seg_t* segs, int32_t nseg, const float* W, int32_t ldw,
                           int32_t trans_w, const float* bias, float* Y, int32_t ldy, int64_t M,
                           int32_t Nout, int32_t act, int32_t flags, const float* out_mask, int32_t ldm,
-                          const uint8_t* row_mask, void* stream) {
+                          const uint8_t* row_mask, const b3d_seg_t* adds, int32_t nadd, void* stream) {
   LinArgs a;
   if (M == 0) return 0;
+  if (nadd < 0 || nadd > 2 || (nadd && (to_dev(adds, nadd, a.add) || !all_f32(a.add, nadd))))
+    return bad_arg("b3d_linear adds");
+  for (int q = 0; q < nadd; ++q)
+    if (a.add[q].width != Nout) return bad_arg("b3d_linear: adds width != Nout");
+  a.nadd = nadd;
   if (to_dev(segs, nseg, a.seg) || !all_f32(a.seg, nseg)) return bad_arg("b3d_linear segments (fp32 only)");
   if (!W || !Y || Nout <= 0 || M < 0) return bad_arg("b3d_linear W/Y/Nout/M");
   a.nseg = nseg; a.W = W; a.ldw = ldw; a.trans_w = trans_w; a.bias = bias; a.Y = Y; a.ldy = ldy;

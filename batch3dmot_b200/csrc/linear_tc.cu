@@ -75,6 +75,8 @@ struct TcArgs {
   const void* out_mask;
   int ldm, mask_bf16;
   const uint8_t* row_mask;
+  SegDev add[2];   // row-gathered fp32 addends of the pre-activation
+  int nadd;
 };
 
 template <int ACT>
@@ -202,15 +204,32 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
     tmem_ld_wait();
     if (!row_ok) continue;
     float o[32];
+    const int cbase = n0 + col0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * q);
-      o[4 * q + 0] = activate<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x);
-      o[4 * q + 1] = activate<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y);
-      o[4 * q + 2] = activate<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z);
-      o[4 * q + 3] = activate<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w);
+      o[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
+      o[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+      o[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+      o[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
     }
-    const int cbase = n0 + col0;
+    for (int t = 0; t < a.nadd; ++t) {   // node-side first-layer blocks, pre-projected per node
+      const SegDev& S = a.add[t];
+      const float* ap = S.ptr + (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase;
+      if (cbase + 31 < a.Nout) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(ap) + q);
+          o[4 * q] += v.x; o[4 * q + 1] += v.y; o[4 * q + 2] += v.z; o[4 * q + 3] += v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cbase + j < a.Nout) o[j] += __ldg(ap + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = activate<ACT>(o[j]);
     if (!plain) {
       if (a.out_mask) {   // ReLU backward of the producing layer: keep the gradient where its output was > 0
         if (a.mask_bf16 && cbase + 31 < a.Nout && (a.ldm & 7) == 0) {
@@ -502,9 +521,16 @@ extern "C" int b3d_tc_pack_weights(const float* W, int32_t ldw, int32_t n_logica
 extern "C" int b3d_linear_tc(const b3d_seg_t* segs, int32_t nseg, const void* Wp, int32_t n_logical,
                              int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype,
                              int64_t M, int32_t act, int32_t flags, const void* out_mask, int32_t ldm,
-                             int32_t mask_dtype, const uint8_t* row_mask, void* stream) {
+                             int32_t mask_dtype, const uint8_t* row_mask, const b3d_seg_t* adds, int32_t nadd,
+                             void* stream) {
   if (M == 0) return 0;
   TcArgs a;
+  if (nadd < 0 || nadd > 2 || (nadd && (to_dev(adds, nadd, a.add) || !all_f32(a.add, nadd))))
+    return bad_arg("b3d_linear_tc adds");
+  for (int q = 0; q < nadd; ++q)
+    if (a.add[q].width != n_logical || (a.add[q].ld & 3) || (reinterpret_cast<uintptr_t>(a.add[q].ptr) & 15))
+      return bad_arg("b3d_linear_tc: adds must be fp32 [*, Nout], 16-byte aligned rows");
+  a.nadd = nadd;
   if (to_dev(segs, nseg, a.seg)) return bad_arg("b3d_linear_tc segments");
   int K = 0;
   for (int s = 0; s < nseg; ++s) {

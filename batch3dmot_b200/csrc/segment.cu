@@ -1,5 +1,7 @@
 // Deterministic warp-per-node segmented reduction (replaces torch_scatter atomics),
 // row gather (its backward) and the modality-present row predicate.
+#include <cuda_bf16.h>
+
 #include "b3d_common.cuh"
 
 namespace b3d {
@@ -88,11 +90,47 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 using namespace b3d;
 
-extern "C" int b3d_segment_sum(const float* src, int32_t ld_src, const int32_t* perm,
+// bf16 rows, fp32 accumulation: warp per node, 8 columns (16 B) per lane per pass.
+__global__ void __launch_bounds__(SEG_WARPS * 32) k_segment_sum_bf16(
+    const __nv_bfloat16* __restrict__ src, int ld, const int32_t* __restrict__ perm,
+    const int32_t* __restrict__ rowptr, long long N, int C, float* __restrict__ out, int ldo, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long node = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int beg = __ldg(rowptr + node), end = __ldg(rowptr + node + 1);
+  for (int c = lane * 8; c < C; c += 256) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = beg; k < end; ++k) {
+      const long long e = perm ? __ldg(perm + k) : k;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + e * ld + c));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(w[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+    }
+    float* o = out + node * ldo + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = accumulate ? o[j] + acc[j] : acc[j];
+  }
+}
+
+extern "C" int b3d_segment_sum(const void* src_v, int32_t src_dtype, int32_t ld_src, const int32_t* perm,
                                const int32_t* rowptr, int64_t N, int32_t C, float* out, int32_t ld_out,
                                int32_t flags, void* stream) {
   if (!rowptr || !out || C <= 0 || N < 0) return bad_arg("b3d_segment_sum");  // src may be NULL when E == 0
   if (N == 0) return 0;
+  if (src_dtype == B3D_BF16) {
+    if ((C & 7) || (ld_src & 7) || (reinterpret_cast<uintptr_t>(src_v) & 15))
+      return bad_arg("b3d_segment_sum: bf16 rows need C % 8 == 0 and 16-byte alignment");
+    k_segment_sum_bf16<<<(unsigned)ceil_div(N, SEG_WARPS), SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(src_v), ld_src, perm, rowptr, N, C, out, ld_out,
+        (flags & B3D_FLAG_ACCUMULATE) ? 1 : 0);
+    B3D_LAUNCH_CHECK("k_segment_sum_bf16");
+    return 0;
+  }
+  const float* src = reinterpret_cast<const float*>(src_v);
   bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
   unsigned grid = (unsigned)ceil_div(N, SEG_WARPS);
   int acc = (flags & B3D_FLAG_ACCUMULATE) ? 1 : 0;

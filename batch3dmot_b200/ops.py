@@ -130,7 +130,7 @@ _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
 
 
 def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accumulate=False,
-               out_mask=None, row_mask=None, n_out=None, tc=None, out_dtype=torch.float32):
+               out_mask=None, row_mask=None, n_out=None, tc=None, out_dtype=torch.float32, adds=None):
     """items: [(tensor, idx32|None, mask|None, mode)]. Returns Y [M, n_out].
     tc=None: use the tensor-core kernel iff the precision mode is bf16 and the shapes fit."""
     segs = L.make_segs(items)
@@ -145,20 +145,24 @@ def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accum
         out = torch.empty((M, n_out), dtype=out_dtype if tc else torch.float32, device=W.device)
     if bias is not None:
         assert bias.is_contiguous() and bias.numel() == n_out
+    add_segs, nadd = None, 0
+    if adds:
+        add_segs, nadd = L.make_segs([(t, i, None, 0) for t, i in adds]), len(adds)
+        assert all(t.dtype == torch.float32 and t.size(1) == n_out for t, _ in adds)
     if tc:
         wp = _packed_weight(W, trans_w)
         L.check(L.lib().b3d_linear_tc(segs, len(items), L.ptr(wp), n_out, K, L.ptr(bias), L.ptr(out),
                                       out.stride(0), _DT[out.dtype], M, act, L.FLAG_ACCUMULATE if accumulate else 0,
                                       L.ptr(out_mask), out_mask.stride(0) if out_mask is not None else 0,
                                       _DT[out_mask.dtype] if out_mask is not None else 0, L.ptr(row_mask),
-                                      L.stream()), "b3d_linear_tc")
+                                      add_segs, nadd, L.stream()), "b3d_linear_tc")
         return out
     assert out.dtype == torch.float32 and (out_mask is None or out_mask.dtype == torch.float32)
     L.check(L.lib().b3d_linear(segs, len(items), L.ptr(W), W.stride(0), int(trans_w), L.ptr(bias),
                                L.ptr(out), out.stride(0), M, n_out, act,
                                L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(out_mask),
                                out_mask.stride(0) if out_mask is not None else 0, L.ptr(row_mask),
-                               L.stream()), "b3d_linear")
+                               add_segs, nadd, L.stream()), "b3d_linear")
     return out
 
 
@@ -193,7 +197,7 @@ def segment_sum_raw(src, nidx, out=None, accumulate=False):
     if out is None:
         out = torch.empty((nidx.n, C_), dtype=torch.float32, device=src.device)
     perm = None if nidx.sorted else nidx.perm
-    L.check(L.lib().b3d_segment_sum(L.ptr(src), src.stride(0), L.ptr(perm), L.ptr(nidx.rowptr), nidx.n, C_,
+    L.check(L.lib().b3d_segment_sum(L.ptr(src), _DT[src.dtype], src.stride(0), L.ptr(perm), L.ptr(nidx.rowptr), nidx.n, C_,
                                     L.ptr(out), out.stride(0), L.FLAG_ACCUMULATE if accumulate else 0,
                                     L.stream()), "b3d_segment_sum")
     return out
@@ -265,10 +269,14 @@ class _FusedMLP(torch.autograd.Function):
     are reduced back to nodes with the CSR segmented sum (no atomics)."""
 
     @staticmethod
-    def forward(ctx, nl, final_act, row_mask, nidx, *tensors):
+    def forward(ctx, nl, final_act, row_mask, nidx, add_nidx, *tensors):
         Ws = [w if w.stride(1) == 1 else w.contiguous() for w in tensors[0:2 * nl:2]]
         bs = [b.contiguous() if b is not None else None for b in tensors[1:2 * nl:2]]
-        xs = [_rows(x) for x in tensors[2 * nl:]]
+        nx = len(nidx)
+        xs = [_rows(x) for x in tensors[2 * nl:2 * nl + nx]]
+        add_ts = [_rows(t) for t in tensors[2 * nl + nx:]]
+        assert len(add_ts) == len(add_nidx) and (not add_ts or (final_act is None or nl > 1))
+        adds = [(t, ni.idx if ni is not None else None) for t, ni in zip(add_ts, add_nidx)]
         M = nidx[0].idx.numel() if nidx[0] is not None else xs[0].size(0)
         for x, ni in zip(xs, nidx):
             assert (ni.idx.numel() if ni is not None else x.size(0)) == M, "segment row counts differ"
@@ -283,10 +291,11 @@ class _FusedMLP(torch.autograd.Function):
             last = l == nl - 1
             y = linear_raw(cur, Ws[l], bs[l], M, _ACT[final_act] if last else L.ACT_RELU,
                            row_mask=rm if last else None, tc=tc,
-                           out_dtype=torch.float32 if last else torch.bfloat16)
+                           out_dtype=torch.float32 if last else torch.bfloat16, adds=adds if l == 0 else None)
             acts.append(y)
             cur = [(y, None, None, 0)]
         ctx.nl, ctx.final_act, ctx.rm, ctx.nidx, ctx.M, ctx.tc = nl, final_act, rm, nidx, M, tc
+        ctx.add_nidx = add_nidx
         ctx.has_bias = [b is not None for b in bs]
         ctx.save_for_backward(*Ws, *acts, *xs)
         return acts[-1]
@@ -305,13 +314,24 @@ class _FusedMLP(torch.autograd.Function):
         dz_item = (dz, None, acts[-1] if ctx.final_act is not None else None, _MASK[ctx.final_act])
         items0 = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
         grads = [None] * (2 * nl)
-        need_x = ctx.needs_input_grad[4 + 2 * nl:]
-        dxs = [None] * len(xs)
+        nx = len(nidx)
+        need_x = ctx.needs_input_grad[5 + 2 * nl:5 + 2 * nl + nx]
+        need_add = ctx.needs_input_grad[5 + 2 * nl + nx:]
+        xs = xs[:nx]
+        dxs = [None] * nx
+        dadds = [None] * len(ctx.add_nidx)
         for l in range(nl - 1, -1, -1):
             W = Ws[l]
             n_out, K = W.shape
             a_items = items0 if l == 0 else [(acts[l - 1], None, None, 0)]
-            if ctx.needs_input_grad[4 + 2 * l]:
+            if l == 0:
+                # dz is now the gradient of layer 0's pre-activation: the node-side addends receive
+                # its per-node sums (deterministic CSR reduction; identity index = plain copy)
+                for t, ni in enumerate(ctx.add_nidx):
+                    if need_add[t]:
+                        assert dz_item[2] is None
+                        dadds[t] = segment_sum_raw(dz_item[0], ni) if ni is not None else dz_item[0].float()
+            if ctx.needs_input_grad[5 + 2 * l]:
                 dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc)
                 grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)
             if l > 0:
@@ -327,23 +347,26 @@ class _FusedMLP(torch.autograd.Function):
                         sl = dA[:, off:off + w]
                         dxs[s] = segment_sum_raw(sl, ni) if ni is not None else sl
                     off += w
-        return (None, None, None, None, *grads, *dxs)
+        return (None, None, None, None, None, *grads, *dxs, *dadds)
 
 
-def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None):
+def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=()):
     """inputs: list of (tensor [rows,w], NodeIndex|None); the concatenation order defines the first
-    weight's input-column layout. weights/biases: per layer."""
+    weight's input-column layout. weights/biases: per layer.
+    adds: up to two (tensor [n, out_features of layer 0] fp32, NodeIndex|None) summed, row-gathered,
+    into layer 0's pre-activation (node-side weight blocks applied per node)."""
     xs = [t for t, _ in inputs]
     nidx = tuple(ni for _, ni in inputs)
     flat = []
     for w, b in zip(weights, biases):
         flat += [w, b]
-    return _FusedMLP.apply(len(weights), final_act, row_mask, nidx, *flat, *xs)
+    return _FusedMLP.apply(len(weights), final_act, row_mask, nidx, tuple(ni for _, ni in adds), *flat, *xs,
+                           *[t for t, _ in adds])
 
 
-def fused_linear(inputs, weight, bias=None, act=None, row_mask=None):
-    """Single layer: act(cat(inputs) W^T + b)."""
-    return fused_mlp(inputs, [weight], [bias], final_act=act, row_mask=row_mask)
+def fused_linear(inputs, weight, bias=None, act=None, row_mask=None, adds=()):
+    """Single layer: act(cat(inputs) W^T + b [+ gathered addends])."""
+    return fused_mlp(inputs, [weight], [bias], final_act=act, row_mask=row_mask, adds=adds)
 
 
 def run_mlp(seq, inputs, final_act=None, row_mask=None):

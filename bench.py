@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("B3D_PRECISION", "fp32"))
     ap.add_argument("--cpu-scenes", type=int, default=1, help="scene graphs in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="timed loop only (for ncu launch lists)")
     return ap.parse_args()
 
 
@@ -207,6 +208,10 @@ def main():
     ms_per_step = float(ms.item()) / a.steps
     value = E_global / (ms_per_step * 1e-3)
 
+    if a.profile_only:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms_per_step, "gpu_launches": launches}))
+        return
     # ---- end-to-end through the public API with host buffers ("e2e")
     def e2e_step():
         dd = to_device()                                   # H2D of this step's inputs (pinned)

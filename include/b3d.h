@@ -79,12 +79,14 @@ int b3d_csr_build(const int64_t* edge_index, int64_t E, int64_t N,
                   int32_t* rowptr_src, int32_t* perm_src,
                   void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 
-/* out[n, 0:C] (+)= sum_{k in [rowptr[n], rowptr[n+1])} src[(perm ? perm[k] : k), 0:C]
+/* src_dtype: B3D_F32 or B3D_BF16 (bf16 rows are accumulated in fp32).
+ * out[n, 0:C] (+)= sum_{k in [rowptr[n], rowptr[n+1])} src[(perm ? perm[k] : k), 0:C]
  * summed in ascending k (== edge order within the node, as sequential CPU
  * scatter_add_ does). Warp-per-node segmented reduction.
  * Replaces torch_scatter.scatter(reduce='add') pose_gnn.py:190-191,240. */
-int b3d_segment_sum(const float* src, int32_t ld_src, const int32_t* perm, const int32_t* rowptr,
-                    int64_t N, int32_t C, float* out, int32_t ld_out, int32_t flags, void* stream);
+int b3d_segment_sum(const void* src, int32_t src_dtype, int32_t ld_src, const int32_t* perm,
+                    const int32_t* rowptr, int64_t N, int32_t C, float* out, int32_t ld_out, int32_t flags,
+                    void* stream);
 
 /* out[r, 0:C] = src[idx[r], 0:C]  (index_select; backward of segment_sum). */
 int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
@@ -98,11 +100,15 @@ int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_
  * (pose_gnn.py:29-53,94-120,210-223; clr_att_gnn.py:35-91,196-222,314-327).
  * out_mask (optional [M,Nout], ld ldm): multiply result by (out_mask > 0) (ReLU backward
  * of the producing layer). row_mask (optional uint8[M]): rows with 0 are written as 0
- * (clr_att_gnn.py:132-133,140-141 zero-fill of missing modalities). */
+ * (clr_att_gnn.py:132-133,140-141 zero-fill of missing modalities).
+ * adds (optional, nadd <= 2, fp32, width == Nout): row-gathered addends summed into the
+ * pre-activation, result = act(A W^T + bias + sum_a adds[a][idx_a[r], :]). This is how the
+ * node-side blocks of a first-layer weight are applied per NODE instead of per edge
+ * (W [x_i|x_j|e] . cat[x_i,x_j,e] = W_xi x[dst] + W_xj x[src] + W_e e). */
 int b3d_linear(const b3d_seg_t* segs /*host*/, int32_t nseg, const float* W, int32_t ldw,
                int32_t trans_w, const float* bias, float* Y, int32_t ldy, int64_t M, int32_t Nout,
                int32_t act, int32_t flags, const float* out_mask, int32_t ldm,
-               const uint8_t* row_mask, void* stream);
+               const uint8_t* row_mask, const b3d_seg_t* adds /*host*/, int32_t nadd, void* stream);
 
 /* dW[Nout,K] (+)= dY^T cat_s(A_s),  db[Nout] (+)= colsum(dY)   (weight gradient)
  * dy: a single segment (may carry a ReLU/Sigmoid mask). Deterministic split over rows
@@ -128,7 +134,7 @@ int b3d_tc_pack_weights(const float* W, int32_t ldw, int32_t n_logical, int32_t 
 int b3d_linear_tc(const b3d_seg_t* segs /*host*/, int32_t nseg, const void* Wp, int32_t n_logical,
                   int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype, int64_t M,
                   int32_t act, int32_t flags, const void* out_mask, int32_t ldm, int32_t mask_dtype,
-                  const uint8_t* row_mask, void* stream);
+                  const uint8_t* row_mask, const b3d_seg_t* adds /*host*/, int32_t nadd, void* stream);
 size_t b3d_wgrad_tc_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
 int b3d_wgrad_tc(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, int32_t nseg,
                  float* dW, int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,
