@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=8, help="scene graphs per rank per step")
-    ap.add_argument("--precision", default=os.environ.get("B3D_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("B3D_PRECISION", "bf16"), choices=["bf16", "fp32"],
+                    help="bf16: tcgen05 tiles (2e-2 parity mode, north_star); fp32: FFMA exact mode (1e-4)")
     ap.add_argument("--cpu-scenes", type=int, default=1, help="scene graphs in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="timed loop only (for ncu launch lists)")
@@ -233,8 +234,30 @@ def main():
 
     # ---- roofline of the dominant kernel
     hbm, tf_burst, tf_sust, src = peaks()
-    roof = model.dominant_kernel_roofline(d, kw) if hasattr(model, "dominant_kernel_roofline") else None
-    if roof is None:
+    def time_kernel(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps * 1e-3
+
+    if a.precision == "bf16":
+        # dominant kernel class: k_linear_tc (tcgen05 tiles); heaviest launch = att_edge_encoder layer 2
+        # ([E,512] bf16 -> 384, ReLU, bf16 out). Algorithmic FLOPs = 2*E*512*384; algorithmic bytes = E*(512+384)*2.
+        lin = model.att_edge_encoder[2]
+        h = torch.randn(E, 512, device=dev).to(torch.bfloat16)
+        out = torch.empty(E, 384, device=dev, dtype=torch.bfloat16)
+        t = time_kernel(lambda: ops.linear_raw([(h, None, None, 0)], lin.weight, lin.bias, E, 1, out=out, tc=True))
+        ach = 2.0 * E * 512 * 384 / t / 1e12
+        roof = {"kernel": "k_linear_tc<relu> (tcgen05 bf16; att_edge_encoder layer 2, [E,512]x[512,384])", "bound": "tensor",
+                "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst, "traffic": None,
+                "peak_source": src + " bf16 dense burst; kernel timed alone",
+                "hbm_view": {"achieved_gbs": E * (512 + 384) * 2 / t / 1e9, "peak_gbs": hbm}}
+    else:
         # fp32 exact path: the dominant launch is k_linear on edge_update layer 0 ([E,320] -> 256, gathered)
         mp = model.message_passing
         lin = mp.edge_update[0]
@@ -242,16 +265,7 @@ def main():
         g = d._b3d_graph
         items = [(x, g.dst32, None, 0), (x, g.src32, None, 0), (e, None, None, 0), (att, None, None, 0)]
         out = torch.empty(E, 256, device=dev)
-        for _ in range(3):
-            ops.linear_raw(items, lin.weight, lin.bias, E, 1, out=out)
-        torch.cuda.synchronize()
-        ev0.record()
-        reps = 10
-        for _ in range(reps):
-            ops.linear_raw(items, lin.weight, lin.bias, E, 1, out=out)
-        ev1.record()
-        torch.cuda.synchronize()
-        t = ev0.elapsed_time(ev1) / reps * 1e-3
+        t = time_kernel(lambda: ops.linear_raw(items, lin.weight, lin.bias, E, 1, out=out))
         ach = 2.0 * E * 320 * 256 / t / 1e12
         roof = {"kernel": "k_linear (fp32 FFMA; edge_update layer 0, gathered [E,320]x[320,256])", "bound": "tensor",
                 "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst, "traffic": None,
