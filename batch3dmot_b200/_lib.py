@@ -43,6 +43,12 @@ _SIGS = {
     "b3d_linear_tc": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p]),
+    "b3d_tma_packed_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "b3d_tma_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p]),
+    "b3d_linear_tma": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p]),
     "b3d_wgrad_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "b3d_wgrad_tc": (C.c_int, [C.POINTER(Seg), C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -11,6 +11,8 @@
 // Pipeline (both kernels): 256 threads stage chunk c+1 while the tensor core works on chunk c
 // (tcgen05.mma is asynchronous; tcgen05.commit -> mbarrier frees the stage). Two CTAs per SM
 // overlap one CTA's epilogue with the other's main loop.
+#include <cuda.h>
+
 #include "b3d_common.cuh"
 #include "tc_common.cuh"
 
@@ -84,6 +86,118 @@ __device__ __forceinline__ float activate(float v) {
   if (ACT == B3D_ACT_RELU) return fmaxf(v, 0.f);
   if (ACT == B3D_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
   return v;
+}
+
+// One 32-column block of one output row: bias + row-gathered addends + activation, then the ReLU
+// mask of the producing layer / row mask / accumulate, then a bf16 or fp32 store.
+// EP is any struct with the TcArgs epilogue fields; sb = bias of this CTA's column block (smem).
+template <int ACT, class EP>
+__device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int n0, int col0, const uint32_t (&r)[32],
+                                                 const float* s_bias, bool plain, bool rz) {
+  using namespace tc;
+    float o[32];
+  const int cbase = n0 + col0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * q);
+    o[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
+    o[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+    o[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+    o[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+  }
+  for (int t = 0; t < a.nadd; ++t) {   // node-side first-layer blocks, pre-projected per node
+    const SegDev& S = a.add[t];
+    const float* ap = S.ptr + (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase;
+    if (cbase + 31 < a.Nout) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(ap) + q);
+        o[4 * q] += v.x; o[4 * q + 1] += v.y; o[4 * q + 2] += v.z; o[4 * q + 3] += v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (cbase + j < a.Nout) o[j] += __ldg(ap + j);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) o[j] = activate<ACT>(o[j]);
+  if (!plain) {
+    if (a.out_mask) {   // ReLU backward of the producing layer: keep the gradient where its output was > 0
+      if (a.mask_bf16 && cbase + 31 < a.Nout && (a.ldm & 7) == 0) {
+        const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 m = __ldg(mp + q);
+          const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if ((int16_t)(w[j] & 0xFFFFu) <= 0) o[8 * q + 2 * j] = 0.f;      // bf16 > 0  <=>  int16 bits > 0
+            if ((int16_t)(w[j] >> 16) <= 0) o[8 * q + 2 * j + 1] = 0.f;
+          }
+        }
+      } else if (!a.mask_bf16 && cbase + 31 < a.Nout && (a.ldm & 3) == 0) {
+        const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.out_mask) + row * a.ldm + cbase);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 m = __ldg(mp + q);
+          if (!(m.x > 0.f)) o[4 * q] = 0.f;
+          if (!(m.y > 0.f)) o[4 * q + 1] = 0.f;
+          if (!(m.z > 0.f)) o[4 * q + 2] = 0.f;
+          if (!(m.w > 0.f)) o[4 * q + 3] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int cc = cbase + j;
+          if (cc < a.Nout) {
+            const float mv = a.mask_bf16
+                ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.out_mask)[row * a.ldm + cc])
+                : reinterpret_cast<const float*>(a.out_mask)[row * a.ldm + cc];
+            o[j] = mv > 0.f ? o[j] : 0.f;
+          }
+        }
+      }
+    }
+    if (rz) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = 0.f;
+    }
+    if ((a.flags & B3D_FLAG_ACCUMULATE) && !a.y_bf16) {
+      const float* yrow = reinterpret_cast<const float*>(a.Y) + row * a.ldy;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (cbase + j < a.Nout) o[j] += yrow[cbase + j];
+    }
+  }
+  if (a.y_bf16) {
+    __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(a.Y) + row * a.ldy + cbase;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (cbase + 8 * q + 7 < a.Nout) {
+        uint4 pk = make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
+                              pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
+        *reinterpret_cast<uint4*>(yrow + 8 * q) = pk;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (cbase + 8 * q + j < a.Nout) yrow[8 * q + j] = __float2bfloat16_rn(o[8 * q + j]);
+      }
+    }
+  } else {
+    float* yrow = reinterpret_cast<float*>(a.Y) + row * a.ldy + cbase;
+    const bool vec_ok = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (vec_ok && cbase + 4 * q + 3 < a.Nout) {
+        *reinterpret_cast<float4*>(yrow + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (cbase + 4 * q + j < a.Nout) yrow[4 * q + j] = o[4 * q + j];
+      }
+    }
+  }
 }
 
 template <int ACT>
@@ -203,109 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
     tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)col0, r);
     tmem_ld_wait();
     if (!row_ok) continue;
-    float o[32];
-    const int cbase = n0 + col0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * q);
-      o[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
-      o[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
-      o[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
-      o[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
-    }
-    for (int t = 0; t < a.nadd; ++t) {   // node-side first-layer blocks, pre-projected per node
-      const SegDev& S = a.add[t];
-      const float* ap = S.ptr + (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase;
-      if (cbase + 31 < a.Nout) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(ap) + q);
-          o[4 * q] += v.x; o[4 * q + 1] += v.y; o[4 * q + 2] += v.z; o[4 * q + 3] += v.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (cbase + j < a.Nout) o[j] += __ldg(ap + j);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = activate<ACT>(o[j]);
-    if (!plain) {
-      if (a.out_mask) {   // ReLU backward of the producing layer: keep the gradient where its output was > 0
-        if (a.mask_bf16 && cbase + 31 < a.Nout && (a.ldm & 7) == 0) {
-          const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 m = __ldg(mp + q);
-            const uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if ((int16_t)(w[j] & 0xFFFFu) <= 0) o[8 * q + 2 * j] = 0.f;      // bf16 > 0  <=>  int16 bits > 0
-              if ((int16_t)(w[j] >> 16) <= 0) o[8 * q + 2 * j + 1] = 0.f;
-            }
-          }
-        } else if (!a.mask_bf16 && cbase + 31 < a.Nout && (a.ldm & 3) == 0) {
-          const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.out_mask) + row * a.ldm + cbase);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 m = __ldg(mp + q);
-            if (!(m.x > 0.f)) o[4 * q] = 0.f;
-            if (!(m.y > 0.f)) o[4 * q + 1] = 0.f;
-            if (!(m.z > 0.f)) o[4 * q + 2] = 0.f;
-            if (!(m.w > 0.f)) o[4 * q + 3] = 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int cc = cbase + j;
-            if (cc < a.Nout) {
-              const float mv = a.mask_bf16
-                  ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.out_mask)[row * a.ldm + cc])
-                  : reinterpret_cast<const float*>(a.out_mask)[row * a.ldm + cc];
-              o[j] = mv > 0.f ? o[j] : 0.f;
-            }
-          }
-        }
-      }
-      if (rz) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = 0.f;
-      }
-      if ((a.flags & B3D_FLAG_ACCUMULATE) && !a.y_bf16) {
-        const float* yrow = reinterpret_cast<const float*>(a.Y) + row * a.ldy;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (cbase + j < a.Nout) o[j] += yrow[cbase + j];
-      }
-    }
-    if (a.y_bf16) {
-      __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(a.Y) + row * a.ldy + cbase;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (cbase + 8 * q + 7 < a.Nout) {
-          uint4 pk = make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
-                                pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
-          *reinterpret_cast<uint4*>(yrow + 8 * q) = pk;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (cbase + 8 * q + j < a.Nout) yrow[8 * q + j] = __float2bfloat16_rn(o[8 * q + j]);
-        }
-      }
-    } else {
-      float* yrow = reinterpret_cast<float*>(a.Y) + row * a.ldy + cbase;
-      const bool vec_ok = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (vec_ok && cbase + 4 * q + 3 < a.Nout) {
-          *reinterpret_cast<float4*>(yrow + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (cbase + 4 * q + j < a.Nout) yrow[4 * q + j] = o[4 * q + j];
-        }
-      }
-    }
+    epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -499,6 +511,193 @@ static bool seg_tc_ok(const SegDev& S) {
   return S.dtype == B3D_BF16 ? (S.ld & 7) == 0 : (S.dtype == B3D_F32 && (S.ld & 3) == 0);
 }
 
+// ------------------------------------------------------------------ TMA-fed persistent forward / dgrad
+// Dense bf16 operands only (1-2 row-major segments, widths multiples of 64 except the last):
+//   warp 0 : TMA producer  (cp.async.bulk.tensor 2D boxes {64 cols, 128 rows}, 128B swizzle)
+//   warp 1 : MMA issuer    (tcgen05.mma, operands straight from the TMA-written tiles)
+//   warps 2-5: epilogue    (TMEM -> registers -> bias/adds/act/masks -> global)
+// The weight block [Nb, K] stays resident in shared memory for the CTA's lifetime; CTAs are
+// persistent over row tiles; two TMEM accumulators let the epilogue of tile t overlap the MMAs of
+// tile t+1. No thread touches the operands: the staging cost of k_linear_tc disappears.
+constexpr int TMA_STAGES = 4;
+constexpr int TMA_THREADS = 192;
+
+struct TmaArgs {
+  int seg0_chunks, nchunks, Nb, acc_stride;
+  long long ntiles;
+  const float* bias;
+  void* Y;
+  int ldy, y_bf16;
+  long long M;
+  int Nout, act, flags;
+  const void* out_mask;
+  int ldm, mask_bf16;
+  const uint8_t* row_mask;
+  SegDev add[2];
+  int nadd;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// K-major operand tile written by TMA with 128-byte swizzle: rows of 128 B, 8-row groups of 1024 B.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major): 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO: next 8-row group
+  d |= (uint64_t)1 << 46;            // descriptor version
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+             const __grid_constant__ CUtensorMap mapW, const TmaArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using namespace tc;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * a.Nb;
+  const uint32_t w_chunk = (uint32_t)a.Nb * 128;
+  const uint32_t pad = (1024u - (smem_u32(smem) & 1023u)) & 1023u;   // 128B-swizzled tiles need 1024-byte alignment
+  const uint32_t sW = smem_u32(smem) + pad;
+  const uint32_t sA = sW + a.nchunks * w_chunk;                 // both multiples of 1024
+  const uint32_t misc = a.nchunks * w_chunk + TMA_STAGES * TC_A_STAGE;
+  const uint32_t sBar = sW + misc;   // full[4] @0, empty[4] @32, accf[2] @64, acce[2] @80, wfull @96, tmem ptr @104
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + pad + misc + 104);
+  float* s_bias = reinterpret_cast<float*>(smem + pad + misc + 128);  // [256]
+  const uint32_t ncols = 2 * (uint32_t)a.acc_stride;
+
+  if (warp == 1) tmem_alloc(sBar + 104, ncols);
+  if (tid == 0) {
+    for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(sBar + 8 * s, 1); mbar_init(sBar + 32 + 8 * s, 1); }
+    mbar_init(sBar + 64, 1); mbar_init(sBar + 72, 1);      // accumulator full (tcgen05.commit)
+    mbar_init(sBar + 80, 4); mbar_init(sBar + 88, 4);      // accumulator empty (4 epilogue warps)
+    mbar_init(sBar + 96, 1);                                // weights resident
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 256; i += TMA_THREADS) s_bias[i] = (a.bias && i < a.Nb && n0 + i < a.Nout) ? __ldg(a.bias + n0 + i) : 0.f;
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(sBar + 96, a.nchunks * w_chunk);
+      for (int c = 0; c < a.nchunks; ++c) tma_load_2d(sW + c * w_chunk, &mapW, c * 64, n0, sBar + 96);
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int c = 0; c < a.nchunks; ++c, ++it) {
+          const int s = it % TMA_STAGES;
+          if (it >= TMA_STAGES) mbar_wait(sBar + 32 + 8 * s, ((it / TMA_STAGES) - 1) & 1);
+          mbar_expect_tx(sBar + 8 * s, TC_A_STAGE);
+          if (c < a.seg0_chunks) tma_load_2d(sA + s * TC_A_STAGE, &mapA0, c * 64, (int)(tile * TC_BM), sBar + 8 * s);
+          else tma_load_2d(sA + s * TC_A_STAGE, &mapA1, (c - a.seg0_chunks) * 64, (int)(tile * TC_BM), sBar + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(TC_BM, (uint32_t)a.Nb, 0, 0);
+      mbar_wait(sBar + 96, 0);
+      int it = 0, tcount = 0;
+      for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount & 1;
+        if (tcount >= 2) mbar_wait(sBar + 80 + 8 * acc, ((tcount >> 1) - 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem + (uint32_t)(acc * a.acc_stride);
+        for (int c = 0; c < a.nchunks; ++c, ++it) {
+          const int s = it % TMA_STAGES;
+          mbar_wait(sBar + 8 * s, (it / TMA_STAGES) & 1);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int j = 0; j < TC_BK / 16; ++j)
+            mma_bf16_ss(d_tmem, make_smem_desc_sw128(sA + s * TC_A_STAGE + j * 32),
+                        make_smem_desc_sw128(sW + c * w_chunk + j * 32), idesc, (c | j) != 0);
+          mma_commit(sBar + 32 + 8 * s);      // stage free once these MMAs have read it
+        }
+        mma_commit(sBar + 64 + 8 * acc);      // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    const int lq = warp & 3;                  // TMEM lane quarter this warp may access
+    const bool plain = !a.out_mask && !a.row_mask && !(a.flags & B3D_FLAG_ACCUMULATE);
+    int tcount = 0;
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      mbar_wait(sBar + 64 + 8 * acc, (tcount >> 1) & 1);
+      tc_fence_after_sync();
+      const long long row = tile * TC_BM + lq * 32 + lane;
+      const bool row_ok = row < a.M;
+      const bool rz = row_ok && a.row_mask && a.row_mask[row] == 0;
+      for (int col0 = 0; col0 < a.Nb; col0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
+        tmem_ld_wait();
+        if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sBar + 80 + 8 * acc);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, ncols);
+}
+
+// Row-major bf16 pack for the TMA path: Wr[n][k] = bf16(B[n][k]) zero padded to [Npad][Kpad].
+__global__ void k_pack_weights_rm(const float* __restrict__ W, int ldw, int n_log, int k_log, int transpose,
+                                  __nv_bfloat16* __restrict__ Wr, int Npad, int Kpad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Npad * Kpad) return;
+  int n = (int)(i / Kpad), k = (int)(i % Kpad);
+  float v = 0.f;
+  if (n < n_log && k < k_log) v = transpose ? W[(long long)k * ldw + n] : W[(long long)n * ldw + k];
+  Wr[i] = __float2bfloat16_rn(v);
+}
+
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tmap_encode_fn get_tmap_encode() {
+  static tmap_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tmap_encode_fn>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols] (row stride ld elements), box {64 cols, box_rows}, 128B swizzle, zero OOB fill.
+static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 }  // namespace b3d
 
 using namespace b3d;
@@ -610,5 +809,97 @@ extern "C" int b3d_wgrad_tc(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t 
   k_wgrad_tc_reduce<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(a.part, S, Nout, K, dW, lddw, db,
                                                                   (flags & B3D_FLAG_ACCUMULATE) ? 1 : 0);
   B3D_LAUNCH_CHECK("k_wgrad_tc_reduce");
+  return 0;
+}
+
+extern "C" size_t b3d_tma_packed_bytes(int32_t n_logical, int32_t k_logical) {
+  return (size_t)round_up(n_logical, 16) * round_up(k_logical, TC_BK) * 2;
+}
+
+extern "C" int b3d_tma_pack_weights(const float* W, int32_t ldw, int32_t n_logical, int32_t k_logical,
+                                    int32_t transpose, void* Wr, void* stream) {
+  if (!W || !Wr || n_logical <= 0 || k_logical <= 0) return bad_arg("b3d_tma_pack_weights");
+  int Npad = round_up(n_logical, 16), Kpad = round_up(k_logical, TC_BK);
+  long long total = (long long)Npad * Kpad;
+  k_pack_weights_rm<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      W, ldw, n_logical, k_logical, transpose, reinterpret_cast<__nv_bfloat16*>(Wr), Npad, Kpad);
+  B3D_LAUNCH_CHECK("k_pack_weights_rm");
+  return 0;
+}
+
+extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* Wr, int32_t n_logical,
+                              int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype,
+                              int64_t M, int32_t act, int32_t flags, const void* out_mask, int32_t ldm,
+                              int32_t mask_dtype, const uint8_t* row_mask, const b3d_seg_t* adds, int32_t nadd,
+                              void* stream) {
+  if (M == 0) return 0;
+  TmaArgs a;
+  SegDev seg[2];
+  if (nseg < 1 || nseg > 2 || to_dev(segs, nseg, seg)) return bad_arg("b3d_linear_tma: 1 or 2 segments");
+  int K = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (seg[s].dtype != B3D_BF16 || seg[s].idx || !seg_tc_ok(seg[s]))
+      return bad_arg("b3d_linear_tma: segments must be dense bf16, widths % 8, 16-byte aligned rows");
+    if (s + 1 < nseg && (seg[s].width % TC_BK)) return bad_arg("b3d_linear_tma: leading segment width % 64");
+    K += seg[s].width;
+  }
+  if (K != k_logical || !Wr || !Y || n_logical <= 0) return bad_arg("b3d_linear_tma: shapes");
+  if (nadd < 0 || nadd > 2 || (nadd && (to_dev(adds, nadd, a.add) || !all_f32(a.add, nadd))))
+    return bad_arg("b3d_linear_tma adds");
+  for (int q = 0; q < nadd; ++q)
+    if (a.add[q].width != n_logical || (a.add[q].ld & 3) || (reinterpret_cast<uintptr_t>(a.add[q].ptr) & 15))
+      return bad_arg("b3d_linear_tma: adds must be fp32 [*, Nout], 16-byte aligned rows");
+  if (y_dtype == B3D_BF16 && ((ldy & 7) || (reinterpret_cast<uintptr_t>(Y) & 15) || (flags & B3D_FLAG_ACCUMULATE)))
+    return bad_arg("b3d_linear_tma: bf16 output needs ld % 8 == 0, 16-byte alignment, no accumulate");
+  const int Npad = round_up(n_logical, 16), Kpad = round_up(k_logical, TC_BK);
+  a.seg0_chunks = nseg == 2 ? seg[0].width / TC_BK : Kpad / TC_BK;
+  a.nchunks = nseg == 2 ? seg[0].width / TC_BK + round_up(seg[1].width, TC_BK) / TC_BK : Kpad / TC_BK;
+  if (a.nchunks * TC_BK != Kpad) return bad_arg("b3d_linear_tma: chunking");
+  // weight block resident in shared memory: Nb * Kpad * 2 <= 144 KB
+  int Nb = (144 * 1024 / (Kpad * 2)) / 16 * 16;
+  if (Nb > TC_NMAX) Nb = TC_NMAX;
+  if (Nb > Npad) Nb = Npad;
+  if (Nb < 16) return bad_arg("b3d_linear_tma: K too large for a resident weight block");
+  const int ny = (Npad + Nb - 1) / Nb;
+  Nb = round_up((Npad + ny - 1) / ny, 16);      // balance the column blocks
+  a.Nb = Nb;
+  a.acc_stride = (int)tmem_cols_for(Nb);
+  a.ntiles = ceil_div(M, TC_BM);
+  a.bias = bias; a.Y = Y; a.ldy = ldy; a.y_bf16 = (y_dtype == B3D_BF16); a.M = M; a.Nout = n_logical; a.act = act;
+  a.flags = flags; a.out_mask = out_mask; a.ldm = ldm; a.mask_bf16 = (mask_dtype == B3D_BF16); a.row_mask = row_mask;
+  a.nadd = nadd;
+  alignas(64) CUtensorMap mA0, mA1, mW;
+  if (make_tmap_bf16(&mA0, seg[0].ptr, M, seg[0].width, seg[0].ld, TC_BM)) return bad_arg("b3d_linear_tma: tensor map A0");
+  if (nseg == 2) {
+    if (make_tmap_bf16(&mA1, seg[1].ptr, M, seg[1].width, seg[1].ld, TC_BM)) return bad_arg("b3d_linear_tma: tensor map A1");
+  } else {
+    mA1 = mA0;
+  }
+  if (make_tmap_bf16(&mW, Wr, Npad, Kpad, Kpad, Nb)) return bad_arg("b3d_linear_tma: tensor map W");
+  size_t smem = (size_t)a.nchunks * Nb * 128 + TMA_STAGES * TC_A_STAGE + 128 + 1024 + 1024;   // + alignment slack
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_linear_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail("k_linear_tma smem attr", e);
+    attr_set = true;
+  }
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  long long gx = n_sm / ny;
+  if (gx < 1) gx = 1;
+  if (gx > a.ntiles) gx = a.ntiles;
+  dim3 grid((unsigned)gx, (unsigned)ny);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act == B3D_ACT_RELU) k_linear_tma<1><<<grid, TMA_THREADS, smem, st>>>(mA0, mA1, mW, a);
+  else if (act == B3D_ACT_SIGMOID) k_linear_tma<2><<<grid, TMA_THREADS, smem, st>>>(mA0, mA1, mW, a);
+  else k_linear_tma<0><<<grid, TMA_THREADS, smem, st>>>(mA0, mA1, mW, a);
+  B3D_LAUNCH_CHECK("k_linear_tma");
   return 0;
 }

@@ -87,19 +87,32 @@ def invalidate_weight_cache():
     _packed.clear()
 
 
-def _packed_weight(W, transpose):
-    key = (W.data_ptr(), W._version, tuple(W.shape), W.stride(0), bool(transpose))
+_USE_TMA = True          # dense bf16 operands go through the TMA-fed persistent kernel
+
+
+def _packed_weight(W, transpose, rowmajor=False):
+    key = (W.data_ptr(), W._version, tuple(W.shape), W.stride(0), bool(transpose), rowmajor)
     wp = _packed.get(key)
     if wp is None:
-        if len(_packed) > 256:
+        if len(_packed) > 512:
             _packed.clear()
         n_log, k_log = (W.size(1), W.size(0)) if transpose else (W.size(0), W.size(1))
         lib = L.lib()
-        wp = torch.empty(lib.b3d_tc_packed_bytes(n_log, k_log), dtype=torch.uint8, device=W.device)
-        L.check(lib.b3d_tc_pack_weights(L.ptr(W), W.stride(0), n_log, k_log, int(transpose), L.ptr(wp),
-                                        L.stream()), "b3d_tc_pack_weights")
+        nbytes, pack = (lib.b3d_tma_packed_bytes, lib.b3d_tma_pack_weights) if rowmajor else \
+            (lib.b3d_tc_packed_bytes, lib.b3d_tc_pack_weights)
+        wp = torch.empty(nbytes(n_log, k_log), dtype=torch.uint8, device=W.device)
+        L.check(pack(L.ptr(W), W.stride(0), n_log, k_log, int(transpose), L.ptr(wp), L.stream()), "pack_weights")
         _packed[key] = wp
     return wp
+
+
+def _tma_ok(items, K, accumulate):
+    if not _USE_TMA or accumulate or len(items) > 2 or K > 1024:
+        return False
+    for n, (t, idx, _, _) in enumerate(items):
+        if t.dtype != torch.bfloat16 or idx is not None or (n + 1 < len(items) and t.size(1) % 64):
+            return False
+    return True
 
 
 def _al16(t):
@@ -149,6 +162,14 @@ def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accum
     if adds:
         add_segs, nadd = L.make_segs([(t, i, None, 0) for t, i in adds]), len(adds)
         assert all(t.dtype == torch.float32 and t.size(1) == n_out for t, _ in adds)
+    if tc and _tma_ok(items, K, accumulate):
+        wr = _packed_weight(W, trans_w, rowmajor=True)
+        L.check(L.lib().b3d_linear_tma(segs, len(items), L.ptr(wr), n_out, K, L.ptr(bias), L.ptr(out),
+                                       out.stride(0), _DT[out.dtype], M, act, 0,
+                                       L.ptr(out_mask), out_mask.stride(0) if out_mask is not None else 0,
+                                       _DT[out_mask.dtype] if out_mask is not None else 0, L.ptr(row_mask),
+                                       add_segs, nadd, L.stream()), "b3d_linear_tma")
+        return out
     if tc:
         wp = _packed_weight(W, trans_w)
         L.check(L.lib().b3d_linear_tc(segs, len(items), L.ptr(wp), n_out, K, L.ptr(bias), L.ptr(out),

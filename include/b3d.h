@@ -135,6 +135,17 @@ int b3d_linear_tc(const b3d_seg_t* segs /*host*/, int32_t nseg, const void* Wp, 
                   int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype, int64_t M,
                   int32_t act, int32_t flags, const void* out_mask, int32_t ldm, int32_t mask_dtype,
                   const uint8_t* row_mask, const b3d_seg_t* adds /*host*/, int32_t nadd, void* stream);
+/* TMA-fed persistent variant of b3d_linear_tc for DENSE bf16 operands (1-2 row-major segments, no
+ * gather; the leading segment's width a multiple of 64): TMA producer warp, single-thread tcgen05
+ * issuer, 4 epilogue warps, weight block resident in shared memory, double-buffered TMEM
+ * accumulators. Weights are packed row-major bf16 [Npad][Kpad] by b3d_tma_pack_weights. */
+size_t b3d_tma_packed_bytes(int32_t n_logical, int32_t k_logical);
+int b3d_tma_pack_weights(const float* W, int32_t ldw, int32_t n_logical, int32_t k_logical,
+                         int32_t transpose, void* Wr, void* stream);
+int b3d_linear_tma(const b3d_seg_t* segs /*host*/, int32_t nseg, const void* Wr, int32_t n_logical,
+                   int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype, int64_t M,
+                   int32_t act, int32_t flags, const void* out_mask, int32_t ldm, int32_t mask_dtype,
+                   const uint8_t* row_mask, const b3d_seg_t* adds /*host*/, int32_t nadd, void* stream);
 size_t b3d_wgrad_tc_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
 int b3d_wgrad_tc(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, int32_t nseg,
                  float* dW, int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,

@@ -151,3 +151,41 @@ def test_mm_gnn_bf16_vs_oracle():
     assert rel(out, out_ref) < BF16_TOL
     assert abs(loss.item() - loss_ref.item()) < BF16_TOL * abs(loss_ref.item())
     _grad_check(m, {k: v.grad for k, v in params.items() if v.grad is not None}, 8e-2)
+
+
+@pytest.mark.parametrize("M,widths,n_out", [(1024, (64,), 64), (5000, (64, 64), 256), (70000, (256,), 128),
+                                            (3000, (192,), 128), (2000, (512,), 384), (9000, (384,), 256),
+                                            (4000, (128, 40), 96), (130, (128,), 64), (100000, (64,), 512)])
+def test_linear_tma_dense_bf16(M, widths, n_out):
+    """TMA-fed persistent kernel (dense bf16 operands): all epilogue variants vs a float64 reference."""
+    torch.manual_seed(M + n_out)
+    xs = [torch.randn(M, w).to(torch.bfloat16) for w in widths]
+    cat = torch.cat([x.double() for x in xs], 1)
+    items = [(x.to(DEV), None, None, 0) for x in xs]
+    W, b = torch.randn(n_out, sum(widths)) * 0.1, torch.randn(n_out)
+    ref = bf(cat) @ bf(W).t() + b.double()
+    before = L.launch_count()
+    y = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, L.ACT_RELU, tc=True, out_dtype=torch.float32)
+    assert L.launch_count() - before == 2          # row-major pack + k_linear_tma
+    assert rel(y, torch.relu(ref)) < 1e-5
+    y16 = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, L.ACT_NONE, tc=True, out_dtype=torch.bfloat16)
+    assert y16.dtype == torch.bfloat16 and rel(y16, ref) < 1e-2
+    # row-gathered addends + ReLU-mask epilogue + row mask
+    N = 501
+    p0, p1 = torch.randn(N, n_out), torch.randn(N, n_out)
+    i0, i1 = torch.randint(0, N, (M,)), torch.randint(0, N, (M,))
+    hm = torch.randn(M, n_out)
+    rm = torch.rand(M) < 0.8
+    y = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, L.ACT_NONE, tc=True, out_mask=hm.to(DEV).to(torch.bfloat16),
+                       row_mask=rm.to(torch.uint8).to(DEV),
+                       adds=[(p0.to(DEV), i0.int().to(DEV)), (p1.to(DEV), i1.int().to(DEV))])
+    ref2 = (ref + p0[i0].double() + p1[i1].double()) * (bf(hm) > 0) * rm[:, None]
+    assert rel(y, ref2) < 1e-5
+    # same result as the thread-staged tcgen05 kernel
+    ops._USE_TMA = False
+    try:
+        y_tc = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, L.ACT_RELU, tc=True, out_dtype=torch.float32)
+    finally:
+        ops._USE_TMA = True
+    y_tma = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, L.ACT_RELU, tc=True, out_dtype=torch.float32)
+    assert rel(y_tma, y_tc) < 1e-6
