@@ -93,7 +93,8 @@ __device__ __forceinline__ float activate(float v) {
 // EP is any struct with the TcArgs epilogue fields; sb = bias of this CTA's column block (smem).
 template <int ACT, class EP>
 __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int n0, int col0, const uint32_t (&r)[32],
-                                                 const float* s_bias, bool plain, bool rz) {
+                                                 const float* s_bias, bool plain, bool rz, int nlim) {
+  // nlim: first global column this CTA must NOT write (min(Nout, end of its column block))
   using namespace tc;
     float o[32];
   const int cbase = n0 + col0;
@@ -108,7 +109,7 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   for (int t = 0; t < a.nadd; ++t) {   // node-side first-layer blocks, pre-projected per node
     const SegDev& S = a.add[t];
     const float* ap = S.ptr + (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase;
-    if (cbase + 31 < a.Nout) {
+    if (cbase + 31 < nlim) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(ap) + q);
@@ -117,14 +118,14 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (cbase + j < a.Nout) o[j] += __ldg(ap + j);
+        if (cbase + j < nlim) o[j] += __ldg(ap + j);
     }
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) o[j] = activate<ACT>(o[j]);
   if (!plain) {
     if (a.out_mask) {   // ReLU backward of the producing layer: keep the gradient where its output was > 0
-      if (a.mask_bf16 && cbase + 31 < a.Nout && (a.ldm & 7) == 0) {
+      if (a.mask_bf16 && cbase + 31 < nlim && (a.ldm & 7) == 0) {
         const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -136,7 +137,7 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
             if ((int16_t)(w[j] >> 16) <= 0) o[8 * q + 2 * j + 1] = 0.f;
           }
         }
-      } else if (!a.mask_bf16 && cbase + 31 < a.Nout && (a.ldm & 3) == 0) {
+      } else if (!a.mask_bf16 && cbase + 31 < nlim && (a.ldm & 3) == 0) {
         const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.out_mask) + row * a.ldm + cbase);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -150,7 +151,7 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int cc = cbase + j;
-          if (cc < a.Nout) {
+          if (cc < nlim) {
             const float mv = a.mask_bf16
                 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.out_mask)[row * a.ldm + cc])
                 : reinterpret_cast<const float*>(a.out_mask)[row * a.ldm + cc];
@@ -167,21 +168,21 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
       const float* yrow = reinterpret_cast<const float*>(a.Y) + row * a.ldy;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (cbase + j < a.Nout) o[j] += yrow[cbase + j];
+        if (cbase + j < nlim) o[j] += yrow[cbase + j];
     }
   }
   if (a.y_bf16) {
     __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(a.Y) + row * a.ldy + cbase;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (cbase + 8 * q + 7 < a.Nout) {
+      if (cbase + 8 * q + 7 < nlim) {
         uint4 pk = make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
                               pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
         *reinterpret_cast<uint4*>(yrow + 8 * q) = pk;
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (cbase + 8 * q + j < a.Nout) yrow[8 * q + j] = __float2bfloat16_rn(o[8 * q + j]);
+          if (cbase + 8 * q + j < nlim) yrow[8 * q + j] = __float2bfloat16_rn(o[8 * q + j]);
       }
     }
   } else {
@@ -189,12 +190,12 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
     const bool vec_ok = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      if (vec_ok && cbase + 4 * q + 3 < a.Nout) {
+      if (vec_ok && cbase + 4 * q + 3 < nlim) {
         *reinterpret_cast<float4*>(yrow + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (cbase + 4 * q + j < a.Nout) yrow[4 * q + j] = o[4 * q + j];
+          if (cbase + 4 * q + j < nlim) yrow[4 * q + j] = o[4 * q + j];
       }
     }
   }
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
     tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)col0, r);
     tmem_ld_wait();
     if (!row_ok) continue;
-    epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz);
+    epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, a.Nout);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -645,7 +646,7 @@ k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
         tmem_ld_wait();
-        if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz);
+        if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, min(a.Nout, n0 + a.Nb));
       }
       tc_fence_before_sync();
       __syncwarp();

@@ -189,3 +189,17 @@ def test_linear_tma_dense_bf16(M, widths, n_out):
         ops._USE_TMA = True
     y_tma = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, L.ACT_RELU, tc=True, out_dtype=torch.float32)
     assert rel(y_tma, y_tc) < 1e-6
+
+
+@pytest.mark.parametrize("k,n,trans", [(288, 512, False), (512, 384, True), (288, 512, True), (320, 176, False)])
+def test_linear_tma_column_blocks_not_multiple_of_32(k, n, trans):
+    """Regression: with several column blocks per row tile whose width is 16 (mod 32), a CTA must not
+    write past its own block (n = output features; trans = input-gradient form)."""
+    torch.manual_seed(k + n)
+    M = 20000
+    x = torch.randn(M, n if trans else k).to(torch.bfloat16)
+    W = torch.randn(n, k) * 0.1
+    ref = bf(x) @ (bf(W) if trans else bf(W).t())
+    for _ in range(3):      # repeated launches expose write races between neighbouring CTAs
+        y = ops.linear_raw([(x.to(DEV), None, None, 0)], W.to(DEV), None, M, 0, trans_w=trans, tc=True)
+        assert rel(y, ref) < 1e-5
