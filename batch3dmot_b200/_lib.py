@@ -30,7 +30,7 @@ _SIGS = {
     "b3d_segment_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_gather_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
-                                  C.c_int32, C.c_void_p]),
+                                  C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_linear": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                              C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                              C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p]),
@@ -52,6 +52,9 @@ _SIGS = {
     "b3d_wgrad_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "b3d_wgrad_tc": (C.c_int, [C.POINTER(Seg), C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b3d_wgrad_tma_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "b3d_wgrad_tma": (C.c_int, [C.POINTER(Seg), C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b3d_knn_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,
                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b3d_gat_aggregate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -113,8 +113,10 @@ class GNN(nn.Module):
             w0, sens = ae[0].weight, [(a_rad, None), (a_lid, None), (a_img, None)]
             p_i = ops.fused_linear(sens, w0[:, :288], ae[0].bias)                  # [N,512]
             p_j = ops.fused_linear(sens, w0[:, 288:576])
+            e0 = e0.to(torch.bfloat16)         # edge-level tensors are kept in bf16 between kernels
             att = ops.fused_mlp([(e0, None)], [w0[:, 576:]] + [m.weight for m in ae[1:]],
-                                [None] + [m.bias for m in ae[1:]], adds=[(p_i, dst), (p_j, src)])
+                                [None] + [m.bias for m in ae[1:]], adds=[(p_i, dst), (p_j, src)],
+                                out_dtype=torch.bfloat16)
         else:
             att_in = [(a_rad, dst), (a_lid, dst), (a_img, dst),    # x_sens_i :161
                       (a_rad, src), (a_lid, src), (a_img, src),    # x_sens_j

@@ -699,6 +699,150 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, long
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// ------------------------------------------------------------------ TMA-fed weight gradient
+// dW[n,k] = sum_r dY[r,n] A[r,k] for DENSE bf16 dY / A (1-2 segments). Both operands are MN-major
+// tiles written by TMA (boxes {64 cols, 64 rows}, 128B swizzle): no thread touches them.
+//   warp 0: TMA producer, warp 1: tcgen05 issuer, all 6 warps: final epilogue (fp32 partials).
+// Bias gradient: a constant MN-major "ones" tile (column 0 = 1) multiplies dY^T in a second, N=16
+// MMA per K step; rows past the end of the split are zero-filled by TMA, so they drop out.
+constexpr int WG_STAGES = 4;
+constexpr int WG_BOX = 64 * 128;   // bytes of one {64 cols, 64 rows} bf16 box
+
+struct WgTmaArgs {
+  int seg0_groups, ngroups_total;   // 64-column groups of A: in segment 0 / in total
+  int Ktot, Nout, ktiles;
+  long long M, rows_per_split;
+  float* part;                       // [S][Nout][Ktot+1]
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // next 64-wide MN group
+  d |= (uint64_t)(1024 >> 4) << 32;                    // next 8-row K group
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+k_wgrad_tma(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapA0,
+            const __grid_constant__ CUtensorMap mapA1, const WgTmaArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using namespace tc;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int nt = blockIdx.y / a.ktiles, kt = blockIdx.y % a.ktiles;
+  const int n0 = nt * TC_BM;
+  const int g0 = kt * 4;                                       // first 64-column group of this k tile
+  const int ng = min(4, a.ngroups_total - g0);                 // groups in this tile (N' = 64*ng)
+  const bool with_bias = (kt == 0);
+  const uint32_t stage_bytes = 2 * WG_BOX + 4 * WG_BOX;        // dY^T (2 boxes) + A^T (<= 4 boxes) = 48 KB
+  const uint32_t pad = (1024u - (smem_u32(smem) & 1023u)) & 1023u;
+  const uint32_t sStage = smem_u32(smem) + pad;
+  const uint32_t sOnes = sStage + WG_STAGES * stage_bytes;     // 8 KB constant tile
+  const uint32_t sBar = sOnes + WG_BOX;                        // full[4] @0, empty[4] @32, done @64, tmem ptr @72
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + pad + WG_STAGES * stage_bytes + WG_BOX + 72);
+  if (warp == 1) tmem_alloc(sBar + 72, 512);
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(sBar + 8 * s, 1); mbar_init(sBar + 32 + 8 * s, 1); }
+    mbar_init(sBar + 64, 1);
+    fence_mbar_init();
+  }
+  // ones tile: element (row r, col 0) = 1.0 -> 16-byte chunk (0 ^ (r & 7)) of row r
+  for (int i = tid; i < WG_BOX / 16; i += TMA_THREADS) {
+    const int r = i >> 3, ch = i & 7;
+    st_shared_v4(sOnes + i * 16, (ch == (r & 7)) ? 0x00003F80u : 0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+
+  const long long r0 = (long long)split * a.rows_per_split;
+  const long long r1 = min(a.M, r0 + a.rows_per_split);
+  const int nchunks = (int)((r1 - r0 + 63) / 64);
+
+  if (warp == 0 && lane == 0) {
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % WG_STAGES;
+      if (c >= WG_STAGES) mbar_wait(sBar + 32 + 8 * s, ((c / WG_STAGES) - 1) & 1);
+      const uint32_t base = sStage + s * stage_bytes;
+      const int row = (int)(r0 + (long long)c * 64);
+      mbar_expect_tx(sBar + 8 * s, (2 + ng) * WG_BOX);
+      tma_load_2d(base, &mapDY, n0, row, sBar + 8 * s);
+      tma_load_2d(base + WG_BOX, &mapDY, n0 + 64, row, sBar + 8 * s);
+      for (int g = 0; g < ng; ++g) {
+        const int gg = g0 + g;
+        if (gg < a.seg0_groups) tma_load_2d(base + (2 + g) * WG_BOX, &mapA0, gg * 64, row, sBar + 8 * s);
+        else tma_load_2d(base + (2 + g) * WG_BOX, &mapA1, (gg - a.seg0_groups) * 64, row, sBar + 8 * s);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = make_idesc_bf16(TC_BM, (uint32_t)(64 * ng), 1, 1);
+    const uint32_t idesc1 = make_idesc_bf16(TC_BM, 16u, 1, 1);
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % WG_STAGES;
+      mbar_wait(sBar + 8 * s, (c / WG_STAGES) & 1);
+      tc_fence_after_sync();
+      const uint32_t base = sStage + s * stage_bytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t ad = make_smem_desc_sw128_mn(base + j * 2048, WG_BOX);
+        mma_bf16_ss(tmem, ad, make_smem_desc_sw128_mn(base + 2 * WG_BOX + j * 2048, WG_BOX), idesc, (c | j) != 0);
+        if (with_bias) mma_bf16_ss(tmem + 256, ad, make_smem_desc_sw128_mn(sOnes + j * 2048, WG_BOX), idesc1, (c | j) != 0);
+      }
+      mma_commit(sBar + 32 + 8 * s);
+    }
+    mma_commit(sBar + 64);
+  }
+  __syncwarp();
+  // ---- epilogue (all warps): TMEM lane = output row n; warps w and w+4 share a lane quarter
+  const int Kw = a.Ktot + 1;
+  if (nchunks > 0) {
+    mbar_wait(sBar + 64, 0);
+    tc_fence_after_sync();
+  }
+  if (warp < 4 || warp < 6) {
+    const int lq = warp & 3;
+    const int n = n0 + lq * 32 + lane;
+    // warps 0-3 take column blocks 0,2,4,..; warps 4,5 (quarters 0,1) help with blocks 1,3,.. of their quarter;
+    // quarters 2,3 have a single warp, which therefore walks every block
+    const bool shared_quarter = lq < 2;
+    const int first = (warp >= 4) ? 1 : 0;
+    const int step = shared_quarter ? 2 : 1;
+    const int nblk = (64 * ng) / 32;
+    if (!(warp >= 4 && !shared_quarter)) {
+      for (int blk = first; blk < nblk; blk += step) {
+        uint32_t r[32];
+        if (nchunks > 0) { tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(blk * 32), r); tmem_ld_wait(); }
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (n < a.Nout) {
+          float* prow = a.part + ((long long)split * a.Nout + n) * Kw;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int k = g0 * 64 + blk * 32 + j;
+            if (k < a.Ktot) prow[k] = __uint_as_float(r[j]);
+          }
+        }
+      }
+      if (with_bias && warp < 4) {
+        uint32_t r[32];
+        if (nchunks > 0) { tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + 256u, r); tmem_ld_wait(); }
+        else r[0] = 0u;
+        if (n < a.Nout) a.part[((long long)split * a.Nout + n) * Kw + a.Ktot] = __uint_as_float(r[0]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace b3d
 
 using namespace b3d;
@@ -902,5 +1046,72 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   else if (act == B3D_ACT_SIGMOID) k_linear_tma<2><<<grid, TMA_THREADS, smem, st>>>(mA0, mA1, mW, a);
   else k_linear_tma<0><<<grid, TMA_THREADS, smem, st>>>(mA0, mA1, mW, a);
   B3D_LAUNCH_CHECK("k_linear_tma");
+  return 0;
+}
+
+extern "C" size_t b3d_wgrad_tma_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {
+  // worst case: one split per 512 rows is never exceeded by the plan below
+  long long tiles = (long long)((Nout + TC_BM - 1) / TC_BM) * ((round_up(K, 64) / 64 + 3) / 4);
+  long long S = (148 + tiles - 1) / tiles;
+  long long smax = (M + 1023) / 1024;
+  if (S > smax) S = smax;
+  if (S < 1) S = 1;
+  return sizeof(float) * (size_t)S * Nout * (K + 1) + 256;
+}
+
+extern "C" int b3d_wgrad_tma(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t nseg, float* dW, int32_t lddw,
+                             float* db, int64_t M, int32_t Nout, int32_t flags, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (M <= 0) return bad_arg("b3d_wgrad_tma: M must be > 0");
+  SegDev seg[2], d;
+  if (nseg < 1 || nseg > 2 || to_dev(segs, nseg, seg) || to_dev(dy, 1, &d)) return bad_arg("b3d_wgrad_tma segments");
+  if (d.idx || d.width != Nout || d.dtype != B3D_BF16 || (d.ld & 7) || (reinterpret_cast<uintptr_t>(d.ptr) & 15) ||
+      d.mask_mode != B3D_MASK_NONE)
+    return bad_arg("b3d_wgrad_tma: dy must be dense bf16 with 16-byte aligned rows");
+  int K = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (seg[s].dtype != B3D_BF16 || seg[s].idx || !seg_tc_ok(seg[s]))
+      return bad_arg("b3d_wgrad_tma: segments must be dense bf16, widths % 8, 16-byte aligned rows");
+    if (s + 1 < nseg && (seg[s].width % 64)) return bad_arg("b3d_wgrad_tma: leading segment width % 64");
+    K += seg[s].width;
+  }
+  WgTmaArgs a;
+  a.seg0_groups = nseg == 2 ? seg[0].width / 64 : round_up(K, 64) / 64;
+  a.ngroups_total = nseg == 2 ? seg[0].width / 64 + round_up(seg[1].width, 64) / 64 : round_up(K, 64) / 64;
+  a.Ktot = K; a.Nout = Nout; a.M = M;
+  a.ktiles = (a.ngroups_total + 3) / 4;
+  long long tiles = (long long)((Nout + TC_BM - 1) / TC_BM) * a.ktiles;
+  long long S = (148 + tiles - 1) / tiles;
+  long long smax = (M + 1023) / 1024;
+  if (S > smax) S = smax;
+  if (S < 1) S = 1;
+  long long rps = ((M + S - 1) / S + 63) / 64 * 64;
+  S = (M + rps - 1) / rps;
+  a.rows_per_split = rps;
+  if (workspace_bytes < sizeof(float) * (size_t)S * Nout * (K + 1)) return bad_arg("b3d_wgrad_tma workspace too small");
+  a.part = reinterpret_cast<float*>(workspace);
+  alignas(64) CUtensorMap mDY, mA0, mA1;
+  if (make_tmap_bf16(&mDY, d.ptr, M, Nout, d.ld, 64)) return bad_arg("b3d_wgrad_tma: tensor map dY");
+  if (make_tmap_bf16(&mA0, seg[0].ptr, M, seg[0].width, seg[0].ld, 64)) return bad_arg("b3d_wgrad_tma: tensor map A0");
+  if (nseg == 2) {
+    if (make_tmap_bf16(&mA1, seg[1].ptr, M, seg[1].width, seg[1].ld, 64)) return bad_arg("b3d_wgrad_tma: tensor map A1");
+  } else {
+    mA1 = mA0;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail("k_wgrad_tma smem attr", e);
+    attr_set = true;
+  }
+  size_t smem = (size_t)WG_STAGES * 6 * WG_BOX + WG_BOX + 128 + 1024;
+  dim3 grid((unsigned)S, (unsigned)tiles);
+  k_wgrad_tma<<<grid, TMA_THREADS, smem, st>>>(mDY, mA0, mA1, a);
+  B3D_LAUNCH_CHECK("k_wgrad_tma");
+  long long tot = (long long)Nout * (K + 1);
+  k_wgrad_tc_reduce<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(a.part, (int)S, Nout, K, dW, lddw, db,
+                                                                  (flags & B3D_FLAG_ACCUMULATE) ? 1 : 0);
+  B3D_LAUNCH_CHECK("k_wgrad_tc_reduce");
   return 0;
 }

@@ -7,6 +7,7 @@
 namespace b3d {
 
 constexpr int SEG_WARPS = 8;
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // One warp per node; lanes cover columns (float4 when aligned); edges summed in ascending
 // k = the order sequential CPU scatter_add_ uses, so results match index_add_ bit-for-bit.
@@ -84,8 +85,6 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) k_row_nonzero(const float* __r
   if (lane == 0) mask[r] = (s != 0.f) ? 1 : 0;
 }
 
-static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
 }  // namespace b3d
 
 using namespace b3d;
@@ -140,10 +139,38 @@ extern "C" int b3d_segment_sum(const void* src_v, int32_t src_dtype, int32_t ld_
   return 0;
 }
 
+// fp32 rows gathered and rounded to bf16 (gradient of a bf16 segment-sum input)
+__global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
+    const float* __restrict__ src, int ld, const int32_t* __restrict__ idx, long long M, int C,
+    __nv_bfloat16* __restrict__ out, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
+  if (r >= M) return;
+  const long long g = __ldg(idx + r);
+  for (int c = lane * 8; c < C; c += 256) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + g * ld + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + g * ld + c) + 1);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                         *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = v;
+  }
+}
+
 extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
-                               float* out, int32_t ld_out, void* stream) {
+                               void* out_v, int32_t out_dtype, int32_t ld_out, void* stream) {
   if (M == 0) return 0;
-  if (!src || !idx || !out || C <= 0 || M < 0) return bad_arg("b3d_gather_rows");
+  if (!src || !idx || !out_v || C <= 0 || M < 0) return bad_arg("b3d_gather_rows");
+  if (out_dtype == B3D_BF16) {
+    if ((C & 7) || (ld_src & 3) || (ld_out & 7) || !al16(src) || !al16(out_v))
+      return bad_arg("b3d_gather_rows: bf16 output needs C % 8 == 0 and 16-byte aligned rows");
+    k_gather_rows_bf16<<<(unsigned)ceil_div(M, SEG_WARPS), SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        src, ld_src, idx, M, C, reinterpret_cast<__nv_bfloat16*>(out_v), ld_out);
+    B3D_LAUNCH_CHECK("k_gather_rows_bf16");
+    return 0;
+  }
+  float* out = reinterpret_cast<float*>(out_v);
   bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
   unsigned grid = (unsigned)ceil_div(M, SEG_WARPS);
   if (vec) k_gather_rows<true><<<grid, SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(src, ld_src, idx, M, C, out, ld_out);

@@ -197,6 +197,13 @@ def wgrad_raw(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=False, w
     if tc is None:
         tc = _PRECISION == "bf16" and M > 0 and _tc_shapes_ok(items, M, max(n_out, 16), K) and \
             _al16(dy_item[0]) and dy_item[2] is None and n_out * K >= 2048
+    if tc and dy_item[0].dtype == torch.bfloat16 and n_out % 8 == 0 and _tma_ok(items, K, False):
+        wsb = lib.b3d_wgrad_tma_workspace_bytes(M, n_out, K)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        L.check(lib.b3d_wgrad_tma(L.make_segs([dy_item]), L.make_segs(items), len(items), L.ptr(dW), dW.stride(0),
+                                  L.ptr(db), M, n_out, L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(ws), wsb,
+                                  L.stream()), "b3d_wgrad_tma")
+        return dW, db
     if tc:
         wsb = lib.b3d_wgrad_tc_workspace_bytes(M, n_out, K)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -215,6 +222,8 @@ def wgrad_raw(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=False, w
 def segment_sum_raw(src, nidx, out=None, accumulate=False):
     src = _rows(src)
     C_ = src.size(1)
+    if src.dtype == torch.bfloat16 and (C_ % 8 or not _al16(src)):
+        src = src.float()
     if out is None:
         out = torch.empty((nidx.n, C_), dtype=torch.float32, device=src.device)
     perm = None if nidx.sorted else nidx.perm
@@ -224,12 +233,16 @@ def segment_sum_raw(src, nidx, out=None, accumulate=False):
     return out
 
 
-def gather_rows_raw(src, idx32):
+def gather_rows_raw(src, idx32, out_dtype=torch.float32):
     src = _rows(src)
+    if src.dtype != torch.float32:
+        src = src.float()
     M = idx32.numel()
-    out = torch.empty((M, src.size(1)), dtype=torch.float32, device=src.device)
+    if out_dtype == torch.bfloat16 and (src.size(1) % 8 or not _al16(src)):
+        out_dtype = torch.float32
+    out = torch.empty((M, src.size(1)), dtype=out_dtype, device=src.device)
     L.check(L.lib().b3d_gather_rows(L.ptr(src), src.stride(0), L.ptr(idx32), M, src.size(1), L.ptr(out),
-                                    out.stride(0), L.stream()), "b3d_gather_rows")
+                                    _DT[out_dtype], out.stride(0), L.stream()), "b3d_gather_rows")
     return out
 
 
@@ -290,7 +303,7 @@ class _FusedMLP(torch.autograd.Function):
     are reduced back to nodes with the CSR segmented sum (no atomics)."""
 
     @staticmethod
-    def forward(ctx, nl, final_act, row_mask, nidx, add_nidx, *tensors):
+    def forward(ctx, nl, final_act, row_mask, nidx, add_nidx, out_dtype, *tensors):
         Ws = [w if w.stride(1) == 1 else w.contiguous() for w in tensors[0:2 * nl:2]]
         bs = [b.contiguous() if b is not None else None for b in tensors[1:2 * nl:2]]
         nx = len(nidx)
@@ -307,12 +320,17 @@ class _FusedMLP(torch.autograd.Function):
         # the whole chain runs on tensor cores or not at all (keeps dtypes of saved activations uniform)
         tc = _PRECISION == "bf16" and M > 0 and final_act is None and _tc_shapes_ok(items, M, Ws[0].size(0), Ws[0].size(1)) \
             and all(w.size(0) % 8 == 0 and w.size(1) % 8 == 0 and w.size(0) >= 16 and w.size(1) >= 32 for w in Ws)
+        if not tc and any(x.dtype != torch.float32 for x in xs):      # fp32 kernels take fp32 operands
+            xs = [x.float() for x in xs]
+            items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
+        ctx.in_dtypes = [t.dtype for t in tensors[2 * nl:2 * nl + nx]]
         acts, cur = [], items
         for l in range(nl):
             last = l == nl - 1
             y = linear_raw(cur, Ws[l], bs[l], M, _ACT[final_act] if last else L.ACT_RELU,
                            row_mask=rm if last else None, tc=tc,
-                           out_dtype=torch.float32 if last else torch.bfloat16, adds=adds if l == 0 else None)
+                           out_dtype=(out_dtype or torch.float32) if last else torch.bfloat16,
+                           adds=adds if l == 0 else None)
             acts.append(y)
             cur = [(y, None, None, 0)]
         ctx.nl, ctx.final_act, ctx.rm, ctx.nidx, ctx.M, ctx.tc = nl, final_act, rm, nidx, M, tc
@@ -327,7 +345,7 @@ class _FusedMLP(torch.autograd.Function):
         saved = ctx.saved_tensors
         Ws, acts, xs = saved[:nl], saved[nl:2 * nl], saved[2 * nl:]
         dz = _rows(dy)
-        if dz.dtype != torch.float32:
+        if dz.dtype != torch.float32 and not tc:
             dz = dz.float()
         if ctx.rm is not None:
             dz = dz * ctx.rm.unsqueeze(1)
@@ -336,8 +354,8 @@ class _FusedMLP(torch.autograd.Function):
         items0 = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
         grads = [None] * (2 * nl)
         nx = len(nidx)
-        need_x = ctx.needs_input_grad[5 + 2 * nl:5 + 2 * nl + nx]
-        need_add = ctx.needs_input_grad[5 + 2 * nl + nx:]
+        need_x = ctx.needs_input_grad[6 + 2 * nl:6 + 2 * nl + nx]
+        need_add = ctx.needs_input_grad[6 + 2 * nl + nx:]
         xs = xs[:nx]
         dxs = [None] * nx
         dadds = [None] * len(ctx.add_nidx)
@@ -352,7 +370,7 @@ class _FusedMLP(torch.autograd.Function):
                     if need_add[t]:
                         assert dz_item[2] is None
                         dadds[t] = segment_sum_raw(dz_item[0], ni) if ni is not None else dz_item[0].float()
-            if ctx.needs_input_grad[5 + 2 * l]:
+            if ctx.needs_input_grad[6 + 2 * l]:
                 dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc)
                 grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)
             if l > 0:
@@ -360,18 +378,23 @@ class _FusedMLP(torch.autograd.Function):
                                 out_dtype=torch.bfloat16)
                 dz_item = (dz, None, None, 0)
             elif any(need_x):
-                dA = linear_raw([dz_item], W, None, M, trans_w=True, tc=tc)      # [M, K] fp32
+                # [M, K]; bf16 when every consumer of the slices is a bf16 tensor (halves the largest
+                # backward tensor), fp32 otherwise
+                low = tc and all(dt == torch.bfloat16 for dt, nd in zip(ctx.in_dtypes, need_x) if nd)
+                dA = linear_raw([dz_item], W, None, M, trans_w=True, tc=tc,
+                                out_dtype=torch.bfloat16 if low else torch.float32)
                 off = 0
                 for s, (x, ni) in enumerate(zip(xs, nidx)):
                     w = x.size(1)
                     if need_x[s]:
                         sl = dA[:, off:off + w]
-                        dxs[s] = segment_sum_raw(sl, ni) if ni is not None else sl
+                        g = segment_sum_raw(sl, ni) if ni is not None else sl
+                        dxs[s] = g if g.dtype == ctx.in_dtypes[s] else g.to(ctx.in_dtypes[s])
                     off += w
-        return (None, None, None, None, None, *grads, *dxs, *dadds)
+        return (None, None, None, None, None, None, *grads, *dxs, *dadds)
 
 
-def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=()):
+def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=(), out_dtype=None):
     """inputs: list of (tensor [rows,w], NodeIndex|None); the concatenation order defines the first
     weight's input-column layout. weights/biases: per layer.
     adds: up to two (tensor [n, out_features of layer 0] fp32, NodeIndex|None) summed, row-gathered,
@@ -381,8 +404,8 @@ def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=()):
     flat = []
     for w, b in zip(weights, biases):
         flat += [w, b]
-    return _FusedMLP.apply(len(weights), final_act, row_mask, nidx, tuple(ni for _, ni in adds), *flat, *xs,
-                           *[t for t, _ in adds])
+    return _FusedMLP.apply(len(weights), final_act, row_mask, nidx, tuple(ni for _, ni in adds), out_dtype,
+                           *flat, *xs, *[t for t, _ in adds])
 
 
 def fused_linear(inputs, weight, bias=None, act=None, row_mask=None, adds=()):
@@ -399,12 +422,13 @@ def run_mlp(seq, inputs, final_act=None, row_mask=None):
 class _SegmentSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, nidx):
-        ctx.nidx = nidx
+        ctx.nidx, ctx.src_dtype = nidx, src.dtype
         return segment_sum_raw(src, nidx)
 
     @staticmethod
     def backward(ctx, dout):
-        return gather_rows_raw(dout, ctx.nidx.idx), None
+        g = gather_rows_raw(dout, ctx.nidx.idx, out_dtype=ctx.src_dtype)
+        return (g if g.dtype == ctx.src_dtype else g.to(ctx.src_dtype)), None
 
 
 def segment_sum(src, nidx):

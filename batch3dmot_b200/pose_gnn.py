@@ -61,15 +61,20 @@ class CausalMessagePassing(nn.Module):
         w1 = eu[0].weight                                              # cols: x_i | x_j | e (| att)
         p_i = ops.fused_linear([(x, None)], w1[:, :D], eu[0].bias)     # [N, H1]
         p_j = ops.fused_linear([(x, None)], w1[:, D:2 * D])
+        # edge-level tensors stay bf16 between kernels: every consumer is a bf16 tensor-core tile
+        # (dense bf16 operands go through the TMA-fed kernels) or the fp32-accumulating segment sum
+        lowp = torch.bfloat16
+        if e.dtype != lowp:
+            e = e.to(lowp)
         dense = [(e, None)] + ([(att, None)] if att is not None else [])
         e_new = ops.fused_mlp(dense, [w1[:, 2 * D:], eu[1].weight, eu[2].weight], [None, eu[1].bias, eu[2].bias],
-                              adds=[(p_i, dst), (p_j, src)])
+                              adds=[(p_i, dst), (p_j, src)], out_dtype=lowp)
         out = []
         for seq, side, pinv in ((self.create_future_msgs, dst, inv[0]), (self.create_past_msgs, src, inv[1])):
             l0, l1 = [m for m in seq if isinstance(m, nn.Linear)]
             p = ops.fused_linear([(x, None)], l0.weight[:, :D], adds=[(pinv, None)])        # x | e' | x0 blocks
             out.append(ops.fused_mlp([(e_new, None)], [l0.weight[:, D:D + E_], l1.weight], [None, l1.bias],
-                                     adds=[(p, side)]))
+                                     adds=[(p, side)], out_dtype=lowp))
         fut, past = out
         m_past = ops.segment_sum(past, dst)
         m_fut = ops.segment_sum(fut, src)

@@ -88,9 +88,10 @@ int b3d_segment_sum(const void* src, int32_t src_dtype, int32_t ld_src, const in
                     const int32_t* rowptr, int64_t N, int32_t C, float* out, int32_t ld_out, int32_t flags,
                     void* stream);
 
-/* out[r, 0:C] = src[idx[r], 0:C]  (index_select; backward of segment_sum). */
+/* out[r, 0:C] = src[idx[r], 0:C]  (index_select; backward of segment_sum). out_dtype B3D_F32 or
+ * B3D_BF16 (rounded on store). */
 int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
-                    float* out, int32_t ld_out, void* stream);
+                    void* out, int32_t out_dtype, int32_t ld_out, void* stream);
 
 /* ---- dense layers with fused gather / concat / activation ------------------
  * Y[M,Nout] (+)= act( cat_s(A_s)[M,K] * op(W) + bias ) [* (out_mask > 0)] [row_mask]
@@ -147,6 +148,11 @@ int b3d_linear_tma(const b3d_seg_t* segs /*host*/, int32_t nseg, const void* Wr,
                    int32_t act, int32_t flags, const void* out_mask, int32_t ldm, int32_t mask_dtype,
                    const uint8_t* row_mask, const b3d_seg_t* adds /*host*/, int32_t nadd, void* stream);
 size_t b3d_wgrad_tc_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
+/* TMA-fed variant of b3d_wgrad_tc for DENSE bf16 dy / segments (see b3d_linear_tma). */
+size_t b3d_wgrad_tma_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
+int b3d_wgrad_tma(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, int32_t nseg,
+                  float* dW, int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,
+                  void* workspace, size_t workspace_bytes, void* stream);
 int b3d_wgrad_tc(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, int32_t nseg,
                  float* dW, int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,
                  void* workspace, size_t workspace_bytes, void* stream);

@@ -203,3 +203,26 @@ def test_linear_tma_column_blocks_not_multiple_of_32(k, n, trans):
     for _ in range(3):      # repeated launches expose write races between neighbouring CTAs
         y = ops.linear_raw([(x.to(DEV), None, None, 0)], W.to(DEV), None, M, 0, trans_w=trans, tc=True)
         assert rel(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,widths,n_out", [(4096, (64,), 64), (70000, (64, 64), 256), (9000, (256,), 128),
+                                            (20000, (512,), 384), (5000, (192,), 128), (3000, (128, 40), 96),
+                                            (1500, (64,), 512), (100000, (128,), 64), (777, (320,), 24)])
+def test_wgrad_tma_dense_bf16(M, widths, n_out):
+    """TMA-fed weight gradient (dense bf16 operands) incl. the ones-tile bias gradient."""
+    torch.manual_seed(M + n_out)
+    xs = [torch.randn(M, w).to(torch.bfloat16) for w in widths]
+    cat = torch.cat([x.double() for x in xs], 1)
+    dy = torch.randn(M, n_out).to(torch.bfloat16)
+    items = [(x.to(DEV), None, None, 0) for x in xs]
+    K = sum(widths)
+    before = L.launch_count()
+    dW, db = ops.wgrad_raw((dy.to(DEV), None, None, 0), items, M, n_out, K, tc=True)
+    assert L.launch_count() - before == 2
+    ref_w, ref_b = dy.double().t() @ cat, dy.double().sum(0)
+    assert rel(dW, ref_w) < 1e-5 and rel(db, ref_b) < 1e-5
+    dW2, db2 = ops.wgrad_raw((dy.to(DEV), None, None, 0), items, M, n_out, K, dW=dW.clone(), db=db.clone(),
+                             accumulate=True, tc=True)
+    assert rel(dW2, 2 * ref_w) < 1e-5 and rel(db2, 2 * ref_b) < 1e-5
+    dW3, _ = ops.wgrad_raw((dy.to(DEV), None, None, 0), items, M, n_out, K, tc=True)
+    assert torch.equal(dW3, dW)
