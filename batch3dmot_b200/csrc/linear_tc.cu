@@ -498,7 +498,7 @@ static void wgrad_tc_plan(long long M, int Nout, int Ktot, int* S, long long* rp
   *ktiles = (*Kp + TC_NMAX - 1) / TC_NMAX;
   long long tiles = (long long)((Nout + TC_BM - 1) / TC_BM) * *ktiles;
   long long s = (2 * 148 + tiles - 1) / tiles;
-  long long smax = (M + 511) / 512;
+  long long smax = (M + 127) / 128;
   if (s > smax) s = smax;
   if (s < 1) s = 1;
   long long r = ((M + s - 1) / s + TC_BK - 1) / TC_BK * TC_BK;
@@ -516,12 +516,13 @@ static bool seg_tc_ok(const SegDev& S) {
 // Dense bf16 operands only (1-2 row-major segments, widths multiples of 64 except the last):
 //   warp 0 : TMA producer  (cp.async.bulk.tensor 2D boxes {64 cols, 128 rows}, 128B swizzle)
 //   warp 1 : MMA issuer    (tcgen05.mma, operands straight from the TMA-written tiles)
-//   warps 2-5: epilogue    (TMEM -> registers -> bias/adds/act/masks -> global)
+//   warps 2-9: epilogue    (TMEM -> registers -> bias/adds/act/masks -> global)
 // The weight block [Nb, K] stays resident in shared memory for the CTA's lifetime; CTAs are
 // persistent over row tiles; two TMEM accumulators let the epilogue of tile t overlap the MMAs of
 // tile t+1. No thread touches the operands: the staging cost of k_linear_tc disappears.
 constexpr int TMA_STAGES = 4;
-constexpr int TMA_THREADS = 192;
+constexpr int TMA_THREADS = 320;   // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
+constexpr int WG_THREADS = 192;
 
 struct TmaArgs {
   int seg0_chunks, nchunks, Nb, acc_stride;
@@ -583,7 +584,7 @@ k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   if (tid == 0) {
     for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(sBar + 8 * s, 1); mbar_init(sBar + 32 + 8 * s, 1); }
     mbar_init(sBar + 64, 1); mbar_init(sBar + 72, 1);      // accumulator full (tcgen05.commit)
-    mbar_init(sBar + 80, 4); mbar_init(sBar + 88, 4);      // accumulator empty (4 epilogue warps)
+    mbar_init(sBar + 80, 8); mbar_init(sBar + 88, 8);      // accumulator empty (8 epilogue warps)
     mbar_init(sBar + 96, 1);                                // weights resident
     fence_mbar_init();
   }
@@ -642,7 +643,7 @@ k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const long long row = tile * TC_BM + lq * 32 + lane;
       const bool row_ok = row < a.M;
       const bool rz = row_ok && a.row_mask && a.row_mask[row] == 0;
-      for (int col0 = 0; col0 < a.Nb; col0 += 32) {
+      for (int col0 = ((warp - 2) >> 2) * 32; col0 < a.Nb; col0 += 64) {   // the two warps of a quarter interleave blocks
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
         tmem_ld_wait();
@@ -725,7 +726,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t saddr, uint
   return d;
 }
 
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 k_wgrad_tma(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapA0,
             const __grid_constant__ CUtensorMap mapA1, const WgTmaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -750,7 +751,7 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ C
     fence_mbar_init();
   }
   // ones tile: element (row r, col 0) = 1.0 -> 16-byte chunk (0 ^ (r & 7)) of row r
-  for (int i = tid; i < WG_BOX / 16; i += TMA_THREADS) {
+  for (int i = tid; i < WG_BOX / 16; i += WG_THREADS) {
     const int r = i >> 3, ch = i & 7;
     st_shared_v4(sOnes + i * 16, (ch == (r & 7)) ? 0x00003F80u : 0u, 0u, 0u, 0u);
   }
@@ -1107,7 +1108,7 @@ extern "C" int b3d_wgrad_tma(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t
   }
   size_t smem = (size_t)WG_STAGES * 6 * WG_BOX + WG_BOX + 128 + 1024;
   dim3 grid((unsigned)S, (unsigned)tiles);
-  k_wgrad_tma<<<grid, TMA_THREADS, smem, st>>>(mDY, mA0, mA1, a);
+  k_wgrad_tma<<<grid, WG_THREADS, smem, st>>>(mDY, mA0, mA1, a);
   B3D_LAUNCH_CHECK("k_wgrad_tma");
   long long tot = (long long)Nout * (K + 1);
   k_wgrad_tc_reduce<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(a.part, (int)S, Nout, K, dW, lddw, db,
