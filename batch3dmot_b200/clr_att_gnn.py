@@ -111,8 +111,8 @@ class GNN(nn.Module):
             # pre-projected form: the two 288-wide node-side blocks of att_edge_encoder.0 applied per node
             ae = [m for m in self.att_edge_encoder if isinstance(m, nn.Linear)]
             w0, sens = ae[0].weight, [(a_rad, None), (a_lid, None), (a_img, None)]
-            p_i = ops.fused_linear(sens, w0[:, :288], ae[0].bias)                  # [N,512]
-            p_j = ops.fused_linear(sens, w0[:, 288:576])
+            p_i = ops.fused_mlp(sens, [w0[:, :288]], [ae[0].bias], out_dtype=torch.bfloat16)    # [N,512]
+            p_j = ops.fused_mlp(sens, [w0[:, 288:576]], [None], out_dtype=torch.bfloat16)
             e0 = e0.to(torch.bfloat16)         # edge-level tensors are kept in bf16 between kernels
             att = ops.fused_mlp([(e0, None)], [w0[:, 576:]] + [m.weight for m in ae[1:]],
                                 [None] + [m.bias for m in ae[1:]], adds=[(p_i, dst), (p_j, src)],

@@ -108,17 +108,38 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   }
   for (int t = 0; t < a.nadd; ++t) {   // node-side first-layer blocks, pre-projected per node
     const SegDev& S = a.add[t];
-    const float* ap = S.ptr + (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase;
-    if (cbase + 31 < nlim) {
+    const long long arow = (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase;
+    if (S.dtype == B3D_BF16) {
+      const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(S.ptr) + arow;
+      if (cbase + 31 < nlim) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(ap) + q);
-        o[4 * q] += v.x; o[4 * q + 1] += v.y; o[4 * q + 2] += v.z; o[4 * q + 3] += v.w;
+        for (int q = 0; q < 4; ++q) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(ap) + q);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o[8 * q + 2 * j] += __uint_as_float(w[j] << 16);
+            o[8 * q + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cbase + j < nlim) o[j] += __bfloat162float(ap[j]);
       }
     } else {
+      const float* ap = S.ptr + arow;
+      if (cbase + 31 < nlim) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (cbase + j < nlim) o[j] += __ldg(ap + j);
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(ap) + q);
+          o[4 * q] += v.x; o[4 * q + 1] += v.y; o[4 * q + 2] += v.z; o[4 * q + 3] += v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cbase + j < nlim) o[j] += __ldg(ap + j);
+      }
     }
   }
 #pragma unroll
@@ -870,11 +891,11 @@ extern "C" int b3d_linear_tc(const b3d_seg_t* segs, int32_t nseg, const void* Wp
                              void* stream) {
   if (M == 0) return 0;
   TcArgs a;
-  if (nadd < 0 || nadd > 2 || (nadd && (to_dev(adds, nadd, a.add) || !all_f32(a.add, nadd))))
-    return bad_arg("b3d_linear_tc adds");
+  if (nadd < 0 || nadd > 2 || (nadd && to_dev(adds, nadd, a.add))) return bad_arg("b3d_linear_tc adds");
   for (int q = 0; q < nadd; ++q)
-    if (a.add[q].width != n_logical || (a.add[q].ld & 3) || (reinterpret_cast<uintptr_t>(a.add[q].ptr) & 15))
-      return bad_arg("b3d_linear_tc: adds must be fp32 [*, Nout], 16-byte aligned rows");
+    if (a.add[q].width != n_logical || (a.add[q].ld & (a.add[q].dtype == B3D_BF16 ? 7 : 3)) ||
+        (reinterpret_cast<uintptr_t>(a.add[q].ptr) & 15))
+      return bad_arg("b3d_linear_tc: adds must be [*, Nout] with 16-byte aligned rows");
   a.nadd = nadd;
   if (to_dev(segs, nseg, a.seg)) return bad_arg("b3d_linear_tc segments");
   int K = 0;
@@ -990,11 +1011,11 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
     K += seg[s].width;
   }
   if (K != k_logical || !Wr || !Y || n_logical <= 0) return bad_arg("b3d_linear_tma: shapes");
-  if (nadd < 0 || nadd > 2 || (nadd && (to_dev(adds, nadd, a.add) || !all_f32(a.add, nadd))))
-    return bad_arg("b3d_linear_tma adds");
+  if (nadd < 0 || nadd > 2 || (nadd && to_dev(adds, nadd, a.add))) return bad_arg("b3d_linear_tma adds");
   for (int q = 0; q < nadd; ++q)
-    if (a.add[q].width != n_logical || (a.add[q].ld & 3) || (reinterpret_cast<uintptr_t>(a.add[q].ptr) & 15))
-      return bad_arg("b3d_linear_tma: adds must be fp32 [*, Nout], 16-byte aligned rows");
+    if (a.add[q].width != n_logical || (a.add[q].ld & (a.add[q].dtype == B3D_BF16 ? 7 : 3)) ||
+        (reinterpret_cast<uintptr_t>(a.add[q].ptr) & 15))
+      return bad_arg("b3d_linear_tma: adds must be [*, Nout] with 16-byte aligned rows");
   if (y_dtype == B3D_BF16 && ((ldy & 7) || (reinterpret_cast<uintptr_t>(Y) & 15) || (flags & B3D_FLAG_ACCUMULATE)))
     return bad_arg("b3d_linear_tma: bf16 output needs ld % 8 == 0, 16-byte alignment, no accumulate");
   const int Npad = round_up(n_logical, 16), Kpad = round_up(k_logical, TC_BK);

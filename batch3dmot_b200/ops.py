@@ -161,7 +161,8 @@ def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accum
     add_segs, nadd = None, 0
     if adds:
         add_segs, nadd = L.make_segs([(t, i, None, 0) for t, i in adds]), len(adds)
-        assert all(t.dtype == torch.float32 and t.size(1) == n_out for t, _ in adds)
+        assert all(t.size(1) == n_out for t, _ in adds)
+        assert tc or all(t.dtype == torch.float32 for t, _ in adds)
     if tc and _tma_ok(items, K, accumulate):
         wr = _packed_weight(W, trans_w, rowmajor=True)
         L.check(L.lib().b3d_linear_tma(segs, len(items), L.ptr(wr), n_out, K, L.ptr(bias), L.ptr(out),
@@ -310,6 +311,7 @@ class _FusedMLP(torch.autograd.Function):
         xs = [_rows(x) for x in tensors[2 * nl:2 * nl + nx]]
         add_ts = [_rows(t) for t in tensors[2 * nl + nx:]]
         assert len(add_ts) == len(add_nidx) and (not add_ts or (final_act is None or nl > 1))
+        ctx.add_dtypes = [t.dtype for t in add_ts]
         adds = [(t, ni.idx if ni is not None else None) for t, ni in zip(add_ts, add_nidx)]
         M = nidx[0].idx.numel() if nidx[0] is not None else xs[0].size(0)
         for x, ni in zip(xs, nidx):
@@ -320,6 +322,8 @@ class _FusedMLP(torch.autograd.Function):
         # the whole chain runs on tensor cores or not at all (keeps dtypes of saved activations uniform)
         tc = _PRECISION == "bf16" and M > 0 and final_act is None and _tc_shapes_ok(items, M, Ws[0].size(0), Ws[0].size(1)) \
             and all(w.size(0) % 8 == 0 and w.size(1) % 8 == 0 and w.size(0) >= 16 and w.size(1) >= 32 for w in Ws)
+        if not tc:
+            adds = [(t.float(), i) for t, i in adds]
         if not tc and any(x.dtype != torch.float32 for x in xs):      # fp32 kernels take fp32 operands
             xs = [x.float() for x in xs]
             items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
@@ -369,7 +373,8 @@ class _FusedMLP(torch.autograd.Function):
                 for t, ni in enumerate(ctx.add_nidx):
                     if need_add[t]:
                         assert dz_item[2] is None
-                        dadds[t] = segment_sum_raw(dz_item[0], ni) if ni is not None else dz_item[0].float()
+                        g = segment_sum_raw(dz_item[0], ni) if ni is not None else dz_item[0]
+                        dadds[t] = g if g.dtype == ctx.add_dtypes[t] else g.to(ctx.add_dtypes[t])
             if ctx.needs_input_grad[6 + 2 * l]:
                 dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc)
                 grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)

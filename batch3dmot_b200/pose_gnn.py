@@ -59,11 +59,11 @@ class CausalMessagePassing(nn.Module):
             inv = self.project_invariants(x0)
         eu = [m for m in self.edge_update if isinstance(m, nn.Linear)]
         w1 = eu[0].weight                                              # cols: x_i | x_j | e (| att)
-        p_i = ops.fused_linear([(x, None)], w1[:, :D], eu[0].bias)     # [N, H1]
-        p_j = ops.fused_linear([(x, None)], w1[:, D:2 * D])
+        lowp = torch.bfloat16
+        p_i = ops.fused_mlp([(x, None)], [w1[:, :D]], [eu[0].bias], out_dtype=lowp)     # [N, H1]
+        p_j = ops.fused_mlp([(x, None)], [w1[:, D:2 * D]], [None], out_dtype=lowp)
         # edge-level tensors stay bf16 between kernels: every consumer is a bf16 tensor-core tile
         # (dense bf16 operands go through the TMA-fed kernels) or the fp32-accumulating segment sum
-        lowp = torch.bfloat16
         if e.dtype != lowp:
             e = e.to(lowp)
         dense = [(e, None)] + ([(att, None)] if att is not None else [])
@@ -72,7 +72,7 @@ class CausalMessagePassing(nn.Module):
         out = []
         for seq, side, pinv in ((self.create_future_msgs, dst, inv[0]), (self.create_past_msgs, src, inv[1])):
             l0, l1 = [m for m in seq if isinstance(m, nn.Linear)]
-            p = ops.fused_linear([(x, None)], l0.weight[:, :D], adds=[(pinv, None)])        # x | e' | x0 blocks
+            p = ops.fused_mlp([(x, None)], [l0.weight[:, :D]], [None], adds=[(pinv, None)], out_dtype=lowp)  # x | e' | x0
             out.append(ops.fused_mlp([(e_new, None)], [l0.weight[:, D:D + E_], l1.weight], [None, l1.bias],
                                      adds=[(p, side)], out_dtype=lowp))
         fut, past = out
