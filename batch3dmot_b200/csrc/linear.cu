@@ -7,7 +7,7 @@
 namespace b3d {
 
 // ------------------------------------------------------------------ forward / dgrad GEMM
-constexpr int BM = 128, BN = 64, BK = 16, LIN_THREADS = 256;
+constexpr int BM = 128, BK = 16, LIN_THREADS = 256;   // BN = 16 * TN columns per CTA (TN = 1, 2, 4)
 
 struct LinArgs {
   SegDev seg[B3D_MAX_SEGS];
@@ -26,7 +26,9 @@ struct LinArgs {
   int nadd;
 };
 
+template <int TN>
 __global__ void __launch_bounds__(LIN_THREADS) k_linear(const LinArgs a) {
+  constexpr int BN = 16 * TN;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -35,18 +37,18 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear(const LinArgs a) {
   const int ty = tid >> 4, tx = tid & 15;
   // loader roles
   const int ar = tid & (BM - 1), akp = tid >> 7;   // A: row, 8-wide k part
-  const int bn = tid & (BN - 1), bkp = tid >> 6;   // B: col, 4-wide k part
+  const int bn = tid & (BN - 1), bkp = tid / BN;   // B: col, TN-wide k part
   const long long arow = m0 + ar;
   const bool arow_ok = arow < a.M;
   const bool bcol_ok = (n0 + bn) < a.Nout;
 
-  float acc[8][4];
+  float acc[8][TN];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  float a_reg[8], b_reg[4];
+  float a_reg[8], b_reg[TN];
   int seg = 0, k0 = 0, koff = 0;  // current chunk: segment, offset in segment, column offset of segment in W
   long long grow = 0;             // gathered row for the current segment
   auto seg_row = [&](int s) { grow = arow_ok ? (a.seg[s].idx ? (long long)a.seg[s].idx[arow] : arow) : 0; };
@@ -84,25 +86,25 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear(const LinArgs a) {
     }
     // ---- B (weights): Bs[k][n]
     {
-      const int kb = bkp * 4;
+      const int kb = bkp * TN;
       if (!bcol_ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b_reg[j] = 0.f;
+        for (int j = 0; j < TN; ++j) b_reg[j] = 0.f;
       } else if (!a.trans_w) {
         const float* p = a.W + (long long)(n0 + bn) * a.ldw + koff + k0 + kb;
-        const bool vec = ((a.ldw & 3) == 0) && (((koff + k0) & 3) == 0) && (kb + 3 < kw) &&
+        const bool vec = (TN == 4) && ((a.ldw & 3) == 0) && (((koff + k0) & 3) == 0) && (kb + 3 < kw) &&
                          ((reinterpret_cast<uintptr_t>(a.W) & 15) == 0);
         if (vec) {
           float4 v = __ldg(reinterpret_cast<const float4*>(p));
-          b_reg[0] = v.x; b_reg[1] = v.y; b_reg[2] = v.z; b_reg[3] = v.w;
+          b_reg[0] = v.x; b_reg[TN > 1 ? 1 : 0] = v.y; b_reg[TN > 2 ? 2 : 0] = v.z; b_reg[TN > 3 ? 3 : 0] = v.w;
         } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) b_reg[j] = (kb + j < kw) ? __ldg(p + j) : 0.f;
+          for (int j = 0; j < TN; ++j) b_reg[j] = (kb + j < kw) ? __ldg(p + j) : 0.f;
         }
       } else {
         const float* p = a.W + (long long)(koff + k0 + kb) * a.ldw + n0 + bn;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b_reg[j] = (kb + j < kw) ? __ldg(p + (long long)j * a.ldw) : 0.f;
+        for (int j = 0; j < TN; ++j) b_reg[j] = (kb + j < kw) ? __ldg(p + (long long)j * a.ldw) : 0.f;
       }
     }
   };
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear(const LinArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) As[akp * 8 + j][ar] = a_reg[j];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) Bs[bkp * 4 + j][bn] = b_reg[j];
+    for (int j = 0; j < TN; ++j) Bs[bkp * TN + j][bn] = b_reg[j];
     __syncthreads();
     more = advance();
     if (more) load_chunk();  // global loads overlap the FMAs below
@@ -132,22 +134,23 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear(const LinArgs a) {
     for (int k = 0; k < BK; ++k) {
       float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
       float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
       float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float bv[4] = {b.x, b.y, b.z, b.w};
+      float bv[TN];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[k][tx * TN + j];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 
   // ---- epilogue
-  float bv[4];
+  float bv[TN];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int c = n0 + tx * 4 + j;
+  for (int j = 0; j < TN; ++j) {
+    int c = n0 + tx * TN + j;
     bv[j] = (a.bias && c < a.Nout) ? __ldg(a.bias + c) : 0.f;
   }
 #pragma unroll
@@ -159,8 +162,8 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear(const LinArgs a) {
     for (int q = 0; q < a.nadd; ++q)
       addp[q] = a.add[q].ptr + (long long)(a.add[q].idx ? __ldg(a.add[q].idx + r) : r) * a.add[q].ld;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int c = n0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      int c = n0 + tx * TN + j;
       if (c >= a.Nout) continue;
       float v = acc[i][j] + bv[j];
       if (addp[0]) v += __ldg(addp[0] + c);
@@ -358,8 +361,12 @@ extern "C" int b3d_linear(const b3d_seg_t* segs, int32_t nseg, const float* W, i
   a.nseg = nseg; a.W = W; a.ldw = ldw; a.trans_w = trans_w; a.bias = bias; a.Y = Y; a.ldy = ldy;
   a.M = M; a.Nout = Nout; a.act = act; a.flags = flags; a.out_mask = out_mask; a.ldm = ldm;
   a.row_mask = row_mask;
-  dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(Nout, BN));
-  k_linear<<<grid, LIN_THREADS, 0, (cudaStream_t)stream>>>(a);
+  // narrow outputs (classifier / encoder layers) use narrower column tiles instead of padding to 64
+  const int TN = Nout <= 16 ? 1 : (Nout <= 32 ? 2 : 4);
+  dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(Nout, 16 * TN));
+  if (TN == 1) k_linear<1><<<grid, LIN_THREADS, 0, (cudaStream_t)stream>>>(a);
+  else if (TN == 2) k_linear<2><<<grid, LIN_THREADS, 0, (cudaStream_t)stream>>>(a);
+  else k_linear<4><<<grid, LIN_THREADS, 0, (cudaStream_t)stream>>>(a);
   B3D_LAUNCH_CHECK("k_linear");
   return 0;
 }
