@@ -1,0 +1,71 @@
+"""Track-ID assignment: the vectorised product implementation must be
+bit-exact against the literal restatement of predict.py's dict loops (oracle/track_assembly.py)."""
+import numpy as np
+import pytest
+import torch
+
+from batch3dmot_b200 import synth, tracking
+from oracle import track_assembly as T
+
+
+def _scene(seed, T_frames=12, npf=14, k=8, quant=None):
+    g = torch.Generator().manual_seed(seed)
+    scene = synth.scene_graph(seed=seed, T=T_frames, nodes_per_frame=npf, k=k)
+    wins = synth.windows(scene, 5)
+    out = []
+    for w in wins:
+        E = w.edge_index.size(1)
+        s = torch.rand(E, generator=g)
+        s = torch.where(torch.rand(E, generator=g) < 0.6, s * 0.05, s)      # many scores near the thresholds
+        if quant:
+            s = torch.round(s * quant) / quant                               # exact ties
+        out.append((w.global_node_id, w.edge_index, s.float()))
+    return scene, out
+
+
+def _oracle(scene, wins):
+    cats = [synth.CATEGORIES[c - 1] for c in scene.node_classes.tolist()]
+    o_w = [(gid.numpy(), ei.t().numpy(), s.numpy()) for gid, ei, s in wins]
+    return T.track_ids(o_w, cats)
+
+
+@pytest.mark.parametrize("seed,quant", [(1, None), (2, None), (3, 50), (4, 8), (5, 1000), (6, None)])
+def test_track_ids_bit_exact(seed, quant):
+    scene, wins = _scene(seed, quant=quant)
+    ids_ref, tracks_ref = _oracle(scene, wins)
+    ids, tracks = tracking.assign_track_ids(wins, scene.node_classes)
+    assert tracks == tracks_ref
+    assert np.array_equal(ids.numpy(), ids_ref)
+    assert len(tracks) > 3 and int((ids >= 0).sum()) > 10
+
+
+def test_stages_match_reference_dict_order():
+    scene, wins = _scene(11, quant=20)
+    cats = [synth.CATEGORIES[c - 1] for c in scene.node_classes.tolist()]
+    o_w = [(gid.numpy(), ei.t().numpy(), s.numpy()) for gid, ei, s in wins]
+    nodes, pred_edges = T.combine_windows(o_w, cats)
+    n = scene.num_nodes
+    e_out, e_in, mean = tracking.average_window_scores(wins, n)
+    g_out, g_in, g_s = tracking.greedy_edges(e_out, e_in, mean, scene.node_classes)
+    got = [((int(a), int(b)), float(s)) for a, b, s in zip(g_out, g_in, g_s)]
+    assert got == [((a, b), float(s)) for (a, b), s in pred_edges]            # same edges, order and float64 scores
+
+
+def test_empty_and_single_edge():
+    scene = synth.scene_graph(seed=3, T=5, nodes_per_frame=3, k=2)
+    w = synth.windows(scene, 5)[0]
+    wins = [(w.global_node_id, w.edge_index, torch.zeros(w.edge_index.size(1)))]   # everything below threshold
+    ids, tracks = tracking.assign_track_ids(wins, scene.node_classes)
+    assert tracks == [] and int((ids >= 0).sum()) == 0
+    s = torch.zeros(w.edge_index.size(1)); s[0] = 0.9
+    ids, tracks = tracking.assign_track_ids([(w.global_node_id, w.edge_index, s)], scene.node_classes)
+    assert tracks == [[int(w.edge_index[0, 0]), int(w.edge_index[1, 0])]]
+
+
+@pytest.mark.gpu
+def test_track_ids_on_device_scores():
+    scene, wins = _scene(21, T_frames=20, npf=30, k=12, quant=200)
+    ids_ref, tracks_ref = _oracle(scene, wins)
+    dw = [(g.cuda(), e.cuda(), s.cuda()) for g, e, s in wins]
+    ids, tracks = tracking.assign_track_ids(dw, scene.node_classes.cuda())
+    assert tracks == tracks_ref and np.array_equal(ids.numpy(), ids_ref)
