@@ -246,15 +246,17 @@ def main():
         return ev0.elapsed_time(ev1) / reps * 1e-3
 
     if a.precision == "bf16":
-        # dominant kernel class: k_linear_tc (tcgen05 tiles); heaviest launch = att_edge_encoder layer 2
+        # dominant kernel class: k_linear_tma (TMA-fed tcgen05 tiles); heaviest launch = att_edge_encoder layer 2
         # ([E,512] bf16 -> 384, ReLU, bf16 out). Algorithmic FLOPs = 2*E*512*384; algorithmic bytes = E*(512+384)*2.
         lin = model.att_edge_encoder[2]
         h = torch.randn(E, 512, device=dev).to(torch.bfloat16)
         out = torch.empty(E, 384, device=dev, dtype=torch.bfloat16)
         t = time_kernel(lambda: ops.linear_raw([(h, None, None, 0)], lin.weight, lin.bias, E, 1, out=out, tc=True))
         ach = 2.0 * E * 512 * 384 / t / 1e12
-        roof = {"kernel": "k_linear_tc<relu> (tcgen05 bf16; att_edge_encoder layer 2, [E,512]x[512,384])", "bound": "tensor",
-                "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst, "traffic": None,
+        roof = {"kernel": "k_linear_tma<relu> (TMA-fed tcgen05 bf16; att_edge_encoder layer 2, [E,512]x[512,384])", "bound": "tensor",
+                "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst,
+                "traffic": 849_273_088 if a.scenes == 8 else None,   # dram read+write bytes per launch, ncu --set full
+                "traffic_source": "profiles/r1_roofline_kernel.md (algorithmic bytes: E*(512+384)*2)",
                 "peak_source": src + " bf16 dense burst; kernel timed alone",
                 "hbm_view": {"achieved_gbs": E * (512 + 384) * 2 / t / 1e9, "peak_gbs": hbm}}
     else:
