@@ -91,9 +91,44 @@ __device__ __forceinline__ float activate(float v) {
 // One 32-column block of one output row: bias + row-gathered addends + activation, then the ReLU
 // mask of the producing layer / row mask / accumulate, then a bf16 or fp32 store.
 // EP is any struct with the TcArgs epilogue fields; sb = bias of this CTA's column block (smem).
+// Global operands of one epilogue block (ReLU mask, gathered addends; bf16 fast paths only), loaded
+// BEFORE the TMEM load is waited on so that the two latencies overlap.
+struct EpiPrefetch {
+  uint4 m[4], a0[4], a1[4];
+  int flags;   // bit0: mask, bit1: addend 0, bit2: addend 1
+};
+template <class EP>
+__device__ __forceinline__ void epilogue_prefetch(const EP& a, long long row, int cbase, int nlim, EpiPrefetch& pf) {
+  pf.flags = 0;
+  if (cbase + 31 >= nlim) return;
+  if (a.out_mask && a.mask_bf16 && (a.ldm & 7) == 0) {
+    const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pf.m[q] = __ldg(mp + q);
+    pf.flags |= 1;
+  }
+  if (a.nadd > 0 && a.add[0].dtype == B3D_BF16) {
+    const SegDev& S = a.add[0];
+    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) +
+                                                     (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pf.a0[q] = __ldg(ap + q);
+    pf.flags |= 2;
+  }
+  if (a.nadd > 1 && a.add[1].dtype == B3D_BF16) {
+    const SegDev& S = a.add[1];
+    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) +
+                                                     (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pf.a1[q] = __ldg(ap + q);
+    pf.flags |= 4;
+  }
+}
+
 template <int ACT, class EP>
 __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int n0, int col0, const uint32_t (&r)[32],
-                                                 const float* s_bias, bool plain, bool rz, int nlim) {
+                                                 const float* s_bias, bool plain, bool rz, int nlim,
+                                                 const EpiPrefetch* pf = nullptr) {
   // nlim: first global column this CTA must NOT write (min(Nout, end of its column block))
   using namespace tc;
     float o[32];
@@ -108,6 +143,19 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   }
   for (int t = 0; t < a.nadd; ++t) {   // node-side first-layer blocks, pre-projected per node
     const SegDev& S = a.add[t];
+    if (pf && (pf->flags & (2 << t))) {   // already in registers
+      const uint4* src = t == 0 ? pf->a0 : pf->a1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {src[q].x, src[q].y, src[q].z, src[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[8 * q + 2 * j] += __uint_as_float(w[j] << 16);
+          o[8 * q + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+      }
+      continue;
+    }
     const long long arow = (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase;
     if (S.dtype == B3D_BF16) {
       const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(S.ptr) + arow;
@@ -148,9 +196,10 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
     if (a.out_mask) {   // ReLU backward of the producing layer: keep the gradient where its output was > 0
       if (a.mask_bf16 && cbase + 31 < nlim && (a.ldm & 7) == 0) {
         const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase);
+        const bool pre = pf && (pf->flags & 1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint4 m = __ldg(mp + q);
+          const uint4 m = pre ? pf->m[q] : __ldg(mp + q);
           const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -664,11 +713,15 @@ k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const long long row = tile * TC_BM + lq * 32 + lane;
       const bool row_ok = row < a.M;
       const bool rz = row_ok && a.row_mask && a.row_mask[row] == 0;
+      const int nlim = min(a.Nout, n0 + a.Nb);
       for (int col0 = ((warp - 2) >> 2) * 32; col0 < a.Nb; col0 += 64) {   // the two warps of a quarter interleave blocks
         uint32_t r[32];
+        EpiPrefetch pf;
+        pf.flags = 0;
         tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
+        if (row_ok) epilogue_prefetch(a, row, n0 + col0, nlim, pf);   // global latency overlaps the TMEM load
         tmem_ld_wait();
-        if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, min(a.Nout, n0 + a.Nb));
+        if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pf);
       }
       tc_fence_before_sync();
       __syncwarp();
