@@ -9,6 +9,40 @@ import torch
 from . import _lib as L
 
 
+# ----------------------------------------------------------------------------- per-op timing (debug)
+_OPTIME = None      # dict signature -> [count, ms, bytes] when enabled by optime_begin()
+
+
+def optime_begin():
+    global _OPTIME
+    _OPTIME = {}
+
+
+def optime_end():
+    global _OPTIME
+    r, _OPTIME = _OPTIME, None
+    return r
+
+
+class _timed:
+    """Debug helper: CUDA-event time of one wrapped launch, keyed by an op signature (synchronises!)."""
+
+    def __init__(self, sig, nbytes):
+        self.sig, self.nbytes = sig, nbytes
+
+    def __enter__(self):
+        if _OPTIME is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _OPTIME is not None:
+            self.e1.record()
+            torch.cuda.synchronize()
+            ent = _OPTIME.setdefault(self.sig, [0, 0.0, 0])
+            ent[0] += 1; ent[1] += self.e0.elapsed_time(self.e1); ent[2] += self.nbytes
+
+
 # ----------------------------------------------------------------------------- graph tables
 class NodeIndex:
     """One endpoint of the edge list: int32 ids per edge plus the CSR that groups edges by
@@ -122,7 +156,7 @@ def _al16(t):
 
 def _tc_shapes_ok(items, M, n_out, K):
     """Tile constraints of the tcgen05 kernels (b3d.h): widths % 8, aligned rows, enough work."""
-    if M < _TC_MIN_ROWS or n_out < 16 or K < 32:
+    if M < _TC_MIN_ROWS or n_out < 8 or K < 8:
         return False
     for t, _, mask, _ in items:
         if t.size(1) % 8 or not _al16(t) or mask is not None:
@@ -142,7 +176,7 @@ def _rows(t):
 _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
 
 
-def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accumulate=False,
+def _linear_raw_impl(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accumulate=False,
                out_mask=None, row_mask=None, n_out=None, tc=None, out_dtype=torch.float32, adds=None):
     """items: [(tensor, idx32|None, mask|None, mode)]. Returns Y [M, n_out].
     tc=None: use the tensor-core kernel iff the precision mode is bf16 and the shapes fit."""
@@ -188,7 +222,36 @@ def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accum
     return out
 
 
+def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accumulate=False, **kw):
+    if _OPTIME is None:
+        return _linear_raw_impl(items, W, bias, M, act, trans_w, out, accumulate, **kw)
+    K = sum(t.size(1) for t, _, _, _ in items)
+    n_out = kw.get("n_out") or (W.size(1) if trans_w else W.size(0))
+    es = lambda t: 2 if t.dtype == torch.bfloat16 else 4
+    od = kw.get("out_dtype", torch.float32)
+    nb = sum(M * t.size(1) * es(t) for t, _, _, _ in items) + M * n_out * (2 if od == torch.bfloat16 else 4)
+    if kw.get("out_mask") is not None:
+        nb += M * n_out * es(kw["out_mask"])
+    for t, _ in (kw.get("adds") or []):
+        nb += M * n_out * es(t)
+    sig = ("dgrad" if trans_w else "fwd", M, K, n_out, tuple(str(t.dtype)[6:] + ("g" if i is not None else "") for t, i, _, _ in items),
+           str(od)[6:], "mask" if kw.get("out_mask") is not None else "", len(kw.get("adds") or []))
+    with _timed(sig, nb):
+        return _linear_raw_impl(items, W, bias, M, act, trans_w, out, accumulate, **kw)
+
+
 def wgrad_raw(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=False, want_bias=True, tc=None):
+    if _OPTIME is not None:
+        es = lambda t: 2 if t.dtype == torch.bfloat16 else 4
+        nb = sum(M * t.size(1) * es(t) for t, _, _, _ in items) + M * n_out * es(dy_item[0])
+        sig = ("wgrad", M, K, n_out, tuple(str(t.dtype)[6:] + ("g" if i is not None else "") for t, i, _, _ in items),
+               str(dy_item[0].dtype)[6:], "", 0)
+        with _timed(sig, nb):
+            return _wgrad_raw_impl(dy_item, items, M, n_out, K, dW, db, accumulate, want_bias, tc)
+    return _wgrad_raw_impl(dy_item, items, M, n_out, K, dW, db, accumulate, want_bias, tc)
+
+
+def _wgrad_raw_impl(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=False, want_bias=True, tc=None):
     dev = dy_item[0].device
     if dW is None:
         dW = torch.empty((n_out, K), dtype=torch.float32, device=dev)
@@ -197,7 +260,7 @@ def wgrad_raw(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=False, w
     lib = L.lib()
     if tc is None:
         tc = _PRECISION == "bf16" and M > 0 and _tc_shapes_ok(items, M, max(n_out, 16), K) and \
-            _al16(dy_item[0]) and dy_item[2] is None and n_out * K >= 2048
+            _al16(dy_item[0]) and dy_item[2] is None
     if tc and dy_item[0].dtype == torch.bfloat16 and n_out % 8 == 0 and _tma_ok(items, K, False):
         wsb = lib.b3d_wgrad_tma_workspace_bytes(M, n_out, K)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -328,12 +391,15 @@ class _FusedMLP(torch.autograd.Function):
             xs = [x.float() for x in xs]
             items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
         ctx.in_dtypes = [t.dtype for t in tensors[2 * nl:2 * nl + nx]]
+        # chains that are not bf16 end to end keep fp32 activations; each launch then picks the bf16
+        # tile kernel on its own when the precision mode allows and its shapes fit (tc=None = auto)
+        tc_arg = True if tc else None
         acts, cur = [], items
         for l in range(nl):
             last = l == nl - 1
             y = linear_raw(cur, Ws[l], bs[l], M, _ACT[final_act] if last else L.ACT_RELU,
-                           row_mask=rm if last else None, tc=tc,
-                           out_dtype=(out_dtype or torch.float32) if last else torch.bfloat16,
+                           row_mask=rm if last else None, tc=tc_arg,
+                           out_dtype=((out_dtype or torch.float32) if last else torch.bfloat16) if tc else torch.float32,
                            adds=adds if l == 0 else None)
             acts.append(y)
             cur = [(y, None, None, 0)]
@@ -346,6 +412,7 @@ class _FusedMLP(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         nl, nidx, M, tc = ctx.nl, ctx.nidx, ctx.M, ctx.tc
+        tc_arg = True if tc else None
         saved = ctx.saved_tensors
         Ws, acts, xs = saved[:nl], saved[nl:2 * nl], saved[2 * nl:]
         dz = _rows(dy)
@@ -376,17 +443,17 @@ class _FusedMLP(torch.autograd.Function):
                         g = segment_sum_raw(dz_item[0], ni) if ni is not None else dz_item[0]
                         dadds[t] = g if g.dtype == ctx.add_dtypes[t] else g.to(ctx.add_dtypes[t])
             if ctx.needs_input_grad[6 + 2 * l]:
-                dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc)
+                dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc_arg)
                 grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)
             if l > 0:
-                dz = linear_raw([dz_item], W, None, M, trans_w=True, out_mask=acts[l - 1], tc=tc,
-                                out_dtype=torch.bfloat16)
+                dz = linear_raw([dz_item], W, None, M, trans_w=True, out_mask=acts[l - 1], tc=tc_arg,
+                                out_dtype=torch.bfloat16 if tc else torch.float32)
                 dz_item = (dz, None, None, 0)
             elif any(need_x):
                 # [M, K]; bf16 when every consumer of the slices is a bf16 tensor (halves the largest
                 # backward tensor), fp32 otherwise
                 low = tc and all(dt == torch.bfloat16 for dt, nd in zip(ctx.in_dtypes, need_x) if nd)
-                dA = linear_raw([dz_item], W, None, M, trans_w=True, tc=tc,
+                dA = linear_raw([dz_item], W, None, M, trans_w=True, tc=tc_arg,
                                 out_dtype=torch.bfloat16 if low else torch.float32)
                 off = 0
                 for s, (x, ni) in enumerate(zip(xs, nidx)):

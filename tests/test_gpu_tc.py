@@ -226,3 +226,20 @@ def test_wgrad_tma_dense_bf16(M, widths, n_out):
     assert rel(dW2, 2 * ref_w) < 1e-5 and rel(db2, 2 * ref_b) < 1e-5
     dW3, _ = ops.wgrad_raw((dy.to(DEV), None, None, 0), items, M, n_out, K, tc=True)
     assert torch.equal(dW3, dW)
+
+
+@pytest.mark.parametrize("M,K,n_out", [(5000, 16, 8), (5000, 8, 16), (70000, 64, 32), (3000, 32, 16), (4000, 16, 32)])
+def test_small_layers_on_tensor_core_tiles(M, K, n_out):
+    """Narrow encoder / classifier layers (fp32 activations) through the thread-staged tcgen05 kernels."""
+    torch.manual_seed(M + K)
+    x, W, b = torch.randn(M, K), torch.randn(n_out, K) * 0.3, torch.randn(n_out)
+    before = L.launch_count()
+    y = ops.linear_raw([(x.to(DEV), None, None, 0)], W.to(DEV), b.to(DEV), M, L.ACT_RELU)
+    assert L.launch_count() - before == 2 and y.dtype == torch.float32
+    assert rel(y, torch.relu(bf(x) @ bf(W).t() + b.double())) < 1e-5
+    dy = torch.randn(M, n_out)
+    dW, db = ops.wgrad_raw((dy.to(DEV), None, None, 0), [(x.to(DEV), None, None, 0)], M, n_out, K)
+    assert rel(dW, bf(dy).t() @ bf(x)) < 1e-5 and rel(db, bf(dy).sum(0)) < 1e-5
+    hm = torch.randn(M, K)
+    dx = ops.linear_raw([(dy.to(DEV), None, None, 0)], W.to(DEV), None, M, trans_w=True, out_mask=hm.to(DEV))
+    assert rel(dx, (bf(dy) @ bf(W)) * (hm > 0)) < 1e-5
