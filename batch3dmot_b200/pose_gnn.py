@@ -40,13 +40,20 @@ class CausalMessagePassing(nn.Module):
         return self.forward_graph(x, g, edge_attr, initial_x, att_edge_attr)
 
     def project_invariants(self, x0):
-        """Iteration-invariant node-side terms of the message MLPs' first layers (the initial_x
-        column blocks): computed once per forward in the pre-projected formulation."""
-        D = self.node_width
-        E_ = self.edge_width
+        """Per-forward constants of the pre-projected formulation: the four node-side first-layer
+        weight blocks stacked into ONE [H1+H1+Hm+Hm, D] matrix (edge_update x_i | x_j, future-message
+        x, past-message x), its bias, and the iteration-invariant initial_x terms of the message MLPs
+        laid out under the same columns."""
+        D, E_ = self.node_width, self.edge_width
+        eu0 = self.edge_update[0]
         wf, wp = self.create_future_msgs[0], self.create_past_msgs[0]
-        return (ops.fused_linear([(x0, None)], wf.weight[:, D + E_:], wf.bias),
-                ops.fused_linear([(x0, None)], wp.weight[:, D + E_:], wp.bias))
+        h1, hm = eu0.out_features, wf.out_features
+        w_cat = torch.cat([eu0.weight[:, :D], eu0.weight[:, D:2 * D], wf.weight[:, :D], wp.weight[:, :D]], 0)
+        b_cat = torch.cat([eu0.bias, eu0.bias.new_zeros(h1), wf.bias, wp.bias])
+        w_inv = torch.cat([wf.weight[:, D + E_:], wp.weight[:, D + E_:]], 0)           # initial_x blocks
+        p_inv = ops.fused_mlp([(x0, None)], [w_inv], [None], out_dtype=torch.bfloat16)  # [N, 2*Hm]
+        inv_all = torch.cat([p_inv.new_zeros(p_inv.size(0), 2 * h1), p_inv], 1)         # [N, 2*H1 + 2*Hm]
+        return w_cat, b_cat, inv_all, (h1, hm)
 
     def forward_preprojected(self, x, g, e, x0, att=None, inv=None):
         """Same math as forward_graph with every first-layer weight split by input block
@@ -57,11 +64,14 @@ class CausalMessagePassing(nn.Module):
         D, E_ = self.node_width, self.edge_width
         if inv is None:
             inv = self.project_invariants(x0)
+        w_cat, b_cat, inv_all, (h1, hm) = inv
+        lowp = torch.bfloat16
+        # one node-level GEMM per iteration for all four node-side blocks: [N, H1 | H1 | Hm | Hm]
+        p_all = ops.fused_mlp([(x, None)], [w_cat], [b_cat], adds=[(inv_all, None)], out_dtype=lowp)
+        p_i, p_j = p_all[:, :h1], p_all[:, h1:2 * h1]
+        p_f, p_p = p_all[:, 2 * h1:2 * h1 + hm], p_all[:, 2 * h1 + hm:]
         eu = [m for m in self.edge_update if isinstance(m, nn.Linear)]
         w1 = eu[0].weight                                              # cols: x_i | x_j | e (| att)
-        lowp = torch.bfloat16
-        p_i = ops.fused_mlp([(x, None)], [w1[:, :D]], [eu[0].bias], out_dtype=lowp)     # [N, H1]
-        p_j = ops.fused_mlp([(x, None)], [w1[:, D:2 * D]], [None], out_dtype=lowp)
         # edge-level tensors stay bf16 between kernels: every consumer is a bf16 tensor-core tile
         # (dense bf16 operands go through the TMA-fed kernels) or the fp32-accumulating segment sum
         if e.dtype != lowp:
@@ -70,11 +80,10 @@ class CausalMessagePassing(nn.Module):
         e_new = ops.fused_mlp(dense, [w1[:, 2 * D:], eu[1].weight, eu[2].weight], [None, eu[1].bias, eu[2].bias],
                               adds=[(p_i, dst), (p_j, src)], out_dtype=lowp)
         out = []
-        for seq, side, pinv in ((self.create_future_msgs, dst, inv[0]), (self.create_past_msgs, src, inv[1])):
+        for seq, side, p in ((self.create_future_msgs, dst, p_f), (self.create_past_msgs, src, p_p)):
             l0, l1 = [m for m in seq if isinstance(m, nn.Linear)]
-            p = ops.fused_mlp([(x, None)], [l0.weight[:, :D]], [None], adds=[(pinv, None)], out_dtype=lowp)  # x | e' | x0
             out.append(ops.fused_mlp([(e_new, None)], [l0.weight[:, D:D + E_], l1.weight], [None, l1.bias],
-                                     adds=[(p, side)], out_dtype=lowp))
+                                     adds=[(p, side)], out_dtype=lowp))                 # x | e' | x0 blocks
         fut, past = out
         m_past = ops.segment_sum(past, dst)
         m_fut = ops.segment_sum(fut, src)
