@@ -142,7 +142,7 @@ extern "C" int b3d_segment_sum(const void* src_v, int32_t src_dtype, int32_t ld_
 // fp32 rows gathered and rounded to bf16 (gradient of a bf16 segment-sum input)
 __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
     const float* __restrict__ src, int ld, const int32_t* __restrict__ idx, long long M, int C,
-    __nv_bfloat16* __restrict__ out, int ldo) {
+    __nv_bfloat16* __restrict__ out, int ldo, const __nv_bfloat16* __restrict__ relu_mask, int ldm) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
   if (r >= M) return;
@@ -154,22 +154,36 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
     __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
     uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
                          *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    if (relu_mask) {   // gradient of a ReLU output: keep it where the output was > 0 (bf16 > 0 <=> int16 bits > 0)
+      const uint4 m = __ldg(reinterpret_cast<const uint4*>(relu_mask + r * ldm + c));
+      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+      const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((int16_t)(mw[j] & 0xFFFFu) <= 0) w[j] &= 0xFFFF0000u;
+        if ((int16_t)(mw[j] >> 16) <= 0) w[j] &= 0x0000FFFFu;
+      }
+    }
     *reinterpret_cast<uint4*>(out + r * ldo + c) = v;
   }
 }
 
 extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
-                               void* out_v, int32_t out_dtype, int32_t ld_out, void* stream) {
+                               void* out_v, int32_t out_dtype, int32_t ld_out, const void* relu_mask,
+                               int32_t ld_mask, void* stream) {
   if (M == 0) return 0;
   if (!src || !idx || !out_v || C <= 0 || M < 0) return bad_arg("b3d_gather_rows");
   if (out_dtype == B3D_BF16) {
     if ((C & 7) || (ld_src & 3) || (ld_out & 7) || !al16(src) || !al16(out_v))
       return bad_arg("b3d_gather_rows: bf16 output needs C % 8 == 0 and 16-byte aligned rows");
+    if (relu_mask && ((ld_mask & 7) || !al16(relu_mask))) return bad_arg("b3d_gather_rows: relu_mask alignment");
     k_gather_rows_bf16<<<(unsigned)ceil_div(M, SEG_WARPS), SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        src, ld_src, idx, M, C, reinterpret_cast<__nv_bfloat16*>(out_v), ld_out);
+        src, ld_src, idx, M, C, reinterpret_cast<__nv_bfloat16*>(out_v), ld_out,
+        reinterpret_cast<const __nv_bfloat16*>(relu_mask), ld_mask);
     B3D_LAUNCH_CHECK("k_gather_rows_bf16");
     return 0;
   }
+  if (relu_mask) return bad_arg("b3d_gather_rows: relu_mask needs bf16 output");
   float* out = reinterpret_cast<float*>(out_v);
   bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
   unsigned grid = (unsigned)ceil_div(M, SEG_WARPS);

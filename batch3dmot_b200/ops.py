@@ -80,6 +80,17 @@ class Graph:
             raise IndexError("edge_index holds node ids outside [0, num_nodes)")
         self.by_dst = NodeIndex(self.dst32, self.rowptr_dst, self.perm_dst, N)
         self.by_src = NodeIndex(self.src32, self.rowptr_src, self.perm_src, N)
+        self._deg = {}
+
+    def degree_block(self, nidx):
+        """fp32 [N,8]: column 0 = number of edges whose endpoint is the node, columns 1-7 zero (an
+        8-wide block so it can be a segment of a tensor-core layer input)."""
+        key = id(nidx)
+        if key not in self._deg:
+            d = torch.zeros((self.N, 8), dtype=torch.float32, device=nidx.rowptr.device)
+            d[:, 0] = (nidx.rowptr[1:] - nidx.rowptr[:-1]).to(torch.float32)
+            self._deg[key] = d
+        return self._deg[key]
 
 
 _graph_cache = {}
@@ -297,7 +308,7 @@ def segment_sum_raw(src, nidx, out=None, accumulate=False):
     return out
 
 
-def gather_rows_raw(src, idx32, out_dtype=torch.float32):
+def gather_rows_raw(src, idx32, out_dtype=torch.float32, relu_mask=None):
     src = _rows(src)
     if src.dtype != torch.float32:
         src = src.float()
@@ -305,8 +316,14 @@ def gather_rows_raw(src, idx32, out_dtype=torch.float32):
     if out_dtype == torch.bfloat16 and (src.size(1) % 8 or not _al16(src)):
         out_dtype = torch.float32
     out = torch.empty((M, src.size(1)), dtype=out_dtype, device=src.device)
+    fused_mask = relu_mask if (relu_mask is not None and out_dtype == torch.bfloat16 and
+                               relu_mask.dtype == torch.bfloat16 and _al16(relu_mask)) else None
     L.check(L.lib().b3d_gather_rows(L.ptr(src), src.stride(0), L.ptr(idx32), M, src.size(1), L.ptr(out),
-                                    _DT[out_dtype], out.stride(0), L.stream()), "b3d_gather_rows")
+                                    _DT[out_dtype], out.stride(0), L.ptr(fused_mask),
+                                    fused_mask.stride(0) if fused_mask is not None else 0, L.stream()),
+            "b3d_gather_rows")
+    if relu_mask is not None and fused_mask is None:
+        out = out * (relu_mask > 0)
     return out
 
 
@@ -367,13 +384,15 @@ class _FusedMLP(torch.autograd.Function):
     are reduced back to nodes with the CSR segmented sum (no atomics)."""
 
     @staticmethod
-    def forward(ctx, nl, final_act, row_mask, nidx, add_nidx, out_dtype, *tensors):
+    def forward(ctx, nl, final_act, row_mask, nidx, add_nidx, out_dtype, premasked, *tensors):
         Ws = [w if w.stride(1) == 1 else w.contiguous() for w in tensors[0:2 * nl:2]]
         bs = [b.contiguous() if b is not None else None for b in tensors[1:2 * nl:2]]
         nx = len(nidx)
         xs = [_rows(x) for x in tensors[2 * nl:2 * nl + nx]]
         add_ts = [_rows(t) for t in tensors[2 * nl + nx:]]
-        assert len(add_ts) == len(add_nidx) and (not add_ts or (final_act is None or nl > 1))
+        assert len(add_ts) == len(add_nidx) and (not add_ts or (final_act is None or nl > 1 or premasked))
+        assert not premasked or final_act == "relu"
+        ctx.premasked = premasked
         ctx.add_dtypes = [t.dtype for t in add_ts]
         adds = [(t, ni.idx if ni is not None else None) for t, ni in zip(add_ts, add_nidx)]
         M = nidx[0].idx.numel() if nidx[0] is not None else xs[0].size(0)
@@ -383,7 +402,8 @@ class _FusedMLP(torch.autograd.Function):
         items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
         rm = row_mask.to(torch.uint8).contiguous() if row_mask is not None else None
         # the whole chain runs on tensor cores or not at all (keeps dtypes of saved activations uniform)
-        tc = _PRECISION == "bf16" and M > 0 and final_act is None and _tc_shapes_ok(items, M, Ws[0].size(0), Ws[0].size(1)) \
+        tc = _PRECISION == "bf16" and M > 0 and (final_act is None or premasked) and \
+            _tc_shapes_ok(items, M, Ws[0].size(0), Ws[0].size(1)) \
             and all(w.size(0) % 8 == 0 and w.size(1) % 8 == 0 and w.size(0) >= 16 and w.size(1) >= 32 for w in Ws)
         if not tc:
             adds = [(t.float(), i) for t, i in adds]
@@ -421,12 +441,14 @@ class _FusedMLP(torch.autograd.Function):
         if ctx.rm is not None:
             dz = dz * ctx.rm.unsqueeze(1)
         # only a chain-final activation needs an operand mask (fp32 path; tc chains end linear)
-        dz_item = (dz, None, acts[-1] if ctx.final_act is not None else None, _MASK[ctx.final_act])
+        # (premasked: the consumer's backward already applied the final ReLU's mask to dy)
+        need_mask = ctx.final_act is not None and not ctx.premasked
+        dz_item = (dz, None, acts[-1] if need_mask else None, _MASK[ctx.final_act] if need_mask else 0)
         items0 = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
         grads = [None] * (2 * nl)
         nx = len(nidx)
-        need_x = ctx.needs_input_grad[6 + 2 * nl:6 + 2 * nl + nx]
-        need_add = ctx.needs_input_grad[6 + 2 * nl + nx:]
+        need_x = ctx.needs_input_grad[7 + 2 * nl:7 + 2 * nl + nx]
+        need_add = ctx.needs_input_grad[7 + 2 * nl + nx:]
         xs = xs[:nx]
         dxs = [None] * nx
         dadds = [None] * len(ctx.add_nidx)
@@ -442,7 +464,7 @@ class _FusedMLP(torch.autograd.Function):
                         assert dz_item[2] is None
                         g = segment_sum_raw(dz_item[0], ni) if ni is not None else dz_item[0]
                         dadds[t] = g if g.dtype == ctx.add_dtypes[t] else g.to(ctx.add_dtypes[t])
-            if ctx.needs_input_grad[6 + 2 * l]:
+            if ctx.needs_input_grad[7 + 2 * l]:
                 dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc_arg)
                 grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)
             if l > 0:
@@ -463,10 +485,10 @@ class _FusedMLP(torch.autograd.Function):
                         g = segment_sum_raw(sl, ni) if ni is not None else sl
                         dxs[s] = g if g.dtype == ctx.in_dtypes[s] else g.to(ctx.in_dtypes[s])
                     off += w
-        return (None, None, None, None, None, None, *grads, *dxs, *dadds)
+        return (None, None, None, None, None, None, None, *grads, *dxs, *dadds)
 
 
-def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=(), out_dtype=None):
+def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=(), out_dtype=None, premasked=False):
     """inputs: list of (tensor [rows,w], NodeIndex|None); the concatenation order defines the first
     weight's input-column layout. weights/biases: per layer.
     adds: up to two (tensor [n, out_features of layer 0] fp32, NodeIndex|None) summed, row-gathered,
@@ -477,7 +499,7 @@ def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=(), o
     for w, b in zip(weights, biases):
         flat += [w, b]
     return _FusedMLP.apply(len(weights), final_act, row_mask, nidx, tuple(ni for _, ni in adds), out_dtype,
-                           *flat, *xs, *[t for t, _ in adds])
+                           premasked, *flat, *xs, *[t for t, _ in adds])
 
 
 def fused_linear(inputs, weight, bias=None, act=None, row_mask=None, adds=()):
@@ -493,19 +515,23 @@ def run_mlp(seq, inputs, final_act=None, row_mask=None):
 
 class _SegmentSum(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, src, nidx):
+    def forward(ctx, src, nidx, relu_src):
         ctx.nidx, ctx.src_dtype = nidx, src.dtype
+        ctx.save_for_backward(src if relu_src else None)
         return segment_sum_raw(src, nidx)
 
     @staticmethod
     def backward(ctx, dout):
-        g = gather_rows_raw(dout, ctx.nidx.idx, out_dtype=ctx.src_dtype)
-        return (g if g.dtype == ctx.src_dtype else g.to(ctx.src_dtype)), None
+        (mask,) = ctx.saved_tensors
+        g = gather_rows_raw(dout, ctx.nidx.idx, out_dtype=ctx.src_dtype, relu_mask=mask)
+        return (g if g.dtype == ctx.src_dtype else g.to(ctx.src_dtype)), None, None
 
 
-def segment_sum(src, nidx):
-    """out[n] = sum of src rows whose endpoint is n (torch_scatter.scatter(reduce='add'))."""
-    return _SegmentSum.apply(src, nidx)
+def segment_sum(src, nidx, relu_src=False):
+    """out[n] = sum of src rows whose endpoint is n (torch_scatter.scatter(reduce='add')).
+    relu_src=True: `src` is the output of a ReLU layer built with premasked=True; the backward then
+    returns the gradient already multiplied by (src > 0), fused into the row gather."""
+    return _SegmentSum.apply(src, nidx, relu_src)
 
 
 class _BCE(torch.autograd.Function):

@@ -53,7 +53,13 @@ class CausalMessagePassing(nn.Module):
         w_inv = torch.cat([wf.weight[:, D + E_:], wp.weight[:, D + E_:]], 0)           # initial_x blocks
         p_inv = ops.fused_mlp([(x0, None)], [w_inv], [None], out_dtype=torch.bfloat16)  # [N, 2*Hm]
         inv_all = torch.cat([p_inv.new_zeros(p_inv.size(0), 2 * h1), p_inv], 1)         # [N, 2*H1 + 2*Hm]
-        return w_cat, b_cat, inv_all, (h1, hm)
+        # last (linear) layer of the message MLPs, applied per node AFTER aggregation:
+        # sum_e (W2 h_e + b2) = W2 (sum_e h_e) + deg * b2  -> weight [W2 | b2 | 0 x 7] against [S | deg | 0 x 7]
+        w_post = []
+        for seq in (self.create_future_msgs, self.create_past_msgs):
+            l1 = seq[2]
+            w_post.append(torch.cat([l1.weight, l1.bias[:, None], l1.weight.new_zeros(l1.out_features, 7)], 1))
+        return w_cat, b_cat, inv_all, (h1, hm), w_post
 
     def forward_preprojected(self, x, g, e, x0, att=None, inv=None):
         """Same math as forward_graph with every first-layer weight split by input block
@@ -64,7 +70,7 @@ class CausalMessagePassing(nn.Module):
         D, E_ = self.node_width, self.edge_width
         if inv is None:
             inv = self.project_invariants(x0)
-        w_cat, b_cat, inv_all, (h1, hm) = inv
+        w_cat, b_cat, inv_all, (h1, hm), w_post = inv
         lowp = torch.bfloat16
         # one node-level GEMM per iteration for all four node-side blocks: [N, H1 | H1 | Hm | Hm]
         p_all = ops.fused_mlp([(x, None)], [w_cat], [b_cat], adds=[(inv_all, None)], out_dtype=lowp)
@@ -79,14 +85,18 @@ class CausalMessagePassing(nn.Module):
         dense = [(e, None)] + ([(att, None)] if att is not None else [])
         e_new = ops.fused_mlp(dense, [w1[:, 2 * D:], eu[1].weight, eu[2].weight], [None, eu[1].bias, eu[2].bias],
                               adds=[(p_i, dst), (p_j, src)], out_dtype=lowp)
-        out = []
-        for seq, side, p in ((self.create_future_msgs, dst, p_f), (self.create_past_msgs, src, p_p)):
-            l0, l1 = [m for m in seq if isinstance(m, nn.Linear)]
-            out.append(ops.fused_mlp([(e_new, None)], [l0.weight[:, D:D + E_], l1.weight], [None, l1.bias],
-                                     adds=[(p, side)], out_dtype=lowp))                 # x | e' | x0 blocks
-        fut, past = out
-        m_past = ops.segment_sum(past, dst)
-        m_fut = ops.segment_sum(fut, src)
+        # message MLPs: first layer per edge (ReLU), then aggregate, then the linear last layer per NODE
+        # (summation order only: sum_e (W2 h_e + b2) = W2 sum_e h_e + deg b2). Future messages use the
+        # later node's features and flow into the EARLIER node (src); past messages the other way round.
+        agg = []
+        for seq, side, into, p, wpost in ((self.create_future_msgs, dst, src, p_f, w_post[0]),
+                                          (self.create_past_msgs, src, dst, p_p, w_post[1])):
+            l0 = seq[0]
+            h = ops.fused_mlp([(e_new, None)], [l0.weight[:, D:D + E_]], [None], final_act="relu",
+                              adds=[(p, side)], out_dtype=lowp, premasked=True)         # x | e' | x0 blocks
+            s_h = ops.segment_sum(h, into, relu_src=True)                                # [N, Hm] fp32
+            agg.append(ops.fused_linear([(s_h, None), (g.degree_block(into), None)], wpost))
+        m_fut, m_past = agg
         x_new = ops.run_mlp(self.combine_future_past, [(m_past, None), (m_fut, None)])
         return x_new, e_new
 

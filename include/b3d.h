@@ -89,9 +89,11 @@ int b3d_segment_sum(const void* src, int32_t src_dtype, int32_t ld_src, const in
                     void* stream);
 
 /* out[r, 0:C] = src[idx[r], 0:C]  (index_select; backward of segment_sum). out_dtype B3D_F32 or
- * B3D_BF16 (rounded on store). */
+ * B3D_BF16 (rounded on store). relu_mask (optional, bf16 [M,C], bf16 output only): the summed rows
+ * were ReLU outputs, so the gathered gradient is zeroed where relu_mask <= 0. */
 int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
-                    void* out, int32_t out_dtype, int32_t ld_out, void* stream);
+                    void* out, int32_t out_dtype, int32_t ld_out, const void* relu_mask, int32_t ld_mask,
+                    void* stream);
 
 /* ---- dense layers with fused gather / concat / activation ------------------
  * Y[M,Nout] (+)= act( cat_s(A_s)[M,K] * op(W) + bias ) [* (out_mask > 0)] [row_mask]
