@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear(const LinArgs a) {
 }
 
 // ------------------------------------------------------------------ weight gradient
-constexpr int WG_T = 64, WG_BR = 16, WG_THREADS = 256;
+constexpr int WG_T = 64, WG_RPT = 4, WG_BR = 16 * WG_RPT, WG_THREADS = 256;   // 64 rows per smem stage
 
 struct WgArgs {
   SegDev dy;
@@ -242,17 +242,19 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad(const WgArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   }
-  float dreg[4], areg[4];
+  float dreg[WG_RPT][4], areg[WG_RPT][4];
   auto load_stage = [&](long long rbase) {
-    const long long r = rbase + lr;
+#pragma unroll
+   for (int q = 0; q < WG_RPT; ++q) {
+    const long long r = rbase + q * 16 + lr;
     const bool ok = r < r1;
     // dY
     if (!ok) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dreg[j] = 0.f;
+      for (int j = 0; j < 4; ++j) dreg[q][j] = 0.f;
     } else if (d_vec) {
       float4 v = __ldg(reinterpret_cast<const float4*>(a.dy.ptr + r * a.dy.ld + n0 + lc));
-      dreg[0] = v.x; dreg[1] = v.y; dreg[2] = v.z; dreg[3] = v.w;
+      dreg[q][0] = v.x; dreg[q][1] = v.y; dreg[q][2] = v.z; dreg[q][3] = v.w;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -262,18 +264,18 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad(const WgArgs a) {
           v = __ldg(a.dy.ptr + r * a.dy.ld + n);
           if (a.dy.mask_mode != B3D_MASK_NONE) v = apply_mask(v, __ldg(a.dy.mask + r * a.dy.ldmask + n), a.dy.mask_mode);
         }
-        dreg[j] = v;
+        dreg[q][j] = v;
       }
     }
     // A
     if (!ok) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) areg[j] = 0.f;
+      for (int j = 0; j < 4; ++j) areg[q][j] = 0.f;
     } else if (a_vec) {
       const SegDev& sg = a.seg[sseg[0]];
       long long gr = sg.idx ? (long long)__ldg(sg.idx + r) : r;
       float4 v = __ldg(reinterpret_cast<const float4*>(sg.ptr + gr * sg.ld + soff[0]));
-      areg[0] = v.x; areg[1] = v.y; areg[2] = v.z; areg[3] = v.w;
+      areg[q][0] = v.x; areg[q][1] = v.y; areg[q][2] = v.z; areg[q][3] = v.w;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -284,15 +286,19 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad(const WgArgs a) {
           v = __ldg(sg.ptr + gr * sg.ld + soff[j]);
           if (sg.mask_mode != B3D_MASK_NONE) v = apply_mask(v, __ldg(sg.mask + gr * sg.ldmask + soff[j]), sg.mask_mode);
         }
-        areg[j] = v;
+        areg[q][j] = v;
       }
     }
+   }
   };
 
   if (r0 < r1) load_stage(r0);
   for (long long rb = r0; rb < r1; rb += WG_BR) {
-    *reinterpret_cast<float4*>(&Ds[lr][lc]) = make_float4(dreg[0], dreg[1], dreg[2], dreg[3]);
-    *reinterpret_cast<float4*>(&As[lr][lc]) = make_float4(areg[0], areg[1], areg[2], areg[3]);
+#pragma unroll
+    for (int q = 0; q < WG_RPT; ++q) {
+      *reinterpret_cast<float4*>(&Ds[q * 16 + lr][lc]) = make_float4(dreg[q][0], dreg[q][1], dreg[q][2], dreg[q][3]);
+      *reinterpret_cast<float4*>(&As[q * 16 + lr][lc]) = make_float4(areg[q][0], areg[q][1], areg[q][2], areg[q][3]);
+    }
     __syncthreads();
     if (rb + WG_BR < r1) load_stage(rb + WG_BR);
 #pragma unroll
