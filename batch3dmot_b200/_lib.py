@@ -55,6 +55,16 @@ _SIGS = {
     "b3d_wgrad_tma_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "b3d_wgrad_tma": (C.c_int, [C.POINTER(Seg), C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                 C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b3d_narrow_mlp_supported": (C.c_int, [C.c_int32, C.POINTER(C.c_int32)]),
+    "b3d_narrow_mlp_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
+                                     C.c_int32, C.c_int32, C.c_void_p]),
+    "b3d_narrow_mlp_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.POINTER(C.c_int32)]),
+    "b3d_narrow_mlp_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
+                                     C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
     "b3d_knn_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,
                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b3d_gat_aggregate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -127,6 +137,18 @@ def make_segs(items):
         else:
             s.mask, s.ldmask, s.mask_mode = None, 0, MASK_NONE
     return arr
+
+
+def ptr_array(ts):
+    """Host array of device pointers (None -> NULL) for the per-layer parameter lists."""
+    arr = (C.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def int_array(vals):
+    return (C.c_int32 * len(vals))(*vals)
 
 
 def launch_count():

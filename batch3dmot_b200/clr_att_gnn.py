@@ -100,7 +100,8 @@ class GNN(nn.Module):
         dst, src = g.by_dst, g.by_src
         if x_img is None:
             x_img, pointnet_out, radarnet_out, lidar_mask, radar_mask = self._encode_modalities(data)
-        e0 = ops.run_mlp(self.edge_encoder, [(data.edge_attr.float(), None)])                  # :123
+        lowp = torch.bfloat16 if ops.get_precision() == "bf16" else None   # edge tensors stay bf16 between kernels
+        e0 = ops.run_mlp(self.edge_encoder, [(data.edge_attr.float(), None)], out_dtype=lowp)   # :123
         x_lidar = ops.run_mlp(self.fc_lidar_encoder, [(pointnet_out, None)], row_mask=lidar_mask)   # :131-133
         x_radar = ops.run_mlp(self.fc_radar_encoder, [(radarnet_out, None)], row_mask=radar_mask)   # :139-141
         x_img = x_img.float()

@@ -488,6 +488,70 @@ class _FusedMLP(torch.autograd.Function):
         return (None, None, None, None, None, None, None, *grads, *dxs, *dadds)
 
 
+class _NarrowMLP(torch.autograd.Function):
+    """nn.Sequential(Linear, ReLU, ..., Linear[, Sigmoid]) with every width <= 64 as ONE kernel per
+    direction (narrow_mlp.cu): hidden activations never leave registers; backward recomputes them."""
+
+    @staticmethod
+    def forward(ctx, nl, final_act, out_dtype, x, *params):
+        Ws = [w.contiguous() for w in params[0::2]]
+        bs = [b.contiguous() if b is not None else None for b in params[1::2]]
+        x = _rows(x)
+        dims = [Ws[0].size(1)] + [w.size(0) for w in Ws]
+        M = x.size(0)
+        y = torch.empty((M, dims[-1]), dtype=out_dtype, device=x.device)
+        ctx.nl, ctx.act, ctx.dims, ctx.has_bias = nl, _ACT[final_act], dims, [b is not None for b in bs]
+        if M > 0:
+            L.check(L.lib().b3d_narrow_mlp_fwd(L.ptr(x), _DT[x.dtype], x.stride(0), M, nl, L.int_array(dims),
+                                               L.ptr_array(Ws), L.ptr_array(bs), ctx.act, L.ptr(y), _DT[y.dtype],
+                                               y.stride(0), L.stream()), "b3d_narrow_mlp_fwd")
+        ctx.save_for_backward(x, *Ws, *[b for b in bs if b is not None])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        nl, dims = ctx.nl, ctx.dims
+        x, Ws = ctx.saved_tensors[0], list(ctx.saved_tensors[1:1 + nl])
+        rest = list(ctx.saved_tensors[1 + nl:])
+        bs = [rest.pop(0) if hb else None for hb in ctx.has_bias]
+        dy = _rows(dy)
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        M = x.size(0)
+        dX = torch.empty_like(x) if ctx.needs_input_grad[3] else None
+        dWs = [torch.empty_like(w) for w in Ws]
+        dbs = [torch.empty_like(b) if b is not None else None for b in bs]
+        if M == 0:
+            for t in dWs + [d for d in dbs if d is not None]:
+                t.zero_()
+        else:
+            lib = L.lib()
+            d32 = L.int_array(dims)
+            wsb = int(lib.b3d_narrow_mlp_bwd_workspace_bytes(M, nl, d32))
+            ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+            L.check(lib.b3d_narrow_mlp_bwd(L.ptr(x), _DT[x.dtype], x.stride(0), M, nl, d32, L.ptr_array(Ws),
+                                           L.ptr_array(bs), ctx.act, L.ptr(dy), _DT[dy.dtype], dy.stride(0),
+                                           L.ptr(dX), _DT[dX.dtype] if dX is not None else 0,
+                                           dX.stride(0) if dX is not None else 0, L.ptr_array(dWs), L.ptr_array(dbs),
+                                           0, L.ptr(ws), wsb, L.stream()), "b3d_narrow_mlp_bwd")
+        flat = []
+        for dw, db in zip(dWs, dbs):
+            flat += [dw, db]
+        return (None, None, None, dX, *flat)
+
+
+def _narrow_ok(inputs, weights, final_act, row_mask, adds, premasked):
+    if len(inputs) != 1 or inputs[0][1] is not None or row_mask is not None or adds or premasked:
+        return False
+    if final_act not in (None, "sigmoid") or len(weights) not in (3, 4) or (final_act and len(weights) != 4):
+        return False
+    x = inputs[0][0]
+    if x.dim() != 2 or x.dtype not in (torch.float32, torch.bfloat16) or x.stride(1) != 1 or not _al16(x):
+        return False
+    dims = [weights[0].size(1)] + [w.size(0) for w in weights]
+    return x.size(1) == dims[0] and bool(L.lib().b3d_narrow_mlp_supported(len(weights), L.int_array(dims)))
+
+
 def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=(), out_dtype=None, premasked=False):
     """inputs: list of (tensor [rows,w], NodeIndex|None); the concatenation order defines the first
     weight's input-column layout. weights/biases: per layer.
@@ -498,6 +562,8 @@ def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=(), o
     flat = []
     for w, b in zip(weights, biases):
         flat += [w, b]
+    if _narrow_ok(inputs, weights, final_act, row_mask, adds, premasked):
+        return _NarrowMLP.apply(len(weights), final_act, out_dtype or torch.float32, xs[0], *flat)
     return _FusedMLP.apply(len(weights), final_act, row_mask, nidx, tuple(ni for _, ni in adds), out_dtype,
                            premasked, *flat, *xs, *[t for t, _ in adds])
 
@@ -507,10 +573,11 @@ def fused_linear(inputs, weight, bias=None, act=None, row_mask=None, adds=()):
     return fused_mlp(inputs, [weight], [bias], final_act=act, row_mask=row_mask, adds=adds)
 
 
-def run_mlp(seq, inputs, final_act=None, row_mask=None):
+def run_mlp(seq, inputs, final_act=None, row_mask=None, out_dtype=None):
     """Run an nn.Sequential of Linear/ReLU(/Sigmoid) parameter containers as one fused chain."""
     linears = [m for m in seq if isinstance(m, torch.nn.Linear)]
-    return fused_mlp(inputs, [m.weight for m in linears], [m.bias for m in linears], final_act, row_mask)
+    return fused_mlp(inputs, [m.weight for m in linears], [m.bias for m in linears], final_act, row_mask,
+                     out_dtype=out_dtype)
 
 
 class _SegmentSum(torch.autograd.Function):

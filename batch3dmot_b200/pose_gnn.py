@@ -134,7 +134,8 @@ class PoseGNN(nn.Module):
     def forward(self, data):
         pose, ei = data.pose_feats, data.edge_index
         g = getattr(data, "_b3d_graph", None) or ops.graph_of(ei, pose.size(0))
-        e = ops.run_mlp(self.edge_encoder, [(data.edge_attr.float(), None)])         # :67
+        lowp = torch.bfloat16 if ops.get_precision() == "bf16" else None
+        e = ops.run_mlp(self.edge_encoder, [(data.edge_attr.float(), None)], out_dtype=lowp)   # :67
         x0 = ops.run_mlp(self.node_encoder, [(pose, None)])                          # :68 (C6: once)
         x, x_enc = x0, x0
         inv = self.message_passing.project_invariants(x0) if ops.get_precision() == "bf16" else None

@@ -159,6 +159,30 @@ int b3d_wgrad_tc(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, i
                  float* dW, int32_t lddw, float* db, int64_t M, int32_t Nout, int32_t flags,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- narrow MLP chains: a whole nn.Sequential per kernel ---------------------
+ * The edge encoders 4->16->32->64 / 4->8->16->32 (clr_att_gnn.py:35-41, pose_gnn.py:29-35) and the
+ * edge classifiers 64->32->16->8->1 [+Sigmoid] / 32->16->8->4->1 (clr_att_gnn.py:49-57,
+ * pose_gnn.py:45-53): Linear/ReLU/.../Linear[/Sigmoid] with every width <= 64. One thread per row,
+ * parameters in shared memory, hidden activations in registers: HBM sees X and Y only. fp32
+ * arithmetic; X / Y / dY / dX may be stored as B3D_F32 or B3D_BF16.
+ * dims: host int32[nl+1] = in, hidden..., out (nl = 3 or 4 Linear layers). W / b / dW / db: HOST
+ * arrays of nl DEVICE pointers to contiguous nn.Linear parameters ([out,in] row-major; b[l], dW[l],
+ * db[l] may be null). final_act: B3D_ACT_NONE, or B3D_ACT_SIGMOID on the 4-layer chains.
+ * Backward recomputes the hidden activations, so only X is needed; dX may be null. Weight gradients
+ * are reduced per CTA in registers and summed over CTAs in fixed order (deterministic). */
+int b3d_narrow_mlp_supported(int32_t nl, const int32_t* dims /*host*/);
+int b3d_narrow_mlp_fwd(const void* X, int32_t x_dtype, int32_t ldx, int64_t M, int32_t nl,
+                       const int32_t* dims /*host*/, const float* const* W /*host*/,
+                       const float* const* b /*host*/, int32_t final_act, void* Y, int32_t y_dtype,
+                       int32_t ldy, void* stream);
+size_t b3d_narrow_mlp_bwd_workspace_bytes(int64_t M, int32_t nl, const int32_t* dims /*host*/);
+int b3d_narrow_mlp_bwd(const void* X, int32_t x_dtype, int32_t ldx, int64_t M, int32_t nl,
+                       const int32_t* dims /*host*/, const float* const* W /*host*/,
+                       const float* const* b /*host*/, int32_t final_act, const void* dY,
+                       int32_t dy_dtype, int32_t lddy, void* dX, int32_t dx_dtype, int32_t lddx,
+                       float* const* dW /*host*/, float* const* db /*host*/, int32_t flags,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- frame-wise k-NN + attention-weighted convolution ----------------------
  * Brute-force frame-local k-NN with warp-level top-k selection. Replaces
  * torch_geometric.nn.knn_graph(x_t, k=20, loop=False) per timestamp

@@ -1,5 +1,5 @@
-"""Per-op timing of one training step (debug; synchronises after every dense-layer launch).
-Prints time, algorithmic bytes and GB/s per (kind, M, K, N, dtypes) signature."""
+"""torch.profiler view of one training step (debug): which torch ops (with shapes) own the
+non-libb3d elementwise kernels."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,9 +8,11 @@ from batch3dmot_b200 import ops
 from batch3dmot_b200.clr_att_gnn import GNN
 from batch3dmot_b200.parallel import Trainer
 from types import SimpleNamespace
+from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda", 0)
 ops.set_precision("bf16")
-host = bench.make_batch(0, int(sys.argv[1]) if len(sys.argv) > 1 else 8)
+scenes = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+host = bench.make_batch(0, scenes)
 d = SimpleNamespace(**{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in vars(host).items()})
 d._b3d_graph = ops.Graph(d.edge_index, d.num_nodes)
 torch.manual_seed(5621)
@@ -18,10 +20,8 @@ tr = Trainer(GNN(None, None, None).to(dev), batch_size=2)
 kw = dict(x_img=d.x_img, pointnet_out=d.pointnet_out, radarnet_out=d.radarnet_out, lidar_mask=d.m_lidar, radar_mask=d.m_radar)
 for _ in range(2):
     tr.step(d, **kw)
-ops.optime_begin()
-tr.step(d, **kw)
-r = ops.optime_end()
-tot = sum(v[1] for v in r.values())
-print(f"dense-layer launches total {tot:.2f} ms")
-for sig, (n, ms, nb) in sorted(r.items(), key=lambda kv: -kv[1][1])[:40]:
-    print(f"{ms:7.3f} ms n={n:3d} avg={ms/n*1e3:7.1f} us  {nb/ms/1e6:7.0f} GB/s  {sig}")
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+    tr.step(d, **kw)
+    torch.cuda.synchronize()
+print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=50, max_shapes_column_width=70))

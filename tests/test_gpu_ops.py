@@ -246,3 +246,66 @@ def test_adam_matches_torch():
         opt.step()
         ops.adam_step(pc, g.to(DEV), m, v, 1e-4, (0.9, 0.999), 1e-8, 1e-4, step)
     assert float((pc.cpu() - p.detach()).abs().max()) < 5e-7   # a few ulp: fused vs foreach op order
+
+
+def _torch_chain(dims, final_sigmoid):
+    mods = []
+    for i in range(len(dims) - 1):
+        mods.append(torch.nn.Linear(dims[i], dims[i + 1]))
+        if i + 2 < len(dims):
+            mods.append(torch.nn.ReLU())
+    if final_sigmoid:
+        mods.append(torch.nn.Sigmoid())
+    return torch.nn.Sequential(*mods)
+
+
+@pytest.mark.parametrize("dims,sig", [((4, 16, 32, 64), False), ((4, 8, 16, 32), False), ((64, 32, 16, 8, 1), True),
+                                      ((64, 32, 16, 8, 1), False), ((32, 16, 8, 4, 1), False)])
+@pytest.mark.parametrize("M", [1, 255, 1000, 70001])
+def test_narrow_mlp_chain_matches_torch(dims, sig, M):
+    """narrow_mlp.cu (whole edge-encoder / edge-classifier chain in one kernel per direction) against
+    torch fp32 autograd: forward 1e-5, input and parameter gradients 1e-4 of each tensor's max."""
+    torch.manual_seed(M + dims[1])
+    seq = _torch_chain(dims, sig).double()
+    x = torch.randn(M, dims[0]).double().requires_grad_(True)
+    y_ref = seq(x)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    dev_seq = _torch_chain(dims, sig).to(DEV)
+    dev_seq.load_state_dict({k: v.float() for k, v in seq.state_dict().items()})
+    xd = x.detach().float().to(DEV).requires_grad_(True)
+    before = L.launch_count()
+    y = ops.run_mlp(dev_seq, [(xd, None)], final_act="sigmoid" if sig else None)
+    assert L.launch_count() - before == 1, "the chain must be ONE k_narrow_fwd launch"
+    assert y.dtype == torch.float32 and rel_err(y, y_ref) < 1e-5
+    before = L.launch_count()
+    y.backward(gy.float().to(DEV))
+    assert L.launch_count() - before == 2, "k_narrow_bwd + k_narrow_reduce"
+    assert rel_err(xd.grad, x.grad) < 1e-4
+    for (n, p), (_, q) in zip(dev_seq.named_parameters(), seq.named_parameters()):
+        assert rel_err(p.grad, q.grad) < 1e-4, n
+
+
+def test_narrow_mlp_bf16_storage():
+    """bf16 X / Y / dY / dX storage around the fp32 chain (the bf16 mode's edge tensors)."""
+    torch.manual_seed(3)
+    M = 5000
+    dims = (64, 32, 16, 8, 1)
+    seq = _torch_chain(dims, True).to(DEV)
+    x16 = torch.randn(M, 64).to(torch.bfloat16).to(DEV).requires_grad_(True)
+    y = ops.run_mlp(seq, [(x16, None)], final_act="sigmoid")
+    x32 = x16.detach().float().requires_grad_(True)
+    y_ref = seq(x32)
+    assert rel_err(y, y_ref) < 1e-5
+    gy = torch.randn_like(y_ref)
+    y.backward(gy); y_ref.backward(gy)
+    assert x16.grad.dtype == torch.bfloat16 and rel_err(x16.grad, x32.grad) < 1e-2
+    enc = _torch_chain((4, 16, 32, 64), False).to(DEV)
+    a = torch.randn(M, 4, device=DEV)
+    e16 = ops.run_mlp(enc, [(a, None)], out_dtype=torch.bfloat16)
+    assert e16.dtype == torch.bfloat16 and rel_err(e16, enc(a)) < 1e-2
+    g16 = torch.randn(M, 64, device=DEV).to(torch.bfloat16)
+    grads = torch.autograd.grad(e16, list(enc.parameters()), g16)
+    grads_ref = torch.autograd.grad(enc(a), list(enc.parameters()), g16.float())
+    for g, r in zip(grads, grads_ref):
+        assert rel_err(g, r) < 1e-4

@@ -181,6 +181,24 @@ def test_linear_tma_dense_bf16(M, widths, n_out):
                        adds=[(p0.to(DEV), i0.int().to(DEV)), (p1.to(DEV), i1.int().to(DEV))])
     ref2 = (ref + p0[i0].double() + p1[i1].double()) * (bf(hm) > 0) * rm[:, None]
     assert rel(y, ref2) < 1e-5
+    # bf16 addends / bf16 mask / bf16 output: the operands the pipelined epilogue prefetches ahead of
+    # the accumulator (mask only, one addend, two addends, mask + addends)
+    p0h, p1h = p0.to(torch.bfloat16), p1.to(torch.bfloat16)
+    a0, a1 = (p0h.to(DEV), i0.int().to(DEV)), (p1h.to(DEV), i1.int().to(DEV))
+    hm16 = hm.to(DEV).to(torch.bfloat16)
+    for adds, mask, act in (([], hm16, L.ACT_NONE), ([a0], None, L.ACT_RELU), ([a0, a1], None, L.ACT_RELU),
+                            ([a0, a1], hm16, L.ACT_NONE), ([(p0h[i0].to(DEV), None)], None, L.ACT_NONE)):
+        r3 = ref.clone()
+        for (t, ix) in adds:
+            r3 = r3 + (t.cpu().double()[ix.cpu().long()] if ix is not None else t.cpu().double())
+        if act == L.ACT_RELU:
+            r3 = torch.relu(r3)
+        if mask is not None:
+            r3 = r3 * (bf(hm) > 0)
+        for od in (torch.bfloat16, torch.float32):
+            y3 = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, act, tc=True, out_mask=mask, adds=adds or None,
+                                out_dtype=od)
+            assert y3.dtype == od and rel(y3, r3) < (1e-2 if od == torch.bfloat16 else 1e-5)
     # same result as the thread-staged tcgen05 kernel
     ops._USE_TMA = False
     try:
