@@ -93,6 +93,32 @@ __device__ __forceinline__ float activate(float v) {
 // EP is any struct with the TcArgs epilogue fields; sb = bias of this CTA's column block (smem).
 // Global operands of one epilogue block (ReLU mask, gathered addends; bf16 fast paths only), loaded
 // BEFORE the TMEM load is waited on so that the two latencies overlap.
+// 256-bit global accesses (sm_100: LDG.256 / STG.256). The epilogue is row-per-lane, so every lane of
+// a warp-wide access lands in a different 128-byte line and costs its own L1 wavefront whatever its
+// width: moving 32 bytes per lane instead of 16 halves the L1 data-pipe load of the epilogue, which
+// ncu shows as the top limiter of the mask / addend variants (profiles/r1_epilogue_l1.md).
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+__device__ __forceinline__ bool al32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+// 64 bytes (32 bf16) at p -> q[0..3]
+__device__ __forceinline__ void ld64B(const void* p, uint4 (&q)[4]) {
+  if (al32(p)) {
+    ldg256(p, q[0], q[1]);
+    ldg256(reinterpret_cast<const uint8_t*>(p) + 32, q[2], q[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
+  }
+}
+
 struct EpiPrefetch {
   uint4 m[4], a0[4], a1[4];
   int flags;   // bit0: mask, bit1: addend 0, bit2: addend 1
@@ -102,25 +128,19 @@ __device__ __forceinline__ void epilogue_prefetch(const EP& a, long long row, in
   pf.flags = 0;
   if (cbase + 31 >= nlim) return;
   if (a.out_mask && a.mask_bf16 && (a.ldm & 7) == 0) {
-    const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) pf.m[q] = __ldg(mp + q);
+    ld64B(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase, pf.m);
     pf.flags |= 1;
   }
   if (a.nadd > 0 && a.add[0].dtype == B3D_BF16) {
     const SegDev& S = a.add[0];
-    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) +
-                                                     (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) pf.a0[q] = __ldg(ap + q);
+    ld64B(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase,
+          pf.a0);
     pf.flags |= 2;
   }
   if (a.nadd > 1 && a.add[1].dtype == B3D_BF16) {
     const SegDev& S = a.add[1];
-    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) +
-                                                     (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) pf.a1[q] = __ldg(ap + q);
+    ld64B(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase,
+          pf.a1);
     pf.flags |= 4;
   }
 }
@@ -160,9 +180,11 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
     if (S.dtype == B3D_BF16) {
       const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(S.ptr) + arow;
       if (cbase + 31 < nlim) {
+        uint4 av[4];
+        ld64B(ap, av);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(ap) + q);
+          const uint4 v = av[q];
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -195,11 +217,12 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   if (!plain) {
     if (a.out_mask) {   // ReLU backward of the producing layer: keep the gradient where its output was > 0
       if (a.mask_bf16 && cbase + 31 < nlim && (a.ldm & 7) == 0) {
-        const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase);
         const bool pre = pf && (pf->flags & 1);
+        uint4 mv4[4];
+        if (!pre) ld64B(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase, mv4);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint4 m = pre ? pf->m[q] : __ldg(mp + q);
+          const uint4 m = pre ? pf->m[q] : mv4[q];
           const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -243,6 +266,16 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   }
   if (a.y_bf16) {
     __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(a.Y) + row * a.ldy + cbase;
+    if (cbase + 31 < nlim && al32(yrow)) {
+      uint4 pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        pk[q] = make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
+                           pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
+      stg256(yrow, pk[0], pk[1]);
+      stg256(yrow + 16, pk[2], pk[3]);
+      return;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (cbase + 8 * q + 7 < nlim) {
@@ -257,6 +290,14 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
     }
   } else {
     float* yrow = reinterpret_cast<float*>(a.Y) + row * a.ldy + cbase;
+    if (cbase + 31 < nlim && al32(yrow)) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        stg256(yrow + 8 * q,
+               make_uint4(__float_as_uint(o[8 * q]), __float_as_uint(o[8 * q + 1]), __float_as_uint(o[8 * q + 2]), __float_as_uint(o[8 * q + 3])),
+               make_uint4(__float_as_uint(o[8 * q + 4]), __float_as_uint(o[8 * q + 5]), __float_as_uint(o[8 * q + 6]), __float_as_uint(o[8 * q + 7])));
+      return;
+    }
     const bool vec_ok = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {

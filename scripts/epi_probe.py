@@ -1,0 +1,33 @@
+"""Epilogue probe for k_linear_tma: plain / ReLU-mask / gathered-addend variants at E = 1.96M rows
+(run under ncu --set full to read stall reasons; prints CUDA-event times otherwise)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from batch3dmot_b200 import _lib as L, ops
+dev = "cuda"
+ops.set_precision("bf16")
+E, N = 1958979, 64000
+torch.manual_seed(0)
+bf = torch.bfloat16
+x256 = torch.randn(E, 256, device=dev).to(bf)
+x128 = torch.randn(E, 128, device=dev).to(bf)
+x64 = torch.randn(E, 64, device=dev).to(bf)
+m256 = torch.randn(E, 256, device=dev).to(bf)
+W = torch.randn(128, 256, device=dev) * 0.05          # Linear(256 -> 128)
+Wm = torch.randn(192, 64, device=dev) * 0.05          # Linear(64 -> 192)
+p = torch.randn(N, 192, device=dev).to(bf)
+idx = torch.randint(0, N, (E,), device=dev).int().sort().values
+cases = {
+    "plain fwd 256->128": lambda: ops.linear_raw([(x256, None, None, 0)], W, None, E, L.ACT_RELU, tc=True, out_dtype=bf),
+    "dgrad 128->256 + mask": lambda: ops.linear_raw([(x128, None, None, 0)], W, None, E, trans_w=True, out_mask=m256, tc=True, out_dtype=bf),
+    "fwd 64->192 + gathered addend + relu": lambda: ops.linear_raw([(x64, None, None, 0)], Wm, None, E, L.ACT_RELU, tc=True, out_dtype=bf, adds=[(p, idx)]),
+}
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+for name, fn in cases.items():
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1) / reps * 1e3:.1f} us")
