@@ -120,27 +120,28 @@ __device__ __forceinline__ void ld64B(const void* p, uint4 (&q)[4]) {
 }
 
 struct EpiPrefetch {
-  uint4 m[4], a0[4], a1[4];
-  int flags;   // bit0: mask, bit1: addend 0, bit2: addend 1
+  uint4 u[4], v[4];   // u: ReLU mask if bit0, else addend 0;  v: addend 0 if bit0, else addend 1
+  int flags;          // bit0: mask prefetched, bit1: addend 0 prefetched, bit2: addend 1 prefetched
 };
+// g0 / g1: source rows of the two addends for output row `row` (already gathered through add[t].idx).
 template <class EP>
-__device__ __forceinline__ void epilogue_prefetch(const EP& a, long long row, int cbase, int nlim, EpiPrefetch& pf) {
+__device__ __forceinline__ void epilogue_prefetch(const EP& a, long long row, int g0, int g1, int cbase, int nlim,
+                                                  EpiPrefetch& pf) {
   pf.flags = 0;
   if (cbase + 31 >= nlim) return;
   if (a.out_mask && a.mask_bf16 && (a.ldm & 7) == 0) {
-    ld64B(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase, pf.m);
+    ld64B(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase, pf.u);
     pf.flags |= 1;
   }
   if (a.nadd > 0 && a.add[0].dtype == B3D_BF16) {
     const SegDev& S = a.add[0];
-    ld64B(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase,
-          pf.a0);
+    const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(S.ptr) + (long long)g0 * S.ld + cbase;
+    if (pf.flags & 1) ld64B(ap, pf.v); else ld64B(ap, pf.u);
     pf.flags |= 2;
   }
-  if (a.nadd > 1 && a.add[1].dtype == B3D_BF16) {
+  if (a.nadd > 1 && a.add[1].dtype == B3D_BF16 && !(pf.flags & 1)) {
     const SegDev& S = a.add[1];
-    ld64B(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + (long long)(S.idx ? __ldg(S.idx + row) : (int32_t)row) * S.ld + cbase,
-          pf.a1);
+    ld64B(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + (long long)g1 * S.ld + cbase, pf.v);
     pf.flags |= 4;
   }
 }
@@ -164,7 +165,7 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   for (int t = 0; t < a.nadd; ++t) {   // node-side first-layer blocks, pre-projected per node
     const SegDev& S = a.add[t];
     if (pf && (pf->flags & (2 << t))) {   // already in registers
-      const uint4* src = t == 0 ? pf->a0 : pf->a1;
+      const uint4* src = (t == 0 && !(pf->flags & 1)) ? pf->u : pf->v;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t w[4] = {src[q].x, src[q].y, src[q].z, src[q].w};
@@ -222,7 +223,7 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
         if (!pre) ld64B(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase, mv4);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint4 m = pre ? pf->m[q] : mv4[q];
+          const uint4 m = pre ? pf->u[q] : mv4[q];
           const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -746,27 +747,87 @@ k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   } else {
     const int lq = warp & 3;                  // TMEM lane quarter this warp may access
     const bool plain = !a.out_mask && !a.row_mask && !(a.flags & B3D_FLAG_ACCUMULATE);
-    int tcount = 0;
+    const int cb0 = ((warp - 2) >> 2) * 32;   // the two warps of a quarter interleave 32-column blocks
+    const int nlim = min(a.Nout, n0 + a.Nb);
+    const long long lrow = lq * 32 + lane;
+    // The global operands of a block (bf16 ReLU mask, row-gathered addends) are requested ONE BLOCK
+    // AHEAD — the next block of this tile, or the first block of this CTA's next tile — so their
+    // latency overlaps the TMEM load, the arithmetic and the stores of the current block. Two register
+    // sets alternate roles (no moves: a move would wait for the load it copies).
+    auto gather_rows = [&](long long tile, int& g0, int& g1) {
+      const long long row = tile * TC_BM + lrow;
+      g0 = g1 = 0;
+      if (tile < a.ntiles && row < a.M) {
+        g0 = (a.nadd > 0 && a.add[0].idx) ? __ldg(a.add[0].idx + row) : (int)row;
+        g1 = (a.nadd > 1 && a.add[1].idx) ? __ldg(a.add[1].idx + row) : (int)row;
+      }
+    };
+    EpiPrefetch pfa, pfb;
+    pfa.flags = pfb.flags = 0;
+    int cg0, cg1, ng0, ng1;                   // addend source rows: this tile / this CTA's next tile
+    gather_rows(blockIdx.x, cg0, cg1);
+    // Measured (scripts/epi_probe.py): the look-ahead pays for the gathered addends (L2-resident node
+    // tables: 437 -> 380 us on the 64->192 message layer) but not for the dense DRAM-streamed ReLU mask
+    // (647 -> 700 us), which keeps the same-block prefetch.
+    if (a.out_mask || a.nadd == 0) {
+      int tcount = 0;
+      for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount & 1;
+        const long long row = tile * TC_BM + lrow;
+        const bool row_ok = row < a.M;
+        const bool rz = row_ok && a.row_mask && a.row_mask[row] == 0;
+        if (tcount) gather_rows(tile, cg0, cg1);
+        mbar_wait(sBar + 64 + 8 * acc, (tcount >> 1) & 1);
+        tc_fence_after_sync();
+        for (int col0 = cb0; col0 < a.Nb; col0 += 64) {
+          uint32_t r[32];
+          tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
+          pfa.flags = 0;
+          if (row_ok) epilogue_prefetch(a, row, cg0, cg1, n0 + col0, nlim, pfa);   // global latency overlaps the TMEM load
+          tmem_ld_wait();
+          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sBar + 80 + 8 * acc);
+      }
+    } else {
+    if ((long long)blockIdx.x < a.ntiles && blockIdx.x * (long long)TC_BM + lrow < a.M && cb0 < a.Nb)
+      epilogue_prefetch(a, blockIdx.x * (long long)TC_BM + lrow, cg0, cg1, n0 + cb0, nlim, pfa);
+    int tcount = 0, parity = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
-      mbar_wait(sBar + 64 + 8 * acc, (tcount >> 1) & 1);
-      tc_fence_after_sync();
-      const long long row = tile * TC_BM + lq * 32 + lane;
+      const long long ntile = tile + gridDim.x;
+      gather_rows(ntile, ng0, ng1);
+      const long long row = tile * TC_BM + lrow, nrow = ntile * TC_BM + lrow;
       const bool row_ok = row < a.M;
       const bool rz = row_ok && a.row_mask && a.row_mask[row] == 0;
-      const int nlim = min(a.Nout, n0 + a.Nb);
-      for (int col0 = ((warp - 2) >> 2) * 32; col0 < a.Nb; col0 += 64) {   // the two warps of a quarter interleave blocks
+      mbar_wait(sBar + 64 + 8 * acc, (tcount >> 1) & 1);
+      tc_fence_after_sync();
+      for (int col0 = cb0; col0 < a.Nb; col0 += 64, parity ^= 1) {
         uint32_t r[32];
-        EpiPrefetch pf;
-        pf.flags = 0;
         tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
-        if (row_ok) epilogue_prefetch(a, row, n0 + col0, nlim, pf);   // global latency overlaps the TMEM load
-        tmem_ld_wait();
-        if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pf);
+        const bool same = col0 + 64 < a.Nb;
+        const long long prow = same ? row : nrow;
+        const int pcol = n0 + (same ? col0 + 64 : cb0);
+        const bool p_ok = same ? row_ok : (ntile < a.ntiles && nrow < a.M);
+        if (parity == 0) {
+          pfb.flags = 0;
+          if (p_ok) epilogue_prefetch(a, prow, same ? cg0 : ng0, same ? cg1 : ng1, pcol, nlim, pfb);
+          tmem_ld_wait();
+          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa);
+        } else {
+          pfa.flags = 0;
+          if (p_ok) epilogue_prefetch(a, prow, same ? cg0 : ng0, same ? cg1 : ng1, pcol, nlim, pfa);
+          tmem_ld_wait();
+          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfb);
+        }
       }
+      cg0 = ng0; cg1 = ng1;
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(sBar + 80 + 8 * acc);
+    }
     }
   }
   tc_fence_before_sync();
