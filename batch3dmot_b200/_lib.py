@@ -31,6 +31,7 @@ _SIGS = {
                                   C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_gather_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "b3d_add_n": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_linear": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                              C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                              C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p]),

@@ -127,8 +127,10 @@ class GNN(nn.Module):
         x0 = ops.run_mlp(self.node_encoder, [(pose, None)])        # :174-176
         x, e = x0, e0
         inv = self.message_passing.project_invariants(x0) if ops.get_precision() == "bf16" else None
+        # att_edge_attr feeds every iteration: one depth-way gradient sum instead of depth-1 additions
+        atts = ops.fanout(att, self.depth) if ops.get_precision() == "bf16" else (att,) * self.depth
         for i in range(self.depth):
             if i % 2 == 0 and self.apply_knn_update:
                 x = knn_attention_conv(self.knn_conv, x, data.node_timestamps)
-            x, e = self.message_passing.forward_graph(x, g, e, x0, att, inv)                    # :186
+            x, e = self.message_passing.forward_graph(x, g, e, x0, atts[i], inv)                # :186
         return ops.run_mlp(self.edge_classifier, [(e, None)], final_act="sigmoid"), x_sens     # :188

@@ -85,6 +85,58 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) k_row_nonzero(const float* __r
   if (lane == 0) mask[r] = (s != 0.f) ? 1 : 0;
 }
 
+
+// out[r, c] = sum_k in_k[r, c] over up to 8 row-major inputs (fp32 or bf16, each with its own leading
+// dimension), summed in fp32 in argument order; one pass instead of the n-1 pairwise additions the
+// autograd engine would run when a tensor feeds several consumers.
+struct AddNArgs {
+  SegDev in[B3D_MAX_SEGS];
+  int n;
+  long long M;
+  int C;
+  void* out;
+  int out_bf16, ldo;
+};
+
+__device__ __forceinline__ void addn_load8(const SegDev& S, long long r, int c, float (&acc)[8]) {
+  if (S.dtype == B3D_BF16) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + r * S.ld + c));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] += __uint_as_float(w[j] << 16);
+      acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(S.ptr + r * S.ld + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(S.ptr + r * S.ld + c + 4));
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_add_n(const AddNArgs a) {
+  const int groups = a.C / 8;
+  const long long total = a.M * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int c = (int)(i % groups) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < a.n; ++k) addn_load8(a.in[k], r, c, acc);
+    if (a.out_bf16) {
+      uint4 q;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + r * a.ldo + c) = q;
+    } else {
+      float* o = reinterpret_cast<float*>(a.out) + r * a.ldo + c;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
 }  // namespace b3d
 
 using namespace b3d;
@@ -198,5 +250,24 @@ extern "C" int b3d_row_nonzero(const float* feats, int64_t row_len, int64_t N, u
   if (N == 0) return 0;
   k_row_nonzero<<<(unsigned)ceil_div(N, SEG_WARPS), SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(feats, row_len, N, mask);
   B3D_LAUNCH_CHECK("k_row_nonzero");
+  return 0;
+}
+
+extern "C" int b3d_add_n(const b3d_seg_t* ins, int32_t n, int64_t M, void* out, int32_t out_dtype, int32_t ldo,
+                         void* stream) {
+  AddNArgs a;
+  if (!out || M < 0 || to_dev(ins, n, a.in)) return bad_arg("b3d_add_n");
+  if (M == 0) return 0;
+  a.n = n; a.M = M; a.C = a.in[0].width; a.out = out; a.out_bf16 = (out_dtype == B3D_BF16); a.ldo = ldo;
+  if (a.C % 8 || !al16(out) || (ldo % (a.out_bf16 ? 8 : 4))) return bad_arg("b3d_add_n: width % 8, 16-byte aligned rows");
+  for (int k = 0; k < n; ++k)
+    if (a.in[k].width != a.C || a.in[k].idx || a.in[k].mask_mode != B3D_MASK_NONE || !al16(a.in[k].ptr) ||
+        (a.in[k].ld % (a.in[k].dtype == B3D_BF16 ? 8 : 4)))
+      return bad_arg("b3d_add_n: inputs must be dense, equally wide, 16-byte aligned rows");
+  const long long total = M * (a.C / 8);
+  long long blocks = ceil_div(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_add_n<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  B3D_LAUNCH_CHECK("k_add_n");
   return 0;
 }

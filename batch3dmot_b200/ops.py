@@ -337,7 +337,7 @@ def row_nonzero(feats):
 
 def knn_frames(x, frame_ptr, k):
     """[N,k] int64 neighbour table (global ids, -1 padded), SURVEY A.5 order."""
-    x = _rows(x.detach())
+    x = _rows(x.detach().float())
     N, D = x.shape
     fp = frame_ptr.to(device=x.device, dtype=torch.int32).contiguous()
     F = fp.numel() - 1
@@ -349,7 +349,7 @@ def knn_frames(x, frame_ptr, k):
 
 
 def gat_aggregate(h, att_src, att_dst, bias, nbr, slope=0.2):
-    h = _rows(h)
+    h = _rows(h.float())
     N, D = h.shape
     out = torch.empty((N, D), dtype=torch.float32, device=h.device)
     scratch = torch.empty(2 * N, dtype=torch.float32, device=h.device)
@@ -599,6 +599,84 @@ def segment_sum(src, nidx, relu_src=False):
     relu_src=True: `src` is the output of a ReLU layer built with premasked=True; the backward then
     returns the gradient already multiplied by (src > 0), fused into the row gather."""
     return _SegmentSum.apply(src, nidx, relu_src)
+
+
+def add_n_raw(ts, out_dtype=None):
+    """sum of equally shaped [M,C] tensors (fp32/bf16, row strides free) in ONE kernel."""
+    ts = [_rows(t) for t in ts]
+    M, C_ = ts[0].shape
+    out = torch.empty((M, C_), dtype=out_dtype or ts[0].dtype, device=ts[0].device)
+    if M == 0:
+        return out
+    ok = C_ % 8 == 0 and all(_al16(t) for t in ts) and len(ts) <= L.MAX_SEGS
+    if not ok:                      # shapes the kernel does not take (never on the model path)
+        acc = ts[0].float()
+        for t in ts[1:]:
+            acc = acc + t.float()
+        return acc.to(out.dtype)
+    L.check(L.lib().b3d_add_n(L.make_segs([(t, None, None, 0) for t in ts]), len(ts), M, L.ptr(out), _DT[out.dtype],
+                              out.stride(0), L.stream()), "b3d_add_n")
+    return out
+
+
+class _Fanout(torch.autograd.Function):
+    """Identity with n outputs. A tensor with several consumers gets its gradient as ONE n-way sum
+    kernel (b3d_add_n) instead of n-1 pairwise additions by the autograd engine (which also fall on
+    the slow strided path when a gradient is a column slice of a wider matrix)."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.dtype = x.dtype
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gs = [g for g in gs if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            g = gs[0]
+            return (g if g.dtype == ctx.dtype else g.to(ctx.dtype)), None
+        return add_n_raw(gs, out_dtype=ctx.dtype), None
+
+
+def fanout(x, n):
+    """n aliases of x whose gradients are summed by one kernel."""
+    if not (torch.is_grad_enabled() and x.requires_grad) or n < 2:
+        return (x,) * n
+    return _Fanout.apply(x, n)
+
+
+class _SplitCols(torch.autograd.Function):
+    """Column split x -> (x[:, :s0], x[:, s0:s0+s1], ...) whose backward is ONE concatenation instead
+    of a zero-filled full-width gradient plus an addition per slice."""
+
+    @staticmethod
+    def forward(ctx, x, sizes):
+        ctx.sizes, ctx.dtype, ctx.rows = sizes, x.dtype, x.size(0)
+        outs, off = [], 0
+        for w in sizes:
+            outs.append(x[:, off:off + w])
+            off += w
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        ref = next(g for g in gs if g is not None)
+        parts = [g.to(ctx.dtype) if g is not None else ref.new_zeros((ctx.rows, w), dtype=ctx.dtype)
+                 for g, w in zip(gs, ctx.sizes)]
+        return torch.cat(parts, 1), None
+
+
+def split_cols(x, sizes):
+    assert sum(sizes) == x.size(1)
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        outs, off = [], 0
+        for w in sizes:
+            outs.append(x[:, off:off + w])
+            off += w
+        return tuple(outs)
+    return _SplitCols.apply(x, tuple(sizes))
 
 
 class _BCE(torch.autograd.Function):

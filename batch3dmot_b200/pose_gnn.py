@@ -74,8 +74,7 @@ class CausalMessagePassing(nn.Module):
         lowp = torch.bfloat16
         # one node-level GEMM per iteration for all four node-side blocks: [N, H1 | H1 | Hm | Hm]
         p_all = ops.fused_mlp([(x, None)], [w_cat], [b_cat], adds=[(inv_all, None)], out_dtype=lowp)
-        p_i, p_j = p_all[:, :h1], p_all[:, h1:2 * h1]
-        p_f, p_p = p_all[:, 2 * h1:2 * h1 + hm], p_all[:, 2 * h1 + hm:]
+        p_i, p_j, p_f, p_p = ops.split_cols(p_all, (h1, h1, hm, hm))
         eu = [m for m in self.edge_update if isinstance(m, nn.Linear)]
         w1 = eu[0].weight                                              # cols: x_i | x_j | e (| att)
         # edge-level tensors stay bf16 between kernels: every consumer is a bf16 tensor-core tile
@@ -85,20 +84,25 @@ class CausalMessagePassing(nn.Module):
         dense = [(e, None)] + ([(att, None)] if att is not None else [])
         e_new = ops.fused_mlp(dense, [w1[:, 2 * D:], eu[1].weight, eu[2].weight], [None, eu[1].bias, eu[2].bias],
                               adds=[(p_i, dst), (p_j, src)], out_dtype=lowp)
+        # e_new has three consumers (the caller: next iteration / classifier, and both message MLPs):
+        # its gradient is ONE three-way sum kernel
+        e_out, e_f, e_p = ops.fanout(e_new, 3)
         # message MLPs: first layer per edge (ReLU), then aggregate, then the linear last layer per NODE
         # (summation order only: sum_e (W2 h_e + b2) = W2 sum_e h_e + deg b2). Future messages use the
         # later node's features and flow into the EARLIER node (src); past messages the other way round.
         agg = []
-        for seq, side, into, p, wpost in ((self.create_future_msgs, dst, src, p_f, w_post[0]),
-                                          (self.create_past_msgs, src, dst, p_p, w_post[1])):
+        for seq, side, into, p, wpost, e_in in ((self.create_future_msgs, dst, src, p_f, w_post[0], e_f),
+                                                (self.create_past_msgs, src, dst, p_p, w_post[1], e_p)):
             l0 = seq[0]
-            h = ops.fused_mlp([(e_new, None)], [l0.weight[:, D:D + E_]], [None], final_act="relu",
+            h = ops.fused_mlp([(e_in, None)], [l0.weight[:, D:D + E_]], [None], final_act="relu",
                               adds=[(p, side)], out_dtype=lowp, premasked=True)         # x | e' | x0 blocks
             s_h = ops.segment_sum(h, into, relu_src=True)                                # [N, Hm] fp32
-            agg.append(ops.fused_linear([(s_h, None), (g.degree_block(into), None)], wpost))
+            agg.append(ops.fused_mlp([(s_h, None), (g.degree_block(into), None)], [wpost], [None], out_dtype=lowp))
         m_fut, m_past = agg
-        x_new = ops.run_mlp(self.combine_future_past, [(m_past, None), (m_fut, None)])
-        return x_new, e_new
+        # node-level tensors are bf16 too (their only consumers are bf16 tiles), which puts the
+        # node-level GEMMs on the TMA-fed kernels as well
+        x_new = ops.run_mlp(self.combine_future_past, [(m_past, None), (m_fut, None)], out_dtype=lowp)
+        return x_new, e_out
 
     def forward_graph(self, x, g, e, x0, att=None, inv=None):
         if ops.get_precision() == "bf16":

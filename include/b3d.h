@@ -95,6 +95,13 @@ int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_
                     void* out, int32_t out_dtype, int32_t ld_out, const void* relu_mask, int32_t ld_mask,
                     void* stream);
 
+/* out[M,C] = sum_k ins[k][M,C] (n <= 8 dense fp32/bf16 inputs of equal width C % 8 == 0, each with its
+ * own leading dimension; fp32 accumulation in argument order). One pass for the gradient of a tensor
+ * with several consumers: the edge features feed edge_update of the next iteration and both message
+ * MLPs (pose_gnn.py:210,215,222), att_edge_attr feeds all six iterations (clr_att_gnn.py:186). */
+int b3d_add_n(const b3d_seg_t* ins /*host*/, int32_t n, int64_t M, void* out, int32_t out_dtype,
+              int32_t ldo, void* stream);
+
 /* ---- dense layers with fused gather / concat / activation ------------------
  * Y[M,Nout] (+)= act( cat_s(A_s)[M,K] * op(W) + bias ) [* (out_mask > 0)] [row_mask]
  *   trans_w == 0: W is [Nout,K] row-major (nn.Linear.weight), Y = A W^T   (forward)
