@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libb3d.so")
 MASK_NONE, MASK_RELU, MASK_SIGMOID = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 FLAG_ACCUMULATE = 1
-F32, BF16 = 0, 1
+F32, BF16, BITS = 0, 1, 2
 MAX_SEGS = 8
 
 
@@ -30,7 +30,7 @@ _SIGS = {
     "b3d_segment_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_gather_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
-                                  C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+                                  C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_add_n": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_linear": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                              C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
@@ -43,13 +43,13 @@ _SIGS = {
                                       C.c_void_p]),
     "b3d_linear_tc": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
-                                C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p]),
+                                C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_void_p]),
     "b3d_tma_packed_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "b3d_tma_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p]),
     "b3d_linear_tma": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
-                                 C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p]),
+                                 C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_void_p]),
     "b3d_wgrad_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "b3d_wgrad_tc": (C.c_int, [C.POINTER(Seg), C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),

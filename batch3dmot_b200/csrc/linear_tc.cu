@@ -79,6 +79,8 @@ struct TcArgs {
   const uint8_t* row_mask;
   SegDev add[2];   // row-gathered fp32 addends of the pre-activation
   int nadd;
+  const uint32_t* mask_bits;   // ReLU mask as sign bits: word [(col / 32) * M + row], bit col % 32
+  uint32_t* bits_out;          // same layout, written for this layer's (post-activation) output
 };
 
 template <int ACT>
@@ -121,13 +123,18 @@ __device__ __forceinline__ void ld64B(const void* p, uint4 (&q)[4]) {
 
 struct EpiPrefetch {
   uint4 u[4], v[4];   // u: ReLU mask if bit0, else addend 0;  v: addend 0 if bit0, else addend 1
-  int flags;          // bit0: mask prefetched, bit1: addend 0 prefetched, bit2: addend 1 prefetched
+  uint32_t bits;      // sign-bit mask word of the block (bit3)
+  int flags;          // bit0: mask prefetched, bit1: addend 0 prefetched, bit2: addend 1 prefetched, bit3: bits
 };
 // g0 / g1: source rows of the two addends for output row `row` (already gathered through add[t].idx).
 template <class EP>
 __device__ __forceinline__ void epilogue_prefetch(const EP& a, long long row, int g0, int g1, int cbase, int nlim,
                                                   EpiPrefetch& pf) {
   pf.flags = 0;
+  if (a.mask_bits && (cbase & 31) == 0 && cbase < nlim) {   // one coalesced word per row
+    pf.bits = __ldg(a.mask_bits + (long long)(cbase >> 5) * a.M + row);
+    pf.flags |= 8;
+  }
   if (cbase + 31 >= nlim) return;
   if (a.out_mask && a.mask_bf16 && (a.ldm & 7) == 0) {
     ld64B(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase, pf.u);
@@ -215,7 +222,18 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) o[j] = activate<ACT>(o[j]);
+  if (a.bits_out && (cbase & 31) == 0 && cbase < nlim) {   // sign bits of this output block for the backward pass
+    uint32_t word = 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) word |= (o[j] > 0.f && cbase + j < nlim) ? (1u << j) : 0u;
+    a.bits_out[(long long)(cbase >> 5) * a.M + row] = word;
+  }
   if (!plain) {
+    if (a.mask_bits && (cbase & 31) == 0 && cbase < nlim) {   // ReLU backward from the producing layer's sign bits
+      const uint32_t word = (pf && (pf->flags & 8)) ? pf->bits : __ldg(a.mask_bits + (long long)(cbase >> 5) * a.M + row);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = ((word >> j) & 1u) ? o[j] : 0.f;
+    }
     if (a.out_mask) {   // ReLU backward of the producing layer: keep the gradient where its output was > 0
       if (a.mask_bf16 && cbase + 31 < nlim && (a.ldm & 7) == 0) {
         const bool pre = pf && (pf->flags & 1);
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
   const int lq = warp & 3;
   const long long row = m0 + lq * 32 + lane;
   const bool row_ok = row < a.M;
-  const bool plain = !a.out_mask && !a.row_mask && !(a.flags & B3D_FLAG_ACCUMULATE);
+  const bool plain = !a.out_mask && !a.mask_bits && !a.row_mask && !(a.flags & B3D_FLAG_ACCUMULATE);
   const bool rz = row_ok && a.row_mask && a.row_mask[row] == 0;
   for (int col0 = (warp >> 2) * 32; col0 < Nb; col0 += 64) {
     uint32_t r[32];
@@ -649,6 +667,8 @@ struct TmaArgs {
   const uint8_t* row_mask;
   SegDev add[2];
   int nadd;
+  const uint32_t* mask_bits;
+  uint32_t* bits_out;
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -746,7 +766,7 @@ k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     }
   } else {
     const int lq = warp & 3;                  // TMEM lane quarter this warp may access
-    const bool plain = !a.out_mask && !a.row_mask && !(a.flags & B3D_FLAG_ACCUMULATE);
+    const bool plain = !a.out_mask && !a.mask_bits && !a.row_mask && !(a.flags & B3D_FLAG_ACCUMULATE);
     const int cb0 = ((warp - 2) >> 2) * 32;   // the two warps of a quarter interleave 32-column blocks
     const int nlim = min(a.Nout, n0 + a.Nb);
     const long long lrow = lq * 32 + lane;
@@ -1043,7 +1063,7 @@ extern "C" int b3d_linear_tc(const b3d_seg_t* segs, int32_t nseg, const void* Wp
                              int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype,
                              int64_t M, int32_t act, int32_t flags, const void* out_mask, int32_t ldm,
                              int32_t mask_dtype, const uint8_t* row_mask, const b3d_seg_t* adds, int32_t nadd,
-                             void* stream) {
+                             void* relu_bits_out, void* stream) {
   if (M == 0) return 0;
   TcArgs a;
   if (nadd < 0 || nadd > 2 || (nadd && to_dev(adds, nadd, a.add))) return bad_arg("b3d_linear_tc adds");
@@ -1066,7 +1086,10 @@ extern "C" int b3d_linear_tc(const b3d_seg_t* segs, int32_t nseg, const void* Wp
   a.nseg = nseg; a.Ktot = K; a.Wp = reinterpret_cast<const __nv_bfloat16*>(Wp);
   a.Npad = round_up(n_logical, 16); a.Kpad = round_up(k_logical, TC_BK);
   a.bias = bias; a.Y = Y; a.ldy = ldy; a.y_bf16 = (y_dtype == B3D_BF16); a.M = M; a.Nout = n_logical; a.act = act;
-  a.flags = flags; a.out_mask = out_mask; a.ldm = ldm; a.mask_bf16 = (mask_dtype == B3D_BF16); a.row_mask = row_mask;
+  a.flags = flags; a.ldm = ldm; a.mask_bf16 = (mask_dtype == B3D_BF16); a.row_mask = row_mask;
+  a.out_mask = mask_dtype == B3D_BITS ? nullptr : out_mask;
+  a.mask_bits = mask_dtype == B3D_BITS ? reinterpret_cast<const uint32_t*>(out_mask) : nullptr;
+  a.bits_out = reinterpret_cast<uint32_t*>(relu_bits_out);
   int Nb = a.Npad < TC_NMAX ? a.Npad : TC_NMAX;
   size_t smem = 2 * TC_A_STAGE + 2 * (size_t)Nb * 128 + 64 + 1024 + 4 * TC_TAB + sizeof(int32_t) * B3D_MAX_SEGS * TC_BM;
   static bool attr_set = false;
@@ -1153,7 +1176,7 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
                               int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype,
                               int64_t M, int32_t act, int32_t flags, const void* out_mask, int32_t ldm,
                               int32_t mask_dtype, const uint8_t* row_mask, const b3d_seg_t* adds, int32_t nadd,
-                              void* stream) {
+                              void* relu_bits_out, void* stream) {
   if (M == 0) return 0;
   TmaArgs a;
   SegDev seg[2];
@@ -1177,18 +1200,23 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   a.seg0_chunks = nseg == 2 ? seg[0].width / TC_BK : Kpad / TC_BK;
   a.nchunks = nseg == 2 ? seg[0].width / TC_BK + round_up(seg[1].width, TC_BK) / TC_BK : Kpad / TC_BK;
   if (a.nchunks * TC_BK != Kpad) return bad_arg("b3d_linear_tma: chunking");
-  // weight block resident in shared memory: Nb * Kpad * 2 <= 144 KB
-  int Nb = (144 * 1024 / (Kpad * 2)) / 16 * 16;
+  // weight block resident in shared memory: Nb * Kpad * 2 <= 144 KB. Sign-bit words cover 32 columns,
+  // so with bit masks every column block must start on a word boundary (granularity 32 instead of 16).
+  const int gran = (relu_bits_out || mask_dtype == B3D_BITS) ? 32 : 16;
+  int Nb = (144 * 1024 / (Kpad * 2)) / gran * gran;
   if (Nb > TC_NMAX) Nb = TC_NMAX;
-  if (Nb > Npad) Nb = Npad;
-  if (Nb < 16) return bad_arg("b3d_linear_tma: K too large for a resident weight block");
+  if (Nb > round_up(Npad, gran)) Nb = round_up(Npad, gran);
+  if (Nb < gran) return bad_arg("b3d_linear_tma: K too large for a resident weight block");
   const int ny = (Npad + Nb - 1) / Nb;
-  Nb = round_up((Npad + ny - 1) / ny, 16);      // balance the column blocks
+  Nb = round_up((Npad + ny - 1) / ny, gran);      // balance the column blocks
   a.Nb = Nb;
   a.acc_stride = (int)tmem_cols_for(Nb);
   a.ntiles = ceil_div(M, TC_BM);
   a.bias = bias; a.Y = Y; a.ldy = ldy; a.y_bf16 = (y_dtype == B3D_BF16); a.M = M; a.Nout = n_logical; a.act = act;
-  a.flags = flags; a.out_mask = out_mask; a.ldm = ldm; a.mask_bf16 = (mask_dtype == B3D_BF16); a.row_mask = row_mask;
+  a.flags = flags; a.ldm = ldm; a.mask_bf16 = (mask_dtype == B3D_BF16); a.row_mask = row_mask;
+  a.out_mask = mask_dtype == B3D_BITS ? nullptr : out_mask;
+  a.mask_bits = mask_dtype == B3D_BITS ? reinterpret_cast<const uint32_t*>(out_mask) : nullptr;
+  a.bits_out = reinterpret_cast<uint32_t*>(relu_bits_out);
   a.nadd = nadd;
   alignas(64) CUtensorMap mA0, mA1, mW;
   if (make_tmap_bf16(&mA0, seg[0].ptr, M, seg[0].width, seg[0].ld, TC_BM)) return bad_arg("b3d_linear_tma: tensor map A0");

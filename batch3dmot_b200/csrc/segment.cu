@@ -194,7 +194,8 @@ extern "C" int b3d_segment_sum(const void* src_v, int32_t src_dtype, int32_t ld_
 // fp32 rows gathered and rounded to bf16 (gradient of a bf16 segment-sum input)
 __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
     const float* __restrict__ src, int ld, const int32_t* __restrict__ idx, long long M, int C,
-    __nv_bfloat16* __restrict__ out, int ldo, const __nv_bfloat16* __restrict__ relu_mask, int ldm) {
+    __nv_bfloat16* __restrict__ out, int ldo, const __nv_bfloat16* __restrict__ relu_mask, int ldm,
+    const uint32_t* __restrict__ relu_bits) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
   if (r >= M) return;
@@ -216,13 +217,22 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
         if ((int16_t)(mw[j] >> 16) <= 0) w[j] &= 0x0000FFFFu;
       }
     }
+    if (relu_bits) {   // the same mask as sign bits: word [(c / 32) * M + r], bit c % 32
+      const uint32_t word = __ldg(relu_bits + (long long)(c >> 5) * M + r) >> (c & 31);
+      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!((word >> (2 * j)) & 1u)) w[j] &= 0xFFFF0000u;
+        if (!((word >> (2 * j + 1)) & 1u)) w[j] &= 0x0000FFFFu;
+      }
+    }
     *reinterpret_cast<uint4*>(out + r * ldo + c) = v;
   }
 }
 
 extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
                                void* out_v, int32_t out_dtype, int32_t ld_out, const void* relu_mask,
-                               int32_t ld_mask, void* stream) {
+                               int32_t ld_mask, int32_t mask_dtype, void* stream) {
   if (M == 0) return 0;
   if (!src || !idx || !out_v || C <= 0 || M < 0) return bad_arg("b3d_gather_rows");
   if (out_dtype == B3D_BF16) {
@@ -231,7 +241,8 @@ extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* 
     if (relu_mask && ((ld_mask & 7) || !al16(relu_mask))) return bad_arg("b3d_gather_rows: relu_mask alignment");
     k_gather_rows_bf16<<<(unsigned)ceil_div(M, SEG_WARPS), SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(
         src, ld_src, idx, M, C, reinterpret_cast<__nv_bfloat16*>(out_v), ld_out,
-        reinterpret_cast<const __nv_bfloat16*>(relu_mask), ld_mask);
+        mask_dtype == B3D_BITS ? nullptr : reinterpret_cast<const __nv_bfloat16*>(relu_mask), ld_mask,
+        mask_dtype == B3D_BITS ? reinterpret_cast<const uint32_t*>(relu_mask) : nullptr);
     B3D_LAUNCH_CHECK("k_gather_rows_bf16");
     return 0;
   }

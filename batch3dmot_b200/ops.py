@@ -133,6 +133,7 @@ def invalidate_weight_cache():
 
 
 _USE_TMA = True          # dense bf16 operands go through the TMA-fed persistent kernel
+_USE_BITS = True         # bf16 chains keep ReLU masks as sign bits (B3D_BITS) for the backward pass
 
 
 def _packed_weight(W, transpose, rowmajor=False):
@@ -187,8 +188,16 @@ def _rows(t):
 _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
 
 
+def new_relu_bits(M, n_out, device):
+    """Sign-bit mask buffer of an [M, n_out] ReLU output: int32 words [ceil(n_out/32), M] (b3d.h B3D_BITS)."""
+    return torch.empty(((n_out + 31) // 32, M), dtype=torch.int32, device=device)
+
+
 def _linear_raw_impl(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accumulate=False,
-               out_mask=None, row_mask=None, n_out=None, tc=None, out_dtype=torch.float32, adds=None):
+               out_mask=None, row_mask=None, n_out=None, tc=None, out_dtype=torch.float32, adds=None,
+               bits_out=None, mask_bits=None):
+    """bits_out / mask_bits (tensor-core kernels only): sign-bit masks (new_relu_bits) written for this
+    layer's output / applied as the producing layer's ReLU mask instead of out_mask."""
     """items: [(tensor, idx32|None, mask|None, mode)]. Returns Y [M, n_out].
     tc=None: use the tensor-core kernel iff the precision mode is bf16 and the shapes fit."""
     segs = L.make_segs(items)
@@ -208,21 +217,26 @@ def _linear_raw_impl(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None,
         add_segs, nadd = L.make_segs([(t, i, None, 0) for t, i in adds]), len(adds)
         assert all(t.size(1) == n_out for t, _ in adds)
         assert tc or all(t.dtype == torch.float32 for t, _ in adds)
+    if mask_bits is not None:
+        assert tc and out_mask is None and mask_bits.shape == ((n_out + 31) // 32, M) and mask_bits.is_contiguous()
+        m_ptr, m_ld, m_dt = L.ptr(mask_bits), 0, L.BITS
+    else:
+        m_ptr, m_ld = L.ptr(out_mask), out_mask.stride(0) if out_mask is not None else 0
+        m_dt = _DT[out_mask.dtype] if out_mask is not None else 0
+    if bits_out is not None:
+        assert tc and bits_out.shape == ((n_out + 31) // 32, M) and bits_out.is_contiguous()
     if tc and _tma_ok(items, K, accumulate):
         wr = _packed_weight(W, trans_w, rowmajor=True)
         L.check(L.lib().b3d_linear_tma(segs, len(items), L.ptr(wr), n_out, K, L.ptr(bias), L.ptr(out),
-                                       out.stride(0), _DT[out.dtype], M, act, 0,
-                                       L.ptr(out_mask), out_mask.stride(0) if out_mask is not None else 0,
-                                       _DT[out_mask.dtype] if out_mask is not None else 0, L.ptr(row_mask),
-                                       add_segs, nadd, L.stream()), "b3d_linear_tma")
+                                       out.stride(0), _DT[out.dtype], M, act, 0, m_ptr, m_ld, m_dt, L.ptr(row_mask),
+                                       add_segs, nadd, L.ptr(bits_out), L.stream()), "b3d_linear_tma")
         return out
     if tc:
         wp = _packed_weight(W, trans_w)
         L.check(L.lib().b3d_linear_tc(segs, len(items), L.ptr(wp), n_out, K, L.ptr(bias), L.ptr(out),
                                       out.stride(0), _DT[out.dtype], M, act, L.FLAG_ACCUMULATE if accumulate else 0,
-                                      L.ptr(out_mask), out_mask.stride(0) if out_mask is not None else 0,
-                                      _DT[out_mask.dtype] if out_mask is not None else 0, L.ptr(row_mask),
-                                      add_segs, nadd, L.stream()), "b3d_linear_tc")
+                                      m_ptr, m_ld, m_dt, L.ptr(row_mask), add_segs, nadd, L.ptr(bits_out),
+                                      L.stream()), "b3d_linear_tc")
         return out
     assert out.dtype == torch.float32 and (out_mask is None or out_mask.dtype == torch.float32)
     L.check(L.lib().b3d_linear(segs, len(items), L.ptr(W), W.stride(0), int(trans_w), L.ptr(bias),
@@ -243,10 +257,15 @@ def linear_raw(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None, accum
     nb = sum(M * t.size(1) * es(t) for t, _, _, _ in items) + M * n_out * (2 if od == torch.bfloat16 else 4)
     if kw.get("out_mask") is not None:
         nb += M * n_out * es(kw["out_mask"])
+    if kw.get("mask_bits") is not None:
+        nb += M * n_out // 8
+    if kw.get("bits_out") is not None:
+        nb += M * n_out // 8
     for t, _ in (kw.get("adds") or []):
         nb += M * n_out * es(t)
     sig = ("dgrad" if trans_w else "fwd", M, K, n_out, tuple(str(t.dtype)[6:] + ("g" if i is not None else "") for t, i, _, _ in items),
-           str(od)[6:], "mask" if kw.get("out_mask") is not None else "", len(kw.get("adds") or []))
+           str(od)[6:], "mask" if kw.get("out_mask") is not None else ("bits" if kw.get("mask_bits") is not None else ""),
+           len(kw.get("adds") or []))
     with _timed(sig, nb):
         return _linear_raw_impl(items, W, bias, M, act, trans_w, out, accumulate, **kw)
 
@@ -308,7 +327,7 @@ def segment_sum_raw(src, nidx, out=None, accumulate=False):
     return out
 
 
-def gather_rows_raw(src, idx32, out_dtype=torch.float32, relu_mask=None):
+def gather_rows_raw(src, idx32, out_dtype=torch.float32, relu_mask=None, relu_bits=None):
     src = _rows(src)
     if src.dtype != torch.float32:
         src = src.float()
@@ -318,9 +337,14 @@ def gather_rows_raw(src, idx32, out_dtype=torch.float32, relu_mask=None):
     out = torch.empty((M, src.size(1)), dtype=out_dtype, device=src.device)
     fused_mask = relu_mask if (relu_mask is not None and out_dtype == torch.bfloat16 and
                                relu_mask.dtype == torch.bfloat16 and _al16(relu_mask)) else None
+    if relu_bits is not None and out_dtype == torch.bfloat16:      # sign bits: 1/16 of the mask bytes
+        L.check(L.lib().b3d_gather_rows(L.ptr(src), src.stride(0), L.ptr(idx32), M, src.size(1), L.ptr(out),
+                                        _DT[out_dtype], out.stride(0), L.ptr(relu_bits), 0, L.BITS, L.stream()),
+                "b3d_gather_rows")
+        return out
     L.check(L.lib().b3d_gather_rows(L.ptr(src), src.stride(0), L.ptr(idx32), M, src.size(1), L.ptr(out),
                                     _DT[out_dtype], out.stride(0), L.ptr(fused_mask),
-                                    fused_mask.stride(0) if fused_mask is not None else 0, L.stream()),
+                                    fused_mask.stride(0) if fused_mask is not None else 0, L.BF16, L.stream()),
             "b3d_gather_rows")
     if relu_mask is not None and fused_mask is None:
         out = out * (relu_mask > 0)
@@ -393,6 +417,7 @@ class _FusedMLP(torch.autograd.Function):
         assert len(add_ts) == len(add_nidx) and (not add_ts or (final_act is None or nl > 1 or premasked))
         assert not premasked or final_act == "relu"
         ctx.premasked = premasked
+        W0dev = Ws[0].device
         ctx.add_dtypes = [t.dtype for t in add_ts]
         adds = [(t, ni.idx if ni is not None else None) for t, ni in zip(add_ts, add_nidx)]
         M = nidx[0].idx.numel() if nidx[0] is not None else xs[0].size(0)
@@ -414,23 +439,34 @@ class _FusedMLP(torch.autograd.Function):
         # chains that are not bf16 end to end keep fp32 activations; each launch then picks the bf16
         # tile kernel on its own when the precision mode allows and its shapes fit (tc=None = auto)
         tc_arg = True if tc else None
-        acts, cur = [], items
+        # bf16 chains record every ReLU output's SIGN BITS (1 bit per element, written by the producing
+        # epilogue): the backward pass masks gradients from them instead of re-reading the activation
+        acts, bits, cur = [], [], items
         for l in range(nl):
             last = l == nl - 1
+            relu_out = (not last) or premasked
+            nb = Ws[l].size(0)
+            bt = new_relu_bits(M, nb, W0dev) if (tc and relu_out and _USE_BITS and nb % 32 == 0) else None
             y = linear_raw(cur, Ws[l], bs[l], M, _ACT[final_act] if last else L.ACT_RELU,
                            row_mask=rm if last else None, tc=tc_arg,
                            out_dtype=((out_dtype or torch.float32) if last else torch.bfloat16) if tc else torch.float32,
-                           adds=adds if l == 0 else None)
+                           adds=adds if l == 0 else None, bits_out=bt)
             acts.append(y)
+            bits.append(bt)
             cur = [(y, None, None, 0)]
         ctx.nl, ctx.final_act, ctx.rm, ctx.nidx, ctx.M, ctx.tc = nl, final_act, rm, nidx, M, tc
         ctx.add_nidx = add_nidx
         ctx.has_bias = [b is not None for b in bs]
+        ctx.bits = bits
         ctx.save_for_backward(*Ws, *acts, *xs)
+        if premasked:      # the consumer (segment_sum) needs the output's sign bits for its own backward
+            out_bits = bits[-1] if bits[-1] is not None else acts[-1].new_zeros(0, dtype=torch.int32)
+            ctx.mark_non_differentiable(out_bits)
+            return acts[-1], out_bits
         return acts[-1]
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *_unused):
         nl, nidx, M, tc = ctx.nl, ctx.nidx, ctx.M, ctx.tc
         tc_arg = True if tc else None
         saved = ctx.saved_tensors
@@ -468,8 +504,9 @@ class _FusedMLP(torch.autograd.Function):
                 dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc_arg)
                 grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)
             if l > 0:
-                dz = linear_raw([dz_item], W, None, M, trans_w=True, out_mask=acts[l - 1], tc=tc_arg,
-                                out_dtype=torch.bfloat16 if tc else torch.float32)
+                mb = ctx.bits[l - 1]
+                dz = linear_raw([dz_item], W, None, M, trans_w=True, out_mask=acts[l - 1] if mb is None else None,
+                                mask_bits=mb, tc=tc_arg, out_dtype=torch.bfloat16 if tc else torch.float32)
                 dz_item = (dz, None, None, 0)
             elif any(need_x):
                 # [M, K]; bf16 when every consumer of the slices is a bf16 tensor (halves the largest
@@ -582,23 +619,29 @@ def run_mlp(seq, inputs, final_act=None, row_mask=None, out_dtype=None):
 
 class _SegmentSum(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, src, nidx, relu_src):
+    def forward(ctx, src, nidx, relu_src, relu_bits):
         ctx.nidx, ctx.src_dtype = nidx, src.dtype
-        ctx.save_for_backward(src if relu_src else None)
+        use_bits = relu_src and relu_bits is not None and relu_bits.numel() > 0 and src.dtype == torch.bfloat16
+        ctx.use_bits = use_bits
+        ctx.save_for_backward(relu_bits if use_bits else (src if relu_src else None))
         return segment_sum_raw(src, nidx)
 
     @staticmethod
     def backward(ctx, dout):
         (mask,) = ctx.saved_tensors
-        g = gather_rows_raw(dout, ctx.nidx.idx, out_dtype=ctx.src_dtype, relu_mask=mask)
-        return (g if g.dtype == ctx.src_dtype else g.to(ctx.src_dtype)), None, None
+        if ctx.use_bits:
+            g = gather_rows_raw(dout, ctx.nidx.idx, out_dtype=ctx.src_dtype, relu_bits=mask)
+        else:
+            g = gather_rows_raw(dout, ctx.nidx.idx, out_dtype=ctx.src_dtype, relu_mask=mask)
+        return (g if g.dtype == ctx.src_dtype else g.to(ctx.src_dtype)), None, None, None
 
 
-def segment_sum(src, nidx, relu_src=False):
+def segment_sum(src, nidx, relu_src=False, relu_bits=None):
     """out[n] = sum of src rows whose endpoint is n (torch_scatter.scatter(reduce='add')).
     relu_src=True: `src` is the output of a ReLU layer built with premasked=True; the backward then
-    returns the gradient already multiplied by (src > 0), fused into the row gather."""
-    return _SegmentSum.apply(src, nidx, relu_src)
+    returns the gradient already multiplied by (src > 0), fused into the row gather (from the
+    layer's sign bits `relu_bits` when given, else from `src` itself)."""
+    return _SegmentSum.apply(src, nidx, relu_src, relu_bits)
 
 
 def add_n_raw(ts, out_dtype=None):

@@ -94,9 +94,9 @@ class CausalMessagePassing(nn.Module):
         for seq, side, into, p, wpost, e_in in ((self.create_future_msgs, dst, src, p_f, w_post[0], e_f),
                                                 (self.create_past_msgs, src, dst, p_p, w_post[1], e_p)):
             l0 = seq[0]
-            h = ops.fused_mlp([(e_in, None)], [l0.weight[:, D:D + E_]], [None], final_act="relu",
-                              adds=[(p, side)], out_dtype=lowp, premasked=True)         # x | e' | x0 blocks
-            s_h = ops.segment_sum(h, into, relu_src=True)                                # [N, Hm] fp32
+            h, h_bits = ops.fused_mlp([(e_in, None)], [l0.weight[:, D:D + E_]], [None], final_act="relu",
+                                      adds=[(p, side)], out_dtype=lowp, premasked=True)  # x | e' | x0 blocks
+            s_h = ops.segment_sum(h, into, relu_src=True, relu_bits=h_bits)              # [N, Hm] fp32
             agg.append(ops.fused_mlp([(s_h, None), (g.degree_block(into), None)], [wpost], [None], out_dtype=lowp))
         m_fut, m_past = agg
         # node-level tensors are bf16 too (their only consumers are bf16 tiles), which puts the

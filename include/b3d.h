@@ -38,6 +38,11 @@ enum { B3D_MASK_NONE = 0, B3D_MASK_RELU = 1, B3D_MASK_SIGMOID = 2 };
 enum { B3D_ACT_NONE = 0, B3D_ACT_RELU = 1, B3D_ACT_SIGMOID = 2 };
 enum { B3D_FLAG_ACCUMULATE = 1 };   /* out += result instead of out = result */
 enum { B3D_F32 = 0, B3D_BF16 = 1 }; /* element type of a segment / output (bf16: tensor-core entry points only) */
+/* mask_dtype only: the ReLU mask of a layer output as SIGN BITS, uint32 words [ceil(N/32)][M]
+ * (word (c / 32) * M + r holds columns 32*(c/32) .. +31 of row r, bit c % 32 set iff output > 0).
+ * Written by the forward tensor-core layers (relu_bits_out), read by the input-gradient layers and
+ * by b3d_gather_rows: 1/16 of the bytes of the bf16 activation and one coalesced word per row. */
+enum { B3D_BITS = 2 };
 
 /* One column block of a (virtually) concatenated, optionally row-gathered
  * operand: rows r = 0..M-1 read ptr[(idx ? idx[r] : r) * ld + 0..width-1].
@@ -93,7 +98,7 @@ int b3d_segment_sum(const void* src, int32_t src_dtype, int32_t ld_src, const in
  * were ReLU outputs, so the gathered gradient is zeroed where relu_mask <= 0. */
 int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
                     void* out, int32_t out_dtype, int32_t ld_out, const void* relu_mask, int32_t ld_mask,
-                    void* stream);
+                    int32_t mask_dtype /* B3D_BF16 or B3D_BITS */, void* stream);
 
 /* out[M,C] = sum_k ins[k][M,C] (n <= 8 dense fp32/bf16 inputs of equal width C % 8 == 0, each with its
  * own leading dimension; fp32 accumulation in argument order). One pass for the gradient of a tensor
@@ -144,7 +149,8 @@ int b3d_tc_pack_weights(const float* W, int32_t ldw, int32_t n_logical, int32_t 
 int b3d_linear_tc(const b3d_seg_t* segs /*host*/, int32_t nseg, const void* Wp, int32_t n_logical,
                   int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype, int64_t M,
                   int32_t act, int32_t flags, const void* out_mask, int32_t ldm, int32_t mask_dtype,
-                  const uint8_t* row_mask, const b3d_seg_t* adds /*host*/, int32_t nadd, void* stream);
+                  const uint8_t* row_mask, const b3d_seg_t* adds /*host*/, int32_t nadd,
+                  void* relu_bits_out /* optional uint32 [ceil(N/32)][M] */, void* stream);
 /* TMA-fed persistent variant of b3d_linear_tc for DENSE bf16 operands (1-2 row-major segments, no
  * gather; the leading segment's width a multiple of 64): TMA producer warp, single-thread tcgen05
  * issuer, 4 epilogue warps, weight block resident in shared memory, double-buffered TMEM
@@ -155,7 +161,8 @@ int b3d_tma_pack_weights(const float* W, int32_t ldw, int32_t n_logical, int32_t
 int b3d_linear_tma(const b3d_seg_t* segs /*host*/, int32_t nseg, const void* Wr, int32_t n_logical,
                    int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype, int64_t M,
                    int32_t act, int32_t flags, const void* out_mask, int32_t ldm, int32_t mask_dtype,
-                   const uint8_t* row_mask, const b3d_seg_t* adds /*host*/, int32_t nadd, void* stream);
+                   const uint8_t* row_mask, const b3d_seg_t* adds /*host*/, int32_t nadd,
+                   void* relu_bits_out /* optional */, void* stream);
 size_t b3d_wgrad_tc_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
 /* TMA-fed variant of b3d_wgrad_tc for DENSE bf16 dy / segments (see b3d_linear_tma). */
 size_t b3d_wgrad_tma_workspace_bytes(int64_t M, int32_t Nout, int32_t K);

@@ -199,6 +199,28 @@ def test_linear_tma_dense_bf16(M, widths, n_out):
             y3 = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, act, tc=True, out_mask=mask, adds=adds or None,
                                 out_dtype=od)
             assert y3.dtype == od and rel(y3, r3) < (1e-2 if od == torch.bfloat16 else 1e-5)
+    # ReLU sign bits: written by the forward epilogue (B3D_BITS layout), then used as the mask of an
+    # input-gradient launch; both kernels (TMA-fed and thread-staged) must agree with the bf16 mask
+    if n_out % 32 == 0:
+        for use_tma in (True, False):
+            ops._USE_TMA = use_tma
+            try:
+                bits = ops.new_relu_bits(M, n_out, DEV)
+                yb = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, L.ACT_RELU, tc=True, out_dtype=torch.bfloat16,
+                                    bits_out=bits)
+                unpacked = ((bits.t().unsqueeze(2) >> torch.arange(32, device=DEV, dtype=torch.int32)) & 1)
+                unpacked = unpacked.reshape(M, -1)[:, :n_out].bool()
+                assert torch.equal(unpacked, yb > 0)
+                # gradient w.r.t. a [M, n_out] ReLU output masked by its sign bits vs by the activation itself
+                Wd = torch.randn(96, n_out, device=DEV) * 0.1          # consumer Linear(n_out -> 96)
+                gz = torch.randn(M, 96).to(torch.bfloat16).to(DEV)
+                d1 = ops.linear_raw([(gz, None, None, 0)], Wd, None, M, trans_w=True, tc=True, mask_bits=bits,
+                                    out_dtype=torch.bfloat16)
+                d2 = ops.linear_raw([(gz, None, None, 0)], Wd, None, M, trans_w=True, tc=True, out_mask=yb,
+                                    out_dtype=torch.bfloat16)
+                assert torch.equal(d1, d2)
+            finally:
+                ops._USE_TMA = True
     # same result as the thread-staged tcgen05 kernel
     ops._USE_TMA = False
     try:
@@ -207,6 +229,28 @@ def test_linear_tma_dense_bf16(M, widths, n_out):
         ops._USE_TMA = True
     y_tma = ops.linear_raw(items, W.to(DEV), b.to(DEV), M, L.ACT_RELU, tc=True, out_dtype=torch.float32)
     assert rel(y_tma, y_tc) < 1e-6
+
+
+def test_sign_bits_with_column_blocks_past_the_last_word():
+    """Regression: N = 512 with K = 384 plans three 192-column blocks (576 > 512); the blocks past the
+    last 32-column word must neither read nor write sign bits (illegal address at full size)."""
+    torch.manual_seed(5)
+    M, n, k = 150000, 512, 384
+    h = torch.randn(M, n, device=DEV).to(torch.bfloat16)
+    bits = ops.new_relu_bits(M, n, DEV)
+    w = (h > 0).reshape(M, n // 32, 32).to(torch.int64) << torch.arange(32, device=DEV)
+    bits.copy_(w.sum(2).t().to(torch.int32))          # low 32 bits, two's complement
+    gz = torch.randn(M, k, device=DEV).to(torch.bfloat16)
+    W = torch.randn(k, n, device=DEV) * 0.1
+    d1 = ops.linear_raw([(gz, None, None, 0)], W, None, M, trans_w=True, tc=True, mask_bits=bits, out_dtype=torch.bfloat16)
+    d2 = ops.linear_raw([(gz, None, None, 0)], W, None, M, trans_w=True, tc=True, out_mask=h, out_dtype=torch.bfloat16)
+    assert torch.equal(d1, d2)
+    x = torch.randn(M, k, device=DEV).to(torch.bfloat16)
+    b2 = ops.new_relu_bits(M, n, DEV)
+    y = ops.linear_raw([(x, None, None, 0)], W.t().contiguous(), None, M, L.ACT_RELU, tc=True, out_dtype=torch.bfloat16,
+                       bits_out=b2)
+    un = ((b2.t().unsqueeze(2) >> torch.arange(32, device=DEV, dtype=torch.int32)) & 1).reshape(M, n).bool()
+    assert torch.equal(un, y > 0)
 
 
 @pytest.mark.parametrize("k,n,trans", [(288, 512, False), (512, 384, True), (288, 512, True), (320, 176, False)])
