@@ -71,10 +71,15 @@ _SIGS = {
     "b3d_gat_aggregate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b3d_gat_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b3d_row_nonzero": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "b3d_bce_partials": (C.c_int64, [C.c_int64]),
     "b3d_bce_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b3d_focal_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_float,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b3d_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int32, C.c_float,
                                                                                   C.c_void_p]),
 }

@@ -169,6 +169,67 @@ __global__ void __launch_bounds__(256) k_gat_aggregate(
   }
 }
 
+
+// ------------------------------------------------------------------ GAT backward
+// Target side (warp per target t, lane l = neighbour slot): d alpha_l = g[t] . h[nbr_l], softmax and
+// LeakyReLU backward give ds[t,l] = d(a_s[nbr_l] + a_d[t]); dad[t] = sum_l ds[t,l].
+__global__ void __launch_bounds__(256) k_gat_bwd_target(
+    const float* __restrict__ g, int ldg, const float* __restrict__ h, int ldh, int D,
+    const float* __restrict__ a_s, const float* __restrict__ a_d, const float* __restrict__ alpha,
+    const int64_t* __restrict__ nbr, int k, long long N, float slope, float* __restrict__ ds,
+    float* __restrict__ dad) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= N) return;
+  const long long nb = (lane < k) ? nbr[t * k + lane] : -1;
+  const float al = (lane < k && nb >= 0) ? alpha[t * k + lane] : 0.f;
+  float dal = 0.f;                       // lane l ends up with g[t] . h[nbr_l]
+  for (int l = 0; l < k; ++l) {
+    const long long nl = __shfl_sync(0xffffffffu, nb, l);
+    float part = 0.f;
+    if (nl >= 0)
+      for (int c = lane; c < D; c += 32) part = fmaf(__ldg(g + t * ldg + c), __ldg(h + nl * ldh + c), part);
+    part = warp_sum(part);
+    if (lane == l) dal = part;
+  }
+  const float dot = warp_sum(al * dal);  // sum_m alpha_m d alpha_m
+  float dsl = 0.f;
+  if (nb >= 0) {
+    const float pre = __ldg(a_s + nb) + __ldg(a_d + t);
+    dsl = al * (dal - dot) * (pre > 0.f ? 1.f : slope);
+  }
+  if (lane < k) ds[t * k + lane] = dsl;
+  const float tot = warp_sum(dsl);
+  if (lane == 0) dad[t] = tot;
+}
+
+// Source side (warp per node n, lanes over feature columns): the entries (t, l) that list n as a
+// neighbour come from the CSR of the flattened table grouped by source (b3d_csr_build; -1 padding is
+// mapped to the dummy node N), visited in ascending position so the sums are deterministic:
+//   dh[n] = sum alpha[t,l] g[t] + (sum ds[t,l]) att_src + dad[n] att_dst ;  das[n] = sum ds[t,l].
+__global__ void __launch_bounds__(256) k_gat_bwd_source(
+    const float* __restrict__ g, int ldg, int D, const float* __restrict__ alpha, const float* __restrict__ ds,
+    const float* __restrict__ dad, const float* __restrict__ att_src, const float* __restrict__ att_dst,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, int k, long long N,
+    float* __restrict__ dh, int lddh, float* __restrict__ das) {
+  const int lane = threadIdx.x & 31;
+  const long long n = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int beg = __ldg(rowptr + n), end = __ldg(rowptr + n + 1);
+  float s = 0.f;
+  for (int q = beg; q < end; ++q) s += __ldg(ds + __ldg(perm + q));
+  if (lane == 0) das[n] = s;
+  const float d = __ldg(dad + n);
+  for (int c = lane; c < D; c += 32) {
+    float acc = 0.f;
+    for (int q = beg; q < end; ++q) {
+      const int p = __ldg(perm + q);
+      acc = fmaf(__ldg(alpha + p), __ldg(g + (long long)(p / k) * ldg + c), acc);
+    }
+    dh[n * lddh + c] = acc + s * __ldg(att_src + c) + d * __ldg(att_dst + c);
+  }
+}
+
 }  // namespace b3d
 
 using namespace b3d;
@@ -211,5 +272,27 @@ extern "C" int b3d_gat_aggregate(const float* h, int32_t ldh, int32_t D, const f
   B3D_LAUNCH_CHECK("k_gat_scores");
   k_gat_aggregate<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(h, ldh, D, a_s, a_d, bias, nbr, k, N, slope, out, ldo, alpha_out);
   B3D_LAUNCH_CHECK("k_gat_aggregate");
+  return 0;
+}
+
+extern "C" int b3d_gat_bwd(const float* dout, int32_t ldg, const float* h, int32_t ldh, int32_t D,
+                           const float* att_src, const float* att_dst, const int64_t* nbr, int32_t k, int64_t N,
+                           float slope, const float* alpha, const float* a_s_a_d, const int32_t* rowptr_src,
+                           const int32_t* perm_src, float* dh, int32_t lddh, float* ds, float* das_dad,
+                           void* stream) {
+  if (!dout || !h || !att_src || !att_dst || !nbr || !alpha || !a_s_a_d || !rowptr_src || !perm_src || !dh || !ds ||
+      !das_dad)
+    return bad_arg("b3d_gat_bwd: null pointer");
+  if (k < 1 || k > 32) return bad_arg("b3d_gat_bwd: k must be in [1,32]");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* das = das_dad;
+  float* dad = das_dad + N;
+  k_gat_bwd_target<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(dout, ldg, h, ldh, D, a_s_a_d, a_s_a_d + N, alpha, nbr, k, N,
+                                                            slope, ds, dad);
+  B3D_LAUNCH_CHECK("k_gat_bwd_target");
+  k_gat_bwd_source<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(dout, ldg, D, alpha, ds, dad, att_src, att_dst, rowptr_src,
+                                                            perm_src, k, N, dh, lddh, das);
+  B3D_LAUNCH_CHECK("k_gat_bwd_source");
   return 0;
 }

@@ -43,6 +43,48 @@ __global__ void __launch_bounds__(BCE_THREADS) k_bce(const float* __restrict__ i
   if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
 }
 
+// Focal loss (config 5 "focal/BCE edge loss"; not in the reference): l = a_t (1 - p_t)^gamma (-log p_t),
+// p_t = p for positives and 1 - p for negatives, a_t = alpha / 1 - alpha. Same two-stage reduction.
+__global__ void __launch_bounds__(BCE_THREADS) k_focal(const float* __restrict__ in, const int64_t* __restrict__ y,
+                                                      const float* __restrict__ w, long long E, float gscale,
+                                                      int from_logits, float alpha, float gamma,
+                                                      float* __restrict__ grad, float* __restrict__ partials) {
+  __shared__ float red[BCE_THREADS];
+  float acc = 0.f;
+  const long long base = (long long)blockIdx.x * BCE_CHUNK;
+#pragma unroll
+  for (int i = 0; i < BCE_PER_THREAD; ++i) {
+    long long e = base + i * BCE_THREADS + threadIdx.x;
+    if (e < E) {
+      const float x = in[e];
+      const float p = from_logits ? 1.f / (1.f + expf(-x)) : x;
+      const bool pos = y[e] != 0;
+      const float we = w ? w[e] : 1.f;
+      const float pt = pos ? p : 1.f - p;
+      const float at = pos ? alpha : 1.f - alpha;
+      const float lg = fmaxf(logf(pt), -100.f);
+      const float om = 1.f - pt;
+      const float f = powf(om, gamma);
+      acc += we * at * f * -lg;
+      if (grad) {
+        // dl/dp_t = a_t [gamma (1-p_t)^(gamma-1) log p_t - (1-p_t)^gamma / p_t]
+        const float fm1 = gamma == 0.f ? 0.f : gamma * powf(om, gamma - 1.f);
+        float g = at * (fm1 * lg - f / fmaxf(pt, 1e-12f));
+        g = pos ? g : -g;                       // dp_t/dp
+        if (from_logits) g *= p * (1.f - p);    // dp/dx
+        grad[e] = we * g * gscale;
+      }
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = BCE_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+
 __global__ void __launch_bounds__(1024) k_bce_final(const float* __restrict__ partials, long long n, float scale,
                                                     float* __restrict__ loss) {
   __shared__ float red[1024];
@@ -87,6 +129,20 @@ extern "C" int b3d_bce_fwd_bwd(const float* input, const int64_t* y, const float
   long long nb = b3d_bce_partials(E);
   k_bce<<<(unsigned)nb, BCE_THREADS, 0, st>>>(input, y, w, E, scale / (float)E, from_logits, grad_out, partials);
   B3D_LAUNCH_CHECK("k_bce");
+  k_bce_final<<<1, 1024, 0, st>>>(partials, nb, scale / (float)E, loss_out);
+  B3D_LAUNCH_CHECK("k_bce_final");
+  return 0;
+}
+
+extern "C" int b3d_focal_fwd_bwd(const float* input, const int64_t* y, const float* w, int64_t E, float scale,
+                                 int32_t from_logits, float alpha, float gamma, float* loss_out, float* grad_out,
+                                 float* partials, void* stream) {
+  if (!input || !y || !loss_out || !partials || E <= 0 || gamma < 0.f) return bad_arg("b3d_focal_fwd_bwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long nb = b3d_bce_partials(E);
+  k_focal<<<(unsigned)nb, BCE_THREADS, 0, st>>>(input, y, w, E, scale / (float)E, from_logits, alpha, gamma, grad_out,
+                                                partials);
+  B3D_LAUNCH_CHECK("k_focal");
   k_bce_final<<<1, 1024, 0, st>>>(partials, nb, scale / (float)E, loss_out);
   B3D_LAUNCH_CHECK("k_bce_final");
   return 0;

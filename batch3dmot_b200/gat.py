@@ -48,8 +48,7 @@ class GATConv(nn.Module):
     def forward_table(self, x, nbr):
         """x [N,D], nbr int64 [N,k] (-1 padded; row t lists the sources of target t)."""
         h = ops.fused_linear([(x, None)], self.lin_src.weight)
-        return ops.gat_aggregate(h.detach(), self.att_src.detach(), self.att_dst.detach(),
-                                 self.bias.detach(), nbr, self.negative_slope)
+        return ops.gat_aggregate(h, self.att_src, self.att_dst, self.bias, nbr, self.negative_slope)
 
     def forward(self, x, edge_index):
         """PyG signature for knn_graph edge lists (row 0 source, row 1 target, grouped by target)."""

@@ -372,16 +372,65 @@ def knn_frames(x, frame_ptr, k):
     return out
 
 
-def gat_aggregate(h, att_src, att_dst, bias, nbr, slope=0.2):
+def _gat_forward(h, att_src, att_dst, bias, nbr, slope, want_alpha):
     h = _rows(h.float())
     N, D = h.shape
     out = torch.empty((N, D), dtype=torch.float32, device=h.device)
     scratch = torch.empty(2 * N, dtype=torch.float32, device=h.device)
+    alpha = torch.empty((N, nbr.size(1)), dtype=torch.float32, device=h.device) if want_alpha else None
     L.check(L.lib().b3d_gat_aggregate(L.ptr(h), h.stride(0), D, L.ptr(att_src.reshape(-1).contiguous()),
                                       L.ptr(att_dst.reshape(-1).contiguous()), L.ptr(bias), L.ptr(nbr),
-                                      nbr.size(1), N, slope, L.ptr(out), out.stride(0), None, L.ptr(scratch),
+                                      nbr.size(1), N, slope, L.ptr(out), out.stride(0), L.ptr(alpha), L.ptr(scratch),
                                       L.stream()), "b3d_gat_aggregate")
-    return out
+    return out, alpha, scratch, h
+
+
+class _GATAggregate(torch.autograd.Function):
+    """GATConv aggregation over a padded neighbour table with its backward (b3d_gat_bwd): softmax /
+    LeakyReLU / score paths per target, then a deterministic per-source reduction over the reversed
+    table (CSR built by the device radix sort, padding mapped to a dummy node)."""
+
+    @staticmethod
+    def forward(ctx, h, att_src, att_dst, bias, nbr, slope):
+        out, alpha, scratch, hf = _gat_forward(h, att_src, att_dst, bias, nbr, slope, True)
+        ctx.slope, ctx.shapes = slope, (att_src.shape, att_dst.shape, h.dtype)
+        ctx.save_for_backward(hf, att_src.reshape(-1).contiguous(), att_dst.reshape(-1).contiguous(), nbr, alpha, scratch)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, a_src, a_dst, nbr, alpha, a_s_a_d = ctx.saved_tensors
+        N, D = h.shape
+        k = nbr.size(1)
+        g = _rows(dout.float())
+        if not g.is_contiguous():
+            g = g.contiguous()
+        # reversed table: entry p = t*k + l is an edge (source nbr[t,l] or dummy N) -> target t
+        src = torch.where(nbr < 0, torch.full_like(nbr, N), nbr).reshape(-1)
+        tgt = torch.arange(N * k, device=nbr.device, dtype=torch.int64) // k
+        rev = Graph(torch.stack([src, tgt]), N + 1)
+        dh = torch.empty((N, D), dtype=torch.float32, device=h.device)
+        ds = torch.empty((N, k), dtype=torch.float32, device=h.device)
+        das_dad = torch.empty(2 * N, dtype=torch.float32, device=h.device)
+        L.check(L.lib().b3d_gat_bwd(L.ptr(g), g.stride(0), L.ptr(h), h.stride(0), D, L.ptr(a_src), L.ptr(a_dst),
+                                    L.ptr(nbr), k, N, ctx.slope, L.ptr(alpha), L.ptr(a_s_a_d), L.ptr(rev.rowptr_src),
+                                    L.ptr(rev.perm_src), L.ptr(dh), dh.stride(0), L.ptr(ds), L.ptr(das_dad),
+                                    L.stream()), "b3d_gat_bwd")
+        # d att_src = das^T h, d att_dst = dad^T h, d bias = colsum(dout): small deterministic wgrads
+        S = das_dad.view(2, N).t().contiguous()
+        datt, _ = wgrad_raw((S, None, None, 0), [(h, None, None, 0)], N, 2, D, want_bias=False, tc=False)
+        _, dbias = wgrad_raw((g, None, None, 0), [(S, None, None, 0)], N, D, 2, want_bias=True, tc=False)
+        s_shape, d_shape, h_dtype = ctx.shapes
+        return (dh.to(h_dtype), datt[0].reshape(s_shape), datt[1].reshape(d_shape),
+                dbias if ctx.has_bias else None, None, None)
+
+
+def gat_aggregate(h, att_src, att_dst, bias, nbr, slope=0.2):
+    """GATConv(heads=1, add_self_loops=False) aggregation; differentiable w.r.t. h, att_src, att_dst, bias."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (h, att_src, att_dst, bias)):
+        return _GATAggregate.apply(h, att_src, att_dst, bias, nbr, slope)
+    return _gat_forward(h, att_src, att_dst, bias, nbr, slope, False)[0]
 
 
 def adam_step(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale=1.0):
@@ -724,7 +773,7 @@ def split_cols(x, sizes):
 
 class _BCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, inp, y, w, scale, from_logits):
+    def forward(ctx, inp, y, w, scale, from_logits, focal=None):
         x = inp.reshape(-1).contiguous().float()
         E = x.numel()
         lib = L.lib()
@@ -733,8 +782,13 @@ class _BCE(torch.autograd.Function):
         part = torch.empty(int(lib.b3d_bce_partials(E)), dtype=torch.float32, device=x.device)
         yy = y.reshape(-1).to(torch.int64).contiguous()
         ww = w.reshape(-1).contiguous().float() if w is not None else None
-        L.check(lib.b3d_bce_fwd_bwd(L.ptr(x), L.ptr(yy), L.ptr(ww), E, float(scale), int(from_logits),
-                                    L.ptr(loss), L.ptr(grad), L.ptr(part), L.stream()), "b3d_bce_fwd_bwd")
+        if focal is not None:
+            L.check(lib.b3d_focal_fwd_bwd(L.ptr(x), L.ptr(yy), L.ptr(ww), E, float(scale), int(from_logits),
+                                          float(focal[0]), float(focal[1]), L.ptr(loss), L.ptr(grad), L.ptr(part),
+                                          L.stream()), "b3d_focal_fwd_bwd")
+        else:
+            L.check(lib.b3d_bce_fwd_bwd(L.ptr(x), L.ptr(yy), L.ptr(ww), E, float(scale), int(from_logits),
+                                        L.ptr(loss), L.ptr(grad), L.ptr(part), L.stream()), "b3d_bce_fwd_bwd")
         ctx.save_for_backward(grad)
         ctx.shape = inp.shape
         return loss.reshape(())
@@ -742,9 +796,15 @@ class _BCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dl):
         (grad,) = ctx.saved_tensors
-        return (grad * dl).reshape(ctx.shape), None, None, None, None
+        return (grad * dl).reshape(ctx.shape), None, None, None, None, None
 
 
 def bce_loss(out, y, weight=None, batch_size=1, from_logits=False):
     """BCELoss(weight)(out, y) / batch_size (train.py:136-141); from_logits for PoseGNN (C11)."""
     return _BCE.apply(out, y, weight, 1.0 / batch_size, from_logits)
+
+
+def focal_loss(out, y, weight=None, batch_size=1, alpha=0.25, gamma=2.0, from_logits=False):
+    """Focal edge loss (BASELINE config 5 "focal/BCE"; not part of the reference, see b3d.h):
+    mean_e w_e * alpha_t (1 - p_t)^gamma (-log p_t) / batch_size."""
+    return _BCE.apply(out, y, weight, 1.0 / batch_size, from_logits, (alpha, gamma))

@@ -67,7 +67,7 @@ class Trainer:
     (Adam lr 1e-4, weight_decay 1e-4, betas .9/.999; loss / batch_size)."""
 
     def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, batch_size=2,
-                 from_logits=False):
+                 from_logits=False, loss="bce", focal_alpha=0.25, focal_gamma=2.0):
         from . import ops
         self.ops = ops
         self.model = model
@@ -76,6 +76,8 @@ class Trainer:
         self.v = torch.zeros_like(self.fp.flat)
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.batch_size, self.from_logits = batch_size, from_logits
+        assert loss in ("bce", "focal")      # "focal": BASELINE config 5's alternative edge loss (not in the reference)
+        self.loss, self.focal = loss, (focal_alpha, focal_gamma)
         self.step_no = 0
 
     def step(self, data, global_edges=None, **fwd_kwargs):
@@ -85,8 +87,12 @@ class Trainer:
         ops = self.ops
         self.fp.zero_grad()
         out, _ = self.model(data, **fwd_kwargs)
-        loss = ops.bce_loss(out, data.y, getattr(data, "edge_weights", None), batch_size=self.batch_size,
-                            from_logits=self.from_logits)
+        if self.loss == "focal":
+            loss = ops.focal_loss(out, data.y, getattr(data, "edge_weights", None), batch_size=self.batch_size,
+                                  alpha=self.focal[0], gamma=self.focal[1], from_logits=self.from_logits)
+        else:
+            loss = ops.bce_loss(out, data.y, getattr(data, "edge_weights", None), batch_size=self.batch_size,
+                                from_logits=self.from_logits)
         if global_edges is not None:
             loss = loss * (out.size(0) / float(global_edges))
         loss.backward()

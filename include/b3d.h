@@ -220,6 +220,19 @@ int b3d_gat_aggregate(const float* h, int32_t ldh, int32_t D, const float* att_s
                       int64_t N, float slope, float* out, int32_t ldo, float* alpha_out,
                       float* scratch, void* stream);
 
+/* Backward of b3d_gat_aggregate (the intended k-NN update trains through GATConv; the reference's own
+ * call discards the result, pose_gnn.py:80). Inputs: dout [N,D]; h, att_src, att_dst, nbr, slope as in the
+ * forward; alpha [N,k] and a_s_a_d [2N] (the forward's alpha_out and scratch); rowptr_src [N+2] / perm_src
+ * [N*k]: CSR of the flattened neighbour table grouped by SOURCE node over N+1 nodes, padding (-1) mapped
+ * to the dummy node N (b3d_csr_build on edge_index = [nbr or N ; position / k]).
+ * Outputs: dh [N,D] = d loss / d h including the att_src / att_dst score paths; ds [N,k] scratch;
+ * das_dad [2N]: d loss / d a_s, d a_d, from which d att_src = das^T h and d att_dst = dad^T h
+ * (b3d_wgrad). d bias = column sum of dout. Deterministic: per-source sums run in ascending position. */
+int b3d_gat_bwd(const float* dout, int32_t ldg, const float* h, int32_t ldh, int32_t D,
+                const float* att_src, const float* att_dst, const int64_t* nbr, int32_t k, int64_t N,
+                float slope, const float* alpha, const float* a_s_a_d, const int32_t* rowptr_src,
+                const int32_t* perm_src, float* dh, int32_t lddh, float* ds, float* das_dad, void* stream);
+
 /* ---- multimodal front end ---------------------------------------------------
  * mask[n] = (sum(feats[n, 0:row_len]) != 0): modality-present predicate
  * (clr_att_gnn.py:107-121, 2N host syncs in the reference). */
@@ -234,6 +247,14 @@ int64_t b3d_bce_partials(int64_t E);
 int b3d_bce_fwd_bwd(const float* input, const int64_t* y, const float* w, int64_t E, float scale,
                     int32_t from_logits, float* loss_out, float* grad_out, float* partials,
                     void* stream);
+
+/* Focal edge loss named by the multimodal training config ("focal/BCE edge loss"); the reference
+ * itself only has BCELoss (train.py:111), so this follows the published definition (Lin et al.):
+ * loss = scale * mean_e w_e * a_t (1 - p_t)^gamma * (-log p_t), p_t = p_e or 1 - p_e, a_t = alpha or
+ * 1 - alpha. Same buffers and two-stage deterministic reduction as b3d_bce_fwd_bwd. */
+int b3d_focal_fwd_bwd(const float* input, const int64_t* y, const float* w, int64_t E, float scale,
+                      int32_t from_logits, float alpha, float gamma, float* loss_out, float* grad_out,
+                      float* partials, void* stream);
 
 /* torch.optim.Adam step on flat buffers (train.py:106-109,160): L2 weight decay,
  * bias correction by `step` (1-based). grad_scale multiplies g first (1/world for DP). */

@@ -217,6 +217,20 @@ def bce_logits_loss(logit, y, weight=None, batch_size=1):
     return F.binary_cross_entropy_with_logits(logit.view(-1), y.view(-1).float(), weight=weight) / batch_size
 
 
+def focal_loss(inp, y, weight=None, batch_size=1, alpha=0.25, gamma=2.0, from_logits=False):
+    """Focal edge loss named by BASELINE.json's config 5 ("focal/BCE edge loss"). NOT in the reference
+    (train.py only has BCELoss): parity unpinned; this states the published definition (Lin et al. 2017,
+    torchvision.ops.sigmoid_focal_loss): mean_e w_e * alpha_t * (1 - p_t)^gamma * (-log p_t) / batch_size."""
+    p = torch.sigmoid(inp.view(-1)) if from_logits else inp.view(-1)
+    t = y.view(-1).float()
+    p_t = p * t + (1 - p) * (1 - t)
+    a_t = alpha * t + (1 - alpha) * (1 - t)
+    l = a_t * (1 - p_t) ** gamma * -torch.log(p_t).clamp_min(-100.0)
+    if weight is not None:
+        l = l * weight
+    return l.mean() / batch_size
+
+
 def csr_build(index, n):
     """Stable argsort + bincount/cumsum: the spec for the device radix sort."""
     perm = torch.argsort(index, stable=True)

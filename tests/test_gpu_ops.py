@@ -179,6 +179,43 @@ def test_knn_golden_and_gat():
     assert rel_err(out, g["gat_out"]) < 1e-5
 
 
+@pytest.mark.parametrize("N,D,k,frame", [(600, 48, 8, 50), (900, 96, 20, 30), (40, 48, 20, 7)])
+def test_gat_backward_matches_oracle_autograd(N, D, k, frame):
+    """b3d_gat_bwd (softmax / LeakyReLU / score paths + deterministic reversed-table reduction) against
+    torch autograd through the oracle's GATConv restatement; frames smaller than k+1 exercise the -1 padding."""
+    torch.manual_seed(N + k)
+    x = torch.randn(N, D)
+    ptr = torch.arange(0, N + 1, frame)
+    if ptr[-1] != N:
+        ptr = torch.cat([ptr, torch.tensor([N])])
+    idx = R.knn_frames(x, ptr, k)
+    params = {"knn_conv.lin_src.weight": (torch.randn(D, D) * 0.2).requires_grad_(True),
+              "knn_conv.att_src": (torch.randn(1, 1, D) * 0.3).requires_grad_(True),
+              "knn_conv.att_dst": (torch.randn(1, 1, D) * 0.3).requires_grad_(True),
+              "knn_conv.bias": torch.randn(D).requires_grad_(True)}
+    xr = x.clone().requires_grad_(True)
+    out_ref = R.gat_conv(params, xr, R.knn_to_edge_index(idx))
+    gout = torch.randn(N, D)
+    out_ref.backward(gout)
+    from batch3dmot_b200.gat import GATConv
+    conv = GATConv(D, D).to(DEV)
+    with torch.no_grad():
+        conv.lin_src.weight.copy_(params["knn_conv.lin_src.weight"]); conv.att_src.copy_(params["knn_conv.att_src"])
+        conv.att_dst.copy_(params["knn_conv.att_dst"]); conv.bias.copy_(params["knn_conv.bias"])
+    xd = x.to(DEV).requires_grad_(True)
+    out = conv.forward_table(xd, idx.to(DEV))
+    assert rel_err(out, out_ref) < 1e-5
+    out.backward(gout.to(DEV))
+    assert rel_err(xd.grad, xr.grad) < 1e-4
+    assert rel_err(conv.lin_src.weight.grad, params["knn_conv.lin_src.weight"].grad) < 1e-4
+    assert rel_err(conv.att_src.grad, params["knn_conv.att_src"].grad) < 1e-4
+    assert rel_err(conv.att_dst.grad, params["knn_conv.att_dst"].grad) < 1e-4
+    assert rel_err(conv.bias.grad, params["knn_conv.bias"].grad) < 1e-4
+    out2 = conv.forward_table(xd, idx.to(DEV)); xd.grad = None; out2.backward(gout.to(DEV))
+    g1 = xd.grad.clone(); out3 = conv.forward_table(xd, idx.to(DEV)); xd.grad = None; out3.backward(gout.to(DEV))
+    assert torch.equal(g1, xd.grad), "the backward must be deterministic"
+
+
 @pytest.mark.parametrize("N,frame,D,k,skewed", [(2000, 250, 48, 8, False), (3000, 250, 96, 16, False),
                                                 (2500, 100, 48, 20, True), (600, 7, 96, 20, False),
                                                 (1500, 300, 19, 32, False)])
@@ -233,6 +270,29 @@ def test_bce(from_logits):
     loss.backward()
     assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
     assert rel_err(ic.grad, inp.grad) < 1e-5
+
+
+@pytest.mark.parametrize("from_logits,gamma,alpha", [(False, 2.0, 0.25), (True, 2.0, 0.25), (False, 0.0, 0.5), (True, 1.5, 0.75)])
+def test_focal_loss(from_logits, gamma, alpha):
+    """Focal loss (not in the reference: published definition restated in oracle.ref_restated.focal_loss);
+    gamma = 0, alpha = 0.5 must reduce to half the BCE."""
+    torch.manual_seed(4)
+    E = 10007
+    z = torch.randn(E).double() * 3
+    y = (torch.rand(E) < 0.1).long()
+    w = (torch.rand(E) + 0.5).double()
+    # the reference sees the SAME fp32-rounded inputs (1 - p loses digits for p near 1 otherwise)
+    inp = (z if from_logits else torch.sigmoid(z)).float().double().requires_grad_(True)
+    ref = R.focal_loss(inp, y, w, batch_size=2, alpha=alpha, gamma=gamma, from_logits=from_logits)
+    ref.backward()
+    ic = inp.detach().float().to(DEV).requires_grad_(True)
+    loss = ops.focal_loss(ic, y.to(DEV), w.float().to(DEV), batch_size=2, alpha=alpha, gamma=gamma, from_logits=from_logits)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) < 2e-5 * abs(ref.item())
+    assert rel_err(ic.grad, inp.grad) < 2e-5
+    if gamma == 0.0:
+        bce = R.bce_loss(inp.detach().float(), y, w.float(), batch_size=2)
+        assert abs(loss.item() - 0.5 * bce.item()) < 2e-5 * abs(bce.item())
 
 
 def test_adam_matches_torch():
