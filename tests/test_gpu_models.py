@@ -133,6 +133,29 @@ def test_pose_gnn_knn_update_mode():
     assert rel(out, ref) < 1e-3    # k-NN near-ties after 6 chained fp32 updates can flip neighbours
 
 
+def test_pose_gnn_knn_update_mode_trains_through_gat():
+    """With apply_knn_update=True the k-NN attention conv is ON the differentiable path: gradients of every
+    parameter, knn_conv.* included, against torch autograd through the oracle (depth 2 keeps the chained
+    fp32 updates far from k-NN near-ties)."""
+    import functools
+    data = synth.add_labels(synth.scene_graph(seed=9, T=6, nodes_per_frame=30, k=10), 9)
+    torch.manual_seed(9)
+    m = PoseGNN(gnn_depth=2, apply_knn_update=True)
+    with torch.no_grad():
+        m.knn_conv.bias.normal_()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    fwd = functools.partial(R.pose_gnn_forward, depth=2, apply_knn_update=True)
+    out_ref, _, loss_ref, gref = oracle_grads(fwd, lambda o: R.bce_logits_loss(o, data.y, data.edge_weights), sd, data)
+    m = m.to(DEV)
+    d = to_dev(data)
+    out, _ = m(d)
+    assert rel(out, out_ref) < 1e-3
+    loss = ops.bce_loss(out, d.y, d.edge_weights, from_logits=True)
+    loss.backward()
+    assert all(p.grad is not None for k, p in m.named_parameters() if k.startswith("knn_conv"))
+    check_grads(m, gref, tol=5e-3, skip_prefix=("never-skip",))
+
+
 # ------------------------------------------------------------------ multimodal GNN
 def _mm_inputs(d):
     return dict(x_img=d.x_img, pointnet_out=d.pointnet_out, radarnet_out=d.radarnet_out,
