@@ -282,7 +282,7 @@ def main():
         ach = Er * (512 + 384) * 2 / t / 1e9
         roof = {"kernel": "k_linear_tma<relu> (TMA-fed tcgen05 bf16; att_edge_encoder layer 2, [E,512]x[512,384])", "bound": "hbm",
                 "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": 849_273_088,   # dram read+write bytes per launch, ncu --set full, same shape
+                "traffic": 848_617_984,   # dram read+write bytes per launch (502,058,240 + 346,559,744), ncu --set full, same shape
                 "traffic_source": "profiles/r1_roofline_kernel.md (algorithmic bytes: E*(512+384)*2 = 877,743,104)",
                 "peak_source": src + " HBM copy bandwidth (burst); kernel timed alone with CUDA events",
                 "rows": Er, "us_per_launch": t * 1e6,
