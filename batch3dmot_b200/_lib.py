@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libb3d.so")
 MASK_NONE, MASK_RELU, MASK_SIGMOID = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 FLAG_ACCUMULATE = 1
+FLAG_OUT_BF16 = 2
 F32, BF16, BITS = 0, 1, 2
 MAX_SEGS = 8
 
@@ -30,7 +31,7 @@ _SIGS = {
     "b3d_segment_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_gather_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
-                                  C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+                                  C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_add_n": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b3d_linear": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                              C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

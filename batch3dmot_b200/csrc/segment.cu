@@ -144,7 +144,8 @@ using namespace b3d;
 // bf16 rows, fp32 accumulation: warp per node, 8 columns (16 B) per lane per pass.
 __global__ void __launch_bounds__(SEG_WARPS * 32) k_segment_sum_bf16(
     const __nv_bfloat16* __restrict__ src, int ld, const int32_t* __restrict__ perm,
-    const int32_t* __restrict__ rowptr, long long N, int C, float* __restrict__ out, int ldo, int accumulate) {
+    const int32_t* __restrict__ rowptr, long long N, int C, float* __restrict__ out, int ldo, int accumulate,
+    int out_bf16) {
   const int lane = threadIdx.x & 31;
   const long long node = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
   if (node >= N) return;
@@ -161,9 +162,17 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) k_segment_sum_bf16(
         acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
       }
     }
-    float* o = out + node * ldo + c;
+    if (out_bf16) {   // the consumer is a bf16 tensor-core tile: round once here instead of in its staging
+      uint4 q;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = accumulate ? o[j] + acc[j] : acc[j];
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + node * ldo + c) = q;
+    } else {
+      float* o = out + node * ldo + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = accumulate ? o[j] + acc[j] : acc[j];
+    }
   }
 }
 
@@ -175,12 +184,16 @@ extern "C" int b3d_segment_sum(const void* src_v, int32_t src_dtype, int32_t ld_
   if (src_dtype == B3D_BF16) {
     if ((C & 7) || (ld_src & 7) || (reinterpret_cast<uintptr_t>(src_v) & 15))
       return bad_arg("b3d_segment_sum: bf16 rows need C % 8 == 0 and 16-byte alignment");
+    const int obf = (flags & B3D_FLAG_OUT_BF16) ? 1 : 0;
+    if (obf && ((flags & B3D_FLAG_ACCUMULATE) || (ld_out & 7) || (reinterpret_cast<uintptr_t>(out) & 15)))
+      return bad_arg("b3d_segment_sum: bf16 output needs ld % 8 == 0, 16-byte alignment, no accumulate");
     k_segment_sum_bf16<<<(unsigned)ceil_div(N, SEG_WARPS), SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(src_v), ld_src, perm, rowptr, N, C, out, ld_out,
-        (flags & B3D_FLAG_ACCUMULATE) ? 1 : 0);
+        (flags & B3D_FLAG_ACCUMULATE) ? 1 : 0, obf);
     B3D_LAUNCH_CHECK("k_segment_sum_bf16");
     return 0;
   }
+  if (flags & B3D_FLAG_OUT_BF16) return bad_arg("b3d_segment_sum: bf16 output needs a bf16 source");
   const float* src = reinterpret_cast<const float*>(src_v);
   bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
   unsigned grid = (unsigned)ceil_div(N, SEG_WARPS);
@@ -195,18 +208,23 @@ extern "C" int b3d_segment_sum(const void* src_v, int32_t src_dtype, int32_t ld_
 __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
     const float* __restrict__ src, int ld, const int32_t* __restrict__ idx, long long M, int C,
     __nv_bfloat16* __restrict__ out, int ldo, const __nv_bfloat16* __restrict__ relu_mask, int ldm,
-    const uint32_t* __restrict__ relu_bits) {
+    const uint32_t* __restrict__ relu_bits, int src_bf16) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
   if (r >= M) return;
   const long long g = __ldg(idx + r);
   for (int c = lane * 8; c < C; c += 256) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src + g * ld + c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(src + g * ld + c) + 1);
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
-    uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                         *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    uint4 v;
+    if (src_bf16) {   // already rounded by the producing input-gradient tile: a pure 16-byte copy
+      v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + g * ld + c));
+    } else {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + g * ld + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + g * ld + c) + 1);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+      v = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                     *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    }
     if (relu_mask) {   // gradient of a ReLU output: keep it where the output was > 0 (bf16 > 0 <=> int16 bits > 0)
       const uint4 m = __ldg(reinterpret_cast<const uint4*>(relu_mask + r * ldm + c));
       uint32_t* w = reinterpret_cast<uint32_t*>(&v);
@@ -232,21 +250,21 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
 
 extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
                                void* out_v, int32_t out_dtype, int32_t ld_out, const void* relu_mask,
-                               int32_t ld_mask, int32_t mask_dtype, void* stream) {
+                               int32_t ld_mask, int32_t mask_dtype, int32_t src_dtype, void* stream) {
   if (M == 0) return 0;
   if (!src || !idx || !out_v || C <= 0 || M < 0) return bad_arg("b3d_gather_rows");
   if (out_dtype == B3D_BF16) {
-    if ((C & 7) || (ld_src & 3) || (ld_out & 7) || !al16(src) || !al16(out_v))
+    if ((C & 7) || (ld_src & (src_dtype == B3D_BF16 ? 7 : 3)) || (ld_out & 7) || !al16(src) || !al16(out_v))
       return bad_arg("b3d_gather_rows: bf16 output needs C % 8 == 0 and 16-byte aligned rows");
     if (relu_mask && ((ld_mask & 7) || !al16(relu_mask))) return bad_arg("b3d_gather_rows: relu_mask alignment");
     k_gather_rows_bf16<<<(unsigned)ceil_div(M, SEG_WARPS), SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(
         src, ld_src, idx, M, C, reinterpret_cast<__nv_bfloat16*>(out_v), ld_out,
         mask_dtype == B3D_BITS ? nullptr : reinterpret_cast<const __nv_bfloat16*>(relu_mask), ld_mask,
-        mask_dtype == B3D_BITS ? reinterpret_cast<const uint32_t*>(relu_mask) : nullptr);
+        mask_dtype == B3D_BITS ? reinterpret_cast<const uint32_t*>(relu_mask) : nullptr, src_dtype == B3D_BF16);
     B3D_LAUNCH_CHECK("k_gather_rows_bf16");
     return 0;
   }
-  if (relu_mask) return bad_arg("b3d_gather_rows: relu_mask needs bf16 output");
+  if (relu_mask || src_dtype == B3D_BF16) return bad_arg("b3d_gather_rows: relu_mask / bf16 source need bf16 output");
   float* out = reinterpret_cast<float*>(out_v);
   bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
   unsigned grid = (unsigned)ceil_div(M, SEG_WARPS);

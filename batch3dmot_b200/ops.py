@@ -82,14 +82,17 @@ class Graph:
         self.by_src = NodeIndex(self.src32, self.rowptr_src, self.perm_src, N)
         self._deg = {}
 
-    def degree_block(self, nidx):
-        """fp32 [N,8]: column 0 = number of edges whose endpoint is the node, columns 1-7 zero (an
-        8-wide block so it can be a segment of a tensor-core layer input)."""
-        key = id(nidx)
+    def degree_block(self, nidx, dtype=torch.float32):
+        """[N,8]: the number of edges whose endpoint is the node, split as column 0 = deg % 256 and
+        column 1 = deg // 256 (both exact in bf16; the matching weight columns are b and 256 b), columns
+        2-7 zero: an 8-wide block so it can be a segment of a tensor-core layer input."""
+        key = (id(nidx), dtype)
         if key not in self._deg:
+            deg = nidx.rowptr[1:] - nidx.rowptr[:-1]
             d = torch.zeros((self.N, 8), dtype=torch.float32, device=nidx.rowptr.device)
-            d[:, 0] = (nidx.rowptr[1:] - nidx.rowptr[:-1]).to(torch.float32)
-            self._deg[key] = d
+            d[:, 0] = (deg % 256).to(torch.float32)
+            d[:, 1] = (deg // 256).to(torch.float32)
+            self._deg[key] = d.to(dtype)
         return self._deg[key]
 
 
@@ -313,23 +316,25 @@ def _wgrad_raw_impl(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=Fa
     return dW, db
 
 
-def segment_sum_raw(src, nidx, out=None, accumulate=False):
+def segment_sum_raw(src, nidx, out=None, accumulate=False, out_dtype=torch.float32):
     src = _rows(src)
     C_ = src.size(1)
     if src.dtype == torch.bfloat16 and (C_ % 8 or not _al16(src)):
         src = src.float()
+    if src.dtype != torch.bfloat16 or accumulate:
+        out_dtype = torch.float32          # bf16 sums are written by the bf16-source kernel only
     if out is None:
-        out = torch.empty((nidx.n, C_), dtype=torch.float32, device=src.device)
+        out = torch.empty((nidx.n, C_), dtype=out_dtype, device=src.device)
     perm = None if nidx.sorted else nidx.perm
+    flags = (L.FLAG_ACCUMULATE if accumulate else 0) | (L.FLAG_OUT_BF16 if out.dtype == torch.bfloat16 else 0)
     L.check(L.lib().b3d_segment_sum(L.ptr(src), _DT[src.dtype], src.stride(0), L.ptr(perm), L.ptr(nidx.rowptr), nidx.n, C_,
-                                    L.ptr(out), out.stride(0), L.FLAG_ACCUMULATE if accumulate else 0,
-                                    L.stream()), "b3d_segment_sum")
+                                    L.ptr(out), out.stride(0), flags, L.stream()), "b3d_segment_sum")
     return out
 
 
 def gather_rows_raw(src, idx32, out_dtype=torch.float32, relu_mask=None, relu_bits=None):
     src = _rows(src)
-    if src.dtype != torch.float32:
+    if src.dtype == torch.bfloat16 and not (out_dtype == torch.bfloat16 and src.size(1) % 8 == 0 and _al16(src)):
         src = src.float()
     M = idx32.numel()
     if out_dtype == torch.bfloat16 and (src.size(1) % 8 or not _al16(src)):
@@ -339,12 +344,14 @@ def gather_rows_raw(src, idx32, out_dtype=torch.float32, relu_mask=None, relu_bi
                                relu_mask.dtype == torch.bfloat16 and _al16(relu_mask)) else None
     if relu_bits is not None and out_dtype == torch.bfloat16:      # sign bits: 1/16 of the mask bytes
         L.check(L.lib().b3d_gather_rows(L.ptr(src), src.stride(0), L.ptr(idx32), M, src.size(1), L.ptr(out),
-                                        _DT[out_dtype], out.stride(0), L.ptr(relu_bits), 0, L.BITS, L.stream()),
+                                        _DT[out_dtype], out.stride(0), L.ptr(relu_bits), 0, L.BITS, _DT[src.dtype],
+                                        L.stream()),
                 "b3d_gather_rows")
         return out
     L.check(L.lib().b3d_gather_rows(L.ptr(src), src.stride(0), L.ptr(idx32), M, src.size(1), L.ptr(out),
                                     _DT[out_dtype], out.stride(0), L.ptr(fused_mask),
-                                    fused_mask.stride(0) if fused_mask is not None else 0, L.BF16, L.stream()),
+                                    fused_mask.stride(0) if fused_mask is not None else 0, L.BF16, _DT[src.dtype],
+                                    L.stream()),
             "b3d_gather_rows")
     if relu_mask is not None and fused_mask is None:
         out = out * (relu_mask > 0)
@@ -668,12 +675,12 @@ def run_mlp(seq, inputs, final_act=None, row_mask=None, out_dtype=None):
 
 class _SegmentSum(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, src, nidx, relu_src, relu_bits):
+    def forward(ctx, src, nidx, relu_src, relu_bits, out_dtype):
         ctx.nidx, ctx.src_dtype = nidx, src.dtype
         use_bits = relu_src and relu_bits is not None and relu_bits.numel() > 0 and src.dtype == torch.bfloat16
         ctx.use_bits = use_bits
         ctx.save_for_backward(relu_bits if use_bits else (src if relu_src else None))
-        return segment_sum_raw(src, nidx)
+        return segment_sum_raw(src, nidx, out_dtype=out_dtype or torch.float32)
 
     @staticmethod
     def backward(ctx, dout):
@@ -682,15 +689,15 @@ class _SegmentSum(torch.autograd.Function):
             g = gather_rows_raw(dout, ctx.nidx.idx, out_dtype=ctx.src_dtype, relu_bits=mask)
         else:
             g = gather_rows_raw(dout, ctx.nidx.idx, out_dtype=ctx.src_dtype, relu_mask=mask)
-        return (g if g.dtype == ctx.src_dtype else g.to(ctx.src_dtype)), None, None, None
+        return (g if g.dtype == ctx.src_dtype else g.to(ctx.src_dtype)), None, None, None, None
 
 
-def segment_sum(src, nidx, relu_src=False, relu_bits=None):
+def segment_sum(src, nidx, relu_src=False, relu_bits=None, out_dtype=None):
     """out[n] = sum of src rows whose endpoint is n (torch_scatter.scatter(reduce='add')).
     relu_src=True: `src` is the output of a ReLU layer built with premasked=True; the backward then
     returns the gradient already multiplied by (src > 0), fused into the row gather (from the
     layer's sign bits `relu_bits` when given, else from `src` itself)."""
-    return _SegmentSum.apply(src, nidx, relu_src, relu_bits)
+    return _SegmentSum.apply(src, nidx, relu_src, relu_bits, out_dtype)
 
 
 def add_n_raw(ts, out_dtype=None):

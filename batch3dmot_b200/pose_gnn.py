@@ -54,11 +54,13 @@ class CausalMessagePassing(nn.Module):
         p_inv = ops.fused_mlp([(x0, None)], [w_inv], [None], out_dtype=torch.bfloat16)  # [N, 2*Hm]
         inv_all = torch.cat([p_inv.new_zeros(p_inv.size(0), 2 * h1), p_inv], 1)         # [N, 2*H1 + 2*Hm]
         # last (linear) layer of the message MLPs, applied per node AFTER aggregation:
-        # sum_e (W2 h_e + b2) = W2 (sum_e h_e) + deg * b2  -> weight [W2 | b2 | 0 x 7] against [S | deg | 0 x 7]
+        # sum_e (W2 h_e + b2) = W2 (sum_e h_e) + deg * b2  -> weight [W2 | b2 | 256 b2 | 0 x 6] against
+        # [S | deg % 256 | deg // 256 | 0 x 6] (the split keeps the degree exact in bf16)
         w_post = []
         for seq in (self.create_future_msgs, self.create_past_msgs):
             l1 = seq[2]
-            w_post.append(torch.cat([l1.weight, l1.bias[:, None], l1.weight.new_zeros(l1.out_features, 7)], 1))
+            w_post.append(torch.cat([l1.weight, l1.bias[:, None], 256.0 * l1.bias[:, None],
+                                     l1.weight.new_zeros(l1.out_features, 6)], 1))
         return w_cat, b_cat, inv_all, (h1, hm), w_post
 
     def forward_preprojected(self, x, g, e, x0, att=None, inv=None):
@@ -96,8 +98,8 @@ class CausalMessagePassing(nn.Module):
             l0 = seq[0]
             h, h_bits = ops.fused_mlp([(e_in, None)], [l0.weight[:, D:D + E_]], [None], final_act="relu",
                                       adds=[(p, side)], out_dtype=lowp, premasked=True)  # x | e' | x0 blocks
-            s_h = ops.segment_sum(h, into, relu_src=True, relu_bits=h_bits)              # [N, Hm] fp32
-            agg.append(ops.fused_mlp([(s_h, None), (g.degree_block(into), None)], [wpost], [None], out_dtype=lowp))
+            s_h = ops.segment_sum(h, into, relu_src=True, relu_bits=h_bits, out_dtype=lowp)   # [N, Hm]
+            agg.append(ops.fused_mlp([(s_h, None), (g.degree_block(into, lowp), None)], [wpost], [None], out_dtype=lowp))
         m_fut, m_past = agg
         # node-level tensors are bf16 too (their only consumers are bf16 tiles), which puts the
         # node-level GEMMs on the TMA-fed kernels as well

@@ -36,7 +36,8 @@ extern "C" {
 /* Operand modifiers for b3d_seg_t.mask_mode / epilogue activations. */
 enum { B3D_MASK_NONE = 0, B3D_MASK_RELU = 1, B3D_MASK_SIGMOID = 2 };
 enum { B3D_ACT_NONE = 0, B3D_ACT_RELU = 1, B3D_ACT_SIGMOID = 2 };
-enum { B3D_FLAG_ACCUMULATE = 1 };   /* out += result instead of out = result */
+enum { B3D_FLAG_ACCUMULATE = 1,     /* out += result instead of out = result */
+       B3D_FLAG_OUT_BF16 = 2 };     /* b3d_segment_sum: `out` is really __nv_bfloat16* (bf16 source, no accumulate) */
 enum { B3D_F32 = 0, B3D_BF16 = 1 }; /* element type of a segment / output (bf16: tensor-core entry points only) */
 /* mask_dtype only: the ReLU mask of a layer output as SIGN BITS, uint32 words [ceil(N/32)][M]
  * (word (c / 32) * M + r holds columns 32*(c/32) .. +31 of row r, bit c % 32 set iff output > 0).
@@ -98,7 +99,8 @@ int b3d_segment_sum(const void* src, int32_t src_dtype, int32_t ld_src, const in
  * were ReLU outputs, so the gathered gradient is zeroed where relu_mask <= 0. */
 int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
                     void* out, int32_t out_dtype, int32_t ld_out, const void* relu_mask, int32_t ld_mask,
-                    int32_t mask_dtype /* B3D_BF16 or B3D_BITS */, void* stream);
+                    int32_t mask_dtype /* B3D_BF16 or B3D_BITS */, int32_t src_dtype /* B3D_F32, or B3D_BF16
+                    (src is really __nv_bfloat16*, ld in elements; bf16 output only) */, void* stream);
 
 /* out[M,C] = sum_k ins[k][M,C] (n <= 8 dense fp32/bf16 inputs of equal width C % 8 == 0, each with its
  * own leading dimension; fp32 accumulation in argument order). One pass for the gradient of a tensor
