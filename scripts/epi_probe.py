@@ -22,6 +22,19 @@ cases = {
     "dgrad 128->256 + mask": lambda: ops.linear_raw([(x128, None, None, 0)], W, None, E, trans_w=True, out_mask=m256, tc=True, out_dtype=bf),
     "fwd 64->192 + gathered addend + relu": lambda: ops.linear_raw([(x64, None, None, 0)], Wm, None, E, L.ACT_RELU, tc=True, out_dtype=bf, adds=[(p, idx)]),
 }
+# the model's edge_update first layer: [e | att] (64 | 64) -> 256, two gathered addends (p_i[dst] streaming,
+# p_j[src] local scatter), ReLU, sign bits out
+W2 = torch.randn(256, 128, device=dev) * 0.05
+pi, pj = torch.randn(N, 256, device=dev).to(bf), torch.randn(N, 256, device=dev).to(bf)
+src_idx = (idx - torch.randint(50, 250, (E,), device=dev, dtype=torch.int32)).clamp_(0, N - 1)
+bits = ops.new_relu_bits(E, 256, dev)
+x64b = torch.randn(E, 64, device=dev).to(bf)
+cases["fwd [64|64]->256 + 2 gathered addends + relu + bits"] = lambda: ops.linear_raw(
+    [(x64, None, None, 0), (x64b, None, None, 0)], W2, None, E, L.ACT_RELU, tc=True, out_dtype=bf,
+    adds=[(pi, idx), (pj, src_idx)], bits_out=bits)
+only = sys.argv[2] if len(sys.argv) > 2 else None
+if only:
+    cases = {k: v for k, v in cases.items() if only in k}
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 for name, fn in cases.items():
     fn(); torch.cuda.synchronize()
