@@ -30,6 +30,11 @@ struct Chain {
   static constexpr int B0 = W3 + D4 * D3, B1 = B0 + D1, B2 = B1 + D2, B3 = B2 + D3;
   static constexpr int NPARAM = B3 + D4;
   static constexpr int NPAD = (NPARAM + 3) & ~3;
+  // second, TRANSPOSED copy of the weights in shared memory (Wt[k][j], row length padded to 4) for the
+  // forward product: one LDS.128 then feeds 4 INDEPENDENT accumulators (4 outputs j..j+3 of one input k)
+  static constexpr int P1 = (D1 + 3) & ~3, P2 = (D2 + 3) & ~3, P3 = (D3 + 3) & ~3, P4 = (D4 + 3) & ~3;
+  static constexpr int T0 = NPAD, T1 = T0 + D0 * P1, T2 = T1 + D1 * P2, T3 = T2 + D2 * P3;
+  static constexpr int NSMEM = T3 + D3 * P4;
   static constexpr int STAGE = cmax(cmax(D0 + D1, D1 + D2), cmax(D2 + D3, D3 + D4));
   static_assert(D0 % 4 == 0 && D1 % 4 == 0 && D2 % 4 == 0 && (D4 == 0 || D3 % 4 == 0), "K widths must be multiples of 4");
 };
@@ -109,23 +114,30 @@ __device__ __forceinline__ void nm_store_row(void* base, int dtype, long long ro
 }
 
 // ------------------------------------------------------------------ per-row layer math
-// out[j] = act(b[j] + sum_k W[j][k] in[k]); the weight reads are warp-uniform shared-memory broadcasts
+// out[j] = act(b[j] + sum_k W[j][k] in[k]) from the TRANSPOSED weights Wt[k][j] (row stride NP = N padded
+// to 4): k is the outer loop, so the N accumulators are independent FMA chains (with W[j][k] row-major and j
+// outer, each output was one serial chain of K dependent FMAs: 25 % of the FFMA rate at 2 warps/scheduler).
+// The weight reads are warp-uniform shared-memory broadcasts.
 template <int K, int N, bool RELU>
-__device__ __forceinline__ void nm_layer(const float* __restrict__ Ws, const float* __restrict__ bs,
+__device__ __forceinline__ void nm_layer(const float* __restrict__ Wt, const float* __restrict__ bs,
                                          const float (&in)[K], float (&out)[N]) {
+  constexpr int NP = (N + 3) & ~3;
+  float acc[NP];
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    float acc = bs[j];
+  for (int j = 0; j < NP; ++j) acc[j] = j < N ? bs[j] : 0.f;
 #pragma unroll
-    for (int k = 0; k < K; k += 4) {
-      const float4 w = *reinterpret_cast<const float4*>(Ws + j * K + k);
-      acc = fmaf(w.x, in[k], acc);
-      acc = fmaf(w.y, in[k + 1], acc);
-      acc = fmaf(w.z, in[k + 2], acc);
-      acc = fmaf(w.w, in[k + 3], acc);
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int j = 0; j < NP; j += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(Wt + k * NP + j);
+      acc[j] = fmaf(w.x, in[k], acc[j]);
+      acc[j + 1] = fmaf(w.y, in[k], acc[j + 1]);
+      acc[j + 2] = fmaf(w.z, in[k], acc[j + 2]);
+      acc[j + 3] = fmaf(w.w, in[k], acc[j + 3]);
     }
-    out[j] = RELU ? fmaxf(acc, 0.f) : acc;
   }
+#pragma unroll
+  for (int j = 0; j < N; ++j) out[j] = RELU ? fmaxf(acc[j], 0.f) : acc[j];
 }
 
 // din[k] = sum_j W[j][k] dz[j], with dz read back from this thread's own column of the staging buffer
@@ -165,23 +177,33 @@ __device__ __forceinline__ void nm_load_params(float* P, const NMParams& w) {
     for (int i = threadIdx.x; i < nw; i += NM_THREADS) P[wo[l] + i] = __ldg(w.W[l] + i);
     for (int i = threadIdx.x; i < d[l + 1]; i += NM_THREADS) P[bo[l] + i] = w.b[l] ? __ldg(w.b[l] + i) : 0.f;
   }
+  constexpr int to[4] = {C::T0, C::T1, C::T2, C::T3};
+  constexpr int np[4] = {C::P1, C::P2, C::P3, C::P4};
+#pragma unroll
+  for (int l = 0; l < C::NL; ++l) {
+    const int K = d[l], N = d[l + 1], NP = np[l];
+    for (int i = threadIdx.x; i < K * NP; i += NM_THREADS) {
+      const int k = i / NP, jj = i % NP;
+      P[to[l] + i] = jj < N ? __ldg(w.W[l] + jj * K + k) : 0.f;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ forward
 template <class C>
-__global__ void __launch_bounds__(NM_THREADS) k_narrow_fwd(const void* __restrict__ X, int x_dtype, int ldx, long long M,
+__global__ void __launch_bounds__(NM_THREADS, 2) k_narrow_fwd(const void* __restrict__ X, int x_dtype, int ldx, long long M,
                                                           const NMParams w, int final_act, void* __restrict__ Y,
                                                           int y_dtype, int ldy) {
-  __shared__ __align__(16) float P[C::NPAD];
+  __shared__ __align__(16) float P[C::NSMEM];
   nm_load_params<C>(P, w);
   __syncthreads();
   for (long long r = (long long)blockIdx.x * NM_THREADS + threadIdx.x; r < M; r += (long long)gridDim.x * NM_THREADS) {
     float x[C::D0], h1[C::D1], h2[C::D2], h3[C::D3];
     nm_load_row<C::D0>(X, x_dtype, r, ldx, x);
-    nm_layer<C::D0, C::D1, true>(P + C::W0, P + C::B0, x, h1);
-    nm_layer<C::D1, C::D2, true>(P + C::W1, P + C::B1, h1, h2);
+    nm_layer<C::D0, C::D1, true>(P + C::T0, P + C::B0, x, h1);
+    nm_layer<C::D1, C::D2, true>(P + C::T1, P + C::B1, h1, h2);
     if constexpr (C::NL == 3) {
-      nm_layer<C::D2, C::D3, false>(P + C::W2, P + C::B2, h2, h3);
+      nm_layer<C::D2, C::D3, false>(P + C::T2, P + C::B2, h2, h3);
       if (final_act == B3D_ACT_SIGMOID) {
 #pragma unroll
         for (int j = 0; j < C::D3; ++j) h3[j] = 1.f / (1.f + expf(-h3[j]));
@@ -189,8 +211,8 @@ __global__ void __launch_bounds__(NM_THREADS) k_narrow_fwd(const void* __restric
       nm_store_row<C::D3>(Y, y_dtype, r, ldy, h3);
     } else {
       float h4[C::D4 > 0 ? C::D4 : 1];
-      nm_layer<C::D2, C::D3, true>(P + C::W2, P + C::B2, h2, h3);
-      nm_layer<C::D3, (C::D4 > 0 ? C::D4 : 1), false>(P + C::W3, P + C::B3, h3, h4);
+      nm_layer<C::D2, C::D3, true>(P + C::T2, P + C::B2, h2, h3);
+      nm_layer<C::D3, (C::D4 > 0 ? C::D4 : 1), false>(P + C::T3, P + C::B3, h3, h4);
       if (final_act == B3D_ACT_SIGMOID) {
 #pragma unroll
         for (int j = 0; j < C::D4; ++j) h4[j] = 1.f / (1.f + expf(-h4[j]));
@@ -269,7 +291,7 @@ k_narrow_bwd(const void* __restrict__ X, int x_dtype, int ldx, long long M, cons
              float* __restrict__ partials) {
   extern __shared__ __align__(16) float nm_smem[];
   float* P = nm_smem;
-  float* S = nm_smem + C::NPAD;
+  float* S = nm_smem + C::NSMEM;
   constexpr int DLAST = C::DL;
   constexpr int D4S = C::D4 > 0 ? C::D4 : 1;
   nm_load_params<C>(P, w);
@@ -297,8 +319,8 @@ k_narrow_bwd(const void* __restrict__ X, int x_dtype, int ldx, long long M, cons
 #pragma unroll
       for (int k = 0; k < C::D0; ++k) x[k] = 0.f;
     }
-    nm_layer<C::D0, C::D1, true>(P + C::W0, P + C::B0, x, h1);
-    nm_layer<C::D1, C::D2, true>(P + C::W1, P + C::B1, h1, h2);
+    nm_layer<C::D0, C::D1, true>(P + C::T0, P + C::B0, x, h1);
+    nm_layer<C::D1, C::D2, true>(P + C::T1, P + C::B1, h1, h2);
     float g[DLAST];   // gradient of the chain's last pre-activation
     if (ok) {
       nm_load_row<DLAST>(dY, dy_dtype, r, lddy, g);
@@ -317,10 +339,10 @@ k_narrow_bwd(const void* __restrict__ X, int x_dtype, int ldx, long long M, cons
       nm_relu_mask<C::D2>(g2, h2);
     } else {
       float h3[C::D3];
-      nm_layer<C::D2, C::D3, true>(P + C::W2, P + C::B2, h2, h3);
+      nm_layer<C::D2, C::D3, true>(P + C::T2, P + C::B2, h2, h3);
       if (final_act == B3D_ACT_SIGMOID) {
         float z[D4S];
-        nm_layer<C::D3, D4S, false>(P + C::W3, P + C::B3, h3, z);
+        nm_layer<C::D3, D4S, false>(P + C::T3, P + C::B3, h3, z);
 #pragma unroll
         for (int j = 0; j < D4S; ++j) {
           const float s = 1.f / (1.f + expf(-z[j]));
@@ -424,7 +446,7 @@ static int launch_fwd(const void* X, int xd, int ldx, long long M, const NMParam
 }
 
 template <class C>
-static size_t bwd_smem() { return (size_t)(C::NPAD + C::STAGE * NM_RS) * sizeof(float); }
+static size_t bwd_smem() { return (size_t)(C::NSMEM + C::STAGE * NM_RS) * sizeof(float); }
 
 static int bwd_grid(long long M) {
   const long long tiles = ceil_div(M > 0 ? M : 1, NM_THREADS);

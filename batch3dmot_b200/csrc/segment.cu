@@ -204,47 +204,71 @@ extern "C" int b3d_segment_sum(const void* src_v, int32_t src_dtype, int32_t ld_
   return 0;
 }
 
-// fp32 rows gathered and rounded to bf16 (gradient of a bf16 segment-sum input)
+// Rows gathered into a bf16 matrix (gradient of a bf16 segment-sum input): out[r] = src[idx[r]], fp32 sources
+// rounded on the way, optionally zeroed where the ReLU mask (bf16 activation or sign bits) says the summed
+// output was <= 0. One warp handles GR_ROWS consecutive output rows, lanes cover 8-column chunks, and the
+// index / row / mask loads of the GR_ROWS rows are issued together (one row at a time left a single
+// dependent idx -> row -> store chain per warp: 1.9 TB/s).
+constexpr int GR_ROWS = 4;
+// SRC_BF16 / MASK (0 none, 1 bf16 activation, 2 sign bits) are compile-time so that only the registers of the
+// path in use are allocated (the all-paths kernel needed ~90 registers: 16 warps per SM, latency-bound again)
+template <bool SRC_BF16, int MASK>
 __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
     const float* __restrict__ src, int ld, const int32_t* __restrict__ idx, long long M, int C,
     __nv_bfloat16* __restrict__ out, int ldo, const __nv_bfloat16* __restrict__ relu_mask, int ldm,
-    const uint32_t* __restrict__ relu_bits, int src_bf16) {
+    const uint32_t* __restrict__ relu_bits) {
   const int lane = threadIdx.x & 31;
-  const long long r = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
-  if (r >= M) return;
-  const long long g = __ldg(idx + r);
+  const long long r0 = ((long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5)) * GR_ROWS;
+  if (r0 >= M) return;
+  long long g[GR_ROWS];
+#pragma unroll
+  for (int u = 0; u < GR_ROWS; ++u) g[u] = (r0 + u < M) ? (long long)__ldg(idx + r0 + u) : -1;
   for (int c = lane * 8; c < C; c += 256) {
-    uint4 v;
-    if (src_bf16) {   // already rounded by the producing input-gradient tile: a pure 16-byte copy
-      v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + g * ld + c));
-    } else {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(src + g * ld + c));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(src + g * ld + c) + 1);
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
-      v = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                     *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-    }
-    if (relu_mask) {   // gradient of a ReLU output: keep it where the output was > 0 (bf16 > 0 <=> int16 bits > 0)
-      const uint4 m = __ldg(reinterpret_cast<const uint4*>(relu_mask + r * ldm + c));
-      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-      const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+    uint4 v[GR_ROWS], mk[GR_ROWS];
+    float4 fa[GR_ROWS], fb[GR_ROWS];
+    uint32_t word[GR_ROWS];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if ((int16_t)(mw[j] & 0xFFFFu) <= 0) w[j] &= 0xFFFF0000u;
-        if ((int16_t)(mw[j] >> 16) <= 0) w[j] &= 0x0000FFFFu;
+    for (int u = 0; u < GR_ROWS; ++u) {
+      if (g[u] < 0) continue;
+      if (SRC_BF16) {   // already rounded by the producing input-gradient tile: a pure 16-byte copy
+        v[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + g[u] * ld + c));
+      } else {
+        fa[u] = __ldg(reinterpret_cast<const float4*>(src + g[u] * ld + c));
+        fb[u] = __ldg(reinterpret_cast<const float4*>(src + g[u] * ld + c) + 1);
       }
+      if (MASK == 2) word[u] = __ldg(relu_bits + (long long)(c >> 5) * M + r0 + u) >> (c & 31);
+      if (MASK == 1) mk[u] = __ldg(reinterpret_cast<const uint4*>(relu_mask + (r0 + u) * ldm + c));
     }
-    if (relu_bits) {   // the same mask as sign bits: word [(c / 32) * M + r], bit c % 32
-      const uint32_t word = __ldg(relu_bits + (long long)(c >> 5) * M + r) >> (c & 31);
-      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!((word >> (2 * j)) & 1u)) w[j] &= 0xFFFF0000u;
-        if (!((word >> (2 * j + 1)) & 1u)) w[j] &= 0x0000FFFFu;
+    for (int u = 0; u < GR_ROWS; ++u) {
+      if (g[u] < 0) continue;
+      uint4 q;
+      if (SRC_BF16) {
+        q = v[u];
+      } else {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(fa[u].x, fa[u].y), p1 = __floats2bfloat162_rn(fa[u].z, fa[u].w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(fb[u].x, fb[u].y), p3 = __floats2bfloat162_rn(fb[u].z, fb[u].w);
+        q = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                       *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
       }
+      uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+      if (MASK == 1) {   // keep the gradient where the ReLU output was > 0 (bf16 > 0 <=> int16 bits > 0)
+        const uint32_t mw[4] = {mk[u].x, mk[u].y, mk[u].z, mk[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((int16_t)(mw[j] & 0xFFFFu) <= 0) w[j] &= 0xFFFF0000u;
+          if ((int16_t)(mw[j] >> 16) <= 0) w[j] &= 0x0000FFFFu;
+        }
+      }
+      if (MASK == 2) {   // the same mask as sign bits: word [(c / 32) * M + r], bit c % 32
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!((word[u] >> (2 * j)) & 1u)) w[j] &= 0xFFFF0000u;
+          if (!((word[u] >> (2 * j + 1)) & 1u)) w[j] &= 0x0000FFFFu;
+        }
+      }
+      *reinterpret_cast<uint4*>(out + (r0 + u) * ldo + c) = q;
     }
-    *reinterpret_cast<uint4*>(out + r * ldo + c) = v;
   }
 }
 
@@ -257,10 +281,16 @@ extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* 
     if ((C & 7) || (ld_src & (src_dtype == B3D_BF16 ? 7 : 3)) || (ld_out & 7) || !al16(src) || !al16(out_v))
       return bad_arg("b3d_gather_rows: bf16 output needs C % 8 == 0 and 16-byte aligned rows");
     if (relu_mask && ((ld_mask & 7) || !al16(relu_mask))) return bad_arg("b3d_gather_rows: relu_mask alignment");
-    k_gather_rows_bf16<<<(unsigned)ceil_div(M, SEG_WARPS), SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        src, ld_src, idx, M, C, reinterpret_cast<__nv_bfloat16*>(out_v), ld_out,
-        mask_dtype == B3D_BITS ? nullptr : reinterpret_cast<const __nv_bfloat16*>(relu_mask), ld_mask,
-        mask_dtype == B3D_BITS ? reinterpret_cast<const uint32_t*>(relu_mask) : nullptr, src_dtype == B3D_BF16);
+    const unsigned grid = (unsigned)ceil_div(M, (long long)SEG_WARPS * GR_ROWS);
+    const int mk = !relu_mask ? 0 : (mask_dtype == B3D_BITS ? 2 : 1);
+    const __nv_bfloat16* m16 = mk == 1 ? reinterpret_cast<const __nv_bfloat16*>(relu_mask) : nullptr;
+    const uint32_t* mb = mk == 2 ? reinterpret_cast<const uint32_t*>(relu_mask) : nullptr;
+    __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out_v);
+    cudaStream_t st = (cudaStream_t)stream;
+#define B3D_GR(SB, MK) k_gather_rows_bf16<SB, MK><<<grid, SEG_WARPS * 32, 0, st>>>(src, ld_src, idx, M, C, o16, ld_out, m16, ld_mask, mb)
+    if (src_dtype == B3D_BF16) { if (mk == 0) B3D_GR(true, 0); else if (mk == 1) B3D_GR(true, 1); else B3D_GR(true, 2); }
+    else { if (mk == 0) B3D_GR(false, 0); else if (mk == 1) B3D_GR(false, 1); else B3D_GR(false, 2); }
+#undef B3D_GR
     B3D_LAUNCH_CHECK("k_gather_rows_bf16");
     return 0;
   }

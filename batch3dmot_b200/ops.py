@@ -497,12 +497,13 @@ class _FusedMLP(torch.autograd.Function):
         tc_arg = True if tc else None
         # bf16 chains record every ReLU output's SIGN BITS (1 bit per element, written by the producing
         # epilogue): the backward pass masks gradients from them instead of re-reading the activation
+        want_bits = any(ctx.needs_input_grad)      # inference (no_grad): nothing reads them
         acts, bits, cur = [], [], items
         for l in range(nl):
             last = l == nl - 1
             relu_out = (not last) or premasked
             nb = Ws[l].size(0)
-            bt = new_relu_bits(M, nb, W0dev) if (tc and relu_out and _USE_BITS and nb % 32 == 0) else None
+            bt = new_relu_bits(M, nb, W0dev) if (tc and relu_out and _USE_BITS and nb % 32 == 0 and want_bits) else None
             y = linear_raw(cur, Ws[l], bs[l], M, _ACT[final_act] if last else L.ACT_RELU,
                            row_mask=rm if last else None, tc=tc_arg,
                            out_dtype=((out_dtype or torch.float32) if last else torch.bfloat16) if tc else torch.float32,
