@@ -116,3 +116,35 @@ def test_cb_weights_match_reference_formula():
     beta, n = 0.8, 5 * synth.REL_FREQ_TRAIN["car"]
     w = synth.cb_weights(torch.tensor([3.0]))
     assert abs(float(w) - (1 - beta) / (1 - beta ** n)) < 1e-7
+
+
+def test_split_cols_and_fanout_host_logic():
+    """ops.split_cols: column slices whose backward is one concatenation (zero blocks for unused slices);
+    ops.fanout degenerates to plain aliases without autograd. Pure host logic, no kernel involved."""
+    from batch3dmot_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(7, 12, requires_grad=True)
+    a, b, c = ops.split_cols(x, (3, 4, 5))
+    assert a.shape == (7, 3) and b.shape == (7, 4) and c.shape == (7, 5)
+    assert torch.equal(torch.cat([a, b, c], 1), x)
+    ga, gc = torch.randn(7, 3), torch.randn(7, 5)
+    (a * ga).sum().add((c * gc).sum()).backward()          # slice b unused: its gradient block is zero
+    assert torch.equal(x.grad, torch.cat([ga, torch.zeros(7, 4), gc], 1))
+    y = torch.randn(4, 8)
+    u, v = ops.fanout(y, 2)
+    assert u is y and v is y
+    with torch.no_grad():
+        p, q = ops.split_cols(x, (6, 6))
+        assert p.shape == (7, 6) and q.shape == (7, 6)
+
+
+def test_focal_loss_oracle_reduces_to_bce():
+    """oracle.ref_restated.focal_loss (published definition; parity unpinned, not in the reference) with gamma = 0,
+    alpha = 0.5 is half the reference's BCELoss; gamma > 0 down-weights easy examples."""
+    from oracle import ref_restated as R
+    torch.manual_seed(1)
+    p = torch.rand(500) * 0.98 + 0.01
+    y = (torch.rand(500) < 0.2).long()
+    w = torch.rand(500) + 0.5
+    assert abs(float(R.focal_loss(p, y, w, gamma=0.0, alpha=0.5)) - 0.5 * float(R.bce_loss(p, y, w))) < 1e-6
+    assert float(R.focal_loss(p, y, w, gamma=2.0, alpha=0.5)) < float(R.focal_loss(p, y, w, gamma=0.0, alpha=0.5))
