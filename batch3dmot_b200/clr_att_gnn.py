@@ -101,7 +101,7 @@ class GNN(nn.Module):
         if x_img is None:
             x_img, pointnet_out, radarnet_out, lidar_mask, radar_mask = self._encode_modalities(data)
         lowp = torch.bfloat16 if ops.get_precision() == "bf16" else None   # edge tensors stay bf16 between kernels
-        e0 = ops.run_mlp(self.edge_encoder, [(data.edge_attr.float(), None)], out_dtype=lowp)   # :123
+        e0 = ops.run_mlp(self.edge_encoder, [(ops.edge_attr_rows(data.edge_attr), None)], out_dtype=lowp)   # :123
         x_lidar = ops.run_mlp(self.fc_lidar_encoder, [(pointnet_out, None)], row_mask=lidar_mask)   # :131-133
         x_radar = ops.run_mlp(self.fc_radar_encoder, [(radarnet_out, None)], row_mask=radar_mask)   # :139-141
         x_img = x_img.float()
@@ -126,11 +126,12 @@ class GNN(nn.Module):
         x_sens = torch.cat([x_img, x_lidar, x_radar], dim=1)       # :172 (C7)
         x0 = ops.run_mlp(self.node_encoder, [(pose, None)])        # :174-176
         x, e = x0, e0
-        inv = self.message_passing.project_invariants(x0) if ops.get_precision() == "bf16" else None
+        invs = self.message_passing.invariants_per_iteration(x0, self.depth) if ops.get_precision() == "bf16" \
+            else [None] * self.depth
         # att_edge_attr feeds every iteration: one depth-way gradient sum instead of depth-1 additions
         atts = ops.fanout(att, self.depth) if ops.get_precision() == "bf16" else (att,) * self.depth
         for i in range(self.depth):
             if i % 2 == 0 and self.apply_knn_update:
                 x = knn_attention_conv(self.knn_conv, x, data.node_timestamps)
-            x, e = self.message_passing.forward_graph(x, g, e, x0, atts[i], inv)                # :186
+            x, e = self.message_passing.forward_graph(x, g, e, x0, atts[i], invs[i])            # :186
         return ops.run_mlp(self.edge_classifier, [(e, None)], final_act="sigmoid"), x_sens     # :188

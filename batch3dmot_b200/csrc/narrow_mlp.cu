@@ -52,6 +52,20 @@ struct NMGradOut {
 // ------------------------------------------------------------------ row I/O (runtime dtype)
 template <int K>
 __device__ __forceinline__ void nm_load_row(const void* base, int dtype, long long row, int ld, float (&v)[K]) {
+  if (dtype == B3D_F64) {   // edge_attr as stored (float64): the reference's `.float()` cast folded into the load
+    const double* p = reinterpret_cast<const double*>(base) + row * ld;
+    if constexpr (K % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < K; k += 2) {
+        const double2 q = __ldg(reinterpret_cast<const double2*>(p + k));
+        v[k] = (float)q.x; v[k + 1] = (float)q.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) v[k] = (float)__ldg(p + k);
+    }
+    return;
+  }
   if (dtype == B3D_BF16) {
     const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + row * ld;
     if constexpr (K % 8 == 0) {
@@ -430,6 +444,7 @@ static int sm_count() {
 }
 
 static bool row_aligned(const void* p, int dtype, int ld, int width) {
+  if (dtype == B3D_F64) return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 2 == 0;   // double2 loads
   const int q = dtype == B3D_BF16 ? 8 : 4;
   if (width % q) return true;   // scalar path
   return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % q == 0;

@@ -104,8 +104,11 @@ def graph_of(edge_index, num_nodes):
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes))
     g = _graph_cache.get(key)
     if g is None:
-        if len(_graph_cache) > 64:
-            _graph_cache.clear()
+        # small FIFO: a stream of fresh edge_index tensors (one per step in an end-to-end loop) must not pin
+        # dozens of E-sized tables, or every step's tables come from a fresh cudaMalloc instead of the
+        # allocator's free list
+        while len(_graph_cache) >= 4:
+            _graph_cache.pop(next(iter(_graph_cache)))
         g = _graph_cache[key] = Graph(edge_index, num_nodes)
         g._keepalive = edge_index
     return g
@@ -188,7 +191,7 @@ def _rows(t):
     return t
 
 
-_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float64: L.F64}
 
 
 def new_relu_bits(M, n_out, device):
@@ -555,7 +558,7 @@ class _FusedMLP(torch.autograd.Function):
                 for t, ni in enumerate(ctx.add_nidx):
                     if need_add[t]:
                         assert dz_item[2] is None
-                        g = segment_sum_raw(dz_item[0], ni) if ni is not None else dz_item[0]
+                        g = segment_sum_raw(dz_item[0], ni, out_dtype=ctx.add_dtypes[t]) if ni is not None else dz_item[0]
                         dadds[t] = g if g.dtype == ctx.add_dtypes[t] else g.to(ctx.add_dtypes[t])
             if ctx.needs_input_grad[7 + 2 * l]:
                 dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc_arg)
@@ -590,7 +593,8 @@ class _NarrowMLP(torch.autograd.Function):
     def forward(ctx, nl, final_act, out_dtype, x, *params):
         Ws = [w.contiguous() for w in params[0::2]]
         bs = [b.contiguous() if b is not None else None for b in params[1::2]]
-        x = _rows(x)
+        if x.dtype != torch.float64:           # float64 rows (edge_attr as stored) are cast inside the kernel
+            x = _rows(x)
         dims = [Ws[0].size(1)] + [w.size(0) for w in Ws]
         M = x.size(0)
         y = torch.empty((M, dims[-1]), dtype=out_dtype, device=x.device)
@@ -640,7 +644,10 @@ def _narrow_ok(inputs, weights, final_act, row_mask, adds, premasked):
     if final_act not in (None, "sigmoid") or len(weights) not in (3, 4) or (final_act and len(weights) != 4):
         return False
     x = inputs[0][0]
-    if x.dim() != 2 or x.dtype not in (torch.float32, torch.bfloat16) or x.stride(1) != 1 or not _al16(x):
+    if x.dim() == 2 and x.dtype == torch.float64 and x.stride(1) == 1 and not x.requires_grad and \
+            x.data_ptr() % 16 == 0 and x.stride(0) % 2 == 0:
+        pass                                   # float64 input rows: loaded as double2, cast in registers
+    elif x.dim() != 2 or x.dtype not in (torch.float32, torch.bfloat16) or x.stride(1) != 1 or not _al16(x):
         return False
     dims = [weights[0].size(1)] + [w.size(0) for w in weights]
     return x.size(1) == dims[0] and bool(L.lib().b3d_narrow_mlp_supported(len(weights), L.int_array(dims)))
@@ -660,6 +667,16 @@ def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=(), o
         return _NarrowMLP.apply(len(weights), final_act, out_dtype or torch.float32, xs[0], *flat)
     return _FusedMLP.apply(len(weights), final_act, row_mask, nidx, tuple(ni for _, ni in adds), out_dtype,
                            premasked, *flat, *xs, *[t for t, _ in adds])
+
+
+def edge_attr_rows(edge_attr):
+    """edge_attr as the edge encoder's input: the stored float64 [E,4] matrix goes to the narrow-chain kernel
+    as is (its `.float()` cast, pose_gnn.py:67 / clr_att_gnn.py:123, happens in the row load); anything
+    else is cast here."""
+    if edge_attr.dtype == torch.float64 and edge_attr.dim() == 2 and edge_attr.is_contiguous() and \
+            not edge_attr.requires_grad:
+        return edge_attr
+    return edge_attr.float()
 
 
 def fused_linear(inputs, weight, bias=None, act=None, row_mask=None, adds=()):

@@ -63,6 +63,12 @@ class CausalMessagePassing(nn.Module):
                                      l1.weight.new_zeros(l1.out_features, 6)], 1))
         return w_cat, b_cat, inv_all, (h1, hm), w_post
 
+    def invariants_per_iteration(self, x0, depth):
+        """project_invariants once, with the iteration-invariant addend block aliased `depth` times through
+        ops.fanout so that its gradient is ONE depth-way sum instead of depth-1 autograd additions."""
+        w_cat, b_cat, inv_all, dims, w_post = self.project_invariants(x0)
+        return [(w_cat, b_cat, ia, dims, w_post) for ia in ops.fanout(inv_all, depth)]
+
     def forward_preprojected(self, x, g, e, x0, att=None, inv=None):
         """Same math as forward_graph with every first-layer weight split by input block
         (SURVEY A.2 column layout) and its node-side blocks applied per NODE instead of per edge:
@@ -141,12 +147,13 @@ class PoseGNN(nn.Module):
         pose, ei = data.pose_feats, data.edge_index
         g = getattr(data, "_b3d_graph", None) or ops.graph_of(ei, pose.size(0))
         lowp = torch.bfloat16 if ops.get_precision() == "bf16" else None
-        e = ops.run_mlp(self.edge_encoder, [(data.edge_attr.float(), None)], out_dtype=lowp)   # :67
+        e = ops.run_mlp(self.edge_encoder, [(ops.edge_attr_rows(data.edge_attr), None)], out_dtype=lowp)   # :67
         x0 = ops.run_mlp(self.node_encoder, [(pose, None)])                          # :68 (C6: once)
         x, x_enc = x0, x0
-        inv = self.message_passing.project_invariants(x0) if ops.get_precision() == "bf16" else None
+        invs = self.message_passing.invariants_per_iteration(x0, self.depth) if ops.get_precision() == "bf16" \
+            else [None] * self.depth
         for i in range(self.depth):
             if i % 2 == 0 and self.apply_knn_update:
                 x = knn_attention_conv(self.knn_conv, x, data.node_timestamps)
-            x, e = self.message_passing.forward_graph(x, g, e, x0, inv=inv)          # :83
+            x, e = self.message_passing.forward_graph(x, g, e, x0, inv=invs[i])      # :83
         return ops.run_mlp(self.edge_classifier, [(e, None)]), x_enc                 # :86

@@ -327,12 +327,31 @@ def main():
                 "peak_source": src + " bf16 dense burst; kernel timed alone",
                 "note": "fp32-exact SIMT path: runs on the FFMA pipe, not the tensor pipe"}
 
+    # ---- step-level view of the same roofline: every edge-level dense-layer launch of ONE extra step timed with
+    # CUDA events around the launch (ops.optime: synchronises per launch, so this step is not part of any
+    # throughput figure); algorithmic operand bytes (inputs + outputs + masks + addends) / summed time
+    roof_step = None
+    if a.precision == "bf16":
+        ops.optime_begin()
+        trainer.step(d, global_edges=E_global, **kw)
+        rec = ops.optime_end()
+        agg = {}
+        for sig, (n, ms_k, nb) in rec.items():
+            if sig[1] != E:            # edge-level launches only (node-level ones are latency-bound and small)
+                continue
+            cls = "k_wgrad_tma" if sig[0] == "wgrad" else "k_linear_tma"
+            ent = agg.setdefault(cls, [0, 0.0, 0])
+            ent[0] += n; ent[1] += ms_k; ent[2] += nb
+        roof_step = {cls: {"launches": n, "ms": ms_k, "algorithmic_gb": nb / 1e9, "achieved_gbs": nb / ms_k / 1e6,
+                           "frac_of_hbm_peak": nb / ms_k / 1e6 / hbm}
+                     for cls, (n, ms_k, nb) in agg.items() if ms_k > 0}
+
     line = {"metric": "gnn_edges_per_s_fwd_bwd", "value": value, "unit": "edges/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
             "config": dict(config, edges_per_step=E_global, nodes_per_gpu=N),
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof,
+            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "roofline_step": roof_step,
             "algorithmic_tflops": value * MM_FWDBWD_FLOPS_PER_EDGE / 1e12, "loss": float(loss.item()),
             "forward_only": {"value": fwd_value, "unit": "edges/s", "ms_per_step": E_global / fwd_value * 1e3,
                              "note": "inference forward of the same batch under torch.no_grad()"},

@@ -44,6 +44,9 @@ enum { B3D_F32 = 0, B3D_BF16 = 1 }; /* element type of a segment / output (bf16:
  * Written by the forward tensor-core layers (relu_bits_out), read by the input-gradient layers and
  * by b3d_gather_rows: 1/16 of the bytes of the bf16 activation and one coalesced word per row. */
 enum { B3D_BITS = 2 };
+/* x_dtype of the narrow MLP chains only: float64 input rows (edge_attr is stored as float64 and cast with
+ * `.float()` at pose_gnn.py:67 / clr_att_gnn.py:123; the cast is folded into the row load). */
+enum { B3D_F64 = 3 };
 
 /* One column block of a (virtually) concatenated, optionally row-gathered
  * operand: rows r = 0..M-1 read ptr[(idx ? idx[r] : r) * ld + 0..width-1].

@@ -364,6 +364,14 @@ def test_narrow_mlp_bf16_storage():
     a = torch.randn(M, 4, device=DEV)
     e16 = ops.run_mlp(enc, [(a, None)], out_dtype=torch.bfloat16)
     assert e16.dtype == torch.bfloat16 and rel_err(e16, enc(a)) < 1e-2
+    # float64 input rows (edge_attr as stored): the `.float()` cast happens in the kernel's row load
+    a64 = a.double()
+    e64in = ops.run_mlp(enc, [(ops.edge_attr_rows(a64), None)], out_dtype=torch.bfloat16)
+    assert torch.equal(e64in, e16)
+    g64 = torch.autograd.grad(e64in, list(enc.parameters()), torch.ones_like(e64in))
+    g32 = torch.autograd.grad(ops.run_mlp(enc, [(a, None)], out_dtype=torch.bfloat16), list(enc.parameters()),
+                              torch.ones_like(e16))
+    assert all(torch.equal(p, q) for p, q in zip(g64, g32))
     g16 = torch.randn(M, 64, device=DEV).to(torch.bfloat16)
     grads = torch.autograd.grad(e16, list(enc.parameters()), g16)
     grads_ref = torch.autograd.grad(enc(a), list(enc.parameters()), g16.float())
