@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE ONLY (oracle): literal restatement of the reference's per-window graph
+construction — k-NN edge selection, edge features and ground-truth edge labels — on plain arrays
+instead of nuScenes `Box` objects. Nothing under batch3dmot_b200/ may import this module.
+
+Follows, line by line:
+  batch_3dmot/utils/geo_utils.py:8-21   angle_diff
+  batch_3dmot/utils/geo_utils.py:24-31  center_distance (xy only)
+  batch_3dmot/utils/geo_utils.py:34-43  velocity_l2 (full 3-vector)
+  batch_3dmot/utils/geo_utils.py:46-57  yaw_diff
+  batch_3dmot/utils/geo_utils.py:102-115 box_volume
+  batch_3dmot/utils/graph_utils.py:7-30  compute_motion_edge_feats
+  batch_3dmot/utils/graph_utils.py:33-88 get_knn_nodes_in_graph
+  batch_3dmot/preprocessing/construct_detection_graph_disjoint_parallel_only_poses.py:204-270
+      (candidate selection per current node, k, edge emission order, GT labels, |dt| feature)
+
+A node is a dict {'node_id', 'center' np.float64[3], 'velocity' np.float64[3], 'yaw' float (what
+quaternion_yaw(box.orientation) returns), 'wlh' np.float64[3], 'category' int, 'token' int or None,
+'time' int (frame index)}. Parity is unpinned upstream only in torch.topk's tie order (exact metric ties).
+"""
+import numpy as np
+import torch
+
+
+def angle_diff(x, y, period):                       # geo_utils.py:8-21
+    diff = (x - y + period / 2) % period - period / 2
+    if diff > np.pi:
+        diff = diff - (2 * np.pi)
+    return diff
+
+
+def center_distance(a, b):                          # geo_utils.py:24-31
+    return np.linalg.norm(a['center'][:2] - b['center'][:2])
+
+
+def velocity_l2(a, b):                              # geo_utils.py:34-43
+    return np.linalg.norm(a['velocity'] - b['velocity'])
+
+
+def yaw_diff(a, b, period=2 * np.pi):               # geo_utils.py:46-57
+    return angle_diff(a['yaw'], b['yaw'], period)
+
+
+def box_volume(a):                                  # geo_utils.py:102-115
+    assert all(a['wlh'] > 0)
+    return np.prod(a['wlh'])
+
+
+def compute_motion_edge_feats(cur_node, oth_node):  # graph_utils.py:7-30
+    l2_3d_dist = center_distance(cur_node, oth_node)
+    yd = np.abs(yaw_diff(cur_node, oth_node))
+    vol_diff = np.log(box_volume(cur_node) / box_volume(oth_node))
+    return [l2_3d_dist, yd, vol_diff]
+
+
+def get_knn_nodes_in_graph(cur_node, other_nodes, k):   # graph_utils.py:33-88
+    transl_3d_dists, vel_dists, yaw_dists = [], [], []
+    for oth_node in other_nodes:
+        l2_3d_dist = center_distance(cur_node, oth_node)
+        l2_vel_dist = velocity_l2(cur_node, oth_node)
+        yd = yaw_diff(cur_node, oth_node)
+        transl_3d_dists.append(l2_3d_dist)
+        vel_dists.append(abs(l2_vel_dist))
+        yaw_dists.append(abs(yd))
+    transl_3d_dists = torch.tensor(transl_3d_dists)     # np.float64 scalars -> float64 tensors
+    yaw_dists = torch.tensor(yaw_dists)
+    vel_dists = torch.tensor(vel_dists)
+    transl_3d_dists = transl_3d_dists / torch.max(transl_3d_dists)
+    yaw_dists = yaw_dists / torch.max(yaw_dists)
+    vel_dists = vel_dists / torch.max(vel_dists)
+    motion_dists = (1 / 2) * transl_3d_dists + (1 / 4) * yaw_dists + (1 / 4) * vel_dists
+    motion_dists = motion_dists / torch.max(motion_dists)
+    top_k_idcs = torch.topk(motion_dists, k, largest=False).indices.tolist()
+    return [other_nodes[i] for i in top_k_idcs]
+
+
+def build_window_graph(frames, top_knn=40):
+    """frames: list (one entry per frame of the window, in time order) of lists of node dicts WITHOUT
+    'node_id' (assigned here in emission order, construct_...:163-201). Returns edges [E,2] int64
+    ([ex_id, cur_id]), gt [E] int64, edge_features [E,4] float64 — construct_...:204-270."""
+    edges, gt_edges, edge_features = [], [], []
+    past_nodes, node_id = [], 0
+    for cur_nodes in frames:
+        for n in cur_nodes:
+            n['node_id'] = node_id
+            node_id += 1
+        if len(past_nodes) > 0:
+            for cur in cur_nodes:
+                past_categ_nodes = [p for p in past_nodes if p['category'] == cur['category']]
+                k = top_knn if len(past_categ_nodes) > top_knn else len(past_categ_nodes)
+                if len(past_categ_nodes) > 0:
+                    knn_past_nodes = get_knn_nodes_in_graph(cur, past_categ_nodes, k)
+                    for ex in knn_past_nodes:
+                        edges.append([ex['node_id'], cur['node_id']])
+                        if ex['token'] is not None and cur['token'] is not None:
+                            if ex['token'] == cur['token']:
+                                cur_ex_time_diff = abs(cur['time'] - ex['time'])
+                                if cur_ex_time_diff == 1:
+                                    gt_edges.append(1)
+                                elif cur_ex_time_diff > 1:
+                                    oth_deltas = []
+                                    for oth_node in knn_past_nodes:
+                                        if oth_node['time'] != ex['time'] and oth_node['token'] == cur['token']:
+                                            oth_deltas.append(abs(cur['time'] - oth_node['time']))
+                                    if len(oth_deltas) == 0:
+                                        gt_edges.append(1)
+                                    else:
+                                        if np.min(oth_deltas) > cur_ex_time_diff:
+                                            gt_edges.append(1)
+                                        elif np.min(oth_deltas) < cur_ex_time_diff:
+                                            gt_edges.append(0)
+                                else:
+                                    gt_edges.append(0)
+                            else:
+                                gt_edges.append(0)
+                        else:
+                            gt_edges.append(0)
+                        box_feats = compute_motion_edge_feats(ex, cur)
+                        box_feats.append(abs(cur['time'] - ex['time']))
+                        edge_features.append(box_feats)
+        past_nodes.extend(cur_nodes)
+    return (torch.tensor(edges, dtype=torch.int64).reshape(-1, 2), torch.tensor(gt_edges, dtype=torch.int64),
+            torch.tensor(edge_features, dtype=torch.float64).reshape(-1, 4))

@@ -1,0 +1,116 @@
+"""Window-graph construction: the vectorised batch3dmot_b200.graph_build against the literal
+restatement of the reference's per-node loops (oracle/graph_construction.py). Edges and ground-truth labels are
+bit-exact; float64 edge features within 4 ulp (numpy's norm may fuse a multiply-add). CPU tests; the same function
+runs on CUDA tensors (gpu-marked test at the bottom)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_construction as G
+from batch3dmot_b200 import graph_build
+
+
+def random_window(seed, T=5, max_per_frame=40, n_cat=7, n_objects=60, p_seen=0.7, dup=False, gap_frames=()):
+    """Objects random-walk over frames and are detected with probability p_seen (so instance tokens repeat with
+    gaps: |dt| > 1 labels), plus false positives without a token."""
+    rng = np.random.default_rng(seed)
+    cat = rng.integers(1, n_cat + 1, n_objects)
+    pos = rng.uniform(-50, 50, (n_objects, 3))
+    vel = rng.normal(0, 3, (n_objects, 3)); vel[:, 2] = 0
+    yaw = rng.uniform(-math.pi, math.pi, n_objects)
+    wlh = np.exp(rng.normal(0.5, 0.3, (n_objects, 3)))
+    frames = []
+    for t in range(T):
+        nodes = []
+        if t in gap_frames:
+            frames.append(nodes); continue
+        seen = np.nonzero(rng.random(n_objects) < p_seen)[0][:max_per_frame]
+        for o in rng.permutation(seen):
+            nodes.append({'center': pos[o] + vel[o] * 0.5 * t + rng.normal(0, 0.2, 3), 'velocity': vel[o] + rng.normal(0, 0.3, 3),
+                          'yaw': float(yaw[o] + rng.normal(0, 0.05)), 'wlh': wlh[o] * np.exp(rng.normal(0, 0.02, 3)),
+                          'category': int(cat[o]), 'token': int(o), 'time': 10 + t})
+        for _ in range(int(rng.integers(0, 6))):            # false positives: no instance token
+            nodes.append({'center': rng.uniform(-50, 50, 3), 'velocity': rng.normal(0, 3, 3), 'yaw': float(rng.uniform(-3, 3)),
+                          'wlh': np.exp(rng.normal(0.5, 0.3, 3)), 'category': int(rng.integers(1, n_cat + 1)), 'token': None,
+                          'time': 10 + t})
+        if dup and nodes:                                  # exact duplicates: genuine metric ties
+            nodes.append({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in nodes[0].items()})
+        frames.append(nodes)
+    return frames
+
+
+def to_tensors(frames, device="cpu"):
+    nodes = [n for f in frames for n in f]
+    f64 = torch.float64
+    if not nodes:
+        z3 = torch.zeros((0, 3), dtype=f64, device=device)
+        zi = torch.zeros(0, dtype=torch.int64, device=device)
+        return z3, z3, torch.zeros(0, dtype=f64, device=device), z3, zi, zi, zi
+    return (torch.tensor(np.stack([n['center'] for n in nodes]), dtype=f64, device=device),
+            torch.tensor(np.stack([n['velocity'] for n in nodes]), dtype=f64, device=device),
+            torch.tensor([n['yaw'] for n in nodes], dtype=f64, device=device),
+            torch.tensor(np.stack([n['wlh'] for n in nodes]), dtype=f64, device=device),
+            torch.tensor([n['category'] for n in nodes], dtype=torch.int64, device=device),
+            torch.tensor([-1 if n['token'] is None else n['token'] for n in nodes], dtype=torch.int64, device=device),
+            torch.tensor([n['time'] for n in nodes], dtype=torch.int64, device=device))
+
+
+def check(frames, top_knn=40, device="cpu"):
+    args = to_tensors(frames, device)
+    e_ref, gt_ref, f_ref = G.build_window_graph(frames, top_knn)
+    e, gt, f = graph_build.build_window_graph(*args, top_knn=top_knn)
+    assert torch.equal(e.cpu(), e_ref), "edges (ex_id, cur_id) must be bit-exact, in the reference's emission order"
+    assert torch.equal(gt.cpu(), gt_ref), "ground-truth labels must be bit-exact"
+    assert f.dtype == torch.float64 and f.shape == f_ref.shape
+    assert torch.allclose(f.cpu(), f_ref, rtol=1e-15 * 4, atol=1e-300)
+    return e_ref, gt_ref
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_windows_bit_exact(seed):
+    e, gt = check(random_window(seed))
+    assert e.size(0) > 500 and int(gt.sum()) > 20
+    assert bool((e[:, 0] < e[:, 1]).all()) and bool((e[1:, 1] >= e[:-1, 1]).all())   # src < dst, dst-sorted
+
+
+def test_k_cap_and_dense_single_category():
+    """one category, > 40 candidates per node: k = top_knn; also a small cap."""
+    frames = random_window(11, n_cat=1, n_objects=70, p_seen=0.9, max_per_frame=60)
+    e, _ = check(frames)
+    assert int(torch.bincount(e[:, 1]).max()) == 40
+    check(frames, top_knn=3)
+
+
+def test_gaps_duplicates_and_degenerate_rows():
+    check(random_window(3, gap_frames=(0,)))            # first frame empty
+    check(random_window(4, gap_frames=(1, 3)))          # gaps: |dt| > 1 positives
+    check(random_window(5, dup=True))                   # exact metric ties -> exact per-row path
+    check([[], [], [], [], []])
+    one = random_window(6)[0][:1]
+    check([one, [], [], [], []])                        # a single node, no edges
+    # a single candidate with identical yaw and velocity: 0/0 = NaN metric, still one edge
+    a = {'center': np.array([1.0, 2.0, 0.0]), 'velocity': np.zeros(3), 'yaw': 0.3, 'wlh': np.ones(3), 'category': 2,
+         'token': 7, 'time': 0}
+    b = dict(a, center=np.array([4.0, 6.0, 0.0]), time=1)
+    e, gt = check([[a], [b]])
+    assert e.tolist() == [[0, 1]] and gt.tolist() == [1]
+
+
+def test_ground_truth_rule():
+    """same instance seen at t-1 and t-3 among the neighbours: only the closest appearance is positive."""
+    mk = lambda x, t, tok: {'center': np.array([x, 0.0, 0.0]), 'velocity': np.array([1.0, 0.0, 0.0]), 'yaw': 0.1 * x,
+                            'wlh': np.ones(3), 'category': 1, 'token': tok, 'time': t}
+    frames = [[mk(0.0, 0, 5), mk(9.0, 0, 6)], [mk(9.5, 1, 6)], [mk(1.0, 2, 5)], [mk(1.5, 3, 5), mk(10.0, 3, 6)]]
+    e, gt = check(frames)
+    lab = {tuple(x): int(g) for x, g in zip(e.tolist(), gt.tolist())}
+    assert lab[(3, 4)] == 1 and lab[(0, 4)] == 0        # node 4 (t=3, token 5): t=2 is positive, t=0 is not
+    assert lab[(2, 5)] == 1 and lab[(1, 5)] == 0        # node 5 (t=3, token 6): t=1 beats t=0
+    assert lab[(0, 3)] == 1                             # node 3 (t=2, token 5): only appearance is two frames back
+
+
+@pytest.mark.gpu
+def test_same_result_on_cuda_tensors():
+    check(random_window(21), device="cuda")
+    check(random_window(22, dup=True), device="cuda")
