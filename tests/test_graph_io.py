@@ -1,0 +1,67 @@
+"""Graph file I/O: batch3dmot_b200.graph_io.load_window_graph against the literal restatement of
+GraphDataset.__getitem__ (oracle/graph_io.py) on file sets written in the reference's layout. Everything bit-exact."""
+import os
+
+import pytest
+import torch
+
+from oracle import graph_io as R
+from batch3dmot_b200 import graph_io, synth
+
+
+def write_window(tmp, seed, T=5, npf=12):
+    scene = synth.add_labels(synth.add_modalities(synth.scene_graph(seed=seed, T=T, nodes_per_frame=npf, k=8, rel_time_mod=5), seed), seed)
+    prefix = os.path.join(str(tmp), f"scene{seed}_len5_0")
+    meta = {n: {"category_name": synth.CATEGORIES[int(c) - 1], "global_node_id": 1000 + 3 * n, "time": int(t)}
+            for n, (c, t) in enumerate(zip(scene.node_classes.tolist(), scene.node_timestamps.tolist()))}
+    boxes = torch.randn(scene.num_nodes, 10)
+    graph_io.save_window_graph(prefix, scene, meta, boxes)
+    return prefix, scene
+
+
+def same(a, b):
+    return a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("seed,inference", [(1, False), (2, True), (3, True)])
+def test_loader_matches_reference_getitem(tmp_path, seed, inference):
+    prefix, scene = write_window(tmp_path, seed)
+    ref = R.getitem(prefix, inference=inference)
+    got = graph_io.load_window_graph(prefix, inference=inference)
+    keys = ["pose_feats", "img_feats", "lidar_feats", "radar_feats", "edge_index", "edge_attr", "y", "node_timestamps",
+            "edge_weights", "edge_classes", "node_classes"] + (["global_edge_index", "global_node_timestamps", "boxes"] if inference else [])
+    for k in keys:
+        assert same(getattr(got, k), getattr(ref, k)), k
+    assert got.num_nodes == ref.num_nodes == scene.num_nodes
+    assert got.edge_index.shape[0] == 2 and got.edge_attr.dtype == torch.float64     # `.float()` happens in the model
+
+
+def test_no_weighting_and_empty_graph(tmp_path):
+    prefix, _ = write_window(tmp_path, 4)
+    ref, got = R.getitem(prefix, edge_weighting=False), graph_io.load_window_graph(prefix, edge_weighting=False)
+    assert same(got.edge_weights, ref.edge_weights) and got.edge_classes is None
+    prefix, scene = write_window(tmp_path, 5, T=1)           # a single frame: no edges
+    assert scene.edge_index.size(1) == 0
+    got = graph_io.load_window_graph(prefix, inference=True)
+    assert got.edge_index.shape == (2, 0) and got.edge_weights.numel() == 0 and got.global_edge_index.shape == (2, 0)
+
+
+def test_mixed_category_edges_are_rejected_like_the_reference(tmp_path):
+    prefix, scene = write_window(tmp_path, 6)
+    meta = {n: {"category_name": "car" if n % 2 else "bus", "global_node_id": n} for n in range(scene.num_nodes)}
+    graph_io.save_window_graph(prefix, scene, meta)
+    with pytest.raises(AttributeError):
+        R.getitem(prefix)
+    with pytest.raises(NotImplementedError):
+        graph_io.load_window_graph(prefix)
+
+
+def test_load_batch_collates_windows(tmp_path):
+    p1, s1 = write_window(tmp_path, 7)
+    p2, s2 = write_window(tmp_path, 8, npf=9)
+    b = graph_io.load_batch([p1, p2], pin=False)
+    assert b.num_nodes == s1.num_nodes + s2.num_nodes
+    E1 = s1.edge_index.size(1)
+    assert torch.equal(b.edge_index[:, E1:], s2.edge_index + s1.num_nodes)
+    assert torch.equal(b.batch, torch.cat([torch.zeros(s1.num_nodes), torch.ones(s2.num_nodes)]).long())
+    assert b.edge_weights.shape == (b.edge_index.size(1),) and b.pose_feats.shape == (b.num_nodes, 19)
