@@ -119,3 +119,13 @@ def build_window_graph(center, velocity, yaw, wlh, category, token, frame, top_k
     feats = torch.stack([dxy, dyaw, lvol, dt.to(f64)], 2)
     edges = torch.stack([ex, cu], 2)
     return edges[keep], gt[keep], feats[keep]
+
+
+def build_pose_features(ego_center, ego_wlh, ego_yaw, ego_velocity, category, score, rel_time, num_classes=7):
+    """The 19-d node feature of construct_...only_poses.py:159-186, for all nodes at once: ego-frame center (3),
+    wlh (3), yaw (1), velocity (3) as float32, one-hot class (class ids 1..num_classes), detection score, and the
+    frame index relative to the window start. Inputs are [N,...] tensors (float64 box parameters as the devkit
+    stores them; `.float()` rounds exactly like the reference's `torch.from_numpy(...).float()`)."""
+    onehot = torch.nn.functional.one_hot(category.to(torch.int64) - 1, num_classes=num_classes).float()
+    return torch.cat([ego_center.float(), ego_wlh.float(), ego_yaw.reshape(-1, 1).float(), ego_velocity.float(), onehot,
+                      score.reshape(-1, 1).to(torch.float32), rel_time.reshape(-1, 1).float()], 1)

@@ -120,3 +120,17 @@ def build_window_graph(frames, top_knn=40):
         past_nodes.extend(cur_nodes)
     return (torch.tensor(edges, dtype=torch.int64).reshape(-1, 2), torch.tensor(gt_edges, dtype=torch.int64),
             torch.tensor(edge_features, dtype=torch.float64).reshape(-1, 4))
+
+
+def node_feature(ego_center, ego_wlh, ego_yaw, ego_velocity, class_id, score, val, i, num_classes=7):
+    """construct_...only_poses.py:159-186 for ONE detection: returns the [1,19] row appended to pose_features."""
+    ego_box_yaw = torch.from_numpy(np.array([ego_yaw]))
+    feat_3d_pose = torch.cat([torch.from_numpy(ego_center).float(), torch.from_numpy(ego_wlh).float(),
+                              ego_box_yaw.float(), torch.from_numpy(ego_velocity).float()], dim=0)
+    feat_3d_pose = feat_3d_pose.reshape(-1, 1)
+    score_feat = torch.tensor(score).reshape(-1, 1)
+    class_label = torch.tensor(int(class_id))
+    class_one_hot = torch.nn.functional.one_hot(class_label - 1, num_classes=num_classes)
+    class_one_hot = class_one_hot.reshape(-1, 1).float()
+    rel_time_tensor = torch.tensor(int(val - i)).reshape(-1, 1).float()
+    return torch.cat([feat_3d_pose, class_one_hot, score_feat, rel_time_tensor], dim=0).reshape(1, -1)

@@ -110,6 +110,45 @@ def test_ground_truth_rule():
     assert lab[(0, 3)] == 1                             # node 3 (t=2, token 5): only appearance is two frames back
 
 
+def test_pose_features_match_reference_rows():
+    rng = np.random.default_rng(0)
+    N = 50
+    c, w, v = rng.normal(0, 20, (N, 3)), np.exp(rng.normal(0.5, 0.3, (N, 3))), rng.normal(0, 3, (N, 3))
+    yaw, score = rng.uniform(-3, 3, N), rng.uniform(0, 1, N)
+    cls, val = rng.integers(1, 8, N), rng.integers(12, 17, N)
+    ref = torch.cat([G.node_feature(c[n], w[n], float(yaw[n]), v[n], int(cls[n]), float(score[n]), int(val[n]), 12)
+                     for n in range(N)], 0)
+    got = graph_build.build_pose_features(torch.tensor(c), torch.tensor(w), torch.tensor(yaw), torch.tensor(v),
+                                          torch.tensor(cls), torch.tensor(score), torch.tensor(val - 12))
+    assert got.shape == (N, 19) and got.dtype == ref.dtype == torch.float32 and torch.equal(got, ref)
+
+
+def test_detections_to_batch_pipeline(tmp_path):
+    """graph construction -> reference file layout -> loader -> batch: the data path in front of the GNN."""
+    from batch3dmot_b200 import graph_io, synth
+    prefixes = []
+    for seed in (31, 32):
+        frames = random_window(seed, max_per_frame=15, n_objects=25)
+        center, velocity, yaw, wlh, category, token, frame = to_tensors(frames)
+        edges, gt, feats = graph_build.build_window_graph(center, velocity, yaw, wlh, category, token, frame)
+        N = center.size(0)
+        pose = graph_build.build_pose_features(center, wlh, yaw, velocity, category, torch.rand(N, dtype=torch.float64),
+                                               frame - frame.min())
+        data = synth.SimpleNamespace(pose_feats=pose, img_feats=torch.zeros(N, 3, 8, 8), lidar_feats=torch.zeros(N, 128, 3),
+                                     radar_feats=torch.zeros(N, 64, 4), node_timestamps=frame, edge_attr=feats,
+                                     edge_index=edges.t().contiguous(), y=gt)
+        meta = {n: {"category_name": synth.CATEGORIES[int(category[n]) - 1], "global_node_id": n} for n in range(N)}
+        prefix = str(tmp_path / f"w{seed}")
+        graph_io.save_window_graph(prefix, data, meta)
+        prefixes.append(prefix)
+        one = graph_io.load_window_graph(prefix)
+        assert torch.equal(one.edge_index, edges.t()) and torch.equal(one.y, gt) and torch.equal(one.edge_attr, feats)
+        assert bool((one.edge_classes == category[edges[:, 1]].float()).all())
+    b = graph_io.load_batch(prefixes, pin=False)
+    assert b.edge_index.size(1) == b.edge_attr.size(0) == b.y.numel() == b.edge_weights.numel()
+    assert bool((b.edge_index[0] < b.edge_index[1]).all())
+
+
 @pytest.mark.gpu
 def test_same_result_on_cuda_tensors():
     """Same edges and labels on CUDA tensors (data without exact metric ties: the order of exactly tied entries is
