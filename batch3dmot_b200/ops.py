@@ -2,7 +2,6 @@
 the drop-in layers train with the reference's own `loss.backward(); optimizer.step()`
 (train.py:157-160). Every FLOP on this path runs in a libb3d kernel; torch provides device
 memory, streams and autograd bookkeeping only."""
-import ctypes as C
 
 import torch
 
