@@ -15,7 +15,10 @@ Follows, line by line:
 
 A node is a dict {'node_id', 'center' np.float64[3], 'velocity' np.float64[3], 'yaw' float (what
 quaternion_yaw(box.orientation) returns), 'wlh' np.float64[3], 'category' int, 'token' int or None,
-'time' int (frame index)}. Parity is unpinned upstream only in torch.topk's tie order (exact metric ties).
+'time' int (frame index)}. Pinned: oracle/gen_golden_graph.py drives the window loop with the UNMODIFIED reference
+get_knn_nodes_in_graph / compute_motion_edge_feats (imported from /root/reference) and requires bit-equal edges,
+labels and float64 features before writing tests/golden/graph_build_small.pt; the loop itself (inline code of
+process_chunk, not importable) is restated. Unpinned upstream: torch.topk's order of exactly tied metrics.
 """
 import numpy as np
 import torch
@@ -73,10 +76,14 @@ def get_knn_nodes_in_graph(cur_node, other_nodes, k):   # graph_utils.py:33-88
     return [other_nodes[i] for i in top_k_idcs]
 
 
-def build_window_graph(frames, top_knn=40):
+def build_window_graph(frames, top_knn=40, knn_fn=None, feat_fn=None):
     """frames: list (one entry per frame of the window, in time order) of lists of node dicts WITHOUT
     'node_id' (assigned here in emission order, construct_...:163-201). Returns edges [E,2] int64
-    ([ex_id, cur_id]), gt [E] int64, edge_features [E,4] float64 — construct_...:204-270."""
+    ([ex_id, cur_id]), gt [E] int64, edge_features [E,4] float64 — construct_...:204-270.
+    knn_fn / feat_fn: replacements for get_knn_nodes_in_graph / compute_motion_edge_feats (gen_golden_graph.py
+    passes the UNMODIFIED reference functions here to pin the restatements above)."""
+    knn_fn = knn_fn or get_knn_nodes_in_graph
+    feat_fn = feat_fn or compute_motion_edge_feats
     edges, gt_edges, edge_features = [], [], []
     past_nodes, node_id = [], 0
     for cur_nodes in frames:
@@ -88,7 +95,7 @@ def build_window_graph(frames, top_knn=40):
                 past_categ_nodes = [p for p in past_nodes if p['category'] == cur['category']]
                 k = top_knn if len(past_categ_nodes) > top_knn else len(past_categ_nodes)
                 if len(past_categ_nodes) > 0:
-                    knn_past_nodes = get_knn_nodes_in_graph(cur, past_categ_nodes, k)
+                    knn_past_nodes = knn_fn(cur, past_categ_nodes, k)
                     for ex in knn_past_nodes:
                         edges.append([ex['node_id'], cur['node_id']])
                         if ex['token'] is not None and cur['token'] is not None:
@@ -114,7 +121,7 @@ def build_window_graph(frames, top_knn=40):
                                 gt_edges.append(0)
                         else:
                             gt_edges.append(0)
-                        box_feats = compute_motion_edge_feats(ex, cur)
+                        box_feats = feat_fn(ex, cur)
                         box_feats.append(abs(cur['time'] - ex['time']))
                         edge_features.append(box_feats)
         past_nodes.extend(cur_nodes)
@@ -134,3 +141,51 @@ def node_feature(ego_center, ego_wlh, ego_yaw, ego_velocity, class_id, score, va
     class_one_hot = class_one_hot.reshape(-1, 1).float()
     rel_time_tensor = torch.tensor(int(val - i)).reshape(-1, 1).float()
     return torch.cat([feat_3d_pose, class_one_hot, score_feat, rel_time_tensor], dim=0).reshape(1, -1)
+
+
+# ----------------------------------------------------------------------------- synthetic windows (test inputs)
+def random_window(seed, T=5, max_per_frame=40, n_cat=7, n_objects=60, p_seen=0.7, dup=False, gap_frames=()):
+    """Objects random-walk over frames and are detected with probability p_seen (so instance tokens repeat with
+    gaps: |dt| > 1 labels), plus false positives without a token; dup adds exact duplicates (metric ties)."""
+    import math
+    rng = np.random.default_rng(seed)
+    cat = rng.integers(1, n_cat + 1, n_objects)
+    pos = rng.uniform(-50, 50, (n_objects, 3))
+    vel = rng.normal(0, 3, (n_objects, 3)); vel[:, 2] = 0
+    yaw = rng.uniform(-math.pi, math.pi, n_objects)
+    wlh = np.exp(rng.normal(0.5, 0.3, (n_objects, 3)))
+    frames = []
+    for t in range(T):
+        nodes = []
+        if t in gap_frames:
+            frames.append(nodes); continue
+        seen = np.nonzero(rng.random(n_objects) < p_seen)[0][:max_per_frame]
+        for o in rng.permutation(seen):
+            nodes.append({'center': pos[o] + vel[o] * 0.5 * t + rng.normal(0, 0.2, 3), 'velocity': vel[o] + rng.normal(0, 0.3, 3),
+                          'yaw': float(yaw[o] + rng.normal(0, 0.05)), 'wlh': wlh[o] * np.exp(rng.normal(0, 0.02, 3)),
+                          'category': int(cat[o]), 'token': int(o), 'time': 10 + t})
+        for _ in range(int(rng.integers(0, 6))):            # false positives: no instance token
+            nodes.append({'center': rng.uniform(-50, 50, 3), 'velocity': rng.normal(0, 3, 3), 'yaw': float(rng.uniform(-3, 3)),
+                          'wlh': np.exp(rng.normal(0.5, 0.3, 3)), 'category': int(rng.integers(1, n_cat + 1)), 'token': None,
+                          'time': 10 + t})
+        if dup and nodes:                                  # exact duplicates: genuine metric ties
+            nodes.append({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in nodes[0].items()})
+        frames.append(nodes)
+    return frames
+
+
+def to_tensors(frames, device="cpu"):
+    """Frames of node dicts -> the tensor arguments of batch3dmot_b200.graph_build.build_window_graph."""
+    nodes = [n for f in frames for n in f]
+    f64 = torch.float64
+    if not nodes:
+        z3 = torch.zeros((0, 3), dtype=f64, device=device)
+        zi = torch.zeros(0, dtype=torch.int64, device=device)
+        return z3, z3, torch.zeros(0, dtype=f64, device=device), z3, zi, zi, zi
+    return (torch.tensor(np.stack([n['center'] for n in nodes]), dtype=f64, device=device),
+            torch.tensor(np.stack([n['velocity'] for n in nodes]), dtype=f64, device=device),
+            torch.tensor([n['yaw'] for n in nodes], dtype=f64, device=device),
+            torch.tensor(np.stack([n['wlh'] for n in nodes]), dtype=f64, device=device),
+            torch.tensor([n['category'] for n in nodes], dtype=torch.int64, device=device),
+            torch.tensor([-1 if n['token'] is None else n['token'] for n in nodes], dtype=torch.int64, device=device),
+            torch.tensor([n['time'] for n in nodes], dtype=torch.int64, device=device))

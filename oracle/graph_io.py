@@ -2,7 +2,8 @@
 GraphDataset.__getitem__ (batch_3dmot/utils/graph_data.py:152-256) with its class-balanced weight
 helper cb_scaling_factor (graph_data.py:126-138), returning a plain namespace instead of a
 torch_geometric.data.Data (only attribute access is used downstream). Nothing under batch3dmot_b200/
-may import this module.
+may import this module. Pinned by tests/test_graph_io.py::test_live_unmodified_reference_getitem, which runs the
+unmodified reference class (imported from /root/reference under oracle/pyg_shim.py) on the same files.
 
 Reference quirk kept: the branch for edges between nodes of DIFFERENT categories reads `self.rel_freq`,
 which the reference never defines (graph_data.py:218-222 would raise AttributeError); the graph construction

@@ -211,3 +211,100 @@ def load_reference(root="/root/reference"):
     for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
         del sys.modules[k]
     return pose, clr
+
+
+# --------------------------------------------------------------------------- graph-construction utilities
+class _Quaternion:
+    """Stand-in for pyquaternion.Quaternion restricted to what geo_utils.quaternion_yaw touches: a rotation
+    about z by `yaw` and its `rotation_matrix`."""
+
+    def __init__(self, yaw):
+        self.yaw = float(yaw)
+
+    @property
+    def rotation_matrix(self):
+        import numpy as np
+        c, s_ = np.cos(self.yaw), np.sin(self.yaw)
+        return np.array([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]])
+
+
+class _Box:
+    """Stand-in for nuscenes.utils.data_classes.Box: the attributes geo_utils / graph_utils read."""
+
+    def __init__(self, center, wlh, yaw, velocity, name="car", token=None, score=1.0):
+        import numpy as np
+        self.center, self.wlh, self.velocity = np.asarray(center, float), np.asarray(wlh, float), np.asarray(velocity, float)
+        self.orientation, self.name, self.token, self.score = _Quaternion(yaw), name, token, score
+
+
+def load_reference_graph_utils(root="/root/reference"):
+    """Import the unmodified batch_3dmot/utils/{geo_utils,graph_utils}.py (build container only) with stand-ins
+    for pyquaternion / nuscenes / shapely. Returns (geo_utils, graph_utils, Box)."""
+    import importlib
+    import os
+    if not os.path.isdir(root):
+        raise RuntimeError(f"reference tree {root} not present (it never is on the GPU box)")
+    _mod("pyquaternion", Quaternion=_Quaternion)
+    ns = _mod("nuscenes"); ns.__path__ = []
+    nu = _mod("nuscenes.utils"); nu.__path__ = []
+    _mod("nuscenes.utils.data_classes", Box=_Box)
+    sh = _mod("shapely"); sh.__path__ = []
+    _mod("shapely.geometry", Polygon=type("Polygon", (), {}))
+    for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
+        del sys.modules[k]
+    top = types.ModuleType("batch_3dmot")
+    top.__path__ = [os.path.join(root, "batch_3dmot")]
+    sys.modules["batch_3dmot"] = top
+    utils = types.ModuleType("batch_3dmot.utils")           # skip the package's other modules (nuScenes devkit imports)
+    utils.__path__ = [os.path.join(root, "batch_3dmot", "utils")]
+    sys.modules["batch_3dmot.utils"] = utils
+    geo = importlib.import_module("batch_3dmot.utils.geo_utils")
+    gu = importlib.import_module("batch_3dmot.utils.graph_utils")
+    for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
+        del sys.modules[k]
+    return geo, gu, _Box
+
+
+def load_reference_graph_dataset(root="/root/reference"):
+    """Import the unmodified batch_3dmot/utils/graph_data.py (build container only) and return its GraphDataset
+    class. Stand-ins: torch_geometric.data.{Dataset, Data} (attribute bags), torch_geometric.{utils, transforms},
+    batch_3dmot.predict_contrastive (an unused import), and batch_3dmot.utils.dataset reduced to get_class_config
+    (dataset.py:33-51; the real module needs PIL and the nuScenes devkit)."""
+    import importlib
+    import os
+    from types import SimpleNamespace
+    if not os.path.isdir(root):
+        raise RuntimeError(f"reference tree {root} not present (it never is on the GPU box)")
+    install()
+
+    class Dataset:
+        def __init__(self, *a, **k):
+            pass
+
+    class Data(SimpleNamespace):
+        pass
+
+    tg = sys.modules["torch_geometric"]
+    tg.data = _mod("torch_geometric.data", Dataset=Dataset, Data=Data)
+    tg.utils = _mod("torch_geometric.utils")
+    tg.transforms = _mod("torch_geometric.transforms")
+    for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
+        del sys.modules[k]
+    top = types.ModuleType("batch_3dmot")
+    top.__path__ = [os.path.join(root, "batch_3dmot")]
+    sys.modules["batch_3dmot"] = top
+    utils = types.ModuleType("batch_3dmot.utils")
+    utils.__path__ = [os.path.join(root, "batch_3dmot", "utils")]
+    sys.modules["batch_3dmot.utils"] = utils
+    top.utils = utils
+    _mod("batch_3dmot.predict_contrastive", inference=None)
+
+    def get_class_config(params, class_dict_name="nuscenes_tracking_eval"):        # dataset.py:33-51
+        assert isinstance(class_dict_name, str)
+        return vars(params.classes)[class_dict_name]
+
+    utils.dataset = _mod("batch_3dmot.utils.dataset", get_class_config=get_class_config)
+    gd = importlib.import_module("batch_3dmot.utils.graph_data")
+    for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
+        del sys.modules[k]
+    return gd.GraphDataset

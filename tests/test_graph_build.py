@@ -3,6 +3,7 @@ restatement of the reference's per-node loops (oracle/graph_construction.py). Ed
 bit-exact; float64 edge features within 4 ulp (numpy's norm may fuse a multiply-add). CPU tests; the same function
 runs on CUDA tensors (gpu-marked test at the bottom)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -12,49 +13,7 @@ from oracle import graph_construction as G
 from batch3dmot_b200 import graph_build
 
 
-def random_window(seed, T=5, max_per_frame=40, n_cat=7, n_objects=60, p_seen=0.7, dup=False, gap_frames=()):
-    """Objects random-walk over frames and are detected with probability p_seen (so instance tokens repeat with
-    gaps: |dt| > 1 labels), plus false positives without a token."""
-    rng = np.random.default_rng(seed)
-    cat = rng.integers(1, n_cat + 1, n_objects)
-    pos = rng.uniform(-50, 50, (n_objects, 3))
-    vel = rng.normal(0, 3, (n_objects, 3)); vel[:, 2] = 0
-    yaw = rng.uniform(-math.pi, math.pi, n_objects)
-    wlh = np.exp(rng.normal(0.5, 0.3, (n_objects, 3)))
-    frames = []
-    for t in range(T):
-        nodes = []
-        if t in gap_frames:
-            frames.append(nodes); continue
-        seen = np.nonzero(rng.random(n_objects) < p_seen)[0][:max_per_frame]
-        for o in rng.permutation(seen):
-            nodes.append({'center': pos[o] + vel[o] * 0.5 * t + rng.normal(0, 0.2, 3), 'velocity': vel[o] + rng.normal(0, 0.3, 3),
-                          'yaw': float(yaw[o] + rng.normal(0, 0.05)), 'wlh': wlh[o] * np.exp(rng.normal(0, 0.02, 3)),
-                          'category': int(cat[o]), 'token': int(o), 'time': 10 + t})
-        for _ in range(int(rng.integers(0, 6))):            # false positives: no instance token
-            nodes.append({'center': rng.uniform(-50, 50, 3), 'velocity': rng.normal(0, 3, 3), 'yaw': float(rng.uniform(-3, 3)),
-                          'wlh': np.exp(rng.normal(0.5, 0.3, 3)), 'category': int(rng.integers(1, n_cat + 1)), 'token': None,
-                          'time': 10 + t})
-        if dup and nodes:                                  # exact duplicates: genuine metric ties
-            nodes.append({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in nodes[0].items()})
-        frames.append(nodes)
-    return frames
-
-
-def to_tensors(frames, device="cpu"):
-    nodes = [n for f in frames for n in f]
-    f64 = torch.float64
-    if not nodes:
-        z3 = torch.zeros((0, 3), dtype=f64, device=device)
-        zi = torch.zeros(0, dtype=torch.int64, device=device)
-        return z3, z3, torch.zeros(0, dtype=f64, device=device), z3, zi, zi, zi
-    return (torch.tensor(np.stack([n['center'] for n in nodes]), dtype=f64, device=device),
-            torch.tensor(np.stack([n['velocity'] for n in nodes]), dtype=f64, device=device),
-            torch.tensor([n['yaw'] for n in nodes], dtype=f64, device=device),
-            torch.tensor(np.stack([n['wlh'] for n in nodes]), dtype=f64, device=device),
-            torch.tensor([n['category'] for n in nodes], dtype=torch.int64, device=device),
-            torch.tensor([-1 if n['token'] is None else n['token'] for n in nodes], dtype=torch.int64, device=device),
-            torch.tensor([n['time'] for n in nodes], dtype=torch.int64, device=device))
+random_window, to_tensors = G.random_window, G.to_tensors
 
 
 def check(frames, top_knn=40, device="cpu", feat_tol=(4e-15, 1e-300)):
@@ -108,6 +67,35 @@ def test_ground_truth_rule():
     assert lab[(3, 4)] == 1 and lab[(0, 4)] == 0        # node 4 (t=3, token 5): t=2 is positive, t=0 is not
     assert lab[(2, 5)] == 1 and lab[(1, 5)] == 0        # node 5 (t=3, token 6): t=1 beats t=0
     assert lab[(0, 3)] == 1                             # node 3 (t=2, token 5): only appearance is two frames back
+
+
+def test_golden_vectors_from_the_unmodified_reference():
+    """tests/golden/graph_build_small.pt was written by oracle/gen_golden_graph.py, which drives the window loop with
+    the UNMODIFIED reference get_knn_nodes_in_graph / compute_motion_edge_feats: the product must reproduce it."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "graph_build_small.pt"), weights_only=True)
+    assert len(g) == 4
+    for name, c in g.items():
+        e, gt, f = graph_build.build_window_graph(c["center"], c["velocity"], c["yaw"], c["wlh"], c["category"],
+                                                  c["token"], c["frame"])
+        assert torch.equal(e, c["edges"]) and torch.equal(gt, c["gt"]), name
+        assert torch.allclose(f, c["edge_features"], rtol=4e-15, atol=1e-300), name
+    assert int(torch.bincount(g["w2"]["edges"][:, 1]).max()) == 40          # the k = 40 cap is exercised
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_live_reference_graph_utils_match_restatement():
+    from oracle import pyg_shim
+    geo, gu, Box = pyg_shim.load_reference_graph_utils()
+    frames = random_window(7, max_per_frame=20, n_objects=30)
+    for f in frames:
+        for n in f:
+            n['box'] = Box(n['center'], n['wlh'], n['yaw'], n['velocity'], "car", n['token'])
+            n['yaw'] = float(geo.quaternion_yaw(n['box'].orientation))
+    ref = G.build_window_graph([[dict(n) for n in f] for f in frames], knn_fn=gu.get_knn_nodes_in_graph,
+                               feat_fn=gu.compute_motion_edge_feats)
+    own = G.build_window_graph([[dict(n) for n in f] for f in frames])
+    assert all(torch.equal(a, b) for a, b in zip(ref, own))
 
 
 def test_pose_features_match_reference_rows():

@@ -65,3 +65,27 @@ def test_load_batch_collates_windows(tmp_path):
     assert torch.equal(b.edge_index[:, E1:], s2.edge_index + s1.num_nodes)
     assert torch.equal(b.batch, torch.cat([torch.zeros(s1.num_nodes), torch.ones(s2.num_nodes)]).long())
     assert b.edge_weights.shape == (b.edge_index.size(1),) and b.pose_feats.shape == (b.num_nodes, 19)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("inference", [False, True])
+def test_live_unmodified_reference_getitem(tmp_path, inference):
+    """The UNMODIFIED GraphDataset.__getitem__ (graph_data.py:152-256, imported from /root/reference under the shim)
+    on the same files: pins both the restatement and the loader."""
+    from types import SimpleNamespace
+    from oracle import pyg_shim
+    GD = pyg_shim.load_reference_graph_dataset()
+    prefix, _ = write_window(tmp_path, 9)
+    ds = object.__new__(GD)                      # __init__ only builds the file list from nuScenes scene records
+    ds.batches, ds.inference, ds.edge_weighting = [prefix], inference, True
+    ds.params = SimpleNamespace(classes=SimpleNamespace(nuscenes_tracking_eval=R.CLASS_DICT),
+                                main=SimpleNamespace(class_dict="nuscenes_tracking_eval"))
+    ds.rel_freq_train = R.REL_FREQ_TRAIN
+    item = ds[0]
+    data = item[0] if inference else item
+    ours, rest = graph_io.load_window_graph(prefix, inference=inference), R.getitem(prefix, inference=inference)
+    keys = ["pose_feats", "img_feats", "lidar_feats", "radar_feats", "edge_index", "edge_attr", "y", "node_timestamps",
+            "edge_weights", "edge_classes", "node_classes"] + (["global_edge_index", "global_node_timestamps", "boxes"] if inference else [])
+    for k in keys:
+        assert same(getattr(data, k), getattr(ours, k)) and same(getattr(data, k), getattr(rest, k)), k
+    assert data.num_nodes == ours.num_nodes
