@@ -308,3 +308,44 @@ def load_reference_graph_dataset(root="/root/reference"):
     for k in [k for k in sys.modules if k == "batch_3dmot" or k.startswith("batch_3dmot.")]:
         del sys.modules[k]
     return gd.GraphDataset
+
+
+def load_reference_predict_functions(root="/root/reference"):
+    """The UNMODIFIED source text of predict.py's track-assembly functions (greedy_filter_node_flux,
+    aggregate_node_flux, get_instance_metadata, combine_batches_to_scene, create_trajectories), cut out of
+    /root/reference/batch_3dmot/predict.py by AST line ranges and exec'd in a namespace of stand-ins (the module
+    itself cannot be imported: it parses argv, opens nuScenes and starts ray at import time). Returns the
+    namespace dict; the caller sets ns['nusc'], ns['load_batch_detections'] and passes a stub gnn. Build
+    container only."""
+    import ast
+    import json
+    import os
+    from collections import defaultdict
+    from types import SimpleNamespace
+    import numpy as np
+    path = os.path.join(root, "batch_3dmot", "predict.py")
+    if not os.path.exists(path):
+        raise RuntimeError(f"reference tree {root} not present (it never is on the GPU box)")
+    src = open(path).read()
+    wanted = ("greedy_filter_node_flux", "aggregate_node_flux", "get_instance_metadata", "combine_batches_to_scene",
+              "create_trajectories")
+
+    def tqdm(it=None, *a, **k):
+        return it
+    tqdm.write = lambda *a, **k: None
+
+    class Data(SimpleNamespace):
+        def to(self, device):
+            return self
+
+    ns = {"np": np, "torch": torch, "os": os, "json": json, "defaultdict": defaultdict, "tqdm": tqdm, "ParamLib": object,
+          "torch_geometric": SimpleNamespace(data=SimpleNamespace(Data=Data)),
+          "batch_3dmot": SimpleNamespace(
+              models=SimpleNamespace(cl_att_gnn=SimpleNamespace(GNN=object)),
+              utils=SimpleNamespace(dataset=SimpleNamespace(
+                  get_class_config=lambda params, class_dict_name: vars(params.classes)[class_dict_name])))}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in wanted:
+            exec(compile(ast.get_source_segment(src, node), path, "exec"), ns)
+    assert all(w in ns for w in wanted)
+    return ns

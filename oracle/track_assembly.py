@@ -4,6 +4,10 @@ clustering that yields track ids. Follows batch_3dmot/predict.py:92-124 (greedy_
 aggregate_node_flux), :199-259 (combine_batches_to_scene) and :290-373 (create_trajectories,
 mode 'hier'); dict insertion order and `max`/`sorted` tie-breaking are kept exactly.
 
+Pinned by tests/test_tracking.py::test_live_unmodified_reference_track_assembly: the unmodified source text of
+those predict.py functions, exec'd under stand-ins (oracle/pyg_shim.load_reference_predict_functions), returns the
+same tracks on synthetic scenes, exact score ties included.
+
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py). The node-metadata hash of the reference
 (predict.py:200-208) is replaced by a provided scene-global node id per window node."""
 from collections import defaultdict
