@@ -7,6 +7,8 @@ loops: class-balanced weights, edge / node classes and global ids are table look
 list. Also the writer (used for fixtures / round trips), batching (`synth.collate`) and pinned staging.
 """
 import json
+import random
+from concurrent.futures import ThreadPoolExecutor
 from types import SimpleNamespace
 
 import torch
@@ -81,3 +83,48 @@ def load_batch(prefixes, pin=True, **kw):
             if torch.is_tensor(v):
                 setattr(batch, k, v.pin_memory())
     return batch
+
+
+class WindowBatchLoader:
+    """Iterates a list of window file prefixes in batches of `batch_size` windows (the reference trains with
+    torch_geometric.loader.DataLoader(dataset, batch_size=2, shuffle=True, num_workers=...), train.py:88-96):
+    each batch is the disjoint union of its windows (`load_batch`), read and collated by `workers` background
+    threads `prefetch` batches ahead and (on a CUDA machine) placed in pinned memory, so the consumer only
+    issues `non_blocking` H2D copies. Order is deterministic for a given seed; with shuffle=False it is the list order."""
+
+    def __init__(self, prefixes, batch_size=2, shuffle=False, seed=0, workers=4, prefetch=4, drop_last=False, pin=True,
+                 **load_kw):
+        self.prefixes, self.batch_size, self.shuffle, self.seed = list(prefixes), int(batch_size), shuffle, seed
+        self.workers, self.prefetch, self.drop_last, self.pin, self.load_kw = workers, max(1, prefetch), drop_last, pin, load_kw
+        self.epoch = 0
+
+    def __len__(self):
+        n = len(self.prefixes)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def batches(self):
+        """The prefix groups of the current epoch (shuffled per epoch like a DataLoader sampler)."""
+        order = list(range(len(self.prefixes)))
+        if self.shuffle:
+            random.Random(self.seed + self.epoch).shuffle(order)
+        groups = [order[i:i + self.batch_size] for i in range(0, len(order), self.batch_size)]
+        if self.drop_last and groups and len(groups[-1]) < self.batch_size:
+            groups.pop()
+        return [[self.prefixes[j] for j in g] for g in groups]
+
+    def __iter__(self):
+        groups = self.batches()
+        self.epoch += 1
+        with ThreadPoolExecutor(max_workers=max(1, self.workers)) as pool:
+            pending = []
+            it = iter(groups)
+            for g in it:
+                pending.append(pool.submit(load_batch, g, self.pin, **self.load_kw))
+                if len(pending) >= self.prefetch:
+                    break
+            while pending:
+                fut = pending.pop(0)
+                nxt = next(it, None)
+                if nxt is not None:
+                    pending.append(pool.submit(load_batch, nxt, self.pin, **self.load_kw))
+                yield fut.result()

@@ -67,6 +67,26 @@ def test_load_batch_collates_windows(tmp_path):
     assert b.edge_weights.shape == (b.edge_index.size(1),) and b.pose_feats.shape == (b.num_nodes, 19)
 
 
+def test_window_batch_loader_order_and_content(tmp_path):
+    prefixes = [write_window(tmp_path, 40 + i, npf=6 + i)[0] for i in range(5)]
+    ld = graph_io.WindowBatchLoader(prefixes, batch_size=2, workers=3, prefetch=2, pin=False)
+    assert len(ld) == 3
+    got = list(ld)
+    assert len(got) == 3
+    for b, grp in zip(got, ld.batches()):
+        ref = graph_io.load_batch(grp, pin=False)
+        for k in ("pose_feats", "edge_index", "edge_attr", "y", "edge_weights", "batch"):
+            assert torch.equal(getattr(b, k), getattr(ref, k)), k
+    assert int(got[-1].batch.max()) == 0                                # the last batch holds the single left-over window
+    assert len(graph_io.WindowBatchLoader(prefixes, batch_size=2, drop_last=True)) == 2
+    sh = graph_io.WindowBatchLoader(prefixes, batch_size=2, shuffle=True, seed=3, pin=False)
+    e0, _ = sh.batches(), list(sh)
+    e1 = sh.batches()
+    assert sorted(sum(e0, [])) == sorted(prefixes) and e0 != e1          # a permutation, reshuffled every epoch
+    sh2 = graph_io.WindowBatchLoader(prefixes, batch_size=2, shuffle=True, seed=3, pin=False)
+    assert sh2.batches() == e0                                           # deterministic for a given seed
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
 @pytest.mark.parametrize("inference", [False, True])
 def test_live_unmodified_reference_getitem(tmp_path, inference):
