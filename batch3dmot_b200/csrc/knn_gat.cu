@@ -29,6 +29,9 @@ __device__ __forceinline__ bool pair_less(float d0, int i0, float d1, int i1) {
 }
 
 // stride: floats per staged row, >= round_up(D,4), == 4 (mod 8) -> conflict-free LDS.128
+// KS = sorted-list slots per lane: rank r of a query's current top-k lives in slot r / 32 of lane r % 32, so
+// k <= 32 * KS (KS = 1 keeps the whole list in one register per lane; KS = 4 covers the k = 100 upstream allows).
+template <int KS>
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_frames(
     const float* __restrict__ x, int ldx, int D, int stride, const int32_t* __restrict__ frame_ptr, int F,
     const int32_t* __restrict__ blk_ptr, int k, int64_t* __restrict__ idx_out) {
@@ -53,10 +56,13 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_frames(
     int r = i / D4, d = i - r * D4;
     q_s[r * stride + d] = (r < nq && d < D) ? __ldg(x + (long long)(q0 + r) * ldx + d) : 0.f;
   }
-  float bd[KNN_QPW];
-  int bi[KNN_QPW];
+  float bd[KNN_QPW][KS];
+  int bi[KNN_QPW][KS];
 #pragma unroll
-  for (int qq = 0; qq < KNN_QPW; ++qq) { bd[qq] = INFINITY; bi[qq] = INT_MAX; }
+  for (int qq = 0; qq < KNN_QPW; ++qq)
+#pragma unroll
+    for (int s = 0; s < KS; ++s) { bd[qq][s] = INFINITY; bi[qq][s] = INT_MAX; }
+  const int kslot = (k - 1) >> 5, klane = (k - 1) & 31;   // where the current k-th best lives
 
   for (int c0 = fs; c0 < fe; c0 += KNN_CT) {
     const int nc = min(KNN_CT, fe - c0);
@@ -92,8 +98,11 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_frames(
       for (int qq = 0; qq < KNN_QPW; ++qq) {
         const int q = q0 + warp * KNN_QPW + qq;
         if (warp * KNN_QPW + qq >= nq) continue;  // warp-uniform
-        const float kd = __shfl_sync(0xffffffffu, bd[qq], k - 1);
-        const int ki = __shfl_sync(0xffffffffu, bi[qq], k - 1);
+        float kd = INFINITY;
+        int ki = INT_MAX;
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+          if (s == kslot) { kd = __shfl_sync(0xffffffffu, bd[qq][s], klane); ki = __shfl_sync(0xffffffffu, bi[qq][s], klane); }
         const bool beats = cvalid && cand != q && pair_less(dist[qq], cand, kd, ki);
         unsigned m = __ballot_sync(0xffffffffu, beats);
         while (m) {
@@ -101,12 +110,26 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_frames(
           m &= m - 1;
           const float cd = __shfl_sync(0xffffffffu, dist[qq], srcl);
           const int ci = __shfl_sync(0xffffffffu, cand, srcl);
-          const int pos = __popc(__ballot_sync(0xffffffffu, pair_less(bd[qq], bi[qq], cd, ci)));
-          const float ud = __shfl_up_sync(0xffffffffu, bd[qq], 1);
-          const int ui = __shfl_up_sync(0xffffffffu, bi[qq], 1);
-          if (pos < k) {
-            if (lane > pos) { bd[qq] = ud; bi[qq] = ui; }
-            else if (lane == pos) { bd[qq] = cd; bi[qq] = ci; }
+          int pos = 0;     // number of list entries ordered before the candidate == its insertion rank
+#pragma unroll
+          for (int s = 0; s < KS; ++s) pos += __popc(__ballot_sync(0xffffffffu, pair_less(bd[qq][s], bi[qq][s], cd, ci)));
+          if (pos < k) {   // warp-uniform
+            // shift ranks > pos up by one: rank r takes rank r-1 (lane-1 of the same slot, or lane 31 of the slot below)
+            float carry_d = 0.f;
+            int carry_i = 0;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+              const float ud = __shfl_up_sync(0xffffffffu, bd[qq][s], 1);
+              const int ui = __shfl_up_sync(0xffffffffu, bi[qq][s], 1);
+              const float top_d = __shfl_sync(0xffffffffu, bd[qq][s], 31);   // leaves this slot (before the shift)
+              const int top_i = __shfl_sync(0xffffffffu, bi[qq][s], 31);
+              const int rank = s * 32 + lane;
+              const float pd = lane == 0 ? carry_d : ud;
+              const int pi = lane == 0 ? carry_i : ui;
+              if (rank > pos) { bd[qq][s] = pd; bi[qq][s] = pi; }
+              else if (rank == pos) { bd[qq][s] = cd; bi[qq][s] = ci; }
+              carry_d = top_d; carry_i = top_i;
+            }
           }
         }
       }
@@ -116,7 +139,11 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_frames(
   for (int qq = 0; qq < KNN_QPW; ++qq) {
     if (warp * KNN_QPW + qq >= nq) continue;
     const long long q = q0 + warp * KNN_QPW + qq;
-    if (lane < k) idx_out[q * k + lane] = (bi[qq] == INT_MAX) ? (int64_t)-1 : (int64_t)bi[qq];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      const int r = s * 32 + lane;
+      if (r < k) idx_out[q * k + r] = (bi[qq][s] == INT_MAX) ? (int64_t)-1 : (int64_t)bi[qq][s];
+    }
   }
 }
 
@@ -138,6 +165,9 @@ __global__ void __launch_bounds__(256) k_gat_scores(const float* __restrict__ h,
   if (lane == 0) { a_s[n] = s; a_d[n] = d; }
 }
 
+// Neighbour slot l of a target lives in register set l / 32 of lane l % 32 (k <= 32 * GAT_KS).
+constexpr int GAT_KS = 4;
+
 __global__ void __launch_bounds__(256) k_gat_aggregate(
     const float* __restrict__ h, int ldh, int D, const float* __restrict__ a_s, const float* __restrict__ a_d,
     const float* __restrict__ bias, const int64_t* __restrict__ nbr, int k, long long N, float slope,
@@ -145,25 +175,47 @@ __global__ void __launch_bounds__(256) k_gat_aggregate(
   const int lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= N) return;
-  long long nb = (lane < k) ? nbr[t * k + lane] : -1;
-  const bool valid = nb >= 0;
-  float z = -INFINITY;
-  if (valid) {
-    z = __ldg(a_s + nb) + __ldg(a_d + t);
-    z = z > 0.f ? z : slope * z;
+  const int ks = (k + 31) >> 5;
+  long long nb[GAT_KS];
+  float z[GAT_KS], alpha[GAT_KS];
+  float zmax = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < GAT_KS; ++s) {
+    const int l = s * 32 + lane;
+    nb[s] = (s < ks && l < k) ? nbr[t * k + l] : -1;
+    z[s] = -INFINITY;
+    if (nb[s] >= 0) {
+      const float v = __ldg(a_s + nb[s]) + __ldg(a_d + t);
+      z[s] = v > 0.f ? v : slope * v;
+    }
+    zmax = fmaxf(zmax, z[s]);
   }
-  const float zmax = warp_max(z);
-  const float ez = valid ? expf(z - zmax) : 0.f;
-  const float den = warp_sum(ez);
-  const float alpha = valid ? ez / (den + 1e-16f) : 0.f;
-  if (alpha_out && lane < k) alpha_out[t * k + lane] = alpha;
+  zmax = warp_max(zmax);
+  float den = 0.f;
+#pragma unroll
+  for (int s = 0; s < GAT_KS; ++s) {      // slot-major partial sums, then one warp reduction
+    alpha[s] = nb[s] >= 0 ? expf(z[s] - zmax) : 0.f;
+    den += alpha[s];
+  }
+  den = warp_sum(den);
+#pragma unroll
+  for (int s = 0; s < GAT_KS; ++s) {
+    alpha[s] = nb[s] >= 0 ? alpha[s] / (den + 1e-16f) : 0.f;
+    const int l = s * 32 + lane;
+    if (alpha_out && s < ks && l < k) alpha_out[t * k + l] = alpha[s];
+  }
   for (int c0 = 0; c0 < D; c0 += 32) {   // uniform trip count: the shuffles below need all lanes
     const int c = c0 + lane;
     float acc = 0.f;
-    for (int l = 0; l < k; ++l) {
-      const float al = __shfl_sync(0xffffffffu, alpha, l);
-      const long long nl = __shfl_sync(0xffffffffu, nb, l);
-      if (nl >= 0 && c < D) acc = __fadd_rn(acc, __fmul_rn(al, __ldg(h + nl * ldh + c)));
+#pragma unroll
+    for (int s = 0; s < GAT_KS; ++s) {
+      if (s >= ks) break;
+      const int lim = min(32, k - s * 32);
+      for (int l = 0; l < lim; ++l) {
+        const float al = __shfl_sync(0xffffffffu, alpha[s], l);
+        const long long nl = __shfl_sync(0xffffffffu, nb[s], l);
+        if (nl >= 0 && c < D) acc = __fadd_rn(acc, __fmul_rn(al, __ldg(h + nl * ldh + c)));
+      }
     }
     if (c < D) out[t * ldo + c] = acc + (bias ? __ldg(bias + c) : 0.f);
   }
@@ -181,25 +233,46 @@ __global__ void __launch_bounds__(256) k_gat_bwd_target(
   const int lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= N) return;
-  const long long nb = (lane < k) ? nbr[t * k + lane] : -1;
-  const float al = (lane < k && nb >= 0) ? alpha[t * k + lane] : 0.f;
-  float dal = 0.f;                       // lane l ends up with g[t] . h[nbr_l]
-  for (int l = 0; l < k; ++l) {
-    const long long nl = __shfl_sync(0xffffffffu, nb, l);
-    float part = 0.f;
-    if (nl >= 0)
-      for (int c = lane; c < D; c += 32) part = fmaf(__ldg(g + t * ldg + c), __ldg(h + nl * ldh + c), part);
-    part = warp_sum(part);
-    if (lane == l) dal = part;
+  const int ks = (k + 31) >> 5;
+  long long nb[GAT_KS];
+  float al[GAT_KS], dal[GAT_KS], dsl[GAT_KS];
+#pragma unroll
+  for (int s = 0; s < GAT_KS; ++s) {
+    const int l = s * 32 + lane;
+    nb[s] = (s < ks && l < k) ? nbr[t * k + l] : -1;
+    al[s] = nb[s] >= 0 ? alpha[t * k + l] : 0.f;
+    dal[s] = 0.f;                        // slot (s, lane) ends up with g[t] . h[nbr]
   }
-  const float dot = warp_sum(al * dal);  // sum_m alpha_m d alpha_m
-  float dsl = 0.f;
-  if (nb >= 0) {
-    const float pre = __ldg(a_s + nb) + __ldg(a_d + t);
-    dsl = al * (dal - dot) * (pre > 0.f ? 1.f : slope);
+#pragma unroll
+  for (int s = 0; s < GAT_KS; ++s) {
+    if (s >= ks) break;
+    const int lim = min(32, k - s * 32);
+    for (int l = 0; l < lim; ++l) {
+      const long long nl = __shfl_sync(0xffffffffu, nb[s], l);
+      float part = 0.f;
+      if (nl >= 0)
+        for (int c = lane; c < D; c += 32) part = fmaf(__ldg(g + t * ldg + c), __ldg(h + nl * ldh + c), part);
+      part = warp_sum(part);
+      if (lane == l) dal[s] = part;
+    }
   }
-  if (lane < k) ds[t * k + lane] = dsl;
-  const float tot = warp_sum(dsl);
+  float dot = 0.f;
+#pragma unroll
+  for (int s = 0; s < GAT_KS; ++s) dot += al[s] * dal[s];
+  dot = warp_sum(dot);                   // sum_m alpha_m d alpha_m
+  float tot = 0.f;
+#pragma unroll
+  for (int s = 0; s < GAT_KS; ++s) {
+    dsl[s] = 0.f;
+    if (nb[s] >= 0) {
+      const float pre = __ldg(a_s + nb[s]) + __ldg(a_d + t);
+      dsl[s] = al[s] * (dal[s] - dot) * (pre > 0.f ? 1.f : slope);
+    }
+    const int l = s * 32 + lane;
+    if (s < ks && l < k) ds[t * k + l] = dsl[s];
+    tot += dsl[s];
+  }
+  tot = warp_sum(tot);
   if (lane == 0) dad[t] = tot;
 }
 
@@ -237,7 +310,7 @@ using namespace b3d;
 extern "C" int b3d_knn_frames(const float* x, int32_t ldx, int32_t D, const int32_t* frame_ptr, int32_t F,
                               int64_t N, int32_t k, int64_t* idx_out, int32_t* scratch, void* stream) {
   if (!x || !frame_ptr || !idx_out || !scratch) return bad_arg("b3d_knn_frames: null pointer");
-  if (k < 1 || k > 32) return bad_arg("b3d_knn_frames: k must be in [1,32]");
+  if (k < 1 || k > 128) return bad_arg("b3d_knn_frames: k must be in [1,128]");
   if (D < 1 || D > 256) return bad_arg("b3d_knn_frames: D must be in [1,256]");
   if (N == 0 || F == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -246,14 +319,18 @@ extern "C" int b3d_knn_frames(const float* x, int32_t ldx, int32_t D, const int3
   size_t smem = sizeof(float) * (size_t)(KNN_QB + KNN_CT) * stride;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_knn_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_knn_frames<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_knn_frames<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_knn_frames<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("knn smem attr", e);
     smem_set = smem;
   }
   k_knn_blockptr<<<1, 32, 0, st>>>(frame_ptr, F, scratch);
   B3D_LAUNCH_CHECK("k_knn_blockptr");
   unsigned grid = (unsigned)(ceil_div(N, KNN_QB) + F);
-  k_knn_frames<<<grid, KNN_WARPS * 32, smem, st>>>(x, ldx, D, stride, frame_ptr, F, scratch, k, idx_out);
+  if (k <= 32) k_knn_frames<1><<<grid, KNN_WARPS * 32, smem, st>>>(x, ldx, D, stride, frame_ptr, F, scratch, k, idx_out);
+  else if (k <= 64) k_knn_frames<2><<<grid, KNN_WARPS * 32, smem, st>>>(x, ldx, D, stride, frame_ptr, F, scratch, k, idx_out);
+  else k_knn_frames<4><<<grid, KNN_WARPS * 32, smem, st>>>(x, ldx, D, stride, frame_ptr, F, scratch, k, idx_out);
   B3D_LAUNCH_CHECK("k_knn_frames");
   return 0;
 }
@@ -263,7 +340,7 @@ extern "C" int b3d_gat_aggregate(const float* h, int32_t ldh, int32_t D, const f
                                  int64_t N, float slope, float* out, int32_t ldo, float* alpha_out,
                                  float* scratch, void* stream) {
   if (!h || !att_src || !att_dst || !nbr || !out || !scratch) return bad_arg("b3d_gat_aggregate: null pointer");
-  if (k < 1 || k > 32) return bad_arg("b3d_gat_aggregate: k must be in [1,32]");
+  if (k < 1 || k > 32 * GAT_KS) return bad_arg("b3d_gat_aggregate: k must be in [1,128]");
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   float* a_s = scratch;
@@ -283,7 +360,7 @@ extern "C" int b3d_gat_bwd(const float* dout, int32_t ldg, const float* h, int32
   if (!dout || !h || !att_src || !att_dst || !nbr || !alpha || !a_s_a_d || !rowptr_src || !perm_src || !dh || !ds ||
       !das_dad)
     return bad_arg("b3d_gat_bwd: null pointer");
-  if (k < 1 || k > 32) return bad_arg("b3d_gat_bwd: k must be in [1,32]");
+  if (k < 1 || k > 32 * GAT_KS) return bad_arg("b3d_gat_bwd: k must be in [1,128]");
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   float* das = das_dad;

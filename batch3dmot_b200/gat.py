@@ -9,9 +9,9 @@ from . import ops
 
 
 def frame_ptr_from_timestamps(node_timestamps):
-    """int32 [F+1] frame offsets. Reference grouping key is node_timestamps alone
-    (pose_gnn.py:76-77). Nodes must be stored grouped by timestamp (true for graphs built by
-    the reference's preprocessing, one window after the other)."""
+    """int32 [F+1] frame offsets of nodes STORED GROUPED by timestamp (runs of equal values). The reference's
+    grouping key is the timestamp value alone (pose_gnn.py:76-77: `for t in node_timestamps.unique()`), so
+    callers with arbitrary node order go through `knn_attention_conv`, which sorts first."""
     _, counts = torch.unique_consecutive(node_timestamps, return_counts=True)
     ptr = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=node_timestamps.device)
     ptr[1:] = counts.cumsum(0)
@@ -36,6 +36,14 @@ class GATConv(nn.Module):
             a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
             with torch.no_grad():
                 t.uniform_(-a, a)
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        """PyG 2.0.x registers the shared Linear twice (`self.lin_dst = self.lin_src`), so its state_dict
+        holds `lin_src.weight` AND `lin_dst.weight`; emit both so a checkpoint written here loads strictly in
+        the reference (predict.py:404)."""
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        w = self.lin_src.weight
+        destination[prefix + "lin_dst.weight"] = w if keep_vars else w.detach()
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         for alt in ("lin_dst.weight", "lin.weight"):
@@ -65,8 +73,20 @@ class GATConv(nn.Module):
 
 def knn_attention_conv(conv, x, node_timestamps, k=20, frame_ptr=None):
     """The frame-wise k-NN graph + GATConv pass (pose_gnn.py:76-79): returns the updated
-    node features. The reference DISCARDS this result (`==` at pose_gnn.py:80, quirk C1)."""
-    if frame_ptr is None:
-        frame_ptr = frame_ptr_from_timestamps(node_timestamps)
-    nbr = ops.knn_frames(x, frame_ptr, k)
-    return conv.forward_table(x, nbr)
+    node features. The reference DISCARDS this result (`==` at pose_gnn.py:80, quirk C1).
+
+    Frames are the sets of nodes with EQUAL timestamp wherever they are stored (the reference masks
+    `node_timestamps == t`): nodes are stably sorted by timestamp, the kernel runs on the grouped copy
+    and the neighbour table is mapped back, so ungrouped inputs give the reference's frames and the
+    (distance, node id) tie order is unchanged (a stable sort keeps ids ascending inside a frame).
+    Pass `frame_ptr` to assert that nodes are already grouped and skip the sort."""
+    if frame_ptr is not None:
+        return conv.forward_table(x, ops.knn_frames(x, frame_ptr, k))
+    ts = node_timestamps.reshape(-1)
+    order = torch.sort(ts, stable=True).indices
+    frame_ptr = frame_ptr_from_timestamps(ts[order])
+    nbr_s = ops.knn_frames(x.detach()[order], frame_ptr, k)            # ids in the sorted numbering
+    nbr = torch.where(nbr_s >= 0, order[nbr_s.clamp(min=0)], nbr_s)   # -> original node ids
+    table = torch.empty_like(nbr)
+    table[order] = nbr                                                # row of sorted node p belongs to node order[p]
+    return conv.forward_table(x, table)

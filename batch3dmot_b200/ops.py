@@ -3,6 +3,8 @@ the drop-in layers train with the reference's own `loss.backward(); optimizer.st
 (train.py:157-160). Every FLOP on this path runs in a libb3d kernel; torch provides device
 memory, streams and autograd bookkeeping only."""
 
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -131,10 +133,16 @@ def get_precision():
     return _PRECISION
 
 
+_weight_epoch = 0        # bumped by invalidate_weight_cache(); part of every derived-weight key
+
+
 def invalidate_weight_cache():
-    """Packed bf16 weights are cached per (storage, version); call after updating weights through
+    """Packed bf16 weights are cached per live tensor object and version; call after updating weights through
     raw pointers (b3d_adam_step does not bump torch's version counter)."""
+    global _weight_epoch
+    _weight_epoch += 1
     _packed.clear()
+    _derived.clear()
 
 
 _USE_TMA = True          # dense bf16 operands go through the TMA-fed persistent kernel
@@ -142,19 +150,48 @@ _USE_BITS = True         # bf16 chains keep ReLU masks as sign bits (B3D_BITS) f
 
 
 def _packed_weight(W, transpose, rowmajor=False):
-    key = (W.data_ptr(), W._version, tuple(W.shape), W.stride(0), bool(transpose), rowmajor)
-    wp = _packed.get(key)
-    if wp is None:
-        if len(_packed) > 512:
-            _packed.clear()
-        n_log, k_log = (W.size(1), W.size(0)) if transpose else (W.size(0), W.size(1))
-        lib = L.lib()
-        nbytes, pack = (lib.b3d_tma_packed_bytes, lib.b3d_tma_pack_weights) if rowmajor else \
-            (lib.b3d_tc_packed_bytes, lib.b3d_tc_pack_weights)
-        wp = torch.empty(nbytes(n_log, k_log), dtype=torch.uint8, device=W.device)
-        L.check(pack(L.ptr(W), W.stride(0), n_log, k_log, int(transpose), L.ptr(wp), L.stream()), "pack_weights")
-        _packed[key] = wp
+    """bf16 pack of W for the tensor-core kernels. An entry belongs to ONE live tensor object: it holds a weak
+    reference and is used only while that very object is alive at the same version. (A key made of
+    (data_ptr, _version) alone would return the old pack for a temporary that the caching allocator placed
+    at a recycled address, or for the parameters of a new model allocated where a freed one lived.)"""
+    key = (id(W), tuple(W.shape), W.stride(0), bool(transpose), rowmajor)
+    ent = _packed.get(key)
+    if ent is not None:
+        ref, ver, ptr, wp = ent
+        if ref() is W and ver == W._version and ptr == W.data_ptr():
+            return wp
+    if len(_packed) > 512:
+        _packed.clear()
+    n_log, k_log = (W.size(1), W.size(0)) if transpose else (W.size(0), W.size(1))
+    lib = L.lib()
+    nbytes, pack = (lib.b3d_tma_packed_bytes, lib.b3d_tma_pack_weights) if rowmajor else \
+        (lib.b3d_tc_packed_bytes, lib.b3d_tc_pack_weights)
+    wp = torch.empty(nbytes(n_log, k_log), dtype=torch.uint8, device=W.device)
+    L.check(pack(L.ptr(W), W.stride(0), n_log, k_log, int(transpose), L.ptr(wp), L.stream()), "pack_weights")
+    _packed[key] = (weakref.ref(W), W._version, W.data_ptr(), wp)
     return wp
+
+
+_derived = {}
+
+
+def derived_weights(tag, sources, build):
+    """Tensors DERIVED from parameters (stacked / sliced weight blocks of the pre-projected formulation),
+    rebuilt only when a source parameter changes: the key holds every source's identity, address and version
+    plus the invalidation epoch, and the entry keeps weak references to the sources, so neither an optimiser
+    step, load_state_dict, nor a new model at a recycled address can hit a stale entry. Under autograd the
+    derived tensors must stay differentiable functions of the parameters, so nothing is cached there."""
+    if torch.is_grad_enabled() and any(s.requires_grad for s in sources):
+        return build()
+    key = (tag, _weight_epoch) + tuple((id(s), s.data_ptr(), s._version) for s in sources)
+    ent = _derived.get(key)
+    if ent is not None and all(r() is s for r, s in zip(ent[0], sources)):
+        return ent[1]
+    if len(_derived) > 64:
+        _derived.clear()
+    val = build()
+    _derived[key] = ([weakref.ref(s) for s in sources], val)
+    return val
 
 
 def _tma_ok(items, K, accumulate):
@@ -800,6 +837,10 @@ class _BCE(torch.autograd.Function):
     def forward(ctx, inp, y, w, scale, from_logits, focal=None):
         x = inp.reshape(-1).contiguous().float()
         E = x.numel()
+        if E == 0:      # a batch whose windows hold no edges: mean over nothing, like torch's BCELoss (nan, no gradient)
+            ctx.save_for_backward(torch.empty_like(x))
+            ctx.shape = inp.shape
+            return x.new_full((), float("nan"))
         lib = L.lib()
         loss = torch.empty(1, dtype=torch.float32, device=x.device)
         grad = torch.empty_like(x)

@@ -30,8 +30,8 @@ class FlatParams:
     buffers, so weight-gradient kernels accumulate straight into ONE contiguous all-reduce
     payload and the optimiser is one kernel."""
 
-    def __init__(self, module):
-        self.params = [p for p in module.parameters() if p.requires_grad]
+    def __init__(self, module, params=None):
+        self.params = [p for p in module.parameters() if p.requires_grad] if params is None else list(params)
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.empty(n, dtype=torch.float32, device=dev)
@@ -64,28 +64,27 @@ def allreduce_sum_(flat_grad):
 
 class Trainer:
     """fwd + weighted BCE + bwd + gradient all-reduce + Adam, mirroring train.py:126-160
-    (Adam lr 1e-4, weight_decay 1e-4, betas .9/.999; loss / batch_size)."""
+    (Adam lr 1e-4, weight_decay 1e-4, betas .9/.999; loss / batch_size).
+
+    Parameters that never receive a gradient (knn_conv.* while its result is discarded, pose_gnn.py:80)
+    are left untouched, exactly like torch.optim.Adam skips parameters whose .grad is None: the first
+    step runs with .grad = None everywhere, and only the parameters autograd reached are re-homed into
+    the flat buffers that the all-reduce and the Adam kernel operate on."""
 
     def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, batch_size=2,
                  from_logits=False, loss="bce", focal_alpha=0.25, focal_gamma=2.0):
         from . import ops
         self.ops = ops
         self.model = model
-        self.fp = FlatParams(model)
-        self.m = torch.zeros_like(self.fp.flat)
-        self.v = torch.zeros_like(self.fp.flat)
+        self.fp = self.m = self.v = None
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.batch_size, self.from_logits = batch_size, from_logits
         assert loss in ("bce", "focal")      # "focal": BASELINE config 5's alternative edge loss (not in the reference)
         self.loss, self.focal = loss, (focal_alpha, focal_gamma)
         self.step_no = 0
 
-    def step(self, data, global_edges=None, **fwd_kwargs):
-        """One optimisation step on this rank's shard. With `global_edges` (sum of E over ranks)
-        the local mean loss is re-weighted so that the SUM all-reduce yields exactly the gradient
-        of the mean loss over the union batch."""
+    def _loss(self, data, global_edges, fwd_kwargs):
         ops = self.ops
-        self.fp.zero_grad()
         out, _ = self.model(data, **fwd_kwargs)
         if self.loss == "focal":
             loss = ops.focal_loss(out, data.y, getattr(data, "edge_weights", None), batch_size=self.batch_size,
@@ -93,9 +92,39 @@ class Trainer:
         else:
             loss = ops.bce_loss(out, data.y, getattr(data, "edge_weights", None), batch_size=self.batch_size,
                                 from_logits=self.from_logits)
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if global_edges is not None:
             loss = loss * (out.size(0) / float(global_edges))
+        elif world > 1:
+            loss = loss / world          # SUM all-reduce of per-rank mean losses -> mean over ranks (DDP convention)
+        return loss
+
+    def _first_step(self, data, global_edges, fwd_kwargs):
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        for p in params:
+            p.grad = None
+        loss = self._loss(data, global_edges, fwd_kwargs)
         loss.backward()
+        used = [p for p in params if p.grad is not None]
+        first = [p.grad for p in used]
+        self.fp = FlatParams(self.model, params=used)
+        for p, g in zip(used, first):
+            p.grad.copy_(g)
+        self.m = torch.zeros_like(self.fp.flat)
+        self.v = torch.zeros_like(self.fp.flat)
+        return loss
+
+    def step(self, data, global_edges=None, **fwd_kwargs):
+        """One optimisation step on this rank's shard. With `global_edges` (sum of E over ranks)
+        the local mean loss is re-weighted so that the SUM all-reduce yields exactly the gradient
+        of the mean loss over the union batch; without it the per-rank mean losses are averaged."""
+        ops = self.ops
+        if self.fp is None:
+            loss = self._first_step(data, global_edges, fwd_kwargs)
+        else:
+            self.fp.zero_grad()
+            loss = self._loss(data, global_edges, fwd_kwargs)
+            loss.backward()
         allreduce_sum_(self.fp.grad)
         self.step_no += 1
         ops.adam_step(self.fp.flat, self.fp.grad, self.m, self.v, self.lr, self.betas, self.eps, self.wd,

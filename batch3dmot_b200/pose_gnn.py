@@ -48,19 +48,28 @@ class CausalMessagePassing(nn.Module):
         eu0 = self.edge_update[0]
         wf, wp = self.create_future_msgs[0], self.create_past_msgs[0]
         h1, hm = eu0.out_features, wf.out_features
-        w_cat = torch.cat([eu0.weight[:, :D], eu0.weight[:, D:2 * D], wf.weight[:, :D], wp.weight[:, :D]], 0)
-        b_cat = torch.cat([eu0.bias, eu0.bias.new_zeros(h1), wf.bias, wp.bias])
-        w_inv = torch.cat([wf.weight[:, D + E_:], wp.weight[:, D + E_:]], 0)           # initial_x blocks
+
+        def stacks():
+            w_cat = torch.cat([eu0.weight[:, :D], eu0.weight[:, D:2 * D], wf.weight[:, :D], wp.weight[:, :D]], 0)
+            b_cat = torch.cat([eu0.bias, eu0.bias.new_zeros(h1), wf.bias, wp.bias])
+            w_inv = torch.cat([wf.weight[:, D + E_:], wp.weight[:, D + E_:]], 0)           # initial_x blocks
+            # last (linear) layer of the message MLPs, applied per node AFTER aggregation:
+            # sum_e (W2 h_e + b2) = W2 (sum_e h_e) + deg * b2  -> weight [W2 | b2 | 256 b2 | 0 x 6] against
+            # [S | deg % 256 | deg // 256 | 0 x 6] (the split keeps the degree exact in bf16)
+            w_post = []
+            for seq in (self.create_future_msgs, self.create_past_msgs):
+                l1 = seq[2]
+                w_post.append(torch.cat([l1.weight, l1.bias[:, None], 256.0 * l1.bias[:, None],
+                                         l1.weight.new_zeros(l1.out_features, 6)], 1))
+            return w_cat, b_cat, w_inv, w_post
+
+        # the stacks are functions of the parameters only: cached per parameter version outside autograd
+        # (inference); under autograd they are rebuilt so that gradients flow into the parameters
+        srcs = [eu0.weight, eu0.bias, wf.weight, wf.bias, wp.weight, wp.bias, self.create_future_msgs[2].weight,
+                self.create_future_msgs[2].bias, self.create_past_msgs[2].weight, self.create_past_msgs[2].bias]
+        w_cat, b_cat, w_inv, w_post = ops.derived_weights(("mp_stacks", id(self)), srcs, stacks)
         p_inv = ops.fused_mlp([(x0, None)], [w_inv], [None], out_dtype=torch.bfloat16)  # [N, 2*Hm]
         inv_all = torch.cat([p_inv.new_zeros(p_inv.size(0), 2 * h1), p_inv], 1)         # [N, 2*H1 + 2*Hm]
-        # last (linear) layer of the message MLPs, applied per node AFTER aggregation:
-        # sum_e (W2 h_e + b2) = W2 (sum_e h_e) + deg * b2  -> weight [W2 | b2 | 256 b2 | 0 x 6] against
-        # [S | deg % 256 | deg // 256 | 0 x 6] (the split keeps the degree exact in bf16)
-        w_post = []
-        for seq in (self.create_future_msgs, self.create_past_msgs):
-            l1 = seq[2]
-            w_post.append(torch.cat([l1.weight, l1.bias[:, None], 256.0 * l1.bias[:, None],
-                                     l1.weight.new_zeros(l1.out_features, 6)], 1))
         return w_cat, b_cat, inv_all, (h1, hm), w_post
 
     def invariants_per_iteration(self, x0, depth):

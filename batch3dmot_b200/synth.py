@@ -185,7 +185,13 @@ def collate(graphs):
     node_edge_keys = [k for k, v in vars(graphs[0]).items()
                       if torch.is_tensor(v) and k not in ("edge_index", "batch")]
     for k in node_edge_keys:
-        setattr(out, k, torch.cat([getattr(gph, k) for gph in graphs], 0))
+        # [2,E]-shaped index pairs (`global_edge_index` of the inference loader, graph_data.py:244-250) are
+        # concatenated along the edge dimension like edge_index. They hold SCENE-global node ids, so they are
+        # NOT offset (PyG's Batch would add the window's node offset to any key containing "index", which
+        # would corrupt the global ids; predict.py never batches windows, so the reference has no behaviour here).
+        dim = 1 if (k.endswith("edge_index") and getattr(graphs[0], k).dim() == 2
+                    and getattr(graphs[0], k).size(0) == 2) else 0
+        setattr(out, k, torch.cat([getattr(gph, k) for gph in graphs], dim))
     return out
 
 

@@ -209,7 +209,7 @@ int b3d_narrow_mlp_bwd(const void* X, int32_t x_dtype, int32_t ldx, int64_t M, i
  * accumulated in fp32 in ascending feature order with separate multiply and
  * add, ordered by (distance, neighbour id), self excluded by id,
  * k_eff = min(k, n_frame-1). Nodes must be grouped by frame; frame_ptr int32
- * [F+1]. idx_out: int64 [N,k] global neighbour ids, -1 padded. k <= 32.
+ * [F+1]. idx_out: int64 [N,k] global neighbour ids, -1 padded. k <= 128 (upstream knn_graph allows 100).
  * scratch: int32 [F+1]. */
 int b3d_knn_frames(const float* x, int32_t ldx, int32_t D, const int32_t* frame_ptr, int32_t F,
                    int64_t N, int32_t k, int64_t* idx_out, int32_t* scratch, void* stream);

@@ -149,6 +149,19 @@ def knn_update(params, x, node_timestamps, k=20):
     return gat_conv(params, x, ei)
 
 
+def knn_update_masked(params, x, node_timestamps, k=20):
+    """The same update written like the reference's loop (pose_gnn.py:76-80 with `=` for `==`): one boolean
+    mask per distinct timestamp value, so nodes need not be stored grouped by frame."""
+    out = x.clone()
+    for t in torch.unique(node_timestamps).tolist():
+        m = node_timestamps == t
+        x_t = x[m]
+        n = x_t.size(0)
+        idx = knn_frames(x_t, torch.tensor([0, n]), k)
+        out[m] = gat_conv(params, x_t, knn_to_edge_index(idx))
+    return out
+
+
 # ----------------------------------------------------------------------------- multimodal GNN
 def mha_len1(params, prefix, v):
     """nn.MultiheadAttention with L=S=1 (clr_att_gnn.py:148-155): softmax over one key is 1,

@@ -1,0 +1,217 @@
+"""Regression tests for the round-1 review findings (ADVICE.md / VERDICT.md "boundary hardening"):
+stale packed weights, multi-window inference collation, empty edge sets in the loss, Adam skipping
+gradient-less parameters, k > 32 / ungrouped timestamps in the k-NN attention conv, checkpoint key aliases."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import ref_restated as R
+from batch3dmot_b200 import ops, synth
+from batch3dmot_b200.gat import GATConv, knn_attention_conv
+
+
+# ----------------------------------------------------------------------------- CPU
+def test_collate_concatenates_global_edge_index_along_edges():
+    """graph_io's inference loader adds `global_edge_index` [2,E] per window; windows have different E."""
+    ws = synth.windows(synth.scene_graph(seed=3, T=8, nodes_per_frame=6, k=4), 5)[:3]
+    for w in ws:
+        w.global_edge_index = torch.stack([w.global_node_id[w.edge_index[0]], w.global_node_id[w.edge_index[1]]])
+    assert len({w.edge_index.size(1) for w in ws}) > 1
+    b = synth.collate(ws)
+    E = sum(w.edge_index.size(1) for w in ws)
+    assert b.global_edge_index.shape == (2, E) and b.edge_index.shape == (2, E)
+    off = 0
+    for w in ws:                       # scene-global ids are kept as they are (no node offset)
+        e = w.edge_index.size(1)
+        assert torch.equal(b.global_edge_index[:, off:off + e], w.global_edge_index)
+        off += e
+
+
+def test_inference_batch_loader_collates_two_windows(tmp_path):
+    from batch3dmot_b200 import graph_io
+    sc = synth.add_labels(synth.scene_graph(seed=4, T=7, nodes_per_frame=5, k=3), 4)
+    ws = synth.windows(sc, 5)[:2]
+    prefixes = []
+    for i, w in enumerate(ws):
+        n = w.pose_feats.size(0)
+        w.img_feats, w.lidar_feats, w.radar_feats = torch.zeros(n, 3, 4, 4), torch.zeros(n, 128, 3), torch.zeros(n, 64, 4)
+        w.y = sc.y[w.global_edge_id]
+        meta = {j: {"category_name": synth.CATEGORIES[int(w.node_classes[j]) - 1], "global_node_id": int(w.global_node_id[j])}
+                for j in range(n)}
+        p = str(tmp_path / f"scene_len5_{i}")
+        graph_io.save_window_graph(p, w, meta, boxes=torch.zeros(n, 7))
+        prefixes.append(p)
+    b = next(iter(graph_io.WindowBatchLoader(prefixes, batch_size=2, inference=True, pin=False)))
+    E = sum(w.edge_index.size(1) for w in ws)
+    assert b.global_edge_index.shape == (2, E)
+    assert torch.equal(b.global_edge_index[0, :ws[0].edge_index.size(1)], ws[0].global_node_id[ws[0].edge_index[0]])
+
+
+def test_gat_state_dict_carries_pyg20_duplicate_key():
+    c = GATConv(48, 48)
+    sd = c.state_dict()
+    assert {"lin_src.weight", "lin_dst.weight", "att_src", "att_dst", "bias"} == set(sd)
+    assert sd["lin_dst.weight"].data_ptr() == sd["lin_src.weight"].data_ptr()
+    c2 = GATConv(48, 48)
+    c2.load_state_dict(sd, strict=True)
+    assert torch.equal(c2.lin_src.weight, c.lin_src.weight)
+
+
+def test_derived_weights_follow_parameter_versions():
+    w = torch.nn.Parameter(torch.ones(4, 4))
+    calls = []
+
+    def build():
+        calls.append(1)
+        return (w.detach() * 2,)
+
+    with torch.no_grad():
+        a = ops.derived_weights("t", [w], build)
+        b = ops.derived_weights("t", [w], build)
+        assert a is b and len(calls) == 1
+        w.add_(1.0)                                   # optimiser step / load_state_dict bump the version
+        c = ops.derived_weights("t", [w], build)
+        assert len(calls) == 2 and torch.equal(c[0], torch.full((4, 4), 4.0))
+        ops.invalidate_weight_cache()                 # raw-pointer updates: explicit invalidation
+        ops.derived_weights("t", [w], build)
+        assert len(calls) == 3
+    ops.derived_weights("t", [w], build)              # under autograd nothing is cached
+    ops.derived_weights("t", [w], build)
+    assert len(calls) == 5
+
+
+# ----------------------------------------------------------------------------- GPU
+DEV = "cuda"
+
+
+def rel(a, b):
+    b = b.double().cpu()
+    return float((a.detach().double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def to_dev(ns):
+    return SimpleNamespace(**{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in vars(ns).items()})
+
+
+@pytest.fixture
+def bf16_mode():
+    ops.set_precision("bf16")
+    yield
+    ops.set_precision("fp32")
+    ops.invalidate_weight_cache()
+
+
+@pytest.mark.gpu
+def test_bf16_weights_follow_torch_optimizer_and_load_state_dict(bf16_mode):
+    """The reference's own flow `loss.backward(); optimizer.step()` (train.py:157-160) and load_state_dict must
+    never see packed weights of an earlier version — no invalidate_weight_cache() call anywhere in this test."""
+    from batch3dmot_b200.clr_att_gnn import GNN
+    data = synth.add_labels(synth.add_modalities(synth.scene_graph(seed=7, T=10, nodes_per_frame=30), 7, raw=False), 7)
+    torch.manual_seed(5621)
+    m = GNN(None, None, None).to(DEV)
+    d = to_dev(data)
+    kw = dict(x_img=d.x_img, pointnet_out=d.pointnet_out, radarnet_out=d.radarnet_out, lidar_mask=d.m_lidar,
+              radar_mask=d.m_radar)
+
+    def oracle():
+        params = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        with torch.no_grad():
+            return R.mm_gnn_forward(params, data)[0]
+
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=2e-2)
+    for _ in range(3):
+        out, _ = m(d, **kw)
+        assert rel(out, oracle()) < 2e-2
+        opt.zero_grad()
+        ops.bce_loss(out, d.y, d.edge_weights, batch_size=2).backward()
+        opt.step()                                    # lr 2e-2: stale weights would be far outside 2e-2
+        with torch.no_grad():                         # inference path (cached derived stacks) after the update
+            assert rel(m(d, **kw)[0], oracle()) < 2e-2
+    torch.manual_seed(99)
+    m.load_state_dict(GNN(None, None, None).state_dict())
+    with torch.no_grad():
+        assert rel(m(d, **kw)[0], oracle()) < 2e-2
+    # a NEW model allocated where a freed one lived must not inherit its packs
+    del m, opt
+    torch.manual_seed(123)
+    m = GNN(None, None, None).to(DEV)
+    with torch.no_grad():
+        assert rel(m(d, **kw)[0], oracle()) < 2e-2
+
+
+@pytest.mark.gpu
+def test_bce_loss_on_empty_edge_set():
+    x = torch.zeros(0, 1, device=DEV, requires_grad=True)
+    loss = ops.bce_loss(x, torch.zeros(0, dtype=torch.long, device=DEV), torch.zeros(0, device=DEV), batch_size=2)
+    assert torch.isnan(loss)                           # torch.nn.BCELoss on empty input: mean over nothing
+    loss.backward()
+    assert x.grad.shape == (0, 1)
+
+
+@pytest.mark.gpu
+def test_trainer_leaves_gradient_less_parameters_untouched():
+    """torch.optim.Adam skips parameters whose .grad is None (knn_conv.* while its result is discarded,
+    pose_gnn.py:80): not even weight decay may move them."""
+    from batch3dmot_b200.pose_gnn import PoseGNN
+    from batch3dmot_b200.parallel import Trainer
+    data = synth.add_labels(synth.scene_graph(seed=8, T=6, nodes_per_frame=20), 8)
+    torch.manual_seed(5621)
+    m = PoseGNN().to(DEV)
+    before = {k: v.detach().clone() for k, v in m.named_parameters()}
+    tr = Trainer(m, lr=1e-2, weight_decay=1e-1, from_logits=True)
+    d = to_dev(data)
+    for _ in range(2):
+        tr.step(d)
+    for k, v in m.named_parameters():
+        if k.startswith("knn_conv"):
+            assert torch.equal(v, before[k]), k
+        else:
+            assert not torch.equal(v, before[k]), k
+    # and the update itself equals torch.optim.Adam's on the same gradients
+    torch.manual_seed(5621)
+    m2 = PoseGNN().to(DEV)
+    opt = torch.optim.Adam(m2.parameters(), lr=1e-2, weight_decay=1e-1)
+    for _ in range(2):
+        opt.zero_grad()
+        ops.bce_loss(m2(d)[0], d.y, d.edge_weights, batch_size=2, from_logits=True).backward()
+        opt.step()
+    for (k, a), (_, b) in zip(m.named_parameters(), m2.named_parameters()):
+        assert rel(a, b) < 1e-4, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [33, 64, 100])
+def test_knn_large_k_bit_exact_and_gat(k):
+    x, ptr = synth.knn_stress(11, 1500, frame=300, D=48)
+    want = R.knn_frames(x, ptr, k)
+    got = ops.knn_frames(x.to(DEV), ptr.to(DEV), k)
+    assert torch.equal(got.cpu(), want)
+    torch.manual_seed(0)
+    conv = GATConv(48, 48).to(DEV)
+    y = conv.forward_table(x.to(DEV), got)
+    sd = {f"knn_conv.{n}": v.detach().cpu() for n, v in conv.state_dict().items()}
+    y_ref = R.gat_conv(sd, x, R.knn_to_edge_index(want))
+    assert rel(y, y_ref) < 1e-4
+    # backward through the attention conv with k > 32
+    xr = x.to(DEV).requires_grad_(True)
+    conv.forward_table(xr, got).square().sum().backward()
+    xc = x.clone().requires_grad_(True)
+    pc = {n: v.clone().requires_grad_(True) for n, v in sd.items()}
+    R.gat_conv(pc, xc, R.knn_to_edge_index(want)).square().sum().backward()
+    assert rel(xr.grad, xc.grad) < 1e-3
+    assert rel(conv.att_src.grad, pc["knn_conv.att_src"].grad) < 1e-3
+
+
+@pytest.mark.gpu
+def test_knn_attention_conv_with_ungrouped_timestamps():
+    """Frames are the sets of equal timestamps wherever the nodes are stored (pose_gnn.py:76-77)."""
+    torch.manual_seed(1)
+    N = 600
+    x = torch.randn(N, 48)
+    ts = torch.randint(0, 7, (N,))                      # NOT grouped
+    conv = GATConv(48, 48).to(DEV)
+    sd = {f"knn_conv.{n}": v.detach().cpu() for n, v in conv.state_dict().items()}
+    got = knn_attention_conv(conv, x.to(DEV), ts.to(DEV), k=20)
+    want = R.knn_update_masked(sd, x, ts, k=20)
+    assert rel(got, want) < 1e-4
