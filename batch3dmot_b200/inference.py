@@ -1,15 +1,19 @@
 """Batched, scene-sharded inference (BASELINE config 4): the reference runs one GNN forward per
 sliding 5-frame window and per scene inside a ray worker pool (predict.py:172-196, :595-650).
-Here every rank takes whole scenes (LPT bin packing by edge count), concatenates ALL windows of its
-scenes into one disjoint batch graph (PyG-Batch style node offsets), runs ONE forward, splits the
-scores back per window and assembles tracks per scene. No collective is needed: scenes are
-independent; results are returned per scene id."""
+Here every rank takes whole scenes (LPT bin packing by edge count), cuts ALL windows of a chunk of its
+scenes on the device with tensor ops (`window_batch`: no per-window Python loop), runs ONE forward over the
+resulting disjoint batch graph (PyG-Batch style node offsets), and assembles the tracks of all scenes of the
+chunk in one pass (`tracking.assign_track_ids_union`). No collective is needed: scenes are independent;
+results are returned per scene id."""
 from types import SimpleNamespace
 
 import torch
 
 from . import synth, tracking
 from .parallel import lpt_partition
+
+_NODE_KEYS = ("pose_feats", "node_timestamps", "node_classes", "x_img", "pointnet_out", "radarnet_out", "m_lidar",
+              "m_radar")
 
 
 def scene_windows(scene, length=5):
@@ -23,45 +27,153 @@ def shard_scenes(scenes, world_size):
     return lpt_partition(costs, world_size)
 
 
-def infer_scene_scores(model, scenes, device, multimodal=True, window=5):
-    """One forward over every window of every given scene. Returns, per scene, the list of
-    (global_node_id, edge_index, scores) triples that tracking.assign_track_ids consumes."""
-    all_w, owner = [], []
-    for si, sc in enumerate(scenes):
-        ws = scene_windows(sc, window)
-        all_w += ws
-        owner += [si] * len(ws)
-    if not all_w:
-        return [[] for _ in scenes]
-    batch = synth.collate(all_w)
-    d = SimpleNamespace(**{k: (v.to(device) if torch.is_tensor(v) else v) for k, v in vars(batch).items()})
+def collate_scenes(scenes, device):
+    """Union of whole scene graphs on `device` (node offsets in edge_index) plus what the window cutter needs:
+    scene_id [N], frame index of every node inside its scene, frames per scene (host ints). Nodes of a scene
+    must be stored frame after frame (true for the reference's preprocessing and for synth.scene_graph)."""
+    u = SimpleNamespace()
+    off, eis, sid, frame, frames = 0, [], [], [], []
+    for i, sc in enumerate(scenes):
+        n = sc.pose_feats.size(0)
+        ts = sc.node_timestamps
+        t0 = int(ts.min()) if n else 0
+        frames.append(int(ts.max()) - t0 + 1 if n else 0)
+        frame.append(ts - t0)
+        eis.append(sc.edge_index + off)
+        sid.append(torch.full((n,), i, dtype=torch.long))
+        off += n
+    u.edge_index = torch.cat(eis, 1).to(device, non_blocking=True)
+    u.scene_id = torch.cat(sid).to(device, non_blocking=True)
+    u.frame = torch.cat(frame).to(device, non_blocking=True)
+    u.edge_attr = torch.cat([sc.edge_attr for sc in scenes]).to(device, non_blocking=True)
+    for k in _NODE_KEYS:
+        if all(hasattr(sc, k) for sc in scenes):
+            setattr(u, k, torch.cat([getattr(sc, k) for sc in scenes]).to(device, non_blocking=True))
+    u.frames, u.num_nodes, u.n_scenes = frames, off, len(scenes)
+    u.node_off = [0]
+    for sc in scenes:
+        u.node_off.append(u.node_off[-1] + sc.pose_feats.size(0))
+    return u
+
+
+def window_batch(u, length=5):
+    """Every sliding window (stride 1, `length` frames; predict.py:172) of every scene of the union `u` as ONE
+    disjoint batch graph, built with tensor ops on u's device. A window's nodes are a contiguous id range
+    (frames are stored one after the other), so node gathering is a range concatenation; an edge (frame fs ->
+    frame fd) belongs to the windows [max(0, fd-length+1), min(fs, W-1)] of its scene and is replicated by
+    repeat_interleave + one stable sort by window, which keeps the edge order of every window (targets
+    ascending) and therefore of the whole batch. Equal to collate(synth.windows(scene) for every scene)."""
+    dev = u.edge_index.device
+    L = length
+    T = torch.tensor(u.frames, dtype=torch.long)
+    W = (T - L + 1).clamp(min=0)
+    fbase = torch.cumsum(T, 0) - T
+    wbase = torch.cumsum(W, 0) - W
+    Wt, Ft = int(W.sum()), int(T.sum())
+    win_scene = torch.repeat_interleave(torch.arange(len(u.frames)), W)
+    win_first = (fbase[win_scene] + torch.arange(Wt) - wbase[win_scene]).to(dev)        # first frame id of each window
+    W_d, fbase_d, wbase_d = W.to(dev), fbase.to(dev), wbase.to(dev)
+    fid = fbase_d[u.scene_id] + u.frame
+    fptr = torch.zeros(Ft + 1, dtype=torch.long, device=dev)
+    fptr[1:] = torch.cumsum(torch.bincount(fid, minlength=Ft), 0)
+    first_node = fptr[win_first]
+    n_w = fptr[win_first + L] - first_node
+    node_off = torch.cumsum(n_w, 0) - n_w
+    win_of_pos = torch.repeat_interleave(torch.arange(Wt, device=dev), n_w)
+    total = win_of_pos.numel()
+    gather = torch.arange(total, device=dev) - node_off[win_of_pos] + first_node[win_of_pos]
+    src, dst = u.edge_index[0], u.edge_index[1]
+    s_e = u.scene_id[dst]
+    lo = (u.frame[dst] - (L - 1)).clamp(min=0)
+    hi = torch.minimum(u.frame[src], W_d[s_e] - 1)
+    cnt = (hi - lo + 1).clamp(min=0)
+    rep = torch.repeat_interleave(torch.arange(src.numel(), device=dev), cnt)
+    start = torch.cumsum(cnt, 0) - cnt
+    gwin = wbase_d[s_e[rep]] + lo[rep] + (torch.arange(rep.numel(), device=dev) - start[rep])
+    order = torch.sort(gwin, stable=True)
+    rep, gwin = rep[order.indices], order.values
+    shift = node_off[gwin] - first_node[gwin]
+    g_out, g_in = src[rep], dst[rep]
+    b = SimpleNamespace(edge_index=torch.stack([g_out + shift, g_in + shift]), edge_attr=u.edge_attr[rep],
+                        num_nodes=total, g_out=g_out, g_in=g_in, window_of_edge=gwin, global_node_id=gather,
+                        n_windows=Wt, window_scene=win_scene, batch=win_of_pos)
+    for k in _NODE_KEYS:
+        if hasattr(u, k):
+            setattr(b, k, getattr(u, k)[gather])
+    return b
+
+
+def forward_scores(model, b, multimodal=True):
+    """Edge scores in (0,1) of a batch graph under torch.no_grad()."""
     with torch.no_grad():
         if multimodal:
-            out, _ = model(d, x_img=d.x_img, pointnet_out=d.pointnet_out, radarnet_out=d.radarnet_out,
-                           lidar_mask=d.m_lidar, radar_mask=d.m_radar)
+            out, _ = model(b, x_img=b.x_img, pointnet_out=b.pointnet_out, radarnet_out=b.radarnet_out,
+                           lidar_mask=b.m_lidar, radar_mask=b.m_radar)
         else:
-            out, _ = model(d)
+            out, _ = model(b)
             out = torch.sigmoid(out)            # PoseGNN returns logits (pose_gnn.py:86)
-    scores = out.reshape(-1).float()
+    return out.reshape(-1).float()
+
+
+def infer_scene_scores(model, scenes, device, multimodal=True, window=5):
+    """One forward over every window of every given scene. Returns, per scene, the list of
+    (global_node_id, edge_index, scores) triples that tracking.assign_track_ids consumes
+    (ids local to the scene / window, like the reference's per-window files)."""
+    if not scenes:
+        return []
+    u = collate_scenes(scenes, device)
+    b = window_batch(u, window)
     per_scene = [[] for _ in scenes]
-    off = 0
-    for w, si in zip(all_w, owner):
-        e = w.edge_index.size(1)
-        per_scene[si].append((w.global_node_id.to(device), w.edge_index.to(device), scores[off:off + e]))
-        off += e
+    if b.n_windows == 0:
+        return per_scene
+    scores = forward_scores(model, b, multimodal) if b.edge_index.size(1) else torch.zeros(0, device=device)
+    e_cnt = torch.bincount(b.window_of_edge, minlength=b.n_windows).tolist()
+    n_cnt = torch.bincount(b.batch, minlength=b.n_windows).tolist()
+    eo = no = 0
+    for w, si in enumerate(b.window_scene.tolist()):
+        e, n = e_cnt[w], n_cnt[w]
+        gid = b.global_node_id[no:no + n] - u.node_off[si]
+        per_scene[si].append((gid, b.edge_index[:, eo:eo + e] - no, scores[eo:eo + e]))
+        eo += e
+        no += n
     return per_scene
 
 
-def track_scenes(model, scenes, device, rank=0, world_size=1, multimodal=True, window=5):
+def chunk_scenes(ids, costs, max_cost):
+    """Consecutive groups of scene ids whose summed cost stays below max_cost (at least one scene per group)."""
+    groups, cur, tot = [], [], 0
+    for i in ids:
+        if cur and tot + costs[i] > max_cost:
+            groups.append(cur)
+            cur, tot = [], 0
+        cur.append(i)
+        tot += costs[i]
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def track_scenes(model, scenes, device, rank=0, world_size=1, multimodal=True, window=5, max_edges=2_500_000,
+                 want_tracks=True):
     """Scene-sharded inference + track assembly. Returns {scene_id: (track_ids [N] int64, tracks)}
-    for the scenes owned by `rank`."""
-    mine = shard_scenes(scenes, world_size)[rank]
-    per_scene = infer_scene_scores(model, [scenes[i] for i in mine], device, multimodal, window)
+    for the scenes owned by `rank`. Scenes are processed in chunks of at most `max_edges` scene edges (each
+    edge sits in ~2.5 windows): per chunk one window cut, one forward, one track assembly."""
+    costs = [int(s.edge_index.size(1)) for s in scenes]
+    mine = lpt_partition(costs, world_size)[rank]
     out = {}
-    for sid, wins in zip(mine, per_scene):
-        sc = scenes[sid]
-        if not wins:
-            out[sid] = (torch.full((sc.num_nodes,), -1, dtype=torch.long), [])
+    for group in chunk_scenes(mine, costs, max_edges):
+        sub = [scenes[i] for i in group]
+        u = collate_scenes(sub, device)
+        b = window_batch(u, window)
+        if b.n_windows == 0 or b.edge_index.size(1) == 0:
+            for sid, sc in zip(group, sub):
+                out[sid] = (torch.full((sc.pose_feats.size(0),), -1, dtype=torch.long), [])
             continue
-        out[sid] = tracking.assign_track_ids(wins, sc.node_classes.to(device))
+        scores = forward_scores(model, b, multimodal)
+        tid, pos, _ = tracking.assign_track_ids_union(b.g_out, b.g_in, scores, u.node_classes, u.scene_id.int(),
+                                                      len(sub))
+        for j, sid in enumerate(group):
+            a, e = u.node_off[j], u.node_off[j + 1]
+            ids = tid[a:e].clone()
+            out[sid] = (ids, tracking.tracks_from_ids(ids, pos[a:e]) if want_tracks else None)
     return out

@@ -21,7 +21,14 @@ def average_window_scores(windows, num_nodes):
     the mean is a sequential float64 sum over the windows that contain the edge, like np.mean."""
     g_out = torch.cat([gid[ei[0]] for gid, ei, _ in windows])
     g_in = torch.cat([gid[ei[1]] for gid, ei, _ in windows])
-    sc = torch.cat([s.reshape(-1) for _, _, s in windows]).to(torch.float64)
+    sc = torch.cat([s.reshape(-1) for _, _, s in windows])
+    return average_edge_scores(g_out, g_in, sc, num_nodes)
+
+
+def average_edge_scores(g_out, g_in, sc, num_nodes):
+    """The same averaging on flat arrays: every window occurrence of an edge as (global out node, global in
+    node, score), listed window after window. Node ids may span many scenes (disjoint id ranges)."""
+    sc = sc.reshape(-1).to(torch.float64)
     key = g_out * num_nodes + g_in
     uniq, inv = torch.unique(key, return_inverse=True)
     occ = torch.arange(key.numel(), device=key.device)
@@ -126,6 +133,46 @@ def hier_tracks(e_out, e_in, score, node_classes):
                 node = nxt[node]
             tracks.append(tr)
     return tracks
+
+
+def hier_tracks_native(e_out, e_in, score, node_classes, scene_of_node=None, n_scenes=1):
+    """hier_tracks for the union of many scenes in ONE device->host transfer and one native loop
+    (libb3d b3d_hier_tracks_host). Returns (track_id [n] int64, per-scene numbering; track_pos [n] int64;
+    tracks_per_scene [n_scenes] int64) as CPU tensors."""
+    from . import _lib as L
+    n = node_classes.numel()
+    host = [t.detach().to("cpu", non_blocking=False).contiguous() for t in
+            (e_out.to(torch.int64), e_in.to(torch.int64), score.to(torch.float64), node_classes.to(torch.int64))]
+    sc_of = scene_of_node.detach().to("cpu", torch.int32).contiguous() if scene_of_node is not None else None
+    tid = torch.empty(n, dtype=torch.int64)
+    pos = torch.empty(n, dtype=torch.int64)
+    per = torch.empty(n_scenes, dtype=torch.int64)
+    thr = THRESHOLDS.contiguous()
+    L.check(L.lib().b3d_hier_tracks_host(L.ptr(host[0]), L.ptr(host[1]), L.ptr(host[2]), host[0].numel(), L.ptr(host[3]),
+                                         L.ptr(sc_of), n, n_scenes, L.ptr(thr), thr.numel(), L.ptr(tid), L.ptr(pos),
+                                         L.ptr(per)), "b3d_hier_tracks_host")
+    return tid, pos, per
+
+
+def tracks_from_ids(track_id, track_pos):
+    """List of tracks (each a list of node ids in order) from the arrays of hier_tracks_native (one scene)."""
+    ids = track_id.numpy()
+    sel = np.nonzero(ids >= 0)[0]
+    order = sel[np.lexsort((track_pos.numpy()[sel], ids[sel]))]
+    n_tr = int(ids.max()) + 1 if sel.size else 0
+    cuts = np.searchsorted(ids[order], np.arange(1, n_tr))
+    return [a.tolist() for a in np.split(order, cuts)] if n_tr else []
+
+
+def assign_track_ids_union(g_out, g_in, scores, node_classes, scene_of_node=None, n_scenes=1):
+    """Track assembly for the union of many scenes (node ids in disjoint ranges): flat per-window edge
+    occurrences -> (track_id, track_pos, tracks_per_scene). Scenes never interact: averaging, thresholds and the
+    best-in / best-out filter are per edge / per node, and the clustering visits each scene's edges in the order
+    its own run would (see track_host.cu)."""
+    n = node_classes.numel()
+    e_out, e_in, mean = average_edge_scores(g_out, g_in, scores, n)
+    k_out, k_in, k_s = greedy_edges(e_out, e_in, mean, node_classes)
+    return hier_tracks_native(k_out, k_in, k_s, node_classes, scene_of_node, n_scenes)
 
 
 def assign_track_ids(windows, node_classes):

@@ -267,6 +267,18 @@ int b3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                   void* stream);
 
+/* ---- track assembly, host side (the only entry point that takes HOST pointers and runs on the CPU) -------------
+ * create_trajectories(mode='hier') + track-id numbering (predict.py:308-373, :437-446) over the surviving edges
+ * of one or many scenes: edges (e_out -> e_in, float64 score) in the reference's greedy_edges insertion order,
+ * clustered in stable descending-score order (new / prepend / append / join, the join gated by the per-class
+ * threshold of the IN node). track_id[n] = position of the node's track among its scene's tracks in insertion
+ * order (-1: none), track_pos[n] = position of the node inside its track, tracks_per_scene[s] = track count.
+ * Returns -1 if an edge would close a cycle inside one track (the reference corrupts its state there). */
+int b3d_hier_tracks_host(const int64_t* e_out, const int64_t* e_in, const double* score, int64_t m,
+                         const int64_t* node_class, const int32_t* scene_of_node /*nullable*/, int64_t n,
+                         int32_t n_scenes, const double* thresholds, int32_t n_classes,
+                         int64_t* track_id, int64_t* track_pos, int64_t* tracks_per_scene);
+
 #ifdef __cplusplus
 }
 #endif

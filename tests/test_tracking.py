@@ -152,3 +152,54 @@ def test_live_unmodified_reference_track_assembly(tmp_path, seed, quant):
     _, tracks_ours = tracking.assign_track_ids(wins, scene.node_classes)
     assert tracks_ref == tracks_restated == tracks_ours
     assert len(tracks_ref) > 3
+
+
+def test_window_batch_equals_per_window_collation():
+    """inference.window_batch (tensor ops over the union of scenes) == collate(synth.windows(scene)) scene by scene."""
+    from batch3dmot_b200 import inference
+    scenes = [synth.add_modalities(synth.scene_graph(seed=60 + i, T=T_, nodes_per_frame=npf, k=6), 60 + i, raw=False)
+              for i, (T_, npf) in enumerate([(8, 7), (4, 5), (11, 3), (5, 9)])]            # one scene shorter than a window
+    u = inference.collate_scenes(scenes, "cpu")
+    b = inference.window_batch(u, 5)
+    wins, gids = [], []
+    for j, sc in enumerate(scenes):
+        for w in synth.windows(sc, 5):
+            wins.append(w)
+            gids.append(w.global_node_id + u.node_off[j])
+    ref = synth.collate(wins)
+    assert b.n_windows == len(wins) and b.num_nodes == ref.num_nodes
+    for k in ("edge_index", "edge_attr", "pose_feats", "node_timestamps", "x_img", "pointnet_out", "m_lidar", "batch"):
+        assert torch.equal(getattr(b, k), getattr(ref, k)), k
+    assert torch.equal(b.global_node_id, torch.cat(gids))
+    assert bool((b.edge_index[1][1:] >= b.edge_index[1][:-1]).all())                        # targets stay sorted
+
+
+@pytest.mark.parametrize("quant", [None, 25])
+def test_union_track_assembly_equals_per_scene_reference(quant):
+    """Many scenes assembled in one pass (device tensor ops + the native clustering loop b3d_hier_tracks_host)
+    give, scene by scene, the tracks of the literal reference assembly."""
+    from batch3dmot_b200 import inference
+    g = torch.Generator().manual_seed(5)
+    scenes = [synth.scene_graph(seed=70 + i, T=9 + i, nodes_per_frame=6 + 2 * i, k=6) for i in range(4)]
+    u = inference.collate_scenes(scenes, "cpu")
+    b = inference.window_batch(u, 5)
+    E = b.edge_index.size(1)
+    s = torch.rand(E, generator=g)
+    s = torch.where(torch.rand(E, generator=g) < 0.6, s * 0.05, s)
+    if quant:
+        s = torch.round(s * quant) / quant
+    tid, pos, per = tracking.assign_track_ids_union(b.g_out, b.g_in, s.float(), u.node_classes, u.scene_id.int(), len(scenes))
+    e_cnt = torch.bincount(b.window_of_edge, minlength=b.n_windows).tolist()
+    n_cnt = torch.bincount(b.batch, minlength=b.n_windows).tolist()
+    per_scene = [[] for _ in scenes]
+    eo = no = 0
+    for w, si in enumerate(b.window_scene.tolist()):
+        gid = b.global_node_id[no:no + n_cnt[w]] - u.node_off[si]
+        per_scene[si].append((gid, b.edge_index[:, eo:eo + e_cnt[w]] - no, s[eo:eo + e_cnt[w]].float()))
+        eo += e_cnt[w]; no += n_cnt[w]
+    for j, sc in enumerate(scenes):
+        ids_ref, tracks_ref = _oracle(sc, per_scene[j])
+        a, e = u.node_off[j], u.node_off[j + 1]
+        assert np.array_equal(tid[a:e].numpy(), ids_ref)
+        assert tracking.tracks_from_ids(tid[a:e], pos[a:e]) == tracks_ref
+        assert int(per[j]) == len(tracks_ref)
