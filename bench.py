@@ -10,15 +10,25 @@ configs[0]-shaped graphs: T=40, N=2000, E~60k per scene; `--scenes` graphs per r
 one directed input edge taken through the whole model once.
 
 Under torchrun every rank holds its own scenes (weak scaling); time = max over ranks.
-`--impl reference` times the CPU port of the reference's op stream (oracle/ref_restated.py,
-faithful mode) on the host cores — rank 0 only."""
+Beside the headline the line carries (extra keys): the forward-only figure, the end-to-end figure, the
+1e-4-tolerance (fp32) mode, the poses-only model (configs[0]), the k-NN / attention-conv stress (configs[2]),
+batched scene-sharded inference + track assembly over 150 val-shaped scenes (configs[3], strong scaling over
+the ranks), the reference's own 2-window training batch (configs[4] small-batch regime) and the bf16-vs-fp32
+output error of the timed batch.
+
+`--impl reference` times the reference's own CPU implementation on the host cores (rank 0 only): the
+UNMODIFIED reference model files from oracle/_ref (written by oracle/make_ref.py in the build container)
+under the PyG stand-ins, forward + BCELoss(weight) + backward + torch.optim.Adam as in train.py:126-160;
+if oracle/_ref is absent, the restated port (oracle/ref_restated.py) with the same optimiser."""
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
 import threading
 import time
+from types import SimpleNamespace
 
 import torch
 
@@ -38,19 +48,21 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=64, help="scene graphs per rank per step")
     ap.add_argument("--precision", default=os.environ.get("B3D_PRECISION", "bf16"), choices=["bf16", "fp32"],
-                    help="bf16: tcgen05 tiles (2e-2 parity mode, north_star); fp32: FFMA exact mode (1e-4)")
-    ap.add_argument("--cpu-scenes", type=int, default=1, help="scene graphs in the CPU baseline sample")
+                    help="bf16: tcgen05 tiles (2e-2 parity mode, north_star); fp32: 1e-4 parity mode")
+    ap.add_argument("--cpu-scenes", type=int, default=4, help="scene graphs in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e + roofline only")
+    ap.add_argument("--val-scenes", type=int, default=150, help="configs[3]: scenes in the batched-inference run")
     ap.add_argument("--profile-only", action="store_true", help="timed loop only (for ncu launch lists)")
     return ap.parse_args()
 
 
-def make_batch(rank, scenes):
+def make_batch(rank, scenes, raw=False):
     from batch3dmot_b200 import synth
     gs = []
     for i in range(scenes):
         s = SEED + 1000 * rank + i
-        gs.append(synth.add_labels(synth.add_modalities(synth.scene_graph(seed=s), s, raw=False), s))
+        gs.append(synth.add_labels(synth.add_modalities(synth.scene_graph(seed=s), s, raw=raw), s))
     return synth.collate(gs)
 
 
@@ -99,24 +111,237 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+# ----------------------------------------------------------------------------- reference arm (CPU)
 def cpu_reference_run(steps, warmup, n_scenes):
-    """The reference's CPU op stream (oracle port, faithful mode) on the host cores."""
-    from oracle import ref_restated as R
-    from batch3dmot_b200.clr_att_gnn import GNN
+    """The reference's own CPU training step on the host cores: (edges/s, ms/step, E, threads, kind, how)."""
+    from batch3dmot_b200 import synth
+    from oracle import make_ref
     torch.set_num_threads(os.cpu_count())
-    data = make_batch(0, n_scenes)
-    torch.manual_seed(SEED)
-    sd = GNN(None, None, None).state_dict()
-    params = {k: v.clone().requires_grad_(not k.startswith("knn_conv")) for k, v in sd.items()}
-    mha = R.build_mha(params)
+    data = make_batch(0, n_scenes, raw=True)
     E = data.edge_index.size(1)
+    root = make_ref.ref_root()
+    if root is not None:
+        from oracle import pyg_shim
+        _, clr = pyg_shim.load_reference(root)
+        torch.manual_seed(SEED)
+        enc = [synth.EmbeddingEncoder(t) for t in (data.x_img, data.pointnet_out, data.radarnet_out)]
+        model = clr.GNN(*enc)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999))   # train.py:106-109
+        gt = data.y.float()
+
+        def step():
+            out, _ = model.forward(data)                                                            # train.py:133
+            loss = torch.nn.BCELoss(weight=data.edge_weights)(out.squeeze(1), gt) / 2               # :139-141
+            opt.zero_grad()
+            loss.backward()                                                                          # :157-160
+            opt.step()
+        kind = "reference"
+        how = ("UNMODIFIED reference clr_att_gnn.py (oracle/_ref) under the PyG stand-ins of oracle/pyg_shim.py "
+               "(scatter / knn_graph / GATConv / MessagePassing restated in torch; PyG's C++ ops are not installable), "
+               "random-embedding encoder stubs, fwd + BCELoss(weight) + bwd + torch.optim.Adam")
+    else:
+        from oracle import ref_restated as R
+        from batch3dmot_b200.clr_att_gnn import GNN
+        torch.manual_seed(SEED)
+        sd = GNN(None, None, None).state_dict()
+        params = {k: v.clone().requires_grad_(not k.startswith("knn_conv")) for k, v in sd.items()}
+        mha = R.build_mha(params)
+        opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-4, weight_decay=1e-4)
+
+        def step():
+            R.cpu_train_step(params, data, mha)
+            opt.step()
+        kind = "port"
+        how = "oracle/ref_restated.py faithful mode (oracle/_ref absent) + torch.optim.Adam"
     for _ in range(warmup):
-        R.cpu_train_step(params, data, mha)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        R.cpu_train_step(params, data, mha)
+        step()
     dt = (time.perf_counter() - t0) / steps
-    return E / dt, dt * 1e3, E, torch.get_num_threads()
+    return E / dt, dt * 1e3, E, torch.get_num_threads(), kind, how
+
+
+# ----------------------------------------------------------------------------- helpers for the GPU arm
+class Timer:
+    def __init__(self, dev, world):
+        self.dev, self.world = dev, world
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier(self):
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def run(self, fn, steps, warmup, reduce=True):
+        """ms per call of fn(): W untimed calls, then K calls between barriers, CUDA events, max over ranks."""
+        import torch.distributed as dist
+        for _ in range(warmup):
+            fn()
+        self.barrier() if reduce else torch.cuda.synchronize()
+        self.e0.record()
+        for _ in range(steps):
+            fn()
+        self.e1.record()
+        self.barrier() if reduce else torch.cuda.synchronize()
+        ms = torch.tensor([self.e0.elapsed_time(self.e1)], device=self.dev)
+        if reduce and self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+
+def to_dev(ns, dev):
+    return SimpleNamespace(**{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in vars(ns).items()})
+
+
+def mm_kwargs(d):
+    return dict(x_img=d.x_img, pointnet_out=d.pointnet_out, radarnet_out=d.radarnet_out, lidar_mask=d.m_lidar,
+                radar_mask=d.m_radar)
+
+
+def val_scene_rates(n, seed=SEED):
+    """configs[3]: per-scene node rate ~ LogNormal(mean 75 / frame, sigma 0.5) clipped to [5, 300]."""
+    g = torch.Generator().manual_seed(seed + 77)
+    r = torch.exp(torch.randn(n, generator=g) * 0.5 + math.log(75.0) - 0.125)
+    return r.clamp(5, 300).round().long().tolist()
+
+
+def extras(a, rank, world, dev, model, d, tm, E_global):
+    """The other BASELINE configs and regimes, as extra keys of the JSON line."""
+    import torch.distributed as dist
+    from batch3dmot_b200 import _lib, ops, synth, inference
+    from batch3dmot_b200.pose_gnn import PoseGNN
+    from batch3dmot_b200.clr_att_gnn import GNN
+    from batch3dmot_b200.parallel import Trainer, lpt_partition
+    from batch3dmot_b200.gat import GATConv
+    x = {}
+    kw = mm_kwargs(d)
+
+    # ---- configs[3]: batched inference over val-shaped scenes, sharded by scene over the ranks (strong scaling):
+    # every rank generates and owns its LPT share, cuts windows on the device, one forward per chunk, track assembly
+    rates = val_scene_rates(a.val_scenes)
+    est = [40 * r * min(40.0, 1.1 * r) for r in rates]          # edge-count estimate known to every rank without generating
+    mine = lpt_partition(est, world)[rank]
+    scenes = {i: synth.add_modalities(synth.scene_graph(seed=SEED + 5000 + i, T=40, frame_sizes=[rates[i]] * 40),
+                                      SEED + 5000 + i, raw=False) for i in mine}
+    lst = [scenes[i] for i in mine]
+    model.eval()
+    n_tracks = [0]
+
+    def infer():
+        res = inference.track_scenes(model, lst, dev, multimodal=True, want_tracks=False)
+        n_tracks[0] = sum(int(v[0].max()) + 1 for v in res.values() if v[0].numel())
+    infer()                                                     # warm-up (allocator, weight packs)
+    tm.barrier()
+    t0 = time.perf_counter()
+    infer()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    win_edges = torch.tensor([sum(int(2.4 * s.edge_index.size(1)) for s in lst)], device=dev)   # ~2.4 windows per edge
+    if world > 1:
+        dist.all_reduce(win_edges)
+    x["batched_inference"] = {
+        "workload": f"configs[3]: {a.val_scenes} val-shaped scenes x 36 sliding 5-frame windows, scene-sharded (LPT) over "
+                    f"{world} GPU(s): host->device copy of the scenes, window cut on device, forward, track assembly",
+        "scenes_per_s": a.val_scenes / float(dt.item()), "seconds": float(dt.item()), "scaling": "strong",
+        "window_edges_approx": int(win_edges.item()), "tracks_rank0": n_tracks[0], "timed": "host wall clock, max over ranks"}
+    model.train()
+    del scenes, lst
+    if rank != 0:
+        return x
+
+    # ---- bf16 output error of the timed batch against the fp32 (1e-4) mode, once
+    if a.precision == "bf16":
+        with torch.no_grad():
+            out16 = model(d, **kw)[0].float()
+            ops.set_precision("fp32")
+            out32 = model(d, **kw)[0].float()
+            ops.set_precision("bf16")
+        diff = (out16 - out32).abs()
+        x["parity_timed_batch"] = {"max_abs_err": float(diff.max()), "max_rel_to_max": float(diff.max() / out32.abs().max()),
+                                   "mean_rel_elementwise": float((diff / out32.abs().clamp_min(1e-6)).mean()),
+                                   "against": "fp32 mode of the same kernels' library on the same batch (inference forward)"}
+        del out16, out32, diff
+
+    # ---- the 1e-4-tolerance mode (fp32 parity arithmetic) on 8 scenes
+    small = to_dev(make_batch(0, 8), dev)
+    small._b3d_graph = ops.Graph(small.edge_index, small.num_nodes)
+    Es = small.edge_index.size(1)
+    ops.set_precision("fp32")
+    torch.manual_seed(SEED)
+    m32 = GNN(None, None, None).to(dev)
+    tr32 = Trainer(m32, batch_size=2)
+    ms = tm.run(lambda: tr32.step(small, **mm_kwargs(small)), 3, 2, reduce=False)
+    with torch.no_grad():
+        msf = tm.run(lambda: m32(small, **mm_kwargs(small)), 3, 1, reduce=False)
+    x["fp32_mode"] = {"fwd_bwd_edges_per_s": Es / ms * 1e3, "forward_edges_per_s": Es / msf * 1e3, "scenes": 8, "edges": Es,
+                      "tolerance": "1e-4 relative (tests/test_gpu_models.py)"}
+    ops.set_precision(a.precision)
+    del m32, tr32
+
+    # ---- configs[0]: poses-only model, forward and forward+backward, 64 scenes and 1 scene
+    torch.manual_seed(SEED)
+    pm = PoseGNN().to(dev)
+    ptr_ = Trainer(pm, batch_size=2, from_logits=True)
+    one = to_dev(synth.add_labels(synth.scene_graph(seed=SEED), SEED), dev)
+    one._b3d_graph = ops.Graph(one.edge_index, one.num_nodes)
+    res = {}
+    for name, dd in (("64_scenes", d), ("1_scene", one)):
+        Ed = dd.edge_index.size(1)
+        ms = tm.run(lambda: ptr_.step(dd), 5, 3, reduce=False)
+        with torch.no_grad():
+            msf = tm.run(lambda: pm(dd), 5, 2, reduce=False)
+        res[name] = {"edges": Ed, "fwd_bwd_edges_per_s": Ed / ms * 1e3, "forward_edges_per_s": Ed / msf * 1e3,
+                     "ms_per_step": ms}
+    x["pose_model"] = dict(res, workload="configs[0]: poses-only PoseGNN, random init, fwd + BCE-with-logits + bwd + Adam")
+    del pm, ptr_
+
+    # ---- configs[4] small-batch regime: the reference's own training batch (cl_config.yaml:99 batch_size 2 =
+    # two 5-frame window graphs) and one scene graph
+    wins = synth.windows(synth.add_labels(synth.add_modalities(synth.scene_graph(seed=SEED), SEED, raw=False), SEED), 5)[:2]
+    for w in wins:
+        synth.add_labels(w, SEED)
+    two = to_dev(synth.collate(wins), dev)
+    one_mm = to_dev(make_batch(0, 1), dev)
+    torch.manual_seed(SEED)
+    ms_ = GNN(None, None, None).to(dev)
+    trs = Trainer(ms_, batch_size=2)
+    res = {}
+    for name, dd in (("2_windows", two), ("1_scene", one_mm)):
+        dd._b3d_graph = ops.Graph(dd.edge_index, dd.num_nodes)
+        Ed = dd.edge_index.size(1)
+        kwd = mm_kwargs(dd)
+        trs.step(dd, **kwd)
+        _lib.reset_launch_count()
+        trs.step(dd, **kwd)
+        lc = _lib.launch_count()
+        ms = tm.run(lambda: trs.step(dd, **kwd), 10, 3, reduce=False)
+        res[name] = {"edges": Ed, "us_per_step": ms * 1e3, "fwd_bwd_edges_per_s": Ed / ms * 1e3, "libb3d_launches_per_step": lc}
+    x["small_batch"] = dict(res, workload="configs[4]: multimodal training step at the reference's batch (2 window graphs) and at 1 scene")
+    del ms_, trs
+
+    # ---- configs[2]: frame-wise k-NN + attention-weighted conv stress (N = 200k nodes, frames of 250)
+    res = {}
+    for D in (48, 96):
+        xk, ptr = synth.knn_stress(SEED, 200_000, frame=250, D=D)
+        xk, ptr = xk.to(dev), ptr.to(dev)
+        conv = GATConv(D, D).to(dev)
+        for k in (8, 16):
+            nbr = ops.knn_frames(xk, ptr, k)
+            us_knn = tm.run(lambda: ops.knn_frames(xk, ptr, k), 5, 2, reduce=False) * 1e3
+            with torch.no_grad():
+                us_gat = tm.run(lambda: conv.forward_table(xk, nbr), 5, 2, reduce=False) * 1e3
+            nbytes = 200_000 * (D * 4 + k * 8)                     # read x once, write the neighbour table
+            res[f"D{D}_k{k}"] = {"knn_us": us_knn, "knn_algorithmic_gbs": nbytes / us_knn / 1e3,
+                                 "knn_gflops": 200_000 * 250 * D * 3 / us_knn / 1e3, "gat_us": us_gat}
+    x["knn_attention_conv"] = dict(res, workload="configs[2]: 200k nodes in frames of 250; brute-force frame-local k-NN "
+                                                 "(sub, mul, add per feature) + GATConv lin / softmax / aggregate")
+    return x
 
 
 def main():
@@ -132,15 +357,16 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        steps, warm = max(1, min(a.steps, 5)), max(1, min(a.warmup, 2))
-        v, ms, E, thr = cpu_reference_run(steps, warm, a.cpu_scenes)
+        steps, warm = max(1, min(a.steps, 3)), max(1, min(a.warmup, 1))
+        v, ms, E, thr, kind, how = cpu_reference_run(steps, warm, a.cpu_scenes)
         print(json.dumps({
             "impl": "reference", "metric": "gnn_edges_per_s_fwd_bwd", "value": v, "unit": "edges/s", "n_gpus": a.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": v, "unit": "edges/s", "cores": thr, "kind": "port",
-                             "sample": f"{a.cpu_scenes} scene graph(s), {E} edges per step, {steps} steps; reference op "
-                                       "stream restated in torch (PyG/torch_scatter are not installable)"},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config, note=f"bounded sample: {a.cpu_scenes} of the {a.scenes} scene graphs per step; edges/s "
+                                        "normalises the batch size"),
+            "cpu_baseline": {"value": v, "unit": "edges/s", "cores": thr, "kind": kind,
+                             "sample": f"{a.cpu_scenes} scene graphs, {E} edges per step, {steps} steps; {how}"},
             "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -157,6 +383,7 @@ def main():
     if world > 1:
         dist.barrier()
     _lib.lib()   # fail loudly if the CUDA library is missing
+    tm = Timer(dev, world)
 
     host = make_batch(rank, a.scenes)
     E, N = host.edge_index.size(1), host.num_nodes
@@ -166,7 +393,6 @@ def main():
     h2d_bytes = sum(t.numel() * t.element_size() for t in pinned.values())
 
     def to_device():
-        from types import SimpleNamespace
         return SimpleNamespace(**{k: t.to(dev, non_blocking=True) for k, t in pinned.items()}, num_nodes=N)
 
     e_tot = torch.tensor([E], dtype=torch.int64, device=dev)
@@ -179,32 +405,21 @@ def main():
     ops.set_precision(a.precision)
     trainer = Trainer(model, batch_size=2)
 
-    def fwd_kwargs(d):
-        return dict(x_img=d.x_img, pointnet_out=d.pointnet_out, radarnet_out=d.radarnet_out, lidar_mask=d.m_lidar,
-                    radar_mask=d.m_radar)
-
     # ---- device-resident timing ("value")
     d = to_device()
     d._b3d_graph = ops.Graph(d.edge_index, N)
-    kw = fwd_kwargs(d)
+    kw = mm_kwargs(d)
     for _ in range(a.warmup):
         trainer.step(d, global_edges=E_global, **kw)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    barrier()
+    tm.barrier()
     _lib.reset_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0, ev1 = tm.e0, tm.e1
     with ClockSampler(local) as clk:
         ev0.record()
         for _ in range(a.steps):
             loss = trainer.step(d, global_edges=E_global, **kw)
         ev1.record()
-        barrier()
+        tm.barrier()
     launches = _lib.launch_count()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
@@ -219,19 +434,9 @@ def main():
     # ---- forward only (inference, configs[3]'s per-rank work): same batch, no autograd, nothing saved
     model.eval()
     with torch.no_grad():
-        for _ in range(2):
-            model(d, **kw)
-        barrier()
-        ev0.record()
-        for _ in range(a.steps):
-            model(d, **kw)
-        ev1.record()
-        barrier()
+        msf = tm.run(lambda: model(d, **kw), a.steps, 2)
     model.train()
-    msf = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(msf, op=dist.ReduceOp.MAX)
-    fwd_value = E_global / (float(msf.item()) / a.steps * 1e-3)
+    fwd_value = E_global / (msf * 1e-3)
 
     # ---- end-to-end through the public API with host buffers ("e2e"): every step copies ITS inputs
     # from pinned host memory (on a copy stream, overlapped with the previous step's kernels), builds
@@ -240,7 +445,6 @@ def main():
     # overwritten only after the step that read it has finished (event), and the in-place copy bumps the
     # tensor version, so the CSR cache misses and the tables are rebuilt from the fresh edge_index.
     copy_stream = torch.cuda.Stream(device=dev)
-    from types import SimpleNamespace
     bufs = [{k: torch.empty(t.shape, dtype=t.dtype, device=dev) for k, t in pinned.items()} for _ in range(2)]
     done = [None, None]
 
@@ -262,35 +466,29 @@ def main():
             torch.cuda.current_stream().wait_event(ready)
             if i + 1 < n:
                 nxt = stage_inputs((i + 1) & 1)             # H2D of step i+1 overlaps step i
-            l = trainer.step(dd, global_edges=E_global, **fwd_kwargs(dd))   # builds CSR from edge_index
+            l = trainer.step(dd, global_edges=E_global, **mm_kwargs(dd))   # builds CSR from edge_index
             done[i & 1] = torch.cuda.Event()
             done[i & 1].record()
             last = float(l.item())                          # D2H of the loss (host sync every step)
         return last
 
     e2e_loop(max(3, a.warmup))     # warm-up: both staging buffer sets and the per-step CSR tables get allocated
-    barrier()
+    tm.barrier()
     ev0.record()
     e2e_loop(a.steps)
     ev1.record()
-    barrier()
+    tm.barrier()
     ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = E_global / (float(ms2.item()) / a.steps * 1e-3)
+    del bufs
 
     # ---- roofline of the dominant kernel
     hbm, tf_burst, tf_sust, src = peaks()
+
     def time_kernel(fn, reps=10):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        ev0.record()
-        for _ in range(reps):
-            fn()
-        ev1.record()
-        torch.cuda.synchronize()
-        return ev0.elapsed_time(ev1) / reps * 1e-3
+        return tm.run(fn, reps, 3, reduce=False) * 1e-3
 
     if a.precision == "bf16":
         # dominant kernel class: k_linear_tma (TMA-fed tcgen05 tiles); heaviest launch = att_edge_encoder layer 2
@@ -312,8 +510,9 @@ def main():
                 "peak_source": src + " HBM copy bandwidth (burst); kernel timed alone with CUDA events",
                 "rows": Er, "us_per_launch": t * 1e6,
                 "tensor_view": {"achieved_tflops": ach_t, "peak_tflops": tf_burst, "frac": ach_t / tf_burst}}
+        del h, out
     else:
-        # fp32 exact path: the dominant launch is k_linear on edge_update layer 0 ([E,320] -> 256, gathered)
+        # fp32 parity path: the dominant launch is the edge_update layer 0 ([E,320] -> 256, gathered)
         mp = model.message_passing
         lin = mp.edge_update[0]
         x = torch.randn(N, 96, device=dev); e = torch.randn(E, 64, device=dev); att = torch.randn(E, 64, device=dev)
@@ -322,10 +521,10 @@ def main():
         out = torch.empty(E, 256, device=dev)
         t = time_kernel(lambda: ops.linear_raw(items, lin.weight, lin.bias, E, 1, out=out))
         ach = 2.0 * E * 320 * 256 / t / 1e12
-        roof = {"kernel": "k_linear (fp32 FFMA; edge_update layer 0, gathered [E,320]x[320,256])", "bound": "tensor",
+        roof = {"kernel": "edge_update layer 0, gathered [E,320]x[320,256] (fp32 parity mode)", "bound": "tensor",
                 "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst, "traffic": None,
-                "peak_source": src + " bf16 dense burst; kernel timed alone",
-                "note": "fp32-exact SIMT path: runs on the FFMA pipe, not the tensor pipe"}
+                "peak_source": src + " bf16 dense burst; kernel timed alone"}
+        del x, e, att, out
 
     # ---- step-level view of the same roofline: every edge-level dense-layer launch of ONE extra step timed with
     # CUDA events around the launch (ops.optime: synchronises per launch, so this step is not part of any
@@ -353,17 +552,20 @@ def main():
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "roofline_step": roof_step,
             "algorithmic_tflops": value * MM_FWDBWD_FLOPS_PER_EDGE / 1e12, "loss": float(loss.item()),
-            "forward_only": {"value": fwd_value, "unit": "edges/s", "ms_per_step": E_global / fwd_value * 1e3,
+            "forward_only": {"value": fwd_value, "unit": "edges/s", "ms_per_step": msf,
                              "note": "inference forward of the same batch under torch.no_grad()"},
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30}
+    if not a.no_extras:
+        line.update(extras(a, rank, world, dev, model, d, tm, E_global))
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, cms, cE, thr = cpu_reference_run(3, 1, a.cpu_scenes)
-        line["cpu_baseline"] = {"value": v, "unit": "edges/s", "cores": thr, "kind": "port",
-                                "sample": f"{a.cpu_scenes} scene graph(s), {cE} edges per step, 3 steps "
-                                          f"({cms:.0f} ms/step); reference op stream restated in torch"}
+        v, cms, cE, thr, kind, how = cpu_reference_run(1, 1, a.cpu_scenes)
+        line["cpu_baseline"] = {"value": v, "unit": "edges/s", "cores": thr, "kind": kind,
+                                "sample": f"{a.cpu_scenes} scene graphs, {cE} edges per step, 1 warm-up + 1 timed step "
+                                          f"({cms:.0f} ms/step); {how}"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
