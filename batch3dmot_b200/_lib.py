@@ -21,6 +21,17 @@ class Seg(C.Structure):
                 ("ld", C.c_int32), ("ldmask", C.c_int32), ("mask_mode", C.c_int32), ("dtype", C.c_int32)]
 
 
+class ChainLayer(C.Structure):
+    """b3d_chain_layer_t"""
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("src", C.c_int32), ("act", C.c_int32), ("nadd", C.c_int32),
+                ("add_idx", C.c_int32 * 2), ("add_ld", C.c_int32 * 2), ("add_ptr", C.c_void_p * 2),
+                ("bias", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int32), ("bits_out", C.c_void_p),
+                ("bits_in", C.c_void_p)]
+
+
+ACT_MASKBITS = 3
+CHAIN_MAX_LAYERS = 6
+
 _SIGS = {
     "b3d_last_error": (C.c_char_p, []),
     "b3d_launch_count": (C.c_int64, []),
@@ -81,6 +92,12 @@ _SIGS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b3d_focal_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_float,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b3d_chain_supported": (C.c_int, [C.POINTER(ChainLayer), C.c_int32, C.c_int32]),
+    "b3d_chain_packed_bytes": (C.c_size_t, [C.POINTER(ChainLayer), C.c_int32, C.c_int32]),
+    "b3d_chain_pack_weights": (C.c_int, [C.POINTER(ChainLayer), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                         C.c_int32, C.c_void_p, C.c_void_p]),
+    "b3d_chain_run": (C.c_int, [C.POINTER(Seg), C.c_int32, C.POINTER(ChainLayer), C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int64, C.c_void_p]),
     "b3d_hier_tracks_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b3d_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int32, C.c_float,

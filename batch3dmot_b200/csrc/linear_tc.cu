@@ -99,28 +99,6 @@ __device__ __forceinline__ float activate(float v) {
 // a warp-wide access lands in a different 128-byte line and costs its own L1 wavefront whatever its
 // width: moving 32 bytes per lane instead of 16 halves the L1 data-pipe load of the epilogue, which
 // ncu shows as the top limiter of the mask / addend variants (profiles/r1_epilogue_l1.md).
-__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
-               : "l"(p));
-}
-__device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
-               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
-               : "memory");
-}
-__device__ __forceinline__ bool al32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
-// 64 bytes (32 bf16) at p -> q[0..3]
-__device__ __forceinline__ void ld64B(const void* p, uint4 (&q)[4]) {
-  if (al32(p)) {
-    ldg256(p, q[0], q[1]);
-    ldg256(reinterpret_cast<const uint8_t*>(p) + 32, q[2], q[3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) q[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
-  }
-}
-
 struct EpiPrefetch {
   uint4 u[4], v[4];   // u: ReLU mask if bit0, else addend 0;  v: addend 0 if bit0, else addend 1
   uint32_t bits;      // sign-bit mask word of the block (bit3)
@@ -671,29 +649,6 @@ struct TmaArgs {
   uint32_t* bits_out;
 };
 
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-// K-major operand tile written by TMA with 128-byte swizzle: rows of 128 B, 8-row groups of 1024 B.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major): 16 B
-  d |= (uint64_t)(1024 >> 4) << 32;  // SBO: next 8-row group
-  d |= (uint64_t)1 << 46;            // descriptor version
-  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
-  return d;
-}
-
 template <int ACT>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -868,36 +823,6 @@ __global__ void k_pack_weights_rm(const float* __restrict__ W, int ldw, int n_lo
   float v = 0.f;
   if (n < n_log && k < k_log) v = transpose ? W[(long long)k * ldw + n] : W[(long long)n * ldw + k];
   Wr[i] = __float2bfloat16_rn(v);
-}
-
-typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static tmap_encode_fn get_tmap_encode() {
-  static tmap_encode_fn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<tmap_encode_fn>(p);
-  }
-  return fn;
-}
-
-// 2D bf16 row-major [rows, cols] (row stride ld elements), box {64 cols, box_rows}, 128B swizzle, zero OOB fill.
-static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
-  tmap_encode_fn enc = get_tmap_encode();
-  if (!enc) return -1;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
 // ------------------------------------------------------------------ TMA-fed weight gradient

@@ -1,7 +1,9 @@
 // Inline-PTX wrappers for the Blackwell (sm_100a) tensor-core path: tcgen05.mma with TMEM
 // accumulators, mbarrier completion, proxy fences. No CUTLASS dependency.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace b3d {
@@ -127,4 +129,85 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 
 }  // namespace tc
+
+// ---- 256-bit global accesses, TMA / mbarrier transaction helpers, swizzled descriptors, tensor maps
+// (shared by linear_tc.cu and chain_tc.cu)
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+__device__ __forceinline__ bool al32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+// 64 bytes (32 bf16) at p -> q[0..3]
+__device__ __forceinline__ void ld64B(const void* p, uint4 (&q)[4]) {
+  if (al32(p)) {
+    ldg256(p, q[0], q[1]);
+    ldg256(reinterpret_cast<const uint8_t*>(p) + 32, q[2], q[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
+  }
+}
+
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// K-major operand tile written by TMA with 128-byte swizzle: rows of 128 B, 8-row groups of 1024 B.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major): 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO: next 8-row group
+  d |= (uint64_t)1 << 46;            // descriptor version
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline tmap_encode_fn get_tmap_encode() {
+  static tmap_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tmap_encode_fn>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols] (row stride ld elements), box {64 cols, box_rows}, 128B swizzle, zero OOB fill.
+static inline int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+
 }  // namespace b3d

@@ -3,6 +3,7 @@ the drop-in layers train with the reference's own `loss.backward(); optimizer.st
 (train.py:157-160). Every FLOP on this path runs in a libb3d kernel; torch provides device
 memory, streams and autograd bookkeeping only."""
 
+import os
 import weakref
 
 import torch
@@ -143,6 +144,7 @@ def invalidate_weight_cache():
     _weight_epoch += 1
     _packed.clear()
     _derived.clear()
+    _chain_packs.clear()
 
 
 _USE_TMA = True          # dense bf16 operands go through the TMA-fed persistent kernel
@@ -192,6 +194,71 @@ def derived_weights(tag, sources, build):
     val = build()
     _derived[key] = ([weakref.ref(s) for s in sources], val)
     return val
+
+
+_chain_packs = {}
+_USE_CHAIN = os.environ.get("B3D_NO_CHAIN") != "1"   # multi-layer bf16 chains run as ONE fused launch (chain_tc.cu)
+
+
+def _wkey(w):
+    """Identity of a weight (or of a column/row slice VIEW of one) for pack caches: the base tensor object,
+    its address and version, plus the view geometry. Slices are re-created on every forward, their base is not."""
+    base = w._base if w._base is not None else w
+    return (id(base), base.data_ptr(), base._version, w.storage_offset(), tuple(w.shape), w.stride()), base
+
+
+def chain_run(inputs, specs, idx0, idx1, M):
+    """One fused launch of a layer program (b3d_chain_run). inputs: 1-2 dense bf16 [M, w] tensors.
+    specs: per layer dict(W fp32 [N,K] or its transpose with transpose=True, src, act, bias, adds=[(bf16 tensor, sel)],
+    out, bits_out, bits_in). Returns False (nothing launched) when the chain does not fit the kernel's plan."""
+    lib = L.lib()
+    nl = len(specs)
+    k_in = sum(t.size(1) for t in inputs)
+    arr = (L.ChainLayer * nl)()
+    for l, sp in enumerate(specs):
+        W = sp["W"]
+        n, k = (W.size(1), W.size(0)) if sp.get("transpose") else (W.size(0), W.size(1))
+        c = arr[l]
+        c.K, c.N, c.src, c.act = k, n, sp.get("src", l - 1), sp.get("act", L.ACT_NONE)
+        adds = sp.get("adds") or []
+        c.nadd = len(adds)
+        for t, (at, sel) in enumerate(adds):
+            assert at.dtype == torch.bfloat16 and at.size(1) == n and at.stride(1) == 1
+            c.add_ptr[t], c.add_ld[t], c.add_idx[t] = at.data_ptr(), at.stride(0), sel
+        b = sp.get("bias")
+        c.bias = b.data_ptr() if b is not None else None
+        o = sp.get("out")
+        if o is not None:
+            assert o.dtype == torch.bfloat16 and o.shape == (M, n) and o.stride(1) == 1
+            c.out, c.ldo = o.data_ptr(), o.stride(0)
+        for name in ("bits_out", "bits_in"):
+            bt = sp.get(name)
+            if bt is not None:
+                assert bt.shape == ((n + 31) // 32, M) and bt.is_contiguous()
+                setattr(c, name, bt.data_ptr())
+    if not lib.b3d_chain_supported(arr, nl, k_in):
+        return False
+    keys, bases = zip(*[_wkey(sp["W"]) for sp in specs])
+    key = (_weight_epoch, k_in, tuple(keys), tuple(bool(sp.get("transpose")) for sp in specs))
+    ent = _chain_packs.get(key)
+    if ent is None or not all(r() is b for r, b in zip(ent[0], bases)):
+        if len(_chain_packs) > 64:
+            _chain_packs.clear()
+        buf = torch.empty(int(lib.b3d_chain_packed_bytes(arr, nl, k_in)), dtype=torch.uint8, device=inputs[0].device)
+        for l, sp in enumerate(specs):
+            W = sp["W"]
+            assert W.dtype == torch.float32 and W.stride(1) == 1
+            L.check(lib.b3d_chain_pack_weights(arr, nl, k_in, l, L.ptr(W), W.stride(0), int(bool(sp.get("transpose"))),
+                                               L.ptr(buf), L.stream()), "b3d_chain_pack_weights")
+        ent = _chain_packs[key] = ([weakref.ref(b) for b in bases], buf)
+    segs = L.make_segs([(t, None, None, 0) for t in inputs])
+    L.check(lib.b3d_chain_run(segs, len(inputs), arr, nl, L.ptr(ent[1]), L.ptr(idx0), L.ptr(idx1), M, L.stream()),
+            "b3d_chain_run")
+    return True
+
+
+def _chain_dims_ok(widths):
+    return all(w % 64 == 0 and 64 <= w <= 512 for w in widths)
 
 
 def _tma_ok(items, K, accumulate):
@@ -538,7 +605,34 @@ class _FusedMLP(torch.autograd.Function):
         # epilogue): the backward pass masks gradients from them instead of re-reading the activation
         want_bits = any(ctx.needs_input_grad)      # inference (no_grad): nothing reads them
         acts, bits, cur = [], [], items
-        for l in range(nl):
+        # the whole chain as ONE launch: hidden activations stay in shared memory (chain_tc.cu). Training keeps
+        # the same saved tensors as the per-layer path (bf16 activations + sign bits), inference writes the output only
+        ctx.chain = False
+        if (tc and _USE_CHAIN and nl >= 2 and nl <= L.CHAIN_MAX_LAYERS and rm is None and _tma_ok(items, Ws[0].size(1), False)
+                and (out_dtype or torch.float32) == torch.bfloat16 and _chain_dims_ok([w.size(0) for w in Ws])
+                and Ws[0].size(1) % 16 == 0 and len(adds) <= 2 and all(t.dtype == torch.bfloat16 and _al16(t) for t, _ in adds)):
+            idxs = []
+            for _, i in adds:
+                if i is not None and not any(i is j for j in idxs):
+                    idxs.append(i)
+            if len(idxs) <= 2:
+                specs = []
+                for l in range(nl):
+                    last = l == nl - 1
+                    relu_out = (not last) or premasked
+                    nb = Ws[l].size(0)
+                    y = torch.empty((M, nb), dtype=torch.bfloat16, device=W0dev) if (last or want_bits) else None
+                    bt = new_relu_bits(M, nb, W0dev) if (relu_out and _USE_BITS and want_bits) else None
+                    specs.append(dict(W=Ws[l], bias=bs[l], act=L.ACT_RELU if relu_out else L.ACT_NONE, out=y, bits_out=bt,
+                                      adds=[(t, -1 if i is None else [k for k, j in enumerate(idxs) if j is i][0])
+                                            for t, i in adds] if l == 0 else None))
+                    acts.append(y)
+                    bits.append(bt)
+                ctx.chain = chain_run([t for t, _, _, _ in items], specs, idxs[0] if idxs else None,
+                                      idxs[1] if len(idxs) > 1 else None, M)
+                if not ctx.chain:
+                    acts, bits = [], []
+        for l in range(nl if not ctx.chain else 0):
             last = l == nl - 1
             relu_out = (not last) or premasked
             nb = Ws[l].size(0)
@@ -554,7 +648,7 @@ class _FusedMLP(torch.autograd.Function):
         ctx.add_nidx = add_nidx
         ctx.has_bias = [b is not None for b in bs]
         ctx.bits = bits
-        ctx.save_for_backward(*Ws, *acts, *xs)
+        ctx.save_for_backward(*Ws, *[t if t is not None else acts[-1] for t in acts], *xs)
         if premasked:      # the consumer (segment_sum) needs the output's sign bits for its own backward
             out_bits = bits[-1] if bits[-1] is not None else acts[-1].new_zeros(0, dtype=torch.int32)
             ctx.mark_non_differentiable(out_bits)
@@ -584,6 +678,24 @@ class _FusedMLP(torch.autograd.Function):
         xs = xs[:nx]
         dxs = [None] * nx
         dadds = [None] * len(ctx.add_nidx)
+        # all input-gradient GEMMs of the chain as ONE fused launch (dZ_{l-1} = (dZ_l W_l) * relu'(z_{l-1}), the
+        # gradient tiles stay in shared memory between layers; every dZ_l is also written for its weight gradient)
+        pre_dz, pre_dA = None, None
+        low_x = tc and all(dt == torch.bfloat16 for dt, nd in zip(ctx.in_dtypes, need_x) if nd)
+        if (getattr(ctx, "chain", False) and not need_mask and nl >= 2 and all(b is not None for b in ctx.bits[:nl - 1])
+                and Ws[-1].size(0) % 16 == 0):
+            dzc = dz if (dz.dtype == torch.bfloat16 and _al16(dz)) else dz.to(torch.bfloat16).contiguous()
+            specs = [dict(W=Ws[l], transpose=True, act=L.ACT_MASKBITS, bits_in=ctx.bits[l - 1],
+                          out=torch.empty((M, Ws[l].size(1)), dtype=torch.bfloat16, device=dz.device))
+                     for l in range(nl - 1, 0, -1)]
+            with_x = any(need_x) and low_x and Ws[0].size(1) % 64 == 0 and Ws[0].size(1) <= 512
+            if with_x:
+                specs.append(dict(W=Ws[0], transpose=True, act=L.ACT_NONE,
+                                  out=torch.empty((M, Ws[0].size(1)), dtype=torch.bfloat16, device=dz.device)))
+            if len(specs) <= L.CHAIN_MAX_LAYERS and chain_run([dzc], specs, None, None, M):
+                pre_dz = {l - 1: sp["out"] for l, sp in zip(range(nl - 1, 0, -1), specs)}
+                pre_dA = specs[-1]["out"] if with_x else None
+                dz_item = (dzc, None, None, 0)
         for l in range(nl - 1, -1, -1):
             W = Ws[l]
             n_out, K = W.shape
@@ -600,16 +712,19 @@ class _FusedMLP(torch.autograd.Function):
                 dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc_arg)
                 grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)
             if l > 0:
-                mb = ctx.bits[l - 1]
-                dz = linear_raw([dz_item], W, None, M, trans_w=True, out_mask=acts[l - 1] if mb is None else None,
-                                mask_bits=mb, tc=tc_arg, out_dtype=torch.bfloat16 if tc else torch.float32)
+                if pre_dz is not None:
+                    dz = pre_dz[l - 1]
+                else:
+                    mb = ctx.bits[l - 1]
+                    dz = linear_raw([dz_item], W, None, M, trans_w=True, out_mask=acts[l - 1] if mb is None else None,
+                                    mask_bits=mb, tc=tc_arg, out_dtype=torch.bfloat16 if tc else torch.float32)
                 dz_item = (dz, None, None, 0)
             elif any(need_x):
                 # [M, K]; bf16 when every consumer of the slices is a bf16 tensor (halves the largest
                 # backward tensor), fp32 otherwise
-                low = tc and all(dt == torch.bfloat16 for dt, nd in zip(ctx.in_dtypes, need_x) if nd)
-                dA = linear_raw([dz_item], W, None, M, trans_w=True, tc=tc_arg,
-                                out_dtype=torch.bfloat16 if low else torch.float32)
+                dA = pre_dA if pre_dA is not None else \
+                    linear_raw([dz_item], W, None, M, trans_w=True, tc=tc_arg,
+                               out_dtype=torch.bfloat16 if low_x else torch.float32)
                 off = 0
                 for s, (x, ni) in enumerate(zip(xs, nidx)):
                     w = x.size(1)

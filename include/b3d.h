@@ -35,7 +35,8 @@ extern "C" {
 
 /* Operand modifiers for b3d_seg_t.mask_mode / epilogue activations. */
 enum { B3D_MASK_NONE = 0, B3D_MASK_RELU = 1, B3D_MASK_SIGMOID = 2 };
-enum { B3D_ACT_NONE = 0, B3D_ACT_RELU = 1, B3D_ACT_SIGMOID = 2 };
+enum { B3D_ACT_NONE = 0, B3D_ACT_RELU = 1, B3D_ACT_SIGMOID = 2,
+       B3D_ACT_MASKBITS = 3 };      /* b3d_chain_run only: multiply by a ReLU mask given as sign bits (backward chains) */
 enum { B3D_FLAG_ACCUMULATE = 1,     /* out += result instead of out = result */
        B3D_FLAG_OUT_BF16 = 2 };     /* b3d_segment_sum: `out` is really __nv_bfloat16* (bf16 source, no accumulate) */
 enum { B3D_F32 = 0, B3D_BF16 = 1 }; /* element type of a segment / output (bf16: tensor-core entry points only) */
@@ -266,6 +267,42 @@ int b3d_focal_fwd_bwd(const float* input, const int64_t* y, const float* w, int6
 int b3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                   void* stream);
+
+/* ---- fused MLP chains (tcgen05, hidden activations stay in shared memory) ------------------------------------
+ * One launch runs a whole nn.Sequential(Linear, ReLU, ..., Linear) over dense bf16 edge rows — edge_update
+ * (clr_att_gnn.py:196-201 applied at :314-317), the first layers of create_future_msgs / create_past_msgs
+ * (:203-213, :319-327; two branches reading the same e'), att_edge_encoder (:82-91, :164) — or the chain of
+ * input-gradient GEMMs of their backward pass (act = B3D_ACT_MASKBITS). Layers form a small DAG in program
+ * order: layer l reads the chain input (src = -1) or the output of an earlier layer (src < l).
+ * Per layer: y = act(x W^T + bias + sum_t add_t[sel_t(row)])  with bf16 row-gathered addends (the node-side
+ * first-layer blocks applied per node: add_idx 0 -> idx0[row], 1 -> idx1[row], -1 -> row). `out` (bf16 [M,N],
+ * optional) receives the layer output, `bits_out` (optional) its sign bits in the B3D_BITS layout; outputs read
+ * by a later layer never leave the SM. Constraints: 1-2 dense bf16 input segments (leading width % 64, total
+ * K % 16), every N % 64 == 0 and <= 512, at most B3D_CHAIN_MAX_LAYERS layers, and the activation working set of a
+ * 128-row tile must fit beside a >= 2-stage weight ring in 227 KB (b3d_chain_supported tells).
+ * Weights are packed once per weight version by b3d_chain_pack_weights (layer by layer, fp32 [N,K] row-major
+ * with leading dimension ldw, or its transpose) into a pre-swizzled chunk stream of b3d_chain_packed_bytes. */
+#define B3D_CHAIN_MAX_LAYERS 6
+typedef struct {
+  int32_t K, N;
+  int32_t src;                 /* -1: chain input; else index of the producing layer */
+  int32_t act;                 /* B3D_ACT_NONE / B3D_ACT_RELU / B3D_ACT_MASKBITS */
+  int32_t nadd;
+  int32_t add_idx[2];
+  int32_t add_ld[2];
+  const void* add_ptr[2];      /* bf16 [*, N] */
+  const float* bias;           /* [N] or NULL */
+  void* out;                   /* bf16 [M, N] or NULL */
+  int32_t ldo;
+  void* bits_out;              /* uint32 [N/32][M] or NULL */
+  const void* bits_in;         /* B3D_ACT_MASKBITS: uint32 [N/32][M] */
+} b3d_chain_layer_t;
+int b3d_chain_supported(const b3d_chain_layer_t* layers /*host*/, int32_t nl, int32_t k_in);
+size_t b3d_chain_packed_bytes(const b3d_chain_layer_t* layers /*host*/, int32_t nl, int32_t k_in);
+int b3d_chain_pack_weights(const b3d_chain_layer_t* layers /*host*/, int32_t nl, int32_t k_in, int32_t layer,
+                           const float* W, int32_t ldw, int32_t transpose, void* packed, void* stream);
+int b3d_chain_run(const b3d_seg_t* in_segs /*host*/, int32_t nseg, const b3d_chain_layer_t* layers /*host*/,
+                  int32_t nl, const void* packed, const int32_t* idx0, const int32_t* idx1, int64_t M, void* stream);
 
 /* ---- track assembly, host side (the only entry point that takes HOST pointers and runs on the CPU) -------------
  * create_trajectories(mode='hier') + track-id numbering (predict.py:308-373, :437-446) over the surviving edges
