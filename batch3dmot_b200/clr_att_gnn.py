@@ -115,9 +115,12 @@ class GNN(nn.Module):
             p_i = ops.fused_mlp(sens, [w0[:, :288]], [ae[0].bias], out_dtype=torch.bfloat16)    # [N,512]
             p_j = ops.fused_mlp(sens, [w0[:, 288:576]], [None], out_dtype=torch.bfloat16)
             e0 = e0.to(torch.bfloat16)         # edge-level tensors are kept in bf16 between kernels
-            att = ops.fused_mlp([(e0, None)], [w0[:, 576:]] + [m.weight for m in ae[1:]],
-                                [None] + [m.bias for m in ae[1:]], adds=[(p_i, dst), (p_j, src)],
-                                out_dtype=torch.bfloat16)
+            if ops.att_edge_encoder_supported(e0, ae):
+                att = ops.att_edge_encoder_block(g, e0, p_i, p_j, w0[:, 576:], ae)      # two fused launches
+            else:
+                att = ops.fused_mlp([(e0, None)], [w0[:, 576:]] + [m.weight for m in ae[1:]],
+                                    [None] + [m.bias for m in ae[1:]], adds=[(p_i, dst), (p_j, src)],
+                                    out_dtype=torch.bfloat16)
         else:
             att_in = [(a_rad, dst), (a_lid, dst), (a_img, dst),    # x_sens_i :161
                       (a_rad, src), (a_lid, src), (a_img, src),    # x_sens_j

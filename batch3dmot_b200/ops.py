@@ -736,6 +736,162 @@ class _FusedMLP(torch.autograd.Function):
         return (None, None, None, None, None, None, None, *grads, *dxs, *dadds)
 
 
+class _MPEdgeBlock(torch.autograd.Function):
+    """The edge side of one message-passing iteration as ONE fused launch per direction (chain_tc.cu):
+        e'  = edge_update(cat[x_i, x_j, e, att])                         (clr_att_gnn.py:314-317)
+        h_f = relu(W_f . cat[x_i, e', x0_i]),  h_p = relu(W_p . cat[x_j, e', x0_j])   (first layers, :319-327)
+    in the pre-projected form (node-side weight blocks applied per node: p_i / p_j / p_f / p_p arrive as
+    row-gathered bf16 addends). Forward program: 128 -> 256 -> 128 -> 64 (= e') -> {192, 192}; the hidden tiles and
+    e' feed the next layer from shared memory. Backward program: cat[dh_f, dh_p] -> de' (+ the direct gradient of e')
+    -> 128 -> 256 -> 128, every tile masked by the forward sign bits; the five weight gradients and the four
+    per-node addend gradients (deterministic CSR sums) follow from the written gradient tiles."""
+
+    @staticmethod
+    def forward(ctx, g, e, att, p_i, p_j, p_f, p_p, W0, W1, b1, W2, b2, Wf, Wp):
+        M = e.size(0)
+        dev = e.device
+        train = any(ctx.needs_input_grad)
+        bf = torch.bfloat16
+        n0, n1, n2, nm = W0.size(0), W1.size(0), W2.size(0), Wf.size(0)
+        mk = lambda n: torch.empty((M, n), dtype=bf, device=dev)
+        x1, x2 = (mk(n0), mk(n1)) if train else (None, None)
+        e_new, h_f, h_p = mk(n2), mk(nm), mk(nm)
+        bt = lambda n: new_relu_bits(M, n, dev) if train else None
+        b_x1, b_x2, b_f, b_p = bt(n0), bt(n1), bt(nm), bt(nm)
+        specs = [dict(W=W0, src=-1, act=L.ACT_RELU, adds=[(p_i, 0), (p_j, 1)], out=x1, bits_out=b_x1),
+                 dict(W=W1, src=0, act=L.ACT_RELU, bias=b1, out=x2, bits_out=b_x2),
+                 dict(W=W2, src=1, act=L.ACT_NONE, bias=b2, out=e_new),
+                 dict(W=Wf, src=2, act=L.ACT_RELU, adds=[(p_f, 0)], out=h_f, bits_out=b_f),
+                 dict(W=Wp, src=2, act=L.ACT_RELU, adds=[(p_p, 1)], out=h_p, bits_out=b_p)]
+        ins = [e] + ([att] if att is not None else [])
+        if not chain_run(ins, specs, g.by_dst.idx, g.by_src.idx, M):
+            raise RuntimeError("mp_edge_block: chain plan rejected (call mp_edge_block_supported first)")
+        ctx.g, ctx.has_att = g, att is not None
+        if train:
+            ctx.save_for_backward(e, att if att is not None else e, x1, x2, e_new, b_x1, b_x2, W0, W1, W2, Wf, Wp)
+        empty = torch.zeros(0, dtype=torch.int32, device=dev)
+        outs = (e_new, h_f, b_f if train else empty, h_p, b_p if train else empty)
+        ctx.mark_non_differentiable(outs[2], outs[4])
+        return outs
+
+    @staticmethod
+    def backward(ctx, de, dhf, _bf, dhp, _bp):
+        e, att, x1, x2, e_new, b_x1, b_x2, W0, W1, W2, Wf, Wp = ctx.saved_tensors
+        g = ctx.g
+        M, dev, bf = e.size(0), e.device, torch.bfloat16
+        n0, n1, n2, nm, k0 = W0.size(0), W1.size(0), W2.size(0), Wf.size(0), W0.size(1)
+        z = lambda t, n: t.contiguous() if t is not None else torch.zeros((M, n), dtype=bf, device=dev)
+        dhf, dhp = z(dhf, nm), z(dhp, nm)
+        mk = lambda n: torch.empty((M, n), dtype=bf, device=dev)
+        dz2, dz1, dz0, dA = mk(n2), mk(n1), mk(n0), mk(k0)
+        w_fp = torch.cat([Wf, Wp], 0)                      # [2*nm, n2]: de' = cat[dh_f, dh_p] . [W_f ; W_p] (+ de)
+        specs = [dict(W=w_fp, transpose=True, src=-1, act=L.ACT_NONE, out=dz2,
+                      adds=[(de.contiguous(), -1)] if de is not None else None),
+                 dict(W=W2, transpose=True, src=0, act=L.ACT_MASKBITS, bits_in=b_x2, out=dz1),
+                 dict(W=W1, transpose=True, src=1, act=L.ACT_MASKBITS, bits_in=b_x1, out=dz0),
+                 dict(W=W0, transpose=True, src=2, act=L.ACT_NONE, out=dA)]
+        if not chain_run([dhf, dhp], specs, None, None, M):
+            raise RuntimeError("mp_edge_block backward: chain plan rejected")
+        it = lambda t: (t, None, None, 0)
+        ins = [it(e)] + ([it(att)] if ctx.has_att else [])
+        dW0, _ = wgrad_raw(it(dz0), ins, M, n0, k0, want_bias=False, tc=True)
+        dW1, db1 = wgrad_raw(it(dz1), [it(x1)], M, n1, n0, tc=True)
+        dW2, db2 = wgrad_raw(it(dz2), [it(x2)], M, n2, n1, tc=True)
+        dWf, _ = wgrad_raw(it(dhf), [it(e_new)], M, nm, n2, want_bias=False, tc=True)
+        dWp, _ = wgrad_raw(it(dhp), [it(e_new)], M, nm, n2, want_bias=False, tc=True)
+        dp_i = segment_sum_raw(dz0, g.by_dst, out_dtype=bf)
+        dp_j = segment_sum_raw(dz0, g.by_src, out_dtype=bf)
+        dp_f = segment_sum_raw(dhf, g.by_dst, out_dtype=bf)
+        dp_p = segment_sum_raw(dhp, g.by_src, out_dtype=bf)
+        d_e = dA[:, :e.size(1)]
+        d_att = dA[:, e.size(1):] if ctx.has_att else None
+        return (None, d_e, d_att, dp_i, dp_j, dp_f, dp_p, dW0, dW1, db1, dW2, db2, dWf, dWp)
+
+
+def mp_edge_block_supported(e, att, W0, W1, W2, Wf):
+    """The fused edge block needs dense bf16 edge tensors and widths the chain kernel plans (multimodal model:
+    64|64 -> 256 -> 128 -> 64 -> 192; the poses-only widths 96 / 32 stay on the per-layer kernels)."""
+    if not _USE_CHAIN or _PRECISION != "bf16" or e.size(0) < _TC_MIN_ROWS:
+        return False
+    ins = [e] + ([att] if att is not None else [])
+    if any(t.dtype != torch.bfloat16 or not _al16(t) or t.size(1) % 64 for t in ins):
+        return False
+    return _chain_dims_ok([W0.size(0), W1.size(0), W2.size(0), Wf.size(0), W0.size(1)]) and 2 * Wf.size(0) <= 512
+
+
+def mp_edge_block(g, e, att, p_i, p_j, p_f, p_p, W0, W1, b1, W2, b2, Wf, Wp):
+    """Returns (e', h_f, bits_f, h_p, bits_p); see _MPEdgeBlock."""
+    return _MPEdgeBlock.apply(g, e, att, p_i, p_j, p_f, p_p, W0, W1, b1, W2, b2, Wf, Wp)
+
+
+class _AttEdgeEncoder(torch.autograd.Function):
+    """att_edge_encoder (clr_att_gnn.py:82-91, :164) 640 -> 512 -> 384 -> 256 -> 128 -> 64 in the pre-projected form
+    (the two 288-wide node-side blocks of layer 0 arrive as row-gathered addends p_i[dst] + p_j[src]) as TWO fused
+    launches: head 64 -> 512 -> 384 (the 512-wide tile alone is 128 KB of shared memory) and tail 384 -> 256 -> 128 ->
+    64. Backward: one fused input-gradient chain 64 -> 128 -> 256 -> 384 (sign-bit masks), the 384 -> 512 step, then
+    the weight gradients and the two per-node addend sums."""
+
+    @staticmethod
+    def forward(ctx, g, e0, p_i, p_j, W0, W1, b1, W2, b2, W3, b3, W4, b4):
+        M, dev, bf = e0.size(0), e0.device, torch.bfloat16
+        train = any(ctx.needs_input_grad)
+        mk = lambda n: torch.empty((M, n), dtype=bf, device=dev)
+        bt = lambda n: new_relu_bits(M, n, dev) if train else None
+        x0 = mk(W0.size(0)) if train else None
+        x1, x2, x3 = mk(W1.size(0)), (mk(W2.size(0)) if train else None), (mk(W3.size(0)) if train else None)
+        y = mk(W4.size(0))
+        bits = [bt(W0.size(0)), bt(W1.size(0)), bt(W2.size(0)), bt(W3.size(0))]
+        head = [dict(W=W0, src=-1, act=L.ACT_RELU, adds=[(p_i, 0), (p_j, 1)], out=x0, bits_out=bits[0]),
+                dict(W=W1, src=0, act=L.ACT_RELU, bias=b1, out=x1, bits_out=bits[1])]
+        tail = [dict(W=W2, src=-1, act=L.ACT_RELU, bias=b2, out=x2, bits_out=bits[2]),
+                dict(W=W3, src=0, act=L.ACT_RELU, bias=b3, out=x3, bits_out=bits[3]),
+                dict(W=W4, src=1, act=L.ACT_NONE, bias=b4, out=y)]
+        if not (chain_run([e0], head, g.by_dst.idx, g.by_src.idx, M) and chain_run([x1], tail, None, None, M)):
+            raise RuntimeError("att_edge_encoder: chain plan rejected")
+        ctx.g = g
+        if train:
+            ctx.save_for_backward(e0, x0, x1, x2, x3, *bits, W0, W1, W2, W3, W4)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        e0, x0, x1, x2, x3, b0, b1_, b2_, b3_, W0, W1, W2, W3, W4 = ctx.saved_tensors
+        g = ctx.g
+        M, dev, bf = e0.size(0), e0.device, torch.bfloat16
+        dy = dy if (dy.dtype == bf and _al16(dy)) else dy.to(bf).contiguous()
+        mk = lambda n: torch.empty((M, n), dtype=bf, device=dev)
+        dz3, dz2, dz1, dz0 = mk(W3.size(0)), mk(W2.size(0)), mk(W1.size(0)), mk(W0.size(0))
+        tail = [dict(W=W4, transpose=True, src=-1, act=L.ACT_MASKBITS, bits_in=b3_, out=dz3),
+                dict(W=W3, transpose=True, src=0, act=L.ACT_MASKBITS, bits_in=b2_, out=dz2),
+                dict(W=W2, transpose=True, src=1, act=L.ACT_MASKBITS, bits_in=b1_, out=dz1)]
+        head = [dict(W=W1, transpose=True, src=-1, act=L.ACT_MASKBITS, bits_in=b0, out=dz0)]
+        if not (chain_run([dy], tail, None, None, M) and chain_run([dz1], head, None, None, M)):
+            raise RuntimeError("att_edge_encoder backward: chain plan rejected")
+        it = lambda t: (t, None, None, 0)
+        d_e0 = linear_raw([it(dz0)], W0, None, M, trans_w=True, tc=True, out_dtype=bf) if ctx.needs_input_grad[1] else None
+        dW0, _ = wgrad_raw(it(dz0), [it(e0)], M, W0.size(0), W0.size(1), want_bias=False, tc=True)
+        dW1, db1 = wgrad_raw(it(dz1), [it(x0)], M, W1.size(0), W1.size(1), tc=True)
+        dW2, db2 = wgrad_raw(it(dz2), [it(x1)], M, W2.size(0), W2.size(1), tc=True)
+        dW3, db3 = wgrad_raw(it(dz3), [it(x2)], M, W3.size(0), W3.size(1), tc=True)
+        dW4, db4 = wgrad_raw(it(dy), [it(x3)], M, W4.size(0), W4.size(1), tc=True)
+        dp_i = segment_sum_raw(dz0, g.by_dst, out_dtype=bf)
+        dp_j = segment_sum_raw(dz0, g.by_src, out_dtype=bf)
+        return (None, d_e0, dp_i, dp_j, dW0, dW1, db1, dW2, db2, dW3, db3, dW4, db4)
+
+
+def att_edge_encoder_supported(e0, linears):
+    dims = [m.out_features for m in linears]
+    return (_USE_CHAIN and _PRECISION == "bf16" and e0.size(0) >= _TC_MIN_ROWS and e0.dtype == torch.bfloat16 and _al16(e0)
+            and e0.size(1) % 64 == 0 and len(linears) == 5 and dims == [512, 384, 256, 128, 64])
+
+
+def att_edge_encoder_block(g, e0, p_i, p_j, w0_edge, linears):
+    """linears: the five nn.Linear of att_edge_encoder; w0_edge = the edge-feature column block of layer 0."""
+    l = linears
+    return _AttEdgeEncoder.apply(g, e0, p_i, p_j, w0_edge, l[1].weight, l[1].bias, l[2].weight, l[2].bias,
+                                 l[3].weight, l[3].bias, l[4].weight, l[4].bias)
+
+
 class _NarrowMLP(torch.autograd.Function):
     """nn.Sequential(Linear, ReLU, ..., Linear[, Sigmoid]) with every width <= 64 as ONE kernel per
     direction (narrow_mlp.cu): hidden activations never leave registers; backward recomputes them."""

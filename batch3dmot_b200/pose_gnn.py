@@ -98,6 +98,19 @@ class CausalMessagePassing(nn.Module):
         # (dense bf16 operands go through the TMA-fed kernels) or the fp32-accumulating segment sum
         if e.dtype != lowp:
             e = e.to(lowp)
+        lf0, lp0 = self.create_future_msgs[0], self.create_past_msgs[0]
+        if ops.mp_edge_block_supported(e, att, w1[:, 2 * D:], eu[1].weight, eu[2].weight, lf0.weight[:, D:D + E_]):
+            # edge_update + both message first layers as one fused launch; hidden tiles and e' stay on the SM
+            e_out, h_f, bits_f, h_p, bits_p = ops.mp_edge_block(
+                g, e, att, p_i, p_j, p_f, p_p, w1[:, 2 * D:], eu[1].weight, eu[1].bias, eu[2].weight, eu[2].bias,
+                lf0.weight[:, D:D + E_], lp0.weight[:, D:D + E_])
+            agg = []
+            for h, bits, into, wpost in ((h_f, bits_f, src, w_post[0]), (h_p, bits_p, dst, w_post[1])):
+                s_h = ops.segment_sum(h, into, relu_src=True, relu_bits=bits, out_dtype=lowp)
+                agg.append(ops.fused_mlp([(s_h, None), (g.degree_block(into, lowp), None)], [wpost], [None], out_dtype=lowp))
+            m_fut, m_past = agg
+            x_new = ops.run_mlp(self.combine_future_past, [(m_past, None), (m_fut, None)], out_dtype=lowp)
+            return x_new, e_out
         dense = [(e, None)] + ([(att, None)] if att is not None else [])
         e_new = ops.fused_mlp(dense, [w1[:, 2 * D:], eu[1].weight, eu[2].weight], [None, eu[1].bias, eu[2].bias],
                               adds=[(p_i, dst), (p_j, src)], out_dtype=lowp)
