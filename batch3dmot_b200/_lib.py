@@ -12,6 +12,7 @@ MASK_NONE, MASK_RELU, MASK_SIGMOID = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 FLAG_ACCUMULATE = 1
 FLAG_OUT_BF16 = 2
+FLAG_SPLIT = 4
 F32, BF16, BITS, F64 = 0, 1, 2, 3
 MAX_SEGS = 8
 

@@ -32,8 +32,10 @@ __host__ __device__ inline uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u 
 // Wp[((k/8) * Npad + n) * 8 + k%8] = bf16(B[n][k]),  B[n][k] = transpose ? W[k*ldw+n] : W[n*ldw+k],
 // zero padded to Npad = round_up(n_logical,16), Kpad = round_up(k_logical,64): every (chunk, k-group)
 // slab is a contiguous run of 16-byte rows == the shared-memory image of a K-major operand.
+// split != 0: a second image of the same shape follows the first and holds the bf16 residual
+// lo = bf16(w - float(hi)) — operands of the 3-MMA "split bf16" mode (hi*hi + lo*hi + hi*lo ~ fp32 products).
 __global__ void k_pack_weights(const float* __restrict__ W, int ldw, int n_log, int k_log, int transpose,
-                               __nv_bfloat16* __restrict__ Wp, int Npad, int Kpad) {
+                               __nv_bfloat16* __restrict__ Wp, int Npad, int Kpad, int split = 0) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)Npad * Kpad;
   if (i >= total) return;
@@ -44,7 +46,9 @@ __global__ void k_pack_weights(const float* __restrict__ W, int ldw, int n_log, 
   int k = kg * 8 + j;
   float v = 0.f;
   if (n < n_log && k < k_log) v = transpose ? W[(long long)k * ldw + n] : W[(long long)n * ldw + k];
-  Wp[i] = __float2bfloat16_rn(v);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  Wp[i] = hi;
+  if (split) Wp[total + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
 // (segment, offset) of every 8-column group of the concatenated operand; -1 past the end.
@@ -309,18 +313,29 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   }
 }
 
-template <int ACT>
+// split-bf16 helpers: v = hi + lo with hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits per operand, so
+// hi*hi + lo*hi + hi*lo reproduces the fp32 product to ~2^-16 relative; accumulation is fp32 in TMEM.
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+  lo = tc::pack_bf16x2(a - __bfloat162float(ha), b - __bfloat162float(hb));
+}
+
+// SPLIT: every operand stage holds a hi image followed by a lo image (A: +TC_A_STAGE, B: +b_stage) and each
+// K step issues three MMAs. This is the tensor-core path of the 1e-4 ("fp32") parity mode.
+template <int ACT, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   using namespace tc;
+  constexpr int NI = SPLIT ? 2 : 1;                      // images per operand stage
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * TC_BM;
   const int n0 = blockIdx.y * TC_NMAX;
   const int Nb = min(TC_NMAX, a.Npad - n0);
   const uint32_t b_stage = (uint32_t)Nb * (TC_BK * 2);   // Nb rows x 128 B
-  const uint32_t base_off = 2 * TC_A_STAGE + 2 * b_stage;
+  const uint32_t base_off = NI * (2 * TC_A_STAGE + 2 * b_stage);
   const uint32_t sA = smem_u32(smem);
-  const uint32_t sB = sA + 2 * TC_A_STAGE;
+  const uint32_t sB = sA + NI * 2 * TC_A_STAGE;
   const uint32_t sBar = sA + base_off;                    // free[0] @0, free[1] @8, done @16, tmem ptr @24
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + base_off + 24);
   float* s_bias = reinterpret_cast<float*>(smem + base_off + 64);                       // [256]
@@ -355,21 +370,25 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
     if (c >= 2) mbar_wait(sBar + 8 * s, ((c >> 1) - 1) & 1);   // MMAs of chunk c-2 released this stage
-    // ---- B: contiguous pre-packed slabs -> cp.async
+    // ---- B: contiguous pre-packed slabs -> cp.async (SPLIT: the lo image lies Npad*Kpad elements further)
     {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.Wp) + ((size_t)(c * 8) * a.Npad + n0) * 16;
-      const uint32_t dst = sB + s * b_stage;
+      const uint32_t dst = sB + s * NI * b_stage;
       if (tid < Nb) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
+        for (int g = 0; g < 8; ++g) {
           cp_async16(dst + (uint32_t)(g * Nb + tid) * 16, wsrc + ((size_t)g * a.Npad + tid) * 16);
+          if (SPLIT)
+            cp_async16(dst + b_stage + (uint32_t)(g * Nb + tid) * 16,
+                       wsrc + (size_t)a.Npad * a.Kpad * 2 + ((size_t)g * a.Npad + tid) * 16);
+        }
       }
     }
     // ---- A: thread = (row, half): 4 groups of 8 columns; bf16 sources by cp.async, fp32 via registers
     {
       float4 v[8];
       int ent[4];
-      const uint32_t dst0 = sA + s * TC_A_STAGE + arow * 16;
+      const uint32_t dst0 = sA + s * NI * TC_A_STAGE + arow * 16;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int g = ahalf * 4 + j;
@@ -380,7 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
           const void* p = seg_addr(S, gr, ent[j] & 0xFFFFFF);
           if (S.dtype == B3D_BF16) {
             cp_async16(dst0 + g * (TC_BM * 16), p);
-            ent[j] = -2;   // done
+            ent[j] = -2;   // done (SPLIT: its residual image is zero)
           } else {
             v[2 * j] = __ldg(reinterpret_cast<const float4*>(p));
             v[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -390,11 +409,24 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int g = ahalf * 4 + j;
-        if (ent[j] >= 0)
-          st_shared_v4(dst0 + g * (TC_BM * 16), pack_bf16x2(v[2 * j].x, v[2 * j].y), pack_bf16x2(v[2 * j].z, v[2 * j].w),
-                       pack_bf16x2(v[2 * j + 1].x, v[2 * j + 1].y), pack_bf16x2(v[2 * j + 1].z, v[2 * j + 1].w));
-        else if (ent[j] == -1)
-          st_shared_v4(dst0 + g * (TC_BM * 16), 0u, 0u, 0u, 0u);
+        const uint32_t d = dst0 + g * (TC_BM * 16);
+        if (ent[j] >= 0) {
+          if (SPLIT) {
+            uint32_t h[4], l[4];
+            split_pack2(v[2 * j].x, v[2 * j].y, h[0], l[0]);
+            split_pack2(v[2 * j].z, v[2 * j].w, h[1], l[1]);
+            split_pack2(v[2 * j + 1].x, v[2 * j + 1].y, h[2], l[2]);
+            split_pack2(v[2 * j + 1].z, v[2 * j + 1].w, h[3], l[3]);
+            st_shared_v4(d, h[0], h[1], h[2], h[3]);
+            st_shared_v4(d + TC_A_STAGE, l[0], l[1], l[2], l[3]);
+          } else {
+            st_shared_v4(d, pack_bf16x2(v[2 * j].x, v[2 * j].y), pack_bf16x2(v[2 * j].z, v[2 * j].w),
+                         pack_bf16x2(v[2 * j + 1].x, v[2 * j + 1].y), pack_bf16x2(v[2 * j + 1].z, v[2 * j + 1].w));
+          }
+        } else {
+          if (ent[j] == -1) st_shared_v4(d, 0u, 0u, 0u, 0u);
+          if (SPLIT) st_shared_v4(d + TC_A_STAGE, 0u, 0u, 0u, 0u);
+        }
       }
     }
     cp_async_wait_all();
@@ -404,9 +436,15 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
       tc_fence_after_sync();
 #pragma unroll
       for (int j = 0; j < TC_BK / 16; ++j) {
-        const uint64_t ad = make_smem_desc(sA + s * TC_A_STAGE + j * 2 * lbo_a, lbo_a, sbo);
-        const uint64_t bd = make_smem_desc(sB + s * b_stage + j * 2 * lbo_b, lbo_b, sbo);
+        const uint64_t ad = make_smem_desc(sA + s * NI * TC_A_STAGE + j * 2 * lbo_a, lbo_a, sbo);
+        const uint64_t bd = make_smem_desc(sB + s * NI * b_stage + j * 2 * lbo_b, lbo_b, sbo);
         mma_bf16_ss(tmem, ad, bd, idesc, (c | j) != 0);
+        if (SPLIT) {
+          const uint64_t al = make_smem_desc(sA + s * NI * TC_A_STAGE + TC_A_STAGE + j * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t bl = make_smem_desc(sB + s * NI * b_stage + b_stage + j * 2 * lbo_b, lbo_b, sbo);
+          mma_bf16_ss(tmem, al, bd, idesc, 1);
+          mma_bf16_ss(tmem, ad, bl, idesc, 1);
+        }
       }
       mma_commit(sBar + 8 * s);
       if (c == nchunks - 1) mma_commit(sBar + 16);
@@ -446,17 +484,28 @@ struct WgTcArgs {
 };
 
 // Stage one 8-element piece (row r, 8 consecutive columns at `p`) of an fp32/bf16 source.
-__device__ __forceinline__ void stage_piece(uint32_t dst, const void* p, int dtype) {
+// lo_off != 0 (split-bf16 mode): the bf16 residual goes to dst + lo_off.
+__device__ __forceinline__ void stage_piece(uint32_t dst, const void* p, int dtype, uint32_t lo_off = 0) {
   using namespace tc;
   if (dtype == B3D_BF16) {
     cp_async16(dst, p);
+    if (lo_off) st_shared_v4(dst + lo_off, 0u, 0u, 0u, 0u);
   } else {
     const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
     const float4 v1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    st_shared_v4(dst, pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+    if (lo_off) {
+      uint32_t h[4], l[4];
+      split_pack2(v0.x, v0.y, h[0], l[0]); split_pack2(v0.z, v0.w, h[1], l[1]);
+      split_pack2(v1.x, v1.y, h[2], l[2]); split_pack2(v1.z, v1.w, h[3], l[3]);
+      st_shared_v4(dst, h[0], h[1], h[2], h[3]);
+      st_shared_v4(dst + lo_off, l[0], l[1], l[2], l[3]);
+    } else {
+      st_shared_v4(dst, pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+    }
   }
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   using namespace tc;
@@ -465,10 +514,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
   const int nt = blockIdx.y / a.ktiles, kt = blockIdx.y % a.ktiles;
   const int n0 = nt * TC_BM, k0 = kt * TC_NMAX;
   const int Nk = min(TC_NMAX, a.Kp - k0);
+  constexpr int NI = SPLIT ? 2 : 1;      // SPLIT: hi image followed by the bf16 residual image in every stage
   const uint32_t b_stage = (uint32_t)Nk * 128;
-  const uint32_t base_off = 2 * TC_A_STAGE + 2 * b_stage;
+  const uint32_t base_off = NI * (2 * TC_A_STAGE + 2 * b_stage);
   const uint32_t sA = smem_u32(smem);
-  const uint32_t sB = sA + 2 * TC_A_STAGE;
+  const uint32_t sB = sA + NI * 2 * TC_A_STAGE;
+  const uint32_t a_lo = SPLIT ? TC_A_STAGE : 0u, b_lo = SPLIT ? b_stage : 0u;
   const uint32_t sBar = sA + base_off;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + base_off + 24);
   int32_t* s_tab = reinterpret_cast<int32_t*>(smem + base_off + 64);   // [TC_TAB]
@@ -505,9 +556,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
       for (int j = 0; j < 4; ++j) {
         const int i = (gq >> 4) * 4 + j;
         const long long r = rbase + i * 8 + rl;
-        const uint32_t dst = sA + s * TC_A_STAGE + ng * 1024 + i * 128 + rl * 16;
+        const uint32_t dst = sA + s * NI * TC_A_STAGE + ng * 1024 + i * 128 + rl * 16;
         if (r < r1 && n + 7 < a.Nout) {
-          stage_piece(dst, seg_addr(a.dy, r, n), a.dy.dtype);
+          stage_piece(dst, seg_addr(a.dy, r, n), a.dy.dtype, a_lo);
         } else if (r < r1 && n < a.Nout) {   // ragged tail of Nout (not a multiple of 8): scalar
           float t[8];
 #pragma unroll
@@ -516,9 +567,18 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
                        ? (a.dy.dtype == B3D_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.dy.ptr)[r * a.dy.ld + n + q])
                                                  : a.dy.ptr[r * a.dy.ld + n + q])
                        : 0.f;
-          st_shared_v4(dst, pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+          if (SPLIT) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_pack2(t[2 * q], t[2 * q + 1], h[q], l[q]);
+            st_shared_v4(dst, h[0], h[1], h[2], h[3]);
+            st_shared_v4(dst + a_lo, l[0], l[1], l[2], l[3]);
+          } else {
+            st_shared_v4(dst, pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+          }
         } else {
           st_shared_v4(dst, 0u, 0u, 0u, 0u);
+          if (SPLIT) st_shared_v4(dst + a_lo, 0u, 0u, 0u, 0u);
         }
       }
     }
@@ -529,13 +589,14 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long long r = rbase + i * 8 + rl;
-        const uint32_t dst = sB + s * b_stage + gq * 1024 + i * 128 + rl * 16;
+        const uint32_t dst = sB + s * NI * b_stage + gq * 1024 + i * 128 + rl * 16;
         if (ent >= 0 && r < r1) {
           const SegDev& S = a.seg[ent >> 24];
           const long long gr = S.idx ? (long long)__ldg(S.idx + r) : r;
-          stage_piece(dst, seg_addr(S, gr, ent & 0xFFFFFF), S.dtype);
+          stage_piece(dst, seg_addr(S, gr, ent & 0xFFFFFF), S.dtype, b_lo);
         } else {
           st_shared_v4(dst, (ones && r < r1) ? 0x00003F80u : 0u, 0u, 0u, 0u);   // bf16(1.0) in element 0
+          if (SPLIT) st_shared_v4(dst + b_lo, 0u, 0u, 0u, 0u);
         }
       }
     }
@@ -546,9 +607,13 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
       tc_fence_after_sync();
 #pragma unroll
       for (int j = 0; j < TC_BK / 16; ++j) {
-        const uint64_t ad = make_smem_desc(sA + s * TC_A_STAGE + j * 256, 128, 1024);   // LBO: next 8-row K group
-        const uint64_t bd = make_smem_desc(sB + s * b_stage + j * 256, 128, 1024);      // SBO: next 8-wide MN group
+        const uint64_t ad = make_smem_desc(sA + s * NI * TC_A_STAGE + j * 256, 128, 1024);   // LBO: next 8-row K group
+        const uint64_t bd = make_smem_desc(sB + s * NI * b_stage + j * 256, 128, 1024);      // SBO: next 8-wide MN group
         mma_bf16_ss(tmem, ad, bd, idesc, (c | j) != 0);
+        if (SPLIT) {
+          mma_bf16_ss(tmem, make_smem_desc(sA + s * NI * TC_A_STAGE + a_lo + j * 256, 128, 1024), bd, idesc, 1);
+          mma_bf16_ss(tmem, ad, make_smem_desc(sB + s * NI * b_stage + b_lo + j * 256, 128, 1024), idesc, 1);
+        }
       }
       mma_commit(sBar + 8 * s);
       if (c == nchunks - 1) mma_commit(sBar + 16);
@@ -982,8 +1047,9 @@ extern "C" int b3d_tc_pack_weights(const float* W, int32_t ldw, int32_t n_logica
   if (!W || !Wp || n_logical <= 0 || k_logical <= 0) return bad_arg("b3d_tc_pack_weights");
   int Npad = round_up(n_logical, 16), Kpad = round_up(k_logical, TC_BK);
   long long total = (long long)Npad * Kpad;
+  // transpose bit 1 (B3D_PACK_SPLIT): also write the bf16 residual image (Wp must hold 2x b3d_tc_packed_bytes)
   k_pack_weights<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      W, ldw, n_logical, k_logical, transpose, reinterpret_cast<__nv_bfloat16*>(Wp), Npad, Kpad);
+      W, ldw, n_logical, k_logical, transpose & 1, reinterpret_cast<__nv_bfloat16*>(Wp), Npad, Kpad, (transpose >> 1) & 1);
   B3D_LAUNCH_CHECK("k_pack_weights");
   return 0;
 }
@@ -1020,20 +1086,31 @@ extern "C" int b3d_linear_tc(const b3d_seg_t* segs, int32_t nseg, const void* Wp
   a.mask_bits = mask_dtype == B3D_BITS ? reinterpret_cast<const uint32_t*>(out_mask) : nullptr;
   a.bits_out = reinterpret_cast<uint32_t*>(relu_bits_out);
   int Nb = a.Npad < TC_NMAX ? a.Npad : TC_NMAX;
-  size_t smem = 2 * TC_A_STAGE + 2 * (size_t)Nb * 128 + 64 + 1024 + 4 * TC_TAB + sizeof(int32_t) * B3D_MAX_SEGS * TC_BM;
+  const bool split = (flags & B3D_FLAG_SPLIT) != 0;   // 3-MMA split-bf16 arithmetic (Wp packed with B3D_PACK_SPLIT)
+  size_t smem = (split ? 2 : 1) * (2 * TC_A_STAGE + 2 * (size_t)Nb * 128) + 64 + 1024 + 4 * TC_TAB +
+                sizeof(int32_t) * B3D_MAX_SEGS * TC_BM;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_linear_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_linear_tc<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tc<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return fail("k_linear_tc smem attr", e);
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(M, TC_BM), (unsigned)ceil_div(a.Npad, TC_NMAX));
   cudaStream_t st = (cudaStream_t)stream;
-  if (act == B3D_ACT_RELU) k_linear_tc<1><<<grid, TC_THREADS, smem, st>>>(a);
-  else if (act == B3D_ACT_SIGMOID) k_linear_tc<2><<<grid, TC_THREADS, smem, st>>>(a);
-  else k_linear_tc<0><<<grid, TC_THREADS, smem, st>>>(a);
+  if (split) {
+    if (act == B3D_ACT_RELU) k_linear_tc<1, true><<<grid, TC_THREADS, smem, st>>>(a);
+    else if (act == B3D_ACT_SIGMOID) k_linear_tc<2, true><<<grid, TC_THREADS, smem, st>>>(a);
+    else k_linear_tc<0, true><<<grid, TC_THREADS, smem, st>>>(a);
+  } else {
+    if (act == B3D_ACT_RELU) k_linear_tc<1, false><<<grid, TC_THREADS, smem, st>>>(a);
+    else if (act == B3D_ACT_SIGMOID) k_linear_tc<2, false><<<grid, TC_THREADS, smem, st>>>(a);
+    else k_linear_tc<0, false><<<grid, TC_THREADS, smem, st>>>(a);
+  }
   B3D_LAUNCH_CHECK("k_linear_tc");
   return 0;
 }
@@ -1070,14 +1147,17 @@ extern "C" int b3d_wgrad_tc(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t 
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return fail("k_wgrad_tc smem attr", e);
     attr_set = true;
   }
   int Nk = Kp < TC_NMAX ? Kp : TC_NMAX;
-  size_t smem = 2 * TC_A_STAGE + 2 * (size_t)Nk * 128 + 64 + 4 * TC_TAB;
+  const bool split = (flags & B3D_FLAG_SPLIT) != 0;
+  size_t smem = (split ? 2 : 1) * (2 * TC_A_STAGE + 2 * (size_t)Nk * 128) + 64 + 4 * TC_TAB;
   dim3 grid((unsigned)S, (unsigned)(ceil_div(Nout, TC_BM) * ktiles));
-  k_wgrad_tc<<<grid, TC_THREADS, smem, st>>>(a);
+  if (split) k_wgrad_tc<true><<<grid, TC_THREADS, smem, st>>>(a);
+  else k_wgrad_tc<false><<<grid, TC_THREADS, smem, st>>>(a);
   B3D_LAUNCH_CHECK("k_wgrad_tc");
   long long tot = (long long)Nout * (K + 1);
   k_wgrad_tc_reduce<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(a.part, S, Nout, K, dW, lddw, db,

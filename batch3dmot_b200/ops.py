@@ -117,7 +117,12 @@ def graph_of(edge_index, num_nodes):
 
 
 # ----------------------------------------------------------------------------- precision mode
-_PRECISION = "fp32"      # "fp32": FFMA kernels, 1e-4 parity mode; "bf16": tcgen05 tiles, 2e-2 mode
+# "fp32" : the 1e-4 parity mode. Dense layers run on the tensor cores in SPLIT-bf16 arithmetic (every fp32 operand
+#          as hi + lo bf16 parts, three tcgen05.mma per K step, fp32 accumulation: ~2^-16 relative per product);
+#          shapes the tiles do not take (tiny M, ragged widths, operand masks) use the FFMA kernel.
+# "exact": FFMA kernels everywhere (plain fp32 arithmetic; kernel-level tests against float64).
+# "bf16" : bf16 operands and bf16 storage between layers, fused chains (2e-2 mode, the benchmarked path).
+_PRECISION = "fp32"
 _TC_MIN_ROWS = 256
 _packed = {}
 
@@ -126,7 +131,7 @@ def set_precision(p):
     """Select the arithmetic of the dense layers: 'fp32' (exact mode) or 'bf16' (tensor-core tiles
     with fp32 accumulation; layers whose shapes do not fit the tile constraints stay fp32)."""
     global _PRECISION
-    assert p in ("fp32", "bf16")
+    assert p in ("fp32", "exact", "bf16")
     _PRECISION = p
 
 
@@ -151,12 +156,12 @@ _USE_TMA = True          # dense bf16 operands go through the TMA-fed persistent
 _USE_BITS = True         # bf16 chains keep ReLU masks as sign bits (B3D_BITS) for the backward pass
 
 
-def _packed_weight(W, transpose, rowmajor=False):
+def _packed_weight(W, transpose, rowmajor=False, split=False):
     """bf16 pack of W for the tensor-core kernels. An entry belongs to ONE live tensor object: it holds a weak
     reference and is used only while that very object is alive at the same version. (A key made of
     (data_ptr, _version) alone would return the old pack for a temporary that the caching allocator placed
     at a recycled address, or for the parameters of a new model allocated where a freed one lived.)"""
-    key = (id(W), tuple(W.shape), W.stride(0), bool(transpose), rowmajor)
+    key = (id(W), tuple(W.shape), W.stride(0), bool(transpose), rowmajor, split)
     ent = _packed.get(key)
     if ent is not None:
         ref, ver, ptr, wp = ent
@@ -168,8 +173,10 @@ def _packed_weight(W, transpose, rowmajor=False):
     lib = L.lib()
     nbytes, pack = (lib.b3d_tma_packed_bytes, lib.b3d_tma_pack_weights) if rowmajor else \
         (lib.b3d_tc_packed_bytes, lib.b3d_tc_pack_weights)
-    wp = torch.empty(nbytes(n_log, k_log), dtype=torch.uint8, device=W.device)
-    L.check(pack(L.ptr(W), W.stride(0), n_log, k_log, int(transpose), L.ptr(wp), L.stream()), "pack_weights")
+    assert not (split and rowmajor)
+    wp = torch.empty(nbytes(n_log, k_log) * (2 if split else 1), dtype=torch.uint8, device=W.device)
+    L.check(pack(L.ptr(W), W.stride(0), n_log, k_log, int(transpose) | (2 if split else 0), L.ptr(wp), L.stream()),
+            "pack_weights")
     _packed[key] = (weakref.ref(W), W._version, W.data_ptr(), wp)
     return wp
 
@@ -317,6 +324,11 @@ def _linear_raw_impl(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None,
     if tc is None:
         tc = _PRECISION == "bf16" and M > 0 and _tc_shapes_ok(items, M, n_out, K) and \
             (out_mask is None or _al16(out_mask))
+    # 1e-4 mode: split-bf16 tensor-core tiles for all-fp32 layers whose shapes fit
+    split = (not tc and _PRECISION == "fp32" and M > 0 and _tc_shapes_ok(items, M, n_out, K)
+             and all(t.dtype == torch.float32 for t, _, _, _ in items) and (out_mask is None or _al16(out_mask))
+             and mask_bits is None and bits_out is None and (out is None or out.dtype == torch.float32)
+             and all(t.dtype == torch.float32 and _al16(t) for t, _ in (adds or [])))
     if out is None:
         out = torch.empty((M, n_out), dtype=out_dtype if tc else torch.float32, device=W.device)
     if bias is not None:
@@ -340,10 +352,11 @@ def _linear_raw_impl(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None,
                                        out.stride(0), _DT[out.dtype], M, act, 0, m_ptr, m_ld, m_dt, L.ptr(row_mask),
                                        add_segs, nadd, L.ptr(bits_out), L.stream()), "b3d_linear_tma")
         return out
-    if tc:
-        wp = _packed_weight(W, trans_w)
+    if tc or split:
+        wp = _packed_weight(W, trans_w, split=split)
         L.check(L.lib().b3d_linear_tc(segs, len(items), L.ptr(wp), n_out, K, L.ptr(bias), L.ptr(out),
-                                      out.stride(0), _DT[out.dtype], M, act, L.FLAG_ACCUMULATE if accumulate else 0,
+                                      out.stride(0), _DT[out.dtype], M, act,
+                                      (L.FLAG_ACCUMULATE if accumulate else 0) | (L.FLAG_SPLIT if split else 0),
                                       m_ptr, m_ld, m_dt, L.ptr(row_mask), add_segs, nadd, L.ptr(bits_out),
                                       L.stream()), "b3d_linear_tc")
         return out
@@ -407,12 +420,15 @@ def _wgrad_raw_impl(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=Fa
                                   L.ptr(db), M, n_out, L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(ws), wsb,
                                   L.stream()), "b3d_wgrad_tma")
         return dW, db
-    if tc:
+    split = (not tc and _PRECISION == "fp32" and M > 0 and _tc_shapes_ok(items, M, max(n_out, 16), K)
+             and _al16(dy_item[0]) and dy_item[2] is None and dy_item[0].dtype == torch.float32
+             and all(t.dtype == torch.float32 for t, _, _, _ in items))
+    if tc or split:
         wsb = lib.b3d_wgrad_tc_workspace_bytes(M, n_out, K)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         L.check(lib.b3d_wgrad_tc(L.make_segs([dy_item]), L.make_segs(items), len(items), L.ptr(dW), dW.stride(0),
-                                 L.ptr(db), M, n_out, L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(ws), wsb,
-                                 L.stream()), "b3d_wgrad_tc")
+                                 L.ptr(db), M, n_out, (L.FLAG_ACCUMULATE if accumulate else 0) | (L.FLAG_SPLIT if split else 0),
+                                 L.ptr(ws), wsb, L.stream()), "b3d_wgrad_tc")
         return dW, db
     wsb = lib.b3d_wgrad_workspace_bytes(M, n_out, K)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)

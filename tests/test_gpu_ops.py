@@ -14,6 +14,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def exact_mode():
+    """Kernel-level tests of the plain-fp32 (FFMA) entry points against float64: the "exact" arithmetic mode.
+    (The default "fp32" mode runs the same layers as split-bf16 tensor-core tiles: tests/test_gpu_split.py.)"""
+    ops.set_precision("exact")
+    yield
+    ops.set_precision("fp32")
+
+
 def rel_err(a, b):
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
