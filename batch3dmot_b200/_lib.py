@@ -99,6 +99,7 @@ _SIGS = {
                                          C.c_int32, C.c_void_p, C.c_void_p]),
     "b3d_chain_run": (C.c_int, [C.POINTER(Seg), C.c_int32, C.POINTER(ChainLayer), C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int64, C.c_void_p]),
+    "b3d_window_knn": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b3d_hier_tracks_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b3d_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int32, C.c_float,

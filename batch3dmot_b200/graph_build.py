@@ -73,6 +73,23 @@ def build_window_graph(center, velocity, yaw, wlh, category, token, frame, top_k
     cmax = int(cnt[cur].max())
     k_row = cnt[cur].clamp(max=top_knn)
     kmax = int(k_row.max())
+    if center.is_cuda and top_knn <= 63:
+        # device path: the libb3d kernel (window_knn.cu) selects per current node without materialising the
+        # [rows, candidates] matrices; exact ties are ordered by candidate position (deterministic), rows whose
+        # metric holds a NaN take the reference's own 1-D sequence below
+        from . import _lib as L
+        ex = torch.empty((cur.numel(), kmax), dtype=torch.int64, device=dev)
+        flags = torch.empty(cur.numel(), dtype=torch.int32, device=dev)
+        cc, vv, yy = center.contiguous(), velocity.contiguous(), yaw.contiguous()
+        first_c, cnt_c = first_of_cat[cur].contiguous(), cnt[cur].contiguous()
+        L.check(L.lib().b3d_window_knn(L.ptr(cc), L.ptr(vv), L.ptr(yy), L.ptr(order), L.ptr(cur), L.ptr(first_c),
+                                       L.ptr(cnt_c), cur.numel(), top_knn, kmax, L.ptr(ex), L.ptr(flags), L.stream()),
+                "b3d_window_knn")
+        for r in torch.nonzero(flags & 1).flatten().tolist():
+            c, n_c, k = int(cur[r]), int(cnt_c[r]), int(k_row[r])
+            ids_r = order[int(first_c[r]):int(first_c[r]) + n_c]
+            ex[r, :k] = ids_r[torch.topk(_metric_1d(center, velocity, yaw, c, ids_r), k, largest=False).indices]
+        return _finish(ex, cur, k_row, kmax, center, yaw, wlh, token, frame)
     col = torch.arange(cmax, device=dev)
     valid = col[None, :] < cnt[cur][:, None]                                     # [R, cmax]
     cand = order[(first_of_cat[cur][:, None] + col[None, :]).clamp(max=N - 1)]   # candidate node ids
@@ -102,8 +119,15 @@ def build_window_graph(center, velocity, yaw, wlh, category, token, frame, top_k
         c, n_c, k = int(cur[r]), int(cnt[cur[r]]), int(k_row[r])
         m1 = _metric_1d(center, velocity, yaw, c, cand[r, :n_c])
         sel[r, :k] = torch.topk(m1, k, largest=False).indices
-    keep = torch.arange(kmax, device=dev)[None, :] < k_row[:, None]              # [R, kmax]
     ex = torch.gather(cand, 1, sel.clamp(max=cmax - 1))                          # neighbour node ids
+    return _finish(ex, cur, k_row, kmax, center, yaw, wlh, token, frame)
+
+
+def _finish(ex, cur, k_row, kmax, center, yaw, wlh, token, frame):
+    """Selected neighbours [R, kmax] -> (edges, ground-truth labels, 4-d edge features) in emission order."""
+    dev, f64 = ex.device, torch.float64
+    keep = torch.arange(kmax, device=dev)[None, :] < k_row[:, None]              # [R, kmax]
+    ex = torch.where(keep, ex, torch.zeros_like(ex))                             # padding -> a valid id (masked below)
     cu = cur[:, None].expand(-1, kmax)
     # ground truth (construct_...:227-260): an edge between two detections of the same instance is positive iff
     # no OTHER selected neighbour of the same instance lies in a frame closer to the current one

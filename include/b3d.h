@@ -310,6 +310,18 @@ int b3d_chain_pack_weights(const b3d_chain_layer_t* layers /*host*/, int32_t nl,
 int b3d_chain_run(const b3d_seg_t* in_segs /*host*/, int32_t nseg, const b3d_chain_layer_t* layers /*host*/,
                   int32_t nl, const void* packed, const int32_t* idx0, const int32_t* idx1, int64_t M, void* stream);
 
+/* ---- graph construction: same-category k-NN under the normalised motion metric ---------------------------------
+ * get_knn_nodes_in_graph (batch_3dmot/utils/graph_utils.py:33-88) for all current nodes of a window at once
+ * (construct_detection_graph_disjoint_parallel_only_poses.py:204-224): row r is current node cur[r]; its
+ * candidates are order[first[r] .. first[r] + cnt[r]) (same-category nodes of earlier frames, ascending id).
+ * center / velocity: float64 [N,3], yaw: float64 [N]. ex: int64 [R, kmax] receives the min(top_knn, cnt[r])
+ * selected node ids in ascending (metric, candidate position) order, -1 padded. flags[r]: bit 0 = the metric holds
+ * a NaN (0/0 when a maximum is 0; the caller resolves such rows with the reference's 1-D sequence), bit 1 = an
+ * exact tie among the first k+1 values (order = candidate position; unspecified upstream). */
+int b3d_window_knn(const double* center, const double* velocity, const double* yaw, const int64_t* order,
+                   const int64_t* cur, const int64_t* first, const int64_t* cnt, int64_t R, int32_t top_knn,
+                   int32_t kmax, int64_t* ex, int32_t* flags, void* stream);
+
 /* ---- track assembly, host side (the only entry point that takes HOST pointers and runs on the CPU) -------------
  * create_trajectories(mode='hier') + track-id numbering (predict.py:308-373, :437-446) over the surviving edges
  * of one or many scenes: edges (e_out -> e_in, float64 score) in the reference's greedy_edges insertion order,

@@ -139,8 +139,43 @@ def test_detections_to_batch_pipeline(tmp_path):
 
 @pytest.mark.gpu
 def test_same_result_on_cuda_tensors():
-    """Same edges and labels on CUDA tensors (data without exact metric ties: the order of exactly tied entries is
-    whatever the device's torch.topk returns, as upstream); features within 1e-12 (device libm: sqrt/log/fmod)."""
-    for seed in (21, 23):
+    """CUDA tensors go through the libb3d selection kernel (window_knn.cu): same edges and labels, bit for bit, on
+    data without exact metric ties; features within 1e-12 (device libm: log)."""
+    from batch3dmot_b200 import _lib as L
+    n0 = L.launch_count()
+    for seed in (21, 23, 0, 1, 2):
         check(random_window(seed), device="cuda", feat_tol=(1e-12, 1e-12))
+    assert L.launch_count() - n0 == 5                       # the kernel really ran
+    check(random_window(11, n_cat=1, n_objects=70, p_seen=0.9, max_per_frame=60), device="cuda", feat_tol=(1e-12, 1e-12))
+    check(random_window(11, n_cat=1, n_objects=70, p_seen=0.9, max_per_frame=60), top_knn=3, device="cuda",
+          feat_tol=(1e-12, 1e-12))
+    check(random_window(4, gap_frames=(1, 3)), device="cuda", feat_tol=(1e-12, 1e-12))
     check([[], [], [], [], []], device="cuda")
+    # NaN metric row (single candidate, identical yaw and velocity): resolved like the reference
+    a = {'center': np.array([1.0, 2.0, 0.0]), 'velocity': np.zeros(3), 'yaw': 0.3, 'wlh': np.ones(3), 'category': 2,
+         'token': 7, 'time': 0}
+    b = dict(a, center=np.array([4.0, 6.0, 0.0]), time=1)
+    e, gt = check([[a], [b]], device="cuda")
+    assert e.tolist() == [[0, 1]] and gt.tolist() == [1]
+
+
+@pytest.mark.gpu
+def test_exact_ties_on_cuda_are_deterministic_and_metric_equivalent():
+    """Exact metric ties: torch.topk leaves their order unspecified upstream; the kernel orders them by candidate
+    position. Per current node the selected METRIC VALUES equal the reference's, and two runs agree bit for bit."""
+    frames = random_window(5, dup=True)
+    args = to_tensors(frames, "cuda")
+    e1, gt1, f1 = graph_build.build_window_graph(*args)
+    e2, gt2, f2 = graph_build.build_window_graph(*args)
+    assert torch.equal(e1, e2) and torch.equal(gt1, gt2) and torch.equal(f1, f2)
+    e_ref, _, _ = G.build_window_graph(frames, 40)
+    e1 = e1.cpu()
+    assert e1.shape == e_ref.shape and torch.equal(e1[:, 1], e_ref[:, 1])
+    center, velocity, yaw, _, category, _, frame = to_tensors(frames, "cpu")
+    for c in torch.unique(e_ref[:, 1]).tolist():
+        cand = torch.nonzero((category == category[c]) & (frame < frame[c])).flatten()
+        m = graph_build._metric_1d(center, velocity, yaw, c, cand)
+        val = {int(n): float(v) for n, v in zip(cand, m)}
+        ours = sorted(val[int(n)] for n in e1[e1[:, 1] == c, 0])
+        ref = sorted(val[int(n)] for n in e_ref[e_ref[:, 1] == c, 0])
+        assert ours == ref, c
