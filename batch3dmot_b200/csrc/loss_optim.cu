@@ -115,9 +115,44 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   p[i] = pi - (lr / bc1) * (mi / denom);
 }
 
+// Same update with the step number kept ON THE DEVICE (bias corrections computed per thread from *step + 1), so
+// that a captured CUDA graph of the training step replays with the right correction; k_adam_tick then advances it.
+__global__ void k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                           float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                           const int32_t* __restrict__ step, float gscale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = (float)(*step + 1);
+  const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  float pi = p[i];
+  float gi = g[i] * gscale;
+  if (wd != 0.f) gi = fmaf(wd, pi, gi);
+  float mi = b1 * m[i] + (1.f - b1) * gi;
+  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
+__global__ void k_adam_tick(int32_t* step) { *step += 1; }
+
 }  // namespace b3d
 
 using namespace b3d;
+
+extern "C" int b3d_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, int32_t* step_counter, float grad_scale,
+                                 void* stream) {
+  if (!p || !g || !m || !v || n < 0 || !step_counter) return bad_arg("b3d_adam_step_dev");
+  if (n > 0) {
+    k_adam_dev<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                              weight_decay, step_counter, grad_scale);
+    B3D_LAUNCH_CHECK("k_adam_dev");
+  }
+  k_adam_tick<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter);
+  B3D_LAUNCH_CHECK("k_adam_tick");
+  return 0;
+}
 
 extern "C" int64_t b3d_bce_partials(int64_t E) { return ceil_div(E > 0 ? E : 1, BCE_CHUNK); }
 

@@ -568,6 +568,12 @@ def adam_step(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale=1.0):
                                   eps, weight_decay, step, grad_scale, L.stream()), "b3d_adam_step")
 
 
+def adam_step_dev(p, g, m, v, lr, betas, eps, weight_decay, step_counter, grad_scale=1.0):
+    """adam_step with the step number read from (and advanced in) the int32 device tensor `step_counter`."""
+    L.check(L.lib().b3d_adam_step_dev(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, betas[0], betas[1],
+                                      eps, weight_decay, L.ptr(step_counter), grad_scale, L.stream()), "b3d_adam_step_dev")
+
+
 # ----------------------------------------------------------------------------- autograd
 _ACT = {None: L.ACT_NONE, "relu": L.ACT_RELU, "sigmoid": L.ACT_SIGMOID}
 _MASK = {None: L.MASK_NONE, "relu": L.MASK_RELU, "sigmoid": L.MASK_SIGMOID}

@@ -82,6 +82,7 @@ class Trainer:
         assert loss in ("bce", "focal")      # "focal": BASELINE config 5's alternative edge loss (not in the reference)
         self.loss, self.focal = loss, (focal_alpha, focal_gamma)
         self.step_no = 0
+        self._step_dev = None
 
     def _loss(self, data, global_edges, fwd_kwargs):
         ops = self.ops
@@ -127,7 +128,41 @@ class Trainer:
             loss.backward()
         allreduce_sum_(self.fp.grad)
         self.step_no += 1
-        ops.adam_step(self.fp.flat, self.fp.grad, self.m, self.v, self.lr, self.betas, self.eps, self.wd,
-                      self.step_no)
+        if self._step_dev is not None:      # graph-capturable form: the step number lives on the device
+            ops.adam_step_dev(self.fp.flat, self.fp.grad, self.m, self.v, self.lr, self.betas, self.eps, self.wd,
+                              self._step_dev)
+        else:
+            ops.adam_step(self.fp.flat, self.fp.grad, self.m, self.v, self.lr, self.betas, self.eps, self.wd,
+                          self.step_no)
         ops.invalidate_weight_cache()      # raw-pointer update: packed bf16 copies are stale
         return loss.detach()
+
+    def capture(self, data, global_edges=None, warmup=2, **fwd_kwargs):
+        """Capture one whole training step on `data` (static shapes and addresses) in a CUDA graph and return
+        `replay() -> loss tensor`. For the launch-bound small-batch regime (the reference trains with 2 window
+        graphs per step, cl_config.yaml:99: a few hundred short kernels per step): the graph removes the Python /
+        ctypes / autograd dispatch between them. Everything the step touches is static: parameters, gradients and
+        Adam moments are the flat buffers, the weight packs are re-made inside the graph from the updated
+        parameters, the step number is a device counter, and NCCL all-reduces are capturable."""
+        dev = self.model.parameters().__next__().device
+        if self.fp is None:
+            self.step(data, global_edges, **fwd_kwargs)             # eager: decides which parameters train
+        if self._step_dev is None:
+            self._step_dev = torch.full((1,), self.step_no, dtype=torch.int32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(data, global_edges, **fwd_kwargs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self.step(data, global_edges, **fwd_kwargs)
+
+        def replay():
+            graph.replay()
+            self.step_no += 1
+            return loss
+        replay.graph = graph
+        return replay

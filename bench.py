@@ -322,6 +322,14 @@ def extras(a, rank, world, dev, model, d, tm, E_global):
         lc = _lib.launch_count()
         ms = tm.run(lambda: trs.step(dd, **kwd), 10, 3, reduce=False)
         res[name] = {"edges": Ed, "us_per_step": ms * 1e3, "fwd_bwd_edges_per_s": Ed / ms * 1e3, "libb3d_launches_per_step": lc}
+        try:                                         # the same step captured in a CUDA graph (Trainer.capture)
+            replay = trs.capture(dd, **kwd)
+            msg = tm.run(replay, 20, 3, reduce=False)
+            res[name].update(cuda_graph_us_per_step=msg * 1e3, cuda_graph_edges_per_s=Ed / msg * 1e3)
+            del replay
+        except Exception as ex:                      # noqa: BLE001 - reported, not fatal for the headline
+            res[name]["cuda_graph_error"] = repr(ex)[:200]
+        trs._step_dev = None
     x["small_batch"] = dict(res, workload="configs[4]: multimodal training step at the reference's batch (2 window graphs) and at 1 scene")
     del ms_, trs
 

@@ -273,6 +273,11 @@ int b3d_focal_fwd_bwd(const float* input, const int64_t* y, const float* w, int6
 int b3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                   void* stream);
+/* The same step with the step number in device memory (*step_counter = number of steps taken so far; read for
+ * the bias corrections, then incremented): lets a captured CUDA graph of the whole training step be replayed. */
+int b3d_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int32_t* step_counter, float grad_scale,
+                      void* stream);
 
 /* ---- fused MLP chains (tcgen05, hidden activations stay in shared memory) ------------------------------------
  * One launch runs a whole nn.Sequential(Linear, ReLU, ..., Linear) over dense bf16 edge rows — edge_update

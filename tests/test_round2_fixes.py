@@ -215,3 +215,36 @@ def test_knn_attention_conv_with_ungrouped_timestamps():
     got = knn_attention_conv(conv, x.to(DEV), ts.to(DEV), k=20)
     want = R.knn_update_masked(sd, x, ts, k=20)
     assert rel(got, want) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_cuda_graph_of_the_training_step_replays_the_eager_trajectory(precision):
+    """Trainer.capture: the whole step (fwd + loss + bwd + Adam with a device-side step counter, weight packs re-made
+    inside the graph) replayed 6 times == 6 eager steps, bit for bit (same kernels, same order, no atomics)."""
+    from batch3dmot_b200.clr_att_gnn import GNN
+    from batch3dmot_b200.parallel import Trainer
+    sc = synth.add_labels(synth.add_modalities(synth.scene_graph(seed=12, T=8, nodes_per_frame=40), 12, raw=False), 12)
+    wins = synth.windows(sc, 5)[:2]                       # the reference's batch: 2 window graphs (cl_config.yaml:99)
+    for w in wins:
+        synth.add_labels(w, 12)
+    d = to_dev(synth.collate(wins))
+    kw = dict(x_img=d.x_img, pointnet_out=d.pointnet_out, radarnet_out=d.radarnet_out, lidar_mask=d.m_lidar,
+              radar_mask=d.m_radar)
+    ops.set_precision(precision)
+    try:
+        torch.manual_seed(5621)
+        m1 = GNN(None, None, None).to(DEV)
+        t1 = Trainer(m1, lr=1e-3)
+        eager = [float(t1.step(d, **kw)) for _ in range(9)]
+        torch.manual_seed(5621)
+        m2 = GNN(None, None, None).to(DEV)
+        t2 = Trainer(m2, lr=1e-3)
+        replay = t2.capture(d, warmup=2, **kw)            # 1 eager + 2 warm-up steps, then the captured one is NOT run
+        got = [float(replay()) for _ in range(6)]
+        assert got == eager[3:9], (got, eager)
+        for a, b in zip(m1.parameters(), m2.parameters()):
+            assert torch.equal(a, b)
+    finally:
+        ops.set_precision("fp32")
+        ops.invalidate_weight_cache()
