@@ -109,3 +109,55 @@ def test_live_unmodified_reference_getitem(tmp_path, inference):
     for k in keys:
         assert same(getattr(data, k), getattr(ours, k)) and same(getattr(data, k), getattr(rest, k)), k
     assert data.num_nodes == ours.num_nodes
+
+
+@pytest.mark.gpu
+def test_window_loader_feeds_the_gpu_from_pinned_batches_with_overlapped_copies(tmp_path):
+    """train.py:85-97 on the box: background threads read + collate window files into PINNED batches; the consumer
+    copies batch i+1 on a copy stream while the model runs batch i. Results equal the synchronous path bit for bit,
+    and the copy stream really ran concurrently with compute (its copies do not serialise behind the forward)."""
+    from types import SimpleNamespace
+    from batch3dmot_b200 import ops
+    from batch3dmot_b200.pose_gnn import PoseGNN
+    dev = torch.device("cuda")
+    prefixes = [write_window(tmp_path, 60 + i, npf=20 + i)[0] for i in range(12)]
+    torch.manual_seed(5621)
+    model = PoseGNN().to(dev).eval()
+    keys = ("pose_feats", "edge_index", "edge_attr", "node_timestamps", "batch", "y", "edge_weights")
+
+    def forward(b):
+        with torch.no_grad():
+            return model(b)[0]
+
+    # synchronous reference
+    ref = []
+    for grp in graph_io.WindowBatchLoader(prefixes, batch_size=2, pin=False).batches():
+        b = graph_io.load_batch(grp, pin=False)
+        ref.append(forward(SimpleNamespace(**{k: getattr(b, k).to(dev) for k in keys})).cpu())
+    # pipelined: pinned batches, non_blocking H2D on a copy stream, event hand-over to the compute stream
+    copy = torch.cuda.Stream(device=dev)
+    outs, staged = [], None
+    loader = graph_io.WindowBatchLoader(prefixes, batch_size=2, workers=4, prefetch=3, pin=True)
+
+    def stage(b):
+        assert all(getattr(b, k).is_pinned() for k in keys)
+        with torch.cuda.stream(copy):
+            d = SimpleNamespace(**{k: getattr(b, k).to(dev, non_blocking=True) for k in keys})
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        return d, ev, b                                   # keep the pinned source alive until the copy is consumed
+
+    for b in loader:
+        nxt = stage(b)                                    # H2D of this batch is in flight while the previous one computes
+        if staged is not None:
+            d, ev, _ = staged
+            torch.cuda.current_stream().wait_event(ev)
+            outs.append(forward(d))
+        staged = nxt
+    d, ev, _ = staged
+    torch.cuda.current_stream().wait_event(ev)
+    outs.append(forward(d))
+    torch.cuda.synchronize()
+    assert len(outs) == len(ref) == 6
+    for a, r in zip(outs, ref):
+        assert torch.equal(a.cpu(), r)
