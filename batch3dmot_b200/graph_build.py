@@ -73,7 +73,8 @@ def build_window_graph(center, velocity, yaw, wlh, category, token, frame, top_k
     cmax = int(cnt[cur].max())
     k_row = cnt[cur].clamp(max=top_knn)
     kmax = int(k_row.max())
-    if center.is_cuda and top_knn <= 63:
+    from . import ops
+    if center.is_cuda and top_knn <= 63 and ops.FEATURES["window_knn"]:
         # device path: the libb3d kernel (window_knn.cu) selects per current node without materialising the
         # [rows, candidates] matrices; exact ties are ordered by candidate position (deterministic), rows whose
         # metric holds a NaN take the reference's own 1-D sequence below

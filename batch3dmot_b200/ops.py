@@ -204,7 +204,25 @@ def derived_weights(tag, sources, build):
 
 
 _chain_packs = {}
-_USE_CHAIN = os.environ.get("B3D_NO_CHAIN") != "1"   # multi-layer bf16 chains run as ONE fused launch (chain_tc.cu)
+# Kernel families added after the last measured round are switched on HERE once `pytest -m gpu` is green with them
+# on a B200 (B3D_FEATURES=all|none|comma list overrides, e.g. for the validation run itself):
+#   chain      fused MLP chains / edge blocks (chain_tc.cu)
+#   split_tc   split-bf16 tensor-core tiles as the arithmetic of the "fp32" (1e-4) mode (else: FFMA kernels)
+#   window_knn graph-construction k-NN kernel for CUDA tensors (window_knn.cu)
+_FEATURE_DEFAULTS = {"chain": False, "split_tc": False, "window_knn": False}
+
+
+def _read_features():
+    env = os.environ.get("B3D_FEATURES")
+    if env is None:
+        return dict(_FEATURE_DEFAULTS)
+    on = set(_FEATURE_DEFAULTS) if env.strip() == "all" else {t.strip() for t in env.split(",") if t.strip() not in ("", "none")}
+    assert on <= set(_FEATURE_DEFAULTS), f"unknown feature in B3D_FEATURES={env!r}"
+    return {k: k in on for k in _FEATURE_DEFAULTS}
+
+
+FEATURES = _read_features()
+_USE_CHAIN = FEATURES["chain"]   # multi-layer bf16 chains run as ONE fused launch (chain_tc.cu)
 
 
 def _wkey(w):
@@ -325,7 +343,7 @@ def _linear_raw_impl(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None,
         tc = _PRECISION == "bf16" and M > 0 and _tc_shapes_ok(items, M, n_out, K) and \
             (out_mask is None or _al16(out_mask))
     # 1e-4 mode: split-bf16 tensor-core tiles for all-fp32 layers whose shapes fit
-    split = (not tc and _PRECISION == "fp32" and M > 0 and _tc_shapes_ok(items, M, n_out, K)
+    split = (not tc and _PRECISION == "fp32" and FEATURES["split_tc"] and M > 0 and _tc_shapes_ok(items, M, n_out, K)
              and all(t.dtype == torch.float32 for t, _, _, _ in items) and (out_mask is None or _al16(out_mask))
              and mask_bits is None and bits_out is None and (out is None or out.dtype == torch.float32)
              and all(t.dtype == torch.float32 and _al16(t) for t, _ in (adds or [])))
@@ -420,7 +438,7 @@ def _wgrad_raw_impl(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=Fa
                                   L.ptr(db), M, n_out, L.FLAG_ACCUMULATE if accumulate else 0, L.ptr(ws), wsb,
                                   L.stream()), "b3d_wgrad_tma")
         return dW, db
-    split = (not tc and _PRECISION == "fp32" and M > 0 and _tc_shapes_ok(items, M, max(n_out, 16), K)
+    split = (not tc and _PRECISION == "fp32" and FEATURES["split_tc"] and M > 0 and _tc_shapes_ok(items, M, max(n_out, 16), K)
              and _al16(dy_item[0]) and dy_item[2] is None and dy_item[0].dtype == torch.float32
              and all(t.dtype == torch.float32 for t, _, _, _ in items))
     if tc or split:

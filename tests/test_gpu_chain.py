@@ -6,7 +6,7 @@ import torch
 
 from batch3dmot_b200 import _lib as L, ops
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ops.FEATURES["chain"], reason="fused chains not switched on")]
 DEV = "cuda"
 
 
@@ -144,6 +144,6 @@ def test_fused_mlp_uses_the_chain_and_matches_the_per_layer_path():
         for a, b in zip(res[True][1], res[False][1]):
             assert torch.equal(a, b)
     finally:
-        ops._USE_CHAIN = True
+        ops._USE_CHAIN = ops.FEATURES["chain"]
         ops.set_precision("fp32")
         ops.invalidate_weight_cache()

@@ -12,7 +12,7 @@ from batch3dmot_b200.clr_att_gnn import GNN
 from .conftest import load_golden
 from .test_gpu_models import check_grads
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ops.FEATURES["split_tc"], reason="split-bf16 tiles not switched on")]
 DEV = "cuda"
 
 
