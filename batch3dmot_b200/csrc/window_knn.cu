@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_window_knn(
     const double below = s > 0 ? __shfl_sync(0xffffffffu, bd[s > 0 ? s - 1 : 0], 31) : 0.0;
     if (lane == 0) prev = below;
     if (rank > 0 && rank < kk && bd[s] == prev) tie = true;
-    if (rank < kmax) ex[r * kmax + rank] = rank < k ? order[f0 + bi[s]] : (int64_t)-1;
+    // (a row whose metric is NaN inserted nothing: its list still holds the sentinels; the caller resolves it)
+    if (rank < kmax) ex[r * kmax + rank] = (rank < k && bi[s] < n) ? order[f0 + bi[s]] : (int64_t)-1;
   }
   const unsigned any_nan = __ballot_sync(0xffffffffu, nan), any_tie = __ballot_sync(0xffffffffu, tie);
   if (lane == 0) flags[r] = (any_nan ? 1 : 0) | (any_tie ? 2 : 0);
