@@ -51,11 +51,30 @@ __global__ void k_pack_weights(const float* __restrict__ W, int ldw, int n_log, 
   if (split) Wp[total + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// tf32 "x3" pack for the 1e-4 parity mode: 4-element (16-byte) K groups of fp32 words,
+//   Wt[((k/4) * Npad + n) * 4 + k%4] = hi(B[n][k]) (low 13 mantissa bits cleared = what the tensor core reads),
+// followed by a second image with the exact fp32 residuals lo = w - hi. Kpad = round_up(k_logical, 32).
+__global__ void k_pack_weights_tf32(const float* __restrict__ W, int ldw, int n_log, int k_log, int transpose,
+                                    float* __restrict__ Wp, int Npad, int Kpad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Npad * Kpad;
+  if (i >= total) return;
+  int j = (int)(i & 3);
+  long long q = i >> 2;
+  int n = (int)(q % Npad);
+  int k = (int)(q / Npad) * 4 + j;
+  float v = 0.f;
+  if (n < n_log && k < k_log) v = transpose ? W[(long long)k * ldw + n] : W[(long long)n * ldw + k];
+  const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  Wp[i] = hi;
+  Wp[total + i] = v - hi;
+}
+
 // (segment, offset) of every 8-column group of the concatenated operand; -1 past the end.
 __device__ __forceinline__ void build_group_table(const SegDev* seg, int nseg, int ngroups, int32_t* tab, int tid,
-                                                  int nthreads) {
+                                                  int nthreads, int gw = 8) {
   for (int g = tid; g < ngroups; g += nthreads) {
-    int off = g * 8, sg = 0;
+    int off = g * gw, sg = 0;
     while (sg < nseg && off >= seg[sg].width) { off -= seg[sg].width; ++sg; }
     tab[g] = (sg < nseg) ? ((sg << 24) | off) : -1;
   }
@@ -313,16 +332,26 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   }
 }
 
-// split-bf16 helpers: v = hi + lo with hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits per operand, so
-// hi*hi + lo*hi + hi*lo reproduces the fp32 product to ~2^-16 relative; accumulation is fp32 in TMEM.
+// split helpers. bf16 pair (weight-gradient kernel): v = hi + lo with hi = bf16(v), lo = bf16(v - hi).
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
   hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
   lo = tc::pack_bf16x2(a - __bfloat162float(ha), b - __bfloat162float(hb));
 }
+// tf32 pair (layer kernel): hi = v with the 13 low mantissa bits cleared (exactly what kind::tf32 reads), lo = v - hi
+// (exact in fp32; the tensor core again reads its top 11 significant bits): 22 significant bits per operand, so
+// hi*hi + lo*hi + hi*lo reproduces the fp32 product to ~2^-21 relative. Accumulation is fp32 in TMEM.
+__device__ __forceinline__ void split_tf32(const float4& v, uint4& hi, uint4& lo) {
+  hi = make_uint4(__float_as_uint(v.x) & 0xFFFFE000u, __float_as_uint(v.y) & 0xFFFFE000u,
+                  __float_as_uint(v.z) & 0xFFFFE000u, __float_as_uint(v.w) & 0xFFFFE000u);
+  lo = make_uint4(__float_as_uint(v.x - __uint_as_float(hi.x)), __float_as_uint(v.y - __uint_as_float(hi.y)),
+                  __float_as_uint(v.z - __uint_as_float(hi.z)), __float_as_uint(v.w - __uint_as_float(hi.w)));
+}
 
-// SPLIT: every operand stage holds a hi image followed by a lo image (A: +TC_A_STAGE, B: +b_stage) and each
-// K step issues three MMAs. This is the tensor-core path of the 1e-4 ("fp32") parity mode.
+// SPLIT ("tf32 x3"): operands are 32-bit words; a K chunk is 32 elements (the same 128 bytes per row, 8 groups of
+// 16 bytes = 4 elements), every operand stage holds a hi image followed by a lo image (A: +TC_A_STAGE, B: +b_stage)
+// and each K step (8 elements = 2 groups) issues three kind::tf32 MMAs. This is the tensor-core path of the 1e-4
+// ("fp32") parity mode.
 template <int ACT, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -357,14 +386,14 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
     for (int s = 0; s < a.nseg; ++s)
       s_grow[s * TC_BM + tid] = arow_ok ? (a.seg[s].idx ? __ldg(a.seg[s].idx + grow_row) : (int32_t)grow_row) : 0;
   if (tid < Nb) s_bias[tid] = (a.bias && n0 + tid < a.Nout) ? __ldg(a.bias + n0 + tid) : 0.f;
-  build_group_table(a.seg, a.nseg, a.Kpad / 8, s_tab, tid, TC_THREADS);
+  build_group_table(a.seg, a.nseg, a.Kpad / (SPLIT ? 4 : 8), s_tab, tid, TC_THREADS, SPLIT ? 4 : 8);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *s_tmem;
 
-  const int nchunks = a.Kpad / TC_BK;
-  const uint32_t idesc = make_idesc_bf16(TC_BM, (uint32_t)Nb, 0, 0);
+  const int nchunks = a.Kpad / (SPLIT ? 32 : TC_BK);
+  const uint32_t idesc = SPLIT ? make_idesc_tf32(TC_BM, (uint32_t)Nb, 0, 0) : make_idesc_bf16(TC_BM, (uint32_t)Nb, 0, 0);
   const uint32_t lbo_a = TC_BM * 16, lbo_b = (uint32_t)Nb * 16, sbo = 128;
 
   for (int c = 0; c < nchunks; ++c) {
@@ -380,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
           cp_async16(dst + (uint32_t)(g * Nb + tid) * 16, wsrc + ((size_t)g * a.Npad + tid) * 16);
           if (SPLIT)
             cp_async16(dst + b_stage + (uint32_t)(g * Nb + tid) * 16,
-                       wsrc + (size_t)a.Npad * a.Kpad * 2 + ((size_t)g * a.Npad + tid) * 16);
+                       wsrc + (size_t)a.Npad * a.Kpad * 4 + ((size_t)g * a.Npad + tid) * 16);
         }
       }
     }
@@ -397,9 +426,17 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
           const SegDev& S = a.seg[ent[j] >> 24];
           const long long gr = s_grow[(ent[j] >> 24) * TC_BM + arow];
           const void* p = seg_addr(S, gr, ent[j] & 0xFFFFFF);
-          if (S.dtype == B3D_BF16) {
+          if (SPLIT) {
+            if (S.dtype == B3D_BF16) {      // 4 bf16 -> 4 exact tf32 words (8 mantissa bits), zero residual
+              const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+              v[2 * j] = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u),
+                                     __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xFFFF0000u));
+            } else {
+              v[2 * j] = __ldg(reinterpret_cast<const float4*>(p));
+            }
+          } else if (S.dtype == B3D_BF16) {
             cp_async16(dst0 + g * (TC_BM * 16), p);
-            ent[j] = -2;   // done (SPLIT: its residual image is zero)
+            ent[j] = -2;   // done
           } else {
             v[2 * j] = __ldg(reinterpret_cast<const float4*>(p));
             v[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -412,20 +449,17 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
         const uint32_t d = dst0 + g * (TC_BM * 16);
         if (ent[j] >= 0) {
           if (SPLIT) {
-            uint32_t h[4], l[4];
-            split_pack2(v[2 * j].x, v[2 * j].y, h[0], l[0]);
-            split_pack2(v[2 * j].z, v[2 * j].w, h[1], l[1]);
-            split_pack2(v[2 * j + 1].x, v[2 * j + 1].y, h[2], l[2]);
-            split_pack2(v[2 * j + 1].z, v[2 * j + 1].w, h[3], l[3]);
-            st_shared_v4(d, h[0], h[1], h[2], h[3]);
-            st_shared_v4(d + TC_A_STAGE, l[0], l[1], l[2], l[3]);
+            uint4 h, l;
+            split_tf32(v[2 * j], h, l);
+            st_shared_v4(d, h.x, h.y, h.z, h.w);
+            st_shared_v4(d + TC_A_STAGE, l.x, l.y, l.z, l.w);
           } else {
             st_shared_v4(d, pack_bf16x2(v[2 * j].x, v[2 * j].y), pack_bf16x2(v[2 * j].z, v[2 * j].w),
                          pack_bf16x2(v[2 * j + 1].x, v[2 * j + 1].y), pack_bf16x2(v[2 * j + 1].z, v[2 * j + 1].w));
           }
         } else {
           if (ent[j] == -1) st_shared_v4(d, 0u, 0u, 0u, 0u);
-          if (SPLIT) st_shared_v4(d + TC_A_STAGE, 0u, 0u, 0u, 0u);
+          if (SPLIT && ent[j] == -1) st_shared_v4(d + TC_A_STAGE, 0u, 0u, 0u, 0u);
         }
       }
     }
@@ -435,15 +469,17 @@ __global__ void __launch_bounds__(TC_THREADS) k_linear_tc(const TcArgs a) {
     if (tid == 0) {
       tc_fence_after_sync();
 #pragma unroll
-      for (int j = 0; j < TC_BK / 16; ++j) {
+      for (int j = 0; j < TC_BK / 16; ++j) {        // 4 K steps per chunk: 16 bf16 or 8 tf32 elements = 2 groups each
         const uint64_t ad = make_smem_desc(sA + s * NI * TC_A_STAGE + j * 2 * lbo_a, lbo_a, sbo);
         const uint64_t bd = make_smem_desc(sB + s * NI * b_stage + j * 2 * lbo_b, lbo_b, sbo);
-        mma_bf16_ss(tmem, ad, bd, idesc, (c | j) != 0);
         if (SPLIT) {
           const uint64_t al = make_smem_desc(sA + s * NI * TC_A_STAGE + TC_A_STAGE + j * 2 * lbo_a, lbo_a, sbo);
           const uint64_t bl = make_smem_desc(sB + s * NI * b_stage + b_stage + j * 2 * lbo_b, lbo_b, sbo);
-          mma_bf16_ss(tmem, al, bd, idesc, 1);
-          mma_bf16_ss(tmem, ad, bl, idesc, 1);
+          mma_tf32_ss(tmem, ad, bd, idesc, (c | j) != 0);
+          mma_tf32_ss(tmem, al, bd, idesc, 1);
+          mma_tf32_ss(tmem, ad, bl, idesc, 1);
+        } else {
+          mma_bf16_ss(tmem, ad, bd, idesc, (c | j) != 0);
         }
       }
       mma_commit(sBar + 8 * s);
@@ -1047,9 +1083,16 @@ extern "C" int b3d_tc_pack_weights(const float* W, int32_t ldw, int32_t n_logica
   if (!W || !Wp || n_logical <= 0 || k_logical <= 0) return bad_arg("b3d_tc_pack_weights");
   int Npad = round_up(n_logical, 16), Kpad = round_up(k_logical, TC_BK);
   long long total = (long long)Npad * Kpad;
-  // transpose bit 1 (B3D_PACK_SPLIT): also write the bf16 residual image (Wp must hold 2x b3d_tc_packed_bytes)
+  if (transpose & 2) {   // B3D_PACK_SPLIT: tf32 hi + lo images for b3d_linear_tc(B3D_FLAG_SPLIT); Wp holds 4x b3d_tc_packed_bytes
+    Kpad = round_up(k_logical, 32);
+    total = (long long)Npad * Kpad;
+    k_pack_weights_tf32<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        W, ldw, n_logical, k_logical, transpose & 1, reinterpret_cast<float*>(Wp), Npad, Kpad);
+    B3D_LAUNCH_CHECK("k_pack_weights_tf32");
+    return 0;
+  }
   k_pack_weights<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      W, ldw, n_logical, k_logical, transpose & 1, reinterpret_cast<__nv_bfloat16*>(Wp), Npad, Kpad, (transpose >> 1) & 1);
+      W, ldw, n_logical, k_logical, transpose & 1, reinterpret_cast<__nv_bfloat16*>(Wp), Npad, Kpad, 0);
   B3D_LAUNCH_CHECK("k_pack_weights");
   return 0;
 }
@@ -1075,18 +1118,20 @@ extern "C" int b3d_linear_tc(const b3d_seg_t* segs, int32_t nseg, const void* Wp
   }
   if (K != k_logical) return bad_arg("b3d_linear_tc: sum of segment widths != k_logical");
   if (!Wp || !Y || n_logical <= 0 || M < 0) return bad_arg("b3d_linear_tc W/Y/N/M");
-  if (round_up(K, TC_BK) / 8 > TC_TAB) return bad_arg("b3d_linear_tc: K too large");
+  const bool split = (flags & B3D_FLAG_SPLIT) != 0;   // tf32 x3 arithmetic (Wp packed with B3D_PACK_SPLIT)
+  if ((split ? round_up(K, 32) / 4 : round_up(K, TC_BK) / 8) > TC_TAB) return bad_arg("b3d_linear_tc: K too large");
+  if (split && (y_dtype != B3D_F32 || relu_bits_out || mask_dtype == B3D_BITS))
+    return bad_arg("b3d_linear_tc: the split (1e-4) mode is fp32 in / fp32 out");
   if (y_dtype == B3D_BF16 && ((ldy & 7) || (reinterpret_cast<uintptr_t>(Y) & 15) || (flags & B3D_FLAG_ACCUMULATE)))
     return bad_arg("b3d_linear_tc: bf16 output needs ld % 8 == 0, 16-byte alignment, no accumulate");
   a.nseg = nseg; a.Ktot = K; a.Wp = reinterpret_cast<const __nv_bfloat16*>(Wp);
-  a.Npad = round_up(n_logical, 16); a.Kpad = round_up(k_logical, TC_BK);
+  a.Npad = round_up(n_logical, 16); a.Kpad = round_up(k_logical, split ? 32 : TC_BK);
   a.bias = bias; a.Y = Y; a.ldy = ldy; a.y_bf16 = (y_dtype == B3D_BF16); a.M = M; a.Nout = n_logical; a.act = act;
   a.flags = flags; a.ldm = ldm; a.mask_bf16 = (mask_dtype == B3D_BF16); a.row_mask = row_mask;
   a.out_mask = mask_dtype == B3D_BITS ? nullptr : out_mask;
   a.mask_bits = mask_dtype == B3D_BITS ? reinterpret_cast<const uint32_t*>(out_mask) : nullptr;
   a.bits_out = reinterpret_cast<uint32_t*>(relu_bits_out);
   int Nb = a.Npad < TC_NMAX ? a.Npad : TC_NMAX;
-  const bool split = (flags & B3D_FLAG_SPLIT) != 0;   // 3-MMA split-bf16 arithmetic (Wp packed with B3D_PACK_SPLIT)
   size_t smem = (split ? 2 : 1) * (2 * TC_A_STAGE + 2 * (size_t)Nb * 128) + 64 + 1024 + 4 * TC_TAB +
                 sizeof(int32_t) * B3D_MAX_SEGS * TC_BM;
   static bool attr_set = false;

@@ -174,7 +174,7 @@ def _packed_weight(W, transpose, rowmajor=False, split=False):
     nbytes, pack = (lib.b3d_tma_packed_bytes, lib.b3d_tma_pack_weights) if rowmajor else \
         (lib.b3d_tc_packed_bytes, lib.b3d_tc_pack_weights)
     assert not (split and rowmajor)
-    wp = torch.empty(nbytes(n_log, k_log) * (2 if split else 1), dtype=torch.uint8, device=W.device)
+    wp = torch.empty(nbytes(n_log, k_log) * (4 if split else 1), dtype=torch.uint8, device=W.device)
     L.check(pack(L.ptr(W), W.stride(0), n_log, k_log, int(transpose) | (2 if split else 0), L.ptr(wp), L.stream()),
             "pack_weights")
     _packed[key] = (weakref.ref(W), W._version, W.data_ptr(), wp)

@@ -39,12 +39,13 @@ enum { B3D_ACT_NONE = 0, B3D_ACT_RELU = 1, B3D_ACT_SIGMOID = 2,
        B3D_ACT_MASKBITS = 3 };      /* b3d_chain_run only: multiply by a ReLU mask given as sign bits (backward chains) */
 enum { B3D_FLAG_ACCUMULATE = 1,     /* out += result instead of out = result */
        B3D_FLAG_OUT_BF16 = 2,       /* b3d_segment_sum: `out` is really __nv_bfloat16* (bf16 source, no accumulate) */
-       B3D_FLAG_SPLIT = 4 };        /* b3d_linear_tc / b3d_wgrad_tc: split-bf16 arithmetic — every fp32 operand enters the
-                                       tensor core as hi + lo bf16 parts and each K step issues hi*hi + lo*hi + hi*lo
-                                       (~2^-16 relative per product, fp32 accumulation): the tensor-core path of the
-                                       1e-4 parity mode. Weights must be packed with B3D_PACK_SPLIT. */
+       B3D_FLAG_SPLIT = 4 };        /* the tensor-core arithmetic of the 1e-4 parity mode. b3d_linear_tc: "tf32 x3" — every fp32
+                                       operand enters the tensor core as hi + lo tf32 words (22 significant bits) and each K
+                                       step issues hi*hi + lo*hi + hi*lo with kind::tf32 (~2^-21 relative per product, fp32
+                                       accumulation); weights packed with B3D_PACK_SPLIT. b3d_wgrad_tc: the same scheme with
+                                       bf16 hi + lo parts (~2^-16; gradients are held to 1e-3). */
 enum { B3D_PACK_TRANSPOSE = 1, B3D_PACK_SPLIT = 2 };   /* bits of b3d_tc_pack_weights' `transpose` argument; a split pack
-                                                          needs 2 x b3d_tc_packed_bytes */
+                                                          needs 4 x b3d_tc_packed_bytes */
 enum { B3D_F32 = 0, B3D_BF16 = 1 }; /* element type of a segment / output (bf16: tensor-core entry points only) */
 /* mask_dtype only: the ReLU mask of a layer output as SIGN BITS, uint32 words [ceil(N/32)][M]
  * (word (c / 32) * M + r holds columns 32*(c/32) .. +31 of row r, bit c % 32 set iff output > 0).
