@@ -28,15 +28,17 @@
 namespace b3d {
 
 constexpr int CH_MAX_LAYERS = B3D_CHAIN_MAX_LAYERS;
-constexpr int CH_THREADS = 320;
+constexpr int CH_EPI_WARPS = 16;              // 4 per TMEM lane quarter
+constexpr int CH_THREADS = 64 + 32 * CH_EPI_WARPS;
 constexpr int CH_BM = 128;
 constexpr int CH_SUB = CH_BM * 128;     // one [128 rows x 64 cols] bf16 sub-tile: 16 KB
 constexpr int CH_MAX_STAGES = 8;
 constexpr int CH_SMEM_LIMIT = 227 * 1024;
 // barrier block (bytes from its base)
+constexpr int CH_ACT_PER_LAYER = 8;             // one "columns written" barrier per 64 output columns (N <= 512)
 constexpr int BAR_IN_FULL = 0, BAR_IN_EMPTY = 8, BAR_ACC_FULL = 16, BAR_ACC_EMPTY = 32, BAR_W_FULL = 48,
               BAR_W_EMPTY = 48 + 8 * CH_MAX_STAGES, BAR_ACT = 48 + 16 * CH_MAX_STAGES,
-              BAR_TMEM = BAR_ACT + 8 * 2 * CH_MAX_LAYERS, BAR_BYTES = 512;
+              BAR_TMEM = BAR_ACT + 8 * CH_ACT_PER_LAYER * CH_MAX_LAYERS, BAR_BYTES = 1024;
 
 struct ChainLayerDev {
   int K, N, nblk, Nb, kchunks;
@@ -68,24 +70,40 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                : "memory");
 }
 
-// Global operands of one 32-column epilogue block, requested one block ahead of their use.
+// tcgen05.ld of 16 consecutive fp32 columns of this warp's 32 lanes.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Per-row state of one (layer, column block): everything the 16-column steps need, resolved ONCE per block so that
+// the steps themselves hold no parameter-space loads or per-layer branches beyond the mode bits.
+struct ChainRow {
+  const __nv_bfloat16* add0;   // row of addend 0 (already gathered through its index), or null
+  const __nv_bfloat16* add1;
+  __nv_bfloat16* out;          // output row or null
+  uint16_t* bits_out;          // this row's sign-bit words viewed as half-words: column c -> [(c / 32) * 2M + (c / 16) % 2]
+  const uint16_t* bits_in;
+  uint32_t smem_row;           // shared-memory address of this row in the destination tile, 0 = not kept
+  const float* bias;           // shared-memory bias of the layer
+  int act;
+};
+
+// Global operands of one 16-column step (32 bytes per addend), requested one step ahead of their use.
 struct ChainPf {
-  uint4 a0[4], a1[4];
+  uint4 a0[2], a1[2];
   uint32_t bits;
 };
 
-__device__ __forceinline__ void chain_prefetch(const ChainLayerDev& L, int c, long long row, int i0, int i1, long long M,
-                                               bool ok, ChainPf& pf) {
-  if (!ok) return;
-  if (L.nadd > 0) {
-    const long long g = L.add_sel[0] == 0 ? i0 : (L.add_sel[0] == 1 ? i1 : row);
-    ld64B(L.add_ptr[0] + g * L.add_ld[0] + c, pf.a0);
-  }
-  if (L.nadd > 1) {
-    const long long g = L.add_sel[1] == 0 ? i0 : (L.add_sel[1] == 1 ? i1 : row);
-    ld64B(L.add_ptr[1] + g * L.add_ld[1] + c, pf.a1);
-  }
-  if (L.act == B3D_ACT_MASKBITS) pf.bits = __ldg(L.bits_in + (long long)(c >> 5) * M + row);
+__device__ __forceinline__ void chain_prefetch(const ChainRow& R, int c, long long M, ChainPf& pf) {
+  if (R.add0) ldg256(R.add0 + c, pf.a0[0], pf.a0[1]);
+  if (R.add1) ldg256(R.add1 + c, pf.a1[0], pf.a1[1]);
+  if (R.bits_in) pf.bits = __ldg(R.bits_in + (long long)(c >> 5) * M * 2 + ((c >> 4) & 1));
 }
 
 __device__ __forceinline__ void add_bf16x8(float* o, const uint4& v) {
@@ -97,66 +115,46 @@ __device__ __forceinline__ void add_bf16x8(float* o, const uint4& v) {
   }
 }
 
-// One 32-column block of one row: c = first column of the block in the layer output.
-__device__ __forceinline__ void chain_block(const ChainLayerDev& L, int c, long long row, long long M, bool ok,
-                                            const uint32_t (&r)[32], const float* s_bias, const ChainPf& pf,
-                                            uint32_t s_arena, int lrow) {
+// One 16-column step of one row: c = first column of the step in the layer output.
+__device__ __forceinline__ void chain_step(const ChainRow& R, int c, long long M, bool ok, const uint32_t (&r)[16],
+                                           const ChainPf& pf, int lrow) {
   using namespace tc;
-  float o[32];
-  const float* sb = s_bias + L.bias_off + c;
+  float o[16];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 b4 = *reinterpret_cast<const float4*>(sb + 4 * q);
+  for (int q = 0; q < 4; ++q) {
+    const float4 b4 = *reinterpret_cast<const float4*>(R.bias + c + 4 * q);
     o[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
     o[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
     o[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
     o[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
   }
-  if (ok && L.nadd > 0) {
+  if (R.add0) { add_bf16x8(o, pf.a0[0]); add_bf16x8(o + 8, pf.a0[1]); }
+  if (R.add1) { add_bf16x8(o, pf.a1[0]); add_bf16x8(o + 8, pf.a1[1]); }
+  if (R.act == B3D_ACT_RELU) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) add_bf16x8(o + 8 * q, pf.a0[q]);
+    for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+  } else if (R.act == B3D_ACT_MASKBITS) {
+    const uint32_t word = R.bits_in ? pf.bits : 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = ((word >> j) & 1u) ? o[j] : 0.f;
   }
-  if (ok && L.nadd > 1) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) add_bf16x8(o + 8 * q, pf.a1[q]);
-  }
-  if (L.act == B3D_ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
-  } else if (L.act == B3D_ACT_MASKBITS) {
-    const uint32_t word = ok ? pf.bits : 0u;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = ((word >> j) & 1u) ? o[j] : 0.f;
-  }
-  if (L.bits_out && ok) {
+  if (R.bits_out) {
     uint32_t word = 0u;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) word |= (o[j] > 0.f) ? (1u << j) : 0u;
-    L.bits_out[(long long)(c >> 5) * M + row] = word;
+    for (int j = 0; j < 16; ++j) word |= (o[j] > 0.f) ? (1u << j) : 0u;
+    R.bits_out[(long long)(c >> 5) * M * 2 + ((c >> 4) & 1)] = (uint16_t)word;
   }
-  uint4 pk[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    pk[q] = make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
-                       pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
-  if (L.out && ok) {
-    __nv_bfloat16* yrow = L.out + row * L.ldo + c;
-    if (al32(yrow)) {
-      stg256(yrow, pk[0], pk[1]);
-      stg256(yrow + 16, pk[2], pk[3]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(yrow + 8 * q) = pk[q];
-    }
-  }
-  if (L.dst_off >= 0) {
+  uint4 p0 = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  uint4 p1 = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+  if (R.out) stg256(R.out + c, p0, p1);
+  if (R.smem_row) {
     // K-major, 128B swizzle: 16-byte chunk ch of row lrow sits at chunk position ch ^ (lrow & 7)
-    const uint32_t base = s_arena + (uint32_t)L.dst_off + (uint32_t)(c >> 6) * CH_SUB + (uint32_t)lrow * 128u;
+    const uint32_t base = R.smem_row + (uint32_t)(c >> 6) * CH_SUB;
     const int ch0 = (c & 63) >> 3;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      st_shared_v4(base + (uint32_t)(((ch0 + q) ^ (lrow & 7)) << 4), pk[q].x, pk[q].y, pk[q].z, pk[q].w);
+    st_shared_v4(base + (uint32_t)((ch0 ^ (lrow & 7)) << 4), p0.x, p0.y, p0.z, p0.w);
+    st_shared_v4(base + (uint32_t)(((ch0 + 1) ^ (lrow & 7)) << 4), p1.x, p1.y, p1.z, p1.w);
   }
+  (void)ok;
 }
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
@@ -178,9 +176,9 @@ k_chain(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUten
   if (tid == 0) {
     mbar_init(sBar + BAR_IN_FULL, 1);
     mbar_init(sBar + BAR_IN_EMPTY, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(sBar + BAR_ACC_FULL + 8 * s, 1); mbar_init(sBar + BAR_ACC_EMPTY + 8 * s, 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(sBar + BAR_ACC_FULL + 8 * s, 1); mbar_init(sBar + BAR_ACC_EMPTY + 8 * s, CH_EPI_WARPS); }
     for (int s = 0; s < CH_MAX_STAGES; ++s) { mbar_init(sBar + BAR_W_FULL + 8 * s, 1); mbar_init(sBar + BAR_W_EMPTY + 8 * s, 1); }
-    for (int s = 0; s < 2 * CH_MAX_LAYERS; ++s) mbar_init(sBar + BAR_ACT + 8 * s, 8);
+    for (int s = 0; s < CH_ACT_PER_LAYER * CH_MAX_LAYERS; ++s) mbar_init(sBar + BAR_ACT + 8 * s, CH_EPI_WARPS);
     fence_mbar_init();
   }
   for (int l = 0; l < a.nl; ++l)
@@ -233,8 +231,8 @@ k_chain(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUten
               if (L.src_layer < 0) {
                 if (kc == 0) mbar_wait(sBar + BAR_IN_FULL, tcount & 1);
               } else {
-                const int nbs = (kc * 64) / a.L[L.src_layer].Nb;      // column block of the producer holding this chunk
-                mbar_wait(sBar + BAR_ACT + 8 * (2 * L.src_layer + nbs), tcount & 1);
+                // the 64 columns of the producing layer that make up this K chunk have been written
+                mbar_wait(sBar + BAR_ACT + 8 * (CH_ACT_PER_LAYER * L.src_layer + kc), tcount & 1);
               }
               const int s = it % S;
               mbar_wait(sBar + BAR_W_FULL + 8 * s, (it / S) & 1);
@@ -255,8 +253,14 @@ k_chain(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUten
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    const int lq = warp & 3;                  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;         // the two warps of a quarter interleave 32-column blocks
+    // 16 warps: warp w may read TMEM lanes 32 * (w % 4) ..; the four warps of a lane quarter split every 64-column
+    // chunk of an accumulator into 16-column steps (sub-warp s takes columns 16 s .. 16 s + 15), so each chunk is
+    // finished by all 16 warps together and its "written" barrier fires as early as possible: the next layer's
+    // MMAs over that K chunk start while the following chunk is still in the epilogue. Four warps per scheduler
+    // cover each other's TMEM-load, shared-memory and global latencies (two per scheduler ran at 27 % issue
+    // utilisation: profiles/r2_chain_v1.md).
+    const int lq = warp & 3;
+    const int sub = (warp - 2) >> 2;
     const int lrow = lq * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
     int tcount = 0, use = 0;
@@ -266,49 +270,58 @@ k_chain(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUten
     bool ok = tile < a.ntiles && row < a.M;
     int i0 = (ok && a.idx0) ? __ldg(a.idx0 + row) : 0, i1 = (ok && a.idx1) ? __ldg(a.idx1 + row) : 0;
     for (; tile < a.ntiles; tile += gridDim.x, ++tcount) {
-      // indices of this CTA's next tile (their latency hides behind this tile)
       const long long ntile = tile + gridDim.x, nrow = ntile * CH_BM + lrow;
       const bool nok = ntile < a.ntiles && nrow < a.M;
       const int n0 = (nok && a.idx0) ? __ldg(a.idx0 + nrow) : 0, n1 = (nok && a.idx1) ? __ldg(a.idx1 + nrow) : 0;
-      int parity = 0;
-      // first block of the tile
-      chain_prefetch(a.L[0], half * 32, row, i0, i1, a.M, ok, pfa);
       for (int l = 0; l < a.nl; ++l) {
         const ChainLayerDev& L = a.L[l];
-        for (int nb = 0; nb < L.nblk; ++nb, ++use) {
+        ChainRow R;
+        R.add0 = R.add1 = nullptr;
+        if (ok && L.nadd > 0) {
+          const long long g = L.add_sel[0] == 0 ? i0 : (L.add_sel[0] == 1 ? i1 : row);
+          R.add0 = L.add_ptr[0] + g * L.add_ld[0];
+        }
+        if (ok && L.nadd > 1) {
+          const long long g = L.add_sel[1] == 0 ? i0 : (L.add_sel[1] == 1 ? i1 : row);
+          R.add1 = L.add_ptr[1] + g * L.add_ld[1];
+        }
+        R.out = (ok && L.out) ? L.out + row * L.ldo : nullptr;
+        R.bits_out = (ok && L.bits_out) ? reinterpret_cast<uint16_t*>(L.bits_out) + row * 2 : nullptr;
+        R.bits_in = (ok && L.act == B3D_ACT_MASKBITS) ? reinterpret_cast<const uint16_t*>(L.bits_in) + row * 2 : nullptr;
+        R.smem_row = L.dst_off >= 0 ? sArena + (uint32_t)L.dst_off + (uint32_t)lrow * 128u : 0u;
+        R.bias = s_bias + L.bias_off;
+        R.act = L.act;
+        const int nblk = L.nblk, Nb = L.Nb, N = L.N;
+        for (int nb = 0; nb < nblk; ++nb, ++use) {
           const int slot = use & 1;
-          const int ncol = min(L.Nb, L.N - nb * L.Nb);
+          const int ncol = min(Nb, N - nb * Nb);
+          const int c0 = nb * Nb + sub * 16;
+          chain_prefetch(R, c0, a.M, pfa);                  // first step of the block: in flight during the wait
           mbar_wait(sBar + BAR_ACC_FULL + 8 * slot, (use >> 1) & 1);
           tc_fence_after_sync();
-          for (int col0 = half * 32; col0 < ncol; col0 += 64, parity ^= 1) {
-            uint32_t r[32];
-            tmem_ld32(t_lane + (uint32_t)(slot * 256 + col0), r);
-            // successor block in program order (same tile): its global operands are requested now
-            int pl = l, pnb = nb, pcol = col0 + 64;
-            if (pcol >= ncol) {
-              pcol = half * 32;
-              if (++pnb >= L.nblk) { pnb = 0; ++pl; }
-            }
-            const bool has_next = pl < a.nl;
-            const int pc = has_next ? pnb * a.L[pl].Nb + pcol : 0;
-            const int c = nb * L.Nb + col0;
-            if (parity == 0) {
-              if (has_next) chain_prefetch(a.L[pl], pc, row, i0, i1, a.M, ok, pfb);
+          const uint32_t t_acc = t_lane + (uint32_t)(slot * 256 + sub * 16);
+          for (int ch = 0; ch < ncol; ch += 128) {        // two 64-column chunks per iteration (static prefetch roles)
+            uint32_t r[16];
+            tmem_ld16(t_acc + (uint32_t)ch, r);
+            if (ch + 64 < ncol) chain_prefetch(R, c0 + ch + 64, a.M, pfb);
+            tmem_ld_wait();
+            chain_step(R, c0 + ch, a.M, ok, r, pfa, lrow);
+            if (R.smem_row) fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sBar + BAR_ACT + 8 * (CH_ACT_PER_LAYER * l + ((nb * Nb + ch) >> 6)));
+            if (ch + 64 < ncol) {
+              tmem_ld16(t_acc + (uint32_t)(ch + 64), r);
+              if (ch + 128 < ncol) chain_prefetch(R, c0 + ch + 128, a.M, pfa);
               tmem_ld_wait();
-              chain_block(L, c, row, a.M, ok, r, s_bias, pfa, sArena, lrow);
-            } else {
-              if (has_next) chain_prefetch(a.L[pl], pc, row, i0, i1, a.M, ok, pfa);
-              tmem_ld_wait();
-              chain_block(L, c, row, a.M, ok, r, s_bias, pfb, sArena, lrow);
+              chain_step(R, c0 + ch + 64, a.M, ok, r, pfb, lrow);
+              if (R.smem_row) fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(sBar + BAR_ACT + 8 * (CH_ACT_PER_LAYER * l + ((nb * Nb + ch + 64) >> 6)));
             }
           }
-          if (L.dst_off >= 0) fence_proxy_async_smem();   // generic-proxy tile writes -> visible to tcgen05.mma
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(sBar + BAR_ACC_EMPTY + 8 * slot);
-            mbar_arrive(sBar + BAR_ACT + 8 * (2 * l + nb));
-          }
+          if (lane == 0) mbar_arrive(sBar + BAR_ACC_EMPTY + 8 * slot);
         }
       }
       row = nrow; ok = nok; i0 = n0; i1 = n1;
@@ -486,15 +499,15 @@ extern "C" int b3d_chain_run(const b3d_seg_t* in_segs, int32_t nseg, const b3d_c
       D.add_sel[t] = H.add_idx[t]; D.add_ld[t] = H.add_ld[t];
       D.add_ptr[t] = reinterpret_cast<const __nv_bfloat16*>(H.add_ptr[t]);
       if (t < H.nadd) {
-        if (!H.add_ptr[t] || (H.add_ld[t] & 7) || (reinterpret_cast<uintptr_t>(H.add_ptr[t]) & 15) || H.add_idx[t] < -1 ||
+        if (!H.add_ptr[t] || (H.add_ld[t] & 15) || (reinterpret_cast<uintptr_t>(H.add_ptr[t]) & 31) || H.add_idx[t] < -1 ||
             H.add_idx[t] > 1 || (H.add_idx[t] == 0 && !idx0) || (H.add_idx[t] == 1 && !idx1))
-          return bad_arg("b3d_chain_run: addends must be bf16 [*, N] with 16-byte aligned rows and a valid index selector");
+          return bad_arg("b3d_chain_run: addends must be bf16 [*, N] with 32-byte aligned rows and a valid index selector");
       }
     }
     D.bias = H.bias;
     D.out = reinterpret_cast<__nv_bfloat16*>(H.out); D.ldo = H.ldo; D.bias_off = P.bias_off[l];
-    if (H.out && ((H.ldo & 7) || (reinterpret_cast<uintptr_t>(H.out) & 15) || H.ldo < H.N))
-      return bad_arg("b3d_chain_run: outputs must be bf16 with ld % 8 == 0 and 16-byte alignment");
+    if (H.out && ((H.ldo & 15) || (reinterpret_cast<uintptr_t>(H.out) & 31) || H.ldo < H.N))
+      return bad_arg("b3d_chain_run: outputs must be bf16 with 32-byte aligned rows (ld % 16 == 0)");
     D.bits_out = reinterpret_cast<uint32_t*>(H.bits_out);
     D.bits_in = reinterpret_cast<const uint32_t*>(H.bits_in);
     if (H.act == B3D_ACT_MASKBITS && !H.bits_in) return bad_arg("b3d_chain_run: B3D_ACT_MASKBITS needs bits_in");

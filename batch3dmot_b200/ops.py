@@ -263,6 +263,10 @@ def chain_run(inputs, specs, idx0, idx1, M):
                 setattr(c, name, bt.data_ptr())
     if not lib.b3d_chain_supported(arr, nl, k_in):
         return False
+    for sp in specs:      # the epilogue moves 32 bytes per lane: rows of addends / outputs must be 32-byte aligned
+        for t in [at for at, _ in (sp.get("adds") or [])] + ([sp["out"]] if sp.get("out") is not None else []):
+            if t.data_ptr() % 32 or t.stride(0) % 16:
+                return False
     keys, bases = zip(*[_wkey(sp["W"]) for sp in specs])
     key = (_weight_epoch, k_in, tuple(keys), tuple(bool(sp.get("transpose")) for sp in specs))
     ent = _chain_packs.get(key)

@@ -302,9 +302,9 @@ typedef struct {
   int32_t nadd;
   int32_t add_idx[2];
   int32_t add_ld[2];
-  const void* add_ptr[2];      /* bf16 [*, N] */
+  const void* add_ptr[2];      /* bf16 [*, N], rows 32-byte aligned (ld % 16 == 0) */
   const float* bias;           /* [N] or NULL */
-  void* out;                   /* bf16 [M, N] or NULL */
+  void* out;                   /* bf16 [M, N] (rows 32-byte aligned) or NULL */
   int32_t ldo;
   void* bits_out;              /* uint32 [N/32][M] or NULL */
   const void* bits_in;         /* B3D_ACT_MASKBITS: uint32 [N/32][M] */
