@@ -102,7 +102,9 @@ def test_scene_sharded_inference_matches_unsharded_and_oracle_assembly():
     with torch.no_grad():
         s0, _ = model(d0, x_img=d0.x_img, pointnet_out=d0.pointnet_out, radarnet_out=d0.radarnet_out,
                       lidar_mask=d0.m_lidar, radar_mask=d0.m_radar)
-    assert torch.equal(s0.reshape(-1), wins[0][2])
+    # (not bit-equal in general: a single small window may take the FFMA kernel where the batch takes tensor-core
+    # tiles of the same 1e-4 mode; disjoint graphs do not interact, so the scores agree to fp32 rounding)
+    assert torch.allclose(s0.reshape(-1), wins[0][2], rtol=1e-5, atol=1e-6)
     cats = [synth.CATEGORIES[c - 1] for c in scenes[sid].node_classes.tolist()]
     o_w = [(g.cpu().numpy(), e.t().cpu().numpy(), s.cpu().numpy()) for g, e, s in wins]
     ids_ref, tracks_ref = T.track_ids(o_w, cats)
