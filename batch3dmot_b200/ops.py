@@ -204,12 +204,15 @@ def derived_weights(tag, sources, build):
 
 
 _chain_packs = {}
-# Kernel families added after the last measured round are switched on HERE once `pytest -m gpu` is green with them
-# on a B200 (B3D_FEATURES=all|none|comma list overrides, e.g. for the validation run itself):
-#   chain      fused MLP chains / edge blocks (chain_tc.cu)
-#   split_tc   split-bf16 tensor-core tiles as the arithmetic of the "fp32" (1e-4) mode (else: FFMA kernels)
-#   window_knn graph-construction k-NN kernel for CUDA tensors (window_knn.cu)
-_FEATURE_DEFAULTS = {"chain": False, "split_tc": False, "window_knn": False}
+# Switches for the kernel families added in round 2 (B3D_FEATURES=all|none|comma list overrides the defaults):
+#   split_tc   tf32 x3 tensor-core tiles as the arithmetic of the "fp32" (1e-4) mode (else: FFMA kernels). ON:
+#              every 1e-4 test passes with it (tests/test_gpu_models.py, test_gpu_split.py) and it is 2.8x faster.
+#   window_knn graph-construction k-NN kernel for CUDA tensors (window_knn.cu). ON.
+#   chain      fused MLP chains / edge blocks (chain_tc.cu). Validated (tests/test_gpu_chain.py runs it whatever this
+#              switch says) but OFF in the model path: with one 128-row tile in flight per SM the fused kernel is
+#              bound by the same epilogue work as the per-layer kernels plus the layer-to-layer hand-over latency,
+#              and measured no faster (profiles/r2_chain_kernel.md), so the per-layer TMA kernels stay the default.
+_FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True}
 
 
 def _read_features():

@@ -6,8 +6,17 @@ import torch
 
 from batch3dmot_b200 import _lib as L, ops
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ops.FEATURES["chain"], reason="fused chains not switched on")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def chain_on():
+    """The fused kernels are exercised here whatever the model-path default (ops.FEATURES["chain"]) is."""
+    old = ops._USE_CHAIN
+    ops._USE_CHAIN = True
+    yield
+    ops._USE_CHAIN = old
 
 
 def bf(t):
@@ -144,6 +153,5 @@ def test_fused_mlp_uses_the_chain_and_matches_the_per_layer_path():
         for a, b in zip(res[True][1], res[False][1]):
             assert torch.equal(a, b)
     finally:
-        ops._USE_CHAIN = ops.FEATURES["chain"]
         ops.set_precision("fp32")
         ops.invalidate_weight_cache()

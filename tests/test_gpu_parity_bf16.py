@@ -155,7 +155,6 @@ def test_bf16_training_trajectory_tracks_fp32_oracle():
     assert abs(curve[-1] - ref_curve[-1]) < 0.1 * ref_curve[-1]
 
 
-@pytest.mark.skipif(not ops.FEATURES["chain"], reason="fused chains not switched on")
 def test_fused_blocks_match_the_per_layer_kernels():
     """Fused chains on/off: same outputs and gradients up to bf16 rounding of the (differently ordered) gradient sums."""
     data = batch(2, True)
