@@ -58,6 +58,9 @@ _SIGS = {
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_void_p]),
     "b3d_tma_packed_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "b3d_tma_packed_bytes_segs": (C.c_size_t, [C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
+    "b3d_tma_pack_weights_segs": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                            C.c_void_p, C.c_void_p]),
     "b3d_tma_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p]),
     "b3d_linear_tma": (C.c_int, [C.POINTER(Seg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,

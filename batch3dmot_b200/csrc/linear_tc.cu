@@ -733,8 +733,25 @@ constexpr int TMA_STAGES = 4;
 constexpr int TMA_THREADS = 320;   // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
 constexpr int WG_THREADS = 192;
 
+// TMA tile::gather4: four rows r0..r3 of a 2D tensor (tensor map encoded with box {64 columns, 1 row}), 64 columns
+// from column c0, land in four consecutive 128-byte rows at dst with the same address-based 128B swizzle as a
+// tile-mode box (verified on B200: scripts/exp/gather4_test.cu); 512 bytes are signalled on the mbarrier.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void* tmap, int c0, int r0, int r1, int r2, int r3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+
+constexpr int TMA_MAX_SEGS = 6;
+struct TmaMaps {
+  CUtensorMap m[TMA_MAX_SEGS];
+};
 struct TmaArgs {
-  int seg0_chunks, nchunks, Nb, acc_stride;
+  int nseg, seg_chunks[TMA_MAX_SEGS], seg_gsel[TMA_MAX_SEGS];   // 64-column chunks per segment; -1 dense, 0/1 = gathered by gidx[.]
+  const int32_t* gidx[2];                                       // row indices of the gathered segments
+  int nchunks, Nb, acc_stride;
   long long ntiles;
   const float* bias;
   void* Y;
@@ -752,8 +769,8 @@ struct TmaArgs {
 
 template <int ACT>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-             const __grid_constant__ CUtensorMap mapW, const TmaArgs a) {
+k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUtensorMap mapW,
+             const __grid_constant__ TmaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using namespace tc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -783,17 +800,39 @@ k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const uint32_t tmem = *s_tmem;
 
   if (warp == 0) {
+    // Producer warp. Dense segments: lane 0 issues one {64 x 128} box per chunk. Row-gathered segments (the
+    // reference's x[edge_index] operands, pose_gnn.py:180 / clr_att_gnn.py:284): every lane owns 4 rows of the tile
+    // and issues one tile::gather4 per chunk for them, so the gather runs in the TMA unit (no registers, no L1
+    // wavefronts, hundreds of rows in flight) instead of in the epilogue.
     if (lane == 0) {
       mbar_expect_tx(sBar + 96, a.nchunks * w_chunk);
       for (int c = 0; c < a.nchunks; ++c) tma_load_2d(sW + c * w_chunk, &mapW, c * 64, n0, sBar + 96);
-      int it = 0;
-      for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        for (int c = 0; c < a.nchunks; ++c, ++it) {
+    }
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      int g[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long r = tile * TC_BM + 4 * lane + j;
+          g[q][j] = (a.gidx[q] && r < a.M) ? __ldg(a.gidx[q] + r) : 0;
+        }
+      }
+      for (int sg = 0; sg < a.nseg; ++sg) {
+        const int sel = a.seg_gsel[sg];
+        for (int c = 0; c < a.seg_chunks[sg]; ++c, ++it) {
           const int s = it % TMA_STAGES;
-          if (it >= TMA_STAGES) mbar_wait(sBar + 32 + 8 * s, ((it / TMA_STAGES) - 1) & 1);
-          mbar_expect_tx(sBar + 8 * s, TC_A_STAGE);
-          if (c < a.seg0_chunks) tma_load_2d(sA + s * TC_A_STAGE, &mapA0, c * 64, (int)(tile * TC_BM), sBar + 8 * s);
-          else tma_load_2d(sA + s * TC_A_STAGE, &mapA1, (c - a.seg0_chunks) * 64, (int)(tile * TC_BM), sBar + 8 * s);
+          if (lane == 0) {
+            if (it >= TMA_STAGES) mbar_wait(sBar + 32 + 8 * s, ((it / TMA_STAGES) - 1) & 1);
+            mbar_expect_tx(sBar + 8 * s, TC_A_STAGE);
+            if (sel < 0) tma_load_2d(sA + s * TC_A_STAGE, &maps.m[sg], c * 64, (int)(tile * TC_BM), sBar + 8 * s);
+          }
+          if (sel >= 0) {
+            __syncwarp();      // the stage is free and its transaction count armed before any lane writes into it
+            tma_gather4(sA + s * TC_A_STAGE + lane * 512, &maps.m[sg], c * 64, g[sel][0], g[sel][1], g[sel][2], g[sel][3],
+                        sBar + 8 * s);
+          }
         }
       }
     }
@@ -913,6 +952,26 @@ k_linear_tma(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, ncols);
+}
+
+// Row-major bf16 pack with every input segment padded to whole 64-column chunks (gathered / ragged segments of
+// b3d_linear_tma each start on a chunk boundary): packed column kp of segment s, offset o < width_s, holds logical
+// column (sum of earlier widths) + o; padding columns are zero.
+struct SegWidths { int n, w[6]; };
+__global__ void k_pack_weights_rm_segs(const float* __restrict__ W, int ldw, int n_log, int transpose, SegWidths sw,
+                                       __nv_bfloat16* __restrict__ Wr, int Npad, int Kpad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Npad * Kpad) return;
+  int n = (int)(i / Kpad), kp = (int)(i % Kpad);
+  int k = -1, base = 0, pbase = 0;
+  for (int s = 0; s < sw.n; ++s) {
+    const int pw = (sw.w[s] + 63) / 64 * 64;
+    if (kp < pbase + pw) { if (kp - pbase < sw.w[s]) k = base + kp - pbase; break; }
+    base += sw.w[s]; pbase += pw;
+  }
+  float v = 0.f;
+  if (n < n_log && k >= 0) v = transpose ? W[(long long)k * ldw + n] : W[(long long)n * ldw + k];
+  Wr[i] = __float2bfloat16_rn(v);
 }
 
 // Row-major bf16 pack for the TMA path: Wr[n][k] = bf16(B[n][k]) zero padded to [Npad][Kpad].
@@ -1226,21 +1285,57 @@ extern "C" int b3d_tma_pack_weights(const float* W, int32_t ldw, int32_t n_logic
   return 0;
 }
 
+static int tma_padded_k(const b3d_seg_t* segs, int nseg) {
+  int kp = 0;
+  for (int s = 0; s < nseg; ++s) kp += round_up(segs[s].width, TC_BK);
+  return kp;
+}
+
+extern "C" size_t b3d_tma_packed_bytes_segs(int32_t n_logical, const int32_t* widths, int32_t nseg) {
+  size_t kp = 0;
+  for (int s = 0; s < nseg; ++s) kp += (size_t)round_up(widths[s], TC_BK);
+  return (size_t)round_up(n_logical, 16) * kp * 2;
+}
+
+extern "C" int b3d_tma_pack_weights_segs(const float* W, int32_t ldw, int32_t n_logical, const int32_t* widths,
+                                         int32_t nseg, int32_t transpose, void* Wr, void* stream) {
+  if (!W || !Wr || !widths || n_logical <= 0 || nseg < 1 || nseg > TMA_MAX_SEGS) return bad_arg("b3d_tma_pack_weights_segs");
+  SegWidths sw;
+  sw.n = nseg;
+  int Kpad = 0;
+  for (int s = 0; s < nseg; ++s) { sw.w[s] = widths[s]; Kpad += round_up(widths[s], TC_BK); }
+  const int Npad = round_up(n_logical, 16);
+  long long total = (long long)Npad * Kpad;
+  k_pack_weights_rm_segs<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      W, ldw, n_logical, transpose, sw, reinterpret_cast<__nv_bfloat16*>(Wr), Npad, Kpad);
+  B3D_LAUNCH_CHECK("k_pack_weights_rm_segs");
+  return 0;
+}
+
 extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* Wr, int32_t n_logical,
                               int32_t k_logical, const float* bias, void* Y, int32_t ldy, int32_t y_dtype,
                               int64_t M, int32_t act, int32_t flags, const void* out_mask, int32_t ldm,
                               int32_t mask_dtype, const uint8_t* row_mask, const b3d_seg_t* adds, int32_t nadd,
                               void* relu_bits_out, void* stream) {
   if (M == 0) return 0;
-  TmaArgs a;
-  SegDev seg[2];
-  if (nseg < 1 || nseg > 2 || to_dev(segs, nseg, seg)) return bad_arg("b3d_linear_tma: 1 or 2 segments");
+  static TmaArgs a;
+  SegDev seg[TMA_MAX_SEGS];
+  if (nseg < 1 || nseg > TMA_MAX_SEGS || to_dev(segs, nseg, seg)) return bad_arg("b3d_linear_tma: 1 to 6 segments");
   int K = 0;
+  a.gidx[0] = a.gidx[1] = nullptr;
   for (int s = 0; s < nseg; ++s) {
-    if (seg[s].dtype != B3D_BF16 || seg[s].idx || !seg_tc_ok(seg[s]))
-      return bad_arg("b3d_linear_tma: segments must be dense bf16, widths % 8, 16-byte aligned rows");
-    if (s + 1 < nseg && (seg[s].width % TC_BK)) return bad_arg("b3d_linear_tma: leading segment width % 64");
+    if (seg[s].dtype != B3D_BF16 || !seg_tc_ok(seg[s]))
+      return bad_arg("b3d_linear_tma: segments must be bf16, widths % 8, 16-byte aligned rows, no operand masks");
     K += seg[s].width;
+    a.seg_chunks[s] = round_up(seg[s].width, TC_BK) / TC_BK;
+    a.seg_gsel[s] = -1;
+    if (seg[s].idx) {       // row-gathered segment: at most two distinct index arrays per launch
+      int q = 0;
+      while (q < 2 && a.gidx[q] && a.gidx[q] != seg[s].idx) ++q;
+      if (q == 2) return bad_arg("b3d_linear_tma: at most two distinct row-index arrays");
+      a.gidx[q] = seg[s].idx;
+      a.seg_gsel[s] = q;
+    }
   }
   if (K != k_logical || !Wr || !Y || n_logical <= 0) return bad_arg("b3d_linear_tma: shapes");
   if (nadd < 0 || nadd > 2 || (nadd && to_dev(adds, nadd, a.add))) return bad_arg("b3d_linear_tma adds");
@@ -1250,10 +1345,11 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
       return bad_arg("b3d_linear_tma: adds must be [*, Nout] with 16-byte aligned rows");
   if (y_dtype == B3D_BF16 && ((ldy & 7) || (reinterpret_cast<uintptr_t>(Y) & 15) || (flags & B3D_FLAG_ACCUMULATE)))
     return bad_arg("b3d_linear_tma: bf16 output needs ld % 8 == 0, 16-byte alignment, no accumulate");
-  const int Npad = round_up(n_logical, 16), Kpad = round_up(k_logical, TC_BK);
-  a.seg0_chunks = nseg == 2 ? seg[0].width / TC_BK : Kpad / TC_BK;
-  a.nchunks = nseg == 2 ? seg[0].width / TC_BK + round_up(seg[1].width, TC_BK) / TC_BK : Kpad / TC_BK;
-  if (a.nchunks * TC_BK != Kpad) return bad_arg("b3d_linear_tma: chunking");
+  // every segment starts on a 64-column chunk boundary of the packed weights (b3d_tma_pack_weights_segs; the
+  // plain pack b3d_tma_pack_weights is the same thing when only the last segment is ragged)
+  const int Npad = round_up(n_logical, 16), Kpad = tma_padded_k(segs, nseg);
+  a.nseg = nseg;
+  a.nchunks = Kpad / TC_BK;
   // weight block resident in shared memory: Nb * Kpad * 2 <= 144 KB. Sign-bit words cover 32 columns,
   // so with bit masks every column block must start on a word boundary (granularity 32 instead of 16).
   const int gran = (relu_bits_out || mask_dtype == B3D_BITS) ? 32 : 16;
@@ -1272,12 +1368,15 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   a.mask_bits = mask_dtype == B3D_BITS ? reinterpret_cast<const uint32_t*>(out_mask) : nullptr;
   a.bits_out = reinterpret_cast<uint32_t*>(relu_bits_out);
   a.nadd = nadd;
-  alignas(64) CUtensorMap mA0, mA1, mW;
-  if (make_tmap_bf16(&mA0, seg[0].ptr, M, seg[0].width, seg[0].ld, TC_BM)) return bad_arg("b3d_linear_tma: tensor map A0");
-  if (nseg == 2) {
-    if (make_tmap_bf16(&mA1, seg[1].ptr, M, seg[1].width, seg[1].ld, TC_BM)) return bad_arg("b3d_linear_tma: tensor map A1");
-  } else {
-    mA1 = mA0;
+  alignas(64) static TmaMaps maps;
+  alignas(64) CUtensorMap mW;
+  for (int s = 0; s < TMA_MAX_SEGS; ++s) {
+    const int src = s < nseg ? s : 0;
+    // gathered segments: the tensor is the whole source table (its row count is not part of b3d_seg_t; the indices
+    // address it, so a bound of 2^28 rows is encoded) and the box is one row; dense segments: M rows, box of 128 rows
+    const long long rows = seg[src].idx ? (1ll << 28) : M;
+    if (make_tmap_bf16(&maps.m[s], seg[src].ptr, rows, seg[src].width, seg[src].ld, seg[src].idx ? 1 : TC_BM))
+      return bad_arg("b3d_linear_tma: tensor map A");
   }
   if (make_tmap_bf16(&mW, Wr, Npad, Kpad, Kpad, Nb)) return bad_arg("b3d_linear_tma: tensor map W");
   size_t smem = (size_t)a.nchunks * Nb * 128 + TMA_STAGES * TC_A_STAGE + 128 + 1024 + 1024;   // + alignment slack
@@ -1301,9 +1400,9 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   if (gx > a.ntiles) gx = a.ntiles;
   dim3 grid((unsigned)gx, (unsigned)ny);
   cudaStream_t st = (cudaStream_t)stream;
-  if (act == B3D_ACT_RELU) k_linear_tma<1><<<grid, TMA_THREADS, smem, st>>>(mA0, mA1, mW, a);
-  else if (act == B3D_ACT_SIGMOID) k_linear_tma<2><<<grid, TMA_THREADS, smem, st>>>(mA0, mA1, mW, a);
-  else k_linear_tma<0><<<grid, TMA_THREADS, smem, st>>>(mA0, mA1, mW, a);
+  if (act == B3D_ACT_RELU) k_linear_tma<1><<<grid, TMA_THREADS, smem, st>>>(maps, mW, a);
+  else if (act == B3D_ACT_SIGMOID) k_linear_tma<2><<<grid, TMA_THREADS, smem, st>>>(maps, mW, a);
+  else k_linear_tma<0><<<grid, TMA_THREADS, smem, st>>>(maps, mW, a);
   B3D_LAUNCH_CHECK("k_linear_tma");
   return 0;
 }

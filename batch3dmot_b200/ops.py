@@ -156,6 +156,26 @@ _USE_TMA = True          # dense bf16 operands go through the TMA-fed persistent
 _USE_BITS = True         # bf16 chains keep ReLU masks as sign bits (B3D_BITS) for the backward pass
 
 
+def _packed_weight_segs(W, transpose, widths):
+    """Row-major TMA pack with every input segment padded to whole 64-column chunks (gathered / ragged segments)."""
+    key = (id(W), tuple(W.shape), W.stride(0), bool(transpose), "segs", tuple(widths))
+    ent = _packed.get(key)
+    if ent is not None:
+        ref, ver, ptr, wp = ent
+        if ref() is W and ver == W._version and ptr == W.data_ptr():
+            return wp
+    if len(_packed) > 512:
+        _packed.clear()
+    n_log = W.size(1) if transpose else W.size(0)
+    lib = L.lib()
+    wa = L.int_array(list(widths))
+    wp = torch.empty(int(lib.b3d_tma_packed_bytes_segs(n_log, wa, len(widths))), dtype=torch.uint8, device=W.device)
+    L.check(lib.b3d_tma_pack_weights_segs(L.ptr(W), W.stride(0), n_log, wa, len(widths), int(transpose), L.ptr(wp),
+                                          L.stream()), "b3d_tma_pack_weights_segs")
+    _packed[key] = (weakref.ref(W), W._version, W.data_ptr(), wp)
+    return wp
+
+
 def _packed_weight(W, transpose, rowmajor=False, split=False):
     """bf16 pack of W for the tensor-core kernels. An entry belongs to ONE live tensor object: it holds a weak
     reference and is used only while that very object is alive at the same version. (A key made of
@@ -208,11 +228,14 @@ _chain_packs = {}
 #   split_tc   tf32 x3 tensor-core tiles as the arithmetic of the "fp32" (1e-4) mode (else: FFMA kernels). ON:
 #              every 1e-4 test passes with it (tests/test_gpu_models.py, test_gpu_split.py) and it is 2.8x faster.
 #   window_knn graph-construction k-NN kernel for CUDA tensors (window_knn.cu). ON.
+#   gather_tma bf16 mode: the node-feature operands of the edge layers are row-gathered by the TMA unit
+#              (tile::gather4) straight into the tensor-core tile — the reference's un-projected cat[x_i, x_j, e, att]
+#              form — instead of arriving as epilogue addends of per-node pre-projections.
 #   chain      fused MLP chains / edge blocks (chain_tc.cu). Validated (tests/test_gpu_chain.py runs it whatever this
 #              switch says) but OFF in the model path: with one 128-row tile in flight per SM the fused kernel is
 #              bound by the same epilogue work as the per-layer kernels plus the layer-to-layer hand-over latency,
 #              and measured no faster (profiles/r2_chain_kernel.md), so the per-layer TMA kernels stay the default.
-_FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True}
+_FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True, "gather_tma": False}
 
 
 def _read_features():
@@ -294,12 +317,39 @@ def _chain_dims_ok(widths):
 
 
 def _tma_ok(items, K, accumulate):
+    """Dense bf16 operands (1-2 segments, only the last ragged): the TMA-fed kernel with the plain weight pack.
+    With the gather_tma feature also up to 6 segments, row-gathered ones included (two index arrays at most)."""
+    if not _USE_TMA or accumulate or K > 1024:
+        return False
+    general = FEATURES["gather_tma"]
+    if len(items) > (6 if general else 2):
+        return False
+    idxs = []
+    for n, (t, idx, mask, _) in enumerate(items):
+        if t.dtype != torch.bfloat16 or mask is not None or not _al16(t) or t.size(1) % 8:
+            return False
+        if idx is not None:
+            if not general:
+                return False
+            if not any(idx is j for j in idxs):
+                idxs.append(idx)
+        elif not general and n + 1 < len(items) and t.size(1) % 64:
+            return False
+    return len(idxs) <= 2 and sum((t.size(1) + 63) // 64 * 64 for t, _, _, _ in items) <= 1024
+
+
+def _tma_dense_ok(items, K, accumulate):
+    """1-2 dense bf16 segments, only the last ragged (weight-gradient TMA kernel, fused chains)."""
     if not _USE_TMA or accumulate or len(items) > 2 or K > 1024:
         return False
     for n, (t, idx, _, _) in enumerate(items):
         if t.dtype != torch.bfloat16 or idx is not None or (n + 1 < len(items) and t.size(1) % 64):
             return False
     return True
+
+
+def _tma_needs_seg_pack(items):
+    return any(idx is not None for _, idx, _, _ in items) or any(t.size(1) % 64 for t, _, _, _ in items[:-1])
 
 
 def _al16(t):
@@ -372,7 +422,8 @@ def _linear_raw_impl(items, W, bias, M, act=L.ACT_NONE, trans_w=False, out=None,
     if bits_out is not None:
         assert tc and bits_out.shape == ((n_out + 31) // 32, M) and bits_out.is_contiguous()
     if tc and _tma_ok(items, K, accumulate):
-        wr = _packed_weight(W, trans_w, rowmajor=True)
+        wr = _packed_weight_segs(W, trans_w, [t.size(1) for t, _, _, _ in items]) if _tma_needs_seg_pack(items) \
+            else _packed_weight(W, trans_w, rowmajor=True)
         L.check(L.lib().b3d_linear_tma(segs, len(items), L.ptr(wr), n_out, K, L.ptr(bias), L.ptr(out),
                                        out.stride(0), _DT[out.dtype], M, act, 0, m_ptr, m_ld, m_dt, L.ptr(row_mask),
                                        add_segs, nadd, L.ptr(bits_out), L.stream()), "b3d_linear_tma")
@@ -438,7 +489,7 @@ def _wgrad_raw_impl(dy_item, items, M, n_out, K, dW=None, db=None, accumulate=Fa
     if tc is None:
         tc = _PRECISION == "bf16" and M > 0 and _tc_shapes_ok(items, M, max(n_out, 16), K) and \
             _al16(dy_item[0]) and dy_item[2] is None
-    if tc and dy_item[0].dtype == torch.bfloat16 and n_out % 8 == 0 and _tma_ok(items, K, False):
+    if tc and dy_item[0].dtype == torch.bfloat16 and n_out % 8 == 0 and _tma_dense_ok(items, K, False):
         wsb = lib.b3d_wgrad_tma_workspace_bytes(M, n_out, K)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         L.check(lib.b3d_wgrad_tma(L.make_segs([dy_item]), L.make_segs(items), len(items), L.ptr(dW), dW.stride(0),
@@ -655,7 +706,7 @@ class _FusedMLP(torch.autograd.Function):
         # the whole chain as ONE launch: hidden activations stay in shared memory (chain_tc.cu). Training keeps
         # the same saved tensors as the per-layer path (bf16 activations + sign bits), inference writes the output only
         ctx.chain = False
-        if (tc and _USE_CHAIN and nl >= 2 and nl <= L.CHAIN_MAX_LAYERS and rm is None and _tma_ok(items, Ws[0].size(1), False)
+        if (tc and _USE_CHAIN and nl >= 2 and nl <= L.CHAIN_MAX_LAYERS and rm is None and _tma_dense_ok(items, Ws[0].size(1), False)
                 and (out_dtype or torch.float32) == torch.bfloat16 and _chain_dims_ok([w.size(0) for w in Ws])
                 and Ws[0].size(1) % 16 == 0 and len(adds) <= 2 and all(t.dtype == torch.bfloat16 and _al16(t) for t, _ in adds)):
             idxs = []
@@ -853,6 +904,93 @@ class _MPEdgeBlock(torch.autograd.Function):
         d_e = dA[:, :e.size(1)]
         d_att = dA[:, e.size(1):] if ctx.has_att else None
         return (None, d_e, d_att, dp_i, dp_j, dp_f, dp_p, dW0, dW1, db1, dW2, db2, dWf, dWp)
+
+
+def _it(t, idx=None):
+    return (t, idx, None, 0)
+
+
+class _MPEdgeBlockG(torch.autograd.Function):
+    """The edge side of one message-passing iteration (clr_att_gnn.py:314-327) with the node-feature operands
+    row-gathered by the TMA unit (b3d_linear_tma, tile::gather4):
+        X1 = relu(W0 . cat[x_i, x_j, e, att] + b0)       — the reference's own un-projected first layer
+        X2 = relu(W1 X1 + b1),  e' = W2 X2 + b2
+        h_f = relu(Wf . cat[x_i, e', x0_i] + bf),  h_p = relu(Wp . cat[x_j, e', x0_j] + bp)
+    so no epilogue waits on gathered addend rows (the forward tiles with addends ran at 1.8-2.2 TB/s, the plain
+    ones at 5.5+; profiles/r1_bf16_launch_summary.md). The BACKWARD keeps the pre-projected form: p_i .. p_p (the
+    per-node first-layer blocks, computed by the caller's node-level GEMM and unused by this forward) receive the
+    per-node sums of the pre-activation gradients, and autograd carries them on into x, x0 and the node-side weight
+    blocks — the same gradients as the un-projected function's, at node-level instead of edge-level cost."""
+
+    @staticmethod
+    def forward(ctx, g, x, x0, e, att, p_i, p_j, p_f, p_p, W0, b0, W1, b1, W2, b2, Wf, bf_, Wp, bp_, W0e, Wfe, Wpe):
+        M, dev, bf = e.size(0), e.device, torch.bfloat16
+        train = any(ctx.needs_input_grad)
+        dst, src = g.by_dst.idx, g.by_src.idx
+        bt = lambda n: new_relu_bits(M, n, dev) if train else None
+        b_x1, b_x2, b_f, b_p = bt(W0.size(0)), bt(W1.size(0)), bt(Wf.size(0)), bt(Wp.size(0))
+        ins = [_it(x, dst), _it(x, src), _it(e)] + ([_it(att)] if att is not None else [])
+        x1 = linear_raw(ins, W0, b0, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_x1)
+        x2 = linear_raw([_it(x1)], W1, b1, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_x2)
+        e_new = linear_raw([_it(x2)], W2, b2, M, L.ACT_NONE, tc=True, out_dtype=bf)
+        h_f = linear_raw([_it(x, dst), _it(e_new), _it(x0, dst)], Wf, bf_, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_f)
+        h_p = linear_raw([_it(x, src), _it(e_new), _it(x0, src)], Wp, bp_, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_p)
+        ctx.g, ctx.has_att = g, att is not None
+        if train:
+            ctx.save_for_backward(e, att if att is not None else e, x1, x2, e_new, b_x1, b_x2, W0e, W1, W2, Wfe, Wpe)
+        empty = torch.zeros(0, dtype=torch.int32, device=dev)
+        outs = (e_new, h_f, b_f if train else empty, h_p, b_p if train else empty)
+        ctx.mark_non_differentiable(outs[2], outs[4])
+        return outs
+
+    @staticmethod
+    def backward(ctx, de, dhf, _bf, dhp, _bp):
+        e, att, x1, x2, e_new, b_x1, b_x2, W0e, W1, W2, Wfe, Wpe = ctx.saved_tensors
+        g = ctx.g
+        M, dev, bf = e.size(0), e.device, torch.bfloat16
+        n0, n1, n2, nm, k0 = W0e.size(0), W1.size(0), W2.size(0), Wfe.size(0), W0e.size(1)
+        z = lambda t, n: t.contiguous() if t is not None else torch.zeros((M, n), dtype=bf, device=dev)
+        dhf, dhp = z(dhf, nm), z(dhp, nm)
+        # de' = cat[dh_f, dh_p] . [Wf_e ; Wp_e] + (direct gradient of e'), then the masked chain back to cat[e, att]
+        w_fp = torch.cat([Wfe, Wpe], 0)
+        dz2 = linear_raw([_it(dhf), _it(dhp)], w_fp, None, M, trans_w=True, tc=True, out_dtype=bf,
+                         adds=[(de.contiguous(), None)] if de is not None else None)
+        dz1 = linear_raw([_it(dz2)], W2, None, M, trans_w=True, mask_bits=b_x2, tc=True, out_dtype=bf)
+        dz0 = linear_raw([_it(dz1)], W1, None, M, trans_w=True, mask_bits=b_x1, tc=True, out_dtype=bf)
+        dA = linear_raw([_it(dz0)], W0e, None, M, trans_w=True, tc=True, out_dtype=bf)
+        ins = [_it(e)] + ([_it(att)] if ctx.has_att else [])
+        dW0e, _ = wgrad_raw(_it(dz0), ins, M, n0, k0, want_bias=False, tc=True)
+        dW1, db1 = wgrad_raw(_it(dz1), [_it(x1)], M, n1, n0, tc=True)
+        dW2, db2 = wgrad_raw(_it(dz2), [_it(x2)], M, n2, n1, tc=True)
+        dWfe, _ = wgrad_raw(_it(dhf), [_it(e_new)], M, nm, n2, want_bias=False, tc=True)
+        dWpe, _ = wgrad_raw(_it(dhp), [_it(e_new)], M, nm, n2, want_bias=False, tc=True)
+        dp_i = segment_sum_raw(dz0, g.by_dst, out_dtype=bf)
+        dp_j = segment_sum_raw(dz0, g.by_src, out_dtype=bf)
+        dp_f = segment_sum_raw(dhf, g.by_dst, out_dtype=bf)
+        dp_p = segment_sum_raw(dhp, g.by_src, out_dtype=bf)
+        d_e = dA[:, :e.size(1)]
+        d_att = dA[:, e.size(1):] if ctx.has_att else None
+        # inputs: g, x, x0, e, att, p_i, p_j, p_f, p_p, W0, b0, W1, b1, W2, b2, Wf, bf_, Wp, bp_, W0e, Wfe, Wpe
+        return (None, None, None, d_e, d_att, dp_i, dp_j, dp_f, dp_p, None, None, dW1, db1, dW2, db2, None, None, None,
+                None, dW0e, dWfe, dWpe)
+
+
+def mp_edge_block_gathered_supported(x, e, att):
+    if not FEATURES["gather_tma"] or _PRECISION != "bf16" or e.size(0) < _TC_MIN_ROWS:
+        return False
+    ts = [x, e] + ([att] if att is not None else [])
+    return all(t.dtype == torch.bfloat16 and _al16(t) and t.size(1) % 8 == 0 and t.is_contiguous() for t in ts)
+
+
+def mp_edge_block_gathered(g, x, x0, e, att, p_i, p_j, p_f, p_p, eu, lf0, lp0, D, E_):
+    """eu: the three nn.Linear of edge_update; lf0 / lp0: first layers of create_future_msgs / create_past_msgs.
+    Returns (e', h_f, bits_f, h_p, bits_p). The full first-layer weights and biases feed the forward only (this
+    block returns no gradient for them: the node-side blocks and biases get theirs through p_i .. p_p); the
+    edge-feature column blocks are passed again as views so that their gradients come back from this block."""
+    return _MPEdgeBlockG.apply(g, x, x0, e, att, p_i, p_j, p_f, p_p, eu[0].weight, eu[0].bias,
+                               eu[1].weight, eu[1].bias, eu[2].weight, eu[2].bias, lf0.weight, lf0.bias,
+                               lp0.weight, lp0.bias, eu[0].weight[:, 2 * D:], lf0.weight[:, D:D + E_],
+                               lp0.weight[:, D:D + E_])
 
 
 def mp_edge_block_supported(e, att, W0, W1, W2, Wf):

@@ -99,6 +99,20 @@ class CausalMessagePassing(nn.Module):
         if e.dtype != lowp:
             e = e.to(lowp)
         lf0, lp0 = self.create_future_msgs[0], self.create_past_msgs[0]
+        xb = x if x.dtype == lowp else x.to(lowp)
+        if ops.mp_edge_block_gathered_supported(xb, e, att):
+            # node features row-gathered by the TMA unit into the edge tiles (the reference's cat[x_i, x_j, e, att]
+            # form in the forward pass; gradients still flow through the per-node pre-projections p_*)
+            x0b = x0 if x0.dtype == lowp else x0.detach().to(lowp)
+            e_out, h_f, bits_f, h_p, bits_p = ops.mp_edge_block_gathered(g, xb.detach(), x0b, e, att, p_i, p_j, p_f, p_p,
+                                                                         eu, lf0, lp0, D, E_)
+            agg = []
+            for h, bits, into, wpost in ((h_f, bits_f, src, w_post[0]), (h_p, bits_p, dst, w_post[1])):
+                s_h = ops.segment_sum(h, into, relu_src=True, relu_bits=bits, out_dtype=lowp)
+                agg.append(ops.fused_mlp([(s_h, None), (g.degree_block(into, lowp), None)], [wpost], [None], out_dtype=lowp))
+            m_fut, m_past = agg
+            x_new = ops.run_mlp(self.combine_future_past, [(m_past, None), (m_fut, None)], out_dtype=lowp)
+            return x_new, e_out
         if ops.mp_edge_block_supported(e, att, w1[:, 2 * D:], eu[1].weight, eu[2].weight, lf0.weight[:, D:D + E_]):
             # edge_update + both message first layers as one fused launch; hidden tiles and e' stay on the SM
             e_out, h_f, bits_f, h_p, bits_p = ops.mp_edge_block(

@@ -168,6 +168,16 @@ int b3d_linear_tc(const b3d_seg_t* segs /*host*/, int32_t nseg, const void* Wp, 
  * gather; the leading segment's width a multiple of 64): TMA producer warp, single-thread tcgen05
  * issuer, 4 epilogue warps, weight block resident in shared memory, double-buffered TMEM
  * accumulators. Weights are packed row-major bf16 [Npad][Kpad] by b3d_tma_pack_weights. */
+/* b3d_linear_tma takes 1-6 bf16 segments; a segment with `idx` is ROW-GATHERED by the TMA unit itself
+ * (cp.async.bulk.tensor tile::gather4: four table rows per request into the swizzled operand tile) — this is how
+ * the reference's x[edge_index[1]] / x[edge_index[0]] operands (MessagePassing.__collect__, pose_gnn.py:180;
+ * torch.cat at :210,215,222 / clr_att_gnn.py:314,319,326) enter the tensor core without an epilogue gather. At most
+ * two distinct index arrays per launch; gathered tables may hold up to 2^28 rows. Every segment occupies whole
+ * 64-column chunks of the packed weights: pack with b3d_tma_pack_weights_segs(widths) unless only the last segment
+ * is ragged (then b3d_tma_pack_weights gives the same image). */
+size_t b3d_tma_packed_bytes_segs(int32_t n_logical, const int32_t* widths /*host*/, int32_t nseg);
+int b3d_tma_pack_weights_segs(const float* W, int32_t ldw, int32_t n_logical, const int32_t* widths /*host*/,
+                              int32_t nseg, int32_t transpose, void* Wr, void* stream);
 size_t b3d_tma_packed_bytes(int32_t n_logical, int32_t k_logical);
 int b3d_tma_pack_weights(const float* W, int32_t ldw, int32_t n_logical, int32_t k_logical,
                          int32_t transpose, void* Wr, void* stream);
