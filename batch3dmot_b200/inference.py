@@ -27,32 +27,47 @@ def shard_scenes(scenes, world_size):
     return lpt_partition(costs, world_size)
 
 
+_SCENE_KEYS = ("edge_attr",) + _NODE_KEYS
+
+
+def pin_scene(scene):
+    """Page-lock the tensors of a host-side scene (what a loader thread does once per scene), so that
+    collate_scenes can issue asynchronous H2D copies instead of staged pageable ones."""
+    for k, v in list(vars(scene).items()):
+        if torch.is_tensor(v) and not v.is_cuda and not v.is_pinned():
+            setattr(scene, k, v.pin_memory())
+    return scene
+
+
 def collate_scenes(scenes, device):
     """Union of whole scene graphs on `device` (node offsets in edge_index) plus what the window cutter needs:
     scene_id [N], frame index of every node inside its scene, frames per scene (host ints). Nodes of a scene
-    must be stored frame after frame (true for the reference's preprocessing and for synth.scene_graph)."""
+    must be stored frame after frame (true for the reference's preprocessing and for synth.scene_graph).
+    Every scene tensor is copied on its own (asynchronously when it is pinned, see pin_scene) and the
+    concatenation happens on the device: no host-side staging copy of the batch."""
     u = SimpleNamespace()
+    on = lambda t: t.to(device, non_blocking=True)
     off, eis, sid, frame, frames = 0, [], [], [], []
+    u.node_off = [0]
     for i, sc in enumerate(scenes):
         n = sc.pose_feats.size(0)
         ts = sc.node_timestamps
-        t0 = int(ts.min()) if n else 0
-        frames.append(int(ts.max()) - t0 + 1 if n else 0)
-        frame.append(ts - t0)
-        eis.append(sc.edge_index + off)
-        sid.append(torch.full((n,), i, dtype=torch.long))
+        if not hasattr(sc, "_t_range"):                       # host ints, computed once per scene
+            sc._t_range = (int(ts.min()), int(ts.max())) if n else (0, -1)
+        t0, t1 = sc._t_range
+        frames.append(t1 - t0 + 1 if n else 0)
+        frame.append(on(ts) - t0)
+        eis.append(on(sc.edge_index) + off)
+        sid.append(torch.full((n,), i, dtype=torch.long, device=device))
         off += n
-    u.edge_index = torch.cat(eis, 1).to(device, non_blocking=True)
-    u.scene_id = torch.cat(sid).to(device, non_blocking=True)
-    u.frame = torch.cat(frame).to(device, non_blocking=True)
-    u.edge_attr = torch.cat([sc.edge_attr for sc in scenes]).to(device, non_blocking=True)
-    for k in _NODE_KEYS:
+        u.node_off.append(off)
+    u.edge_index = torch.cat(eis, 1)
+    u.scene_id = torch.cat(sid)
+    u.frame = torch.cat(frame)
+    for k in _SCENE_KEYS:
         if all(hasattr(sc, k) for sc in scenes):
-            setattr(u, k, torch.cat([getattr(sc, k) for sc in scenes]).to(device, non_blocking=True))
+            setattr(u, k, torch.cat([on(getattr(sc, k)) for sc in scenes]))
     u.frames, u.num_nodes, u.n_scenes = frames, off, len(scenes)
-    u.node_off = [0]
-    for sc in scenes:
-        u.node_off.append(u.node_off[-1] + sc.pose_feats.size(0))
     return u
 
 
@@ -157,23 +172,58 @@ def track_scenes(model, scenes, device, rank=0, world_size=1, multimodal=True, w
                  want_tracks=True):
     """Scene-sharded inference + track assembly. Returns {scene_id: (track_ids [N] int64, tracks)}
     for the scenes owned by `rank`. Scenes are processed in chunks of at most `max_edges` scene edges (each
-    edge sits in ~2.5 windows): per chunk one window cut, one forward, one track assembly."""
+    edge sits in ~2.5 windows): per chunk one window cut, one forward, one track assembly. The chunks form a
+    three-stage pipeline: the H2D copies of chunk k+1 run on a copy stream while chunk k is in the model, and the
+    sequential clustering of chunk k-1 runs on a host thread (b3d_hier_tracks_host releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
     costs = [int(s.edge_index.size(1)) for s in scenes]
     mine = lpt_partition(costs, world_size)[rank]
+    groups = chunk_scenes(mine, costs, max_edges)
     out = {}
-    for group in chunk_scenes(mine, costs, max_edges):
+    cuda = torch.device(device).type == "cuda"
+    copy_stream = torch.cuda.Stream(device=device) if cuda else None
+
+    def stage(group):
         sub = [scenes[i] for i in group]
-        u = collate_scenes(sub, device)
-        b = window_batch(u, window)
-        if b.n_windows == 0 or b.edge_index.size(1) == 0:
-            for sid, sc in zip(group, sub):
-                out[sid] = (torch.full((sc.pose_feats.size(0),), -1, dtype=torch.long), [])
-            continue
-        scores = forward_scores(model, b, multimodal)
-        tid, pos, _ = tracking.assign_track_ids_union(b.g_out, b.g_in, scores, u.node_classes, u.scene_id.int(),
-                                                      len(sub))
+        if copy_stream is None:
+            return sub, collate_scenes(sub, device), None
+        with torch.cuda.stream(copy_stream):
+            u = collate_scenes(sub, device)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return sub, u, ev
+
+    def finish(group, sub, u, fut):
+        tid, pos, _ = fut.result()
         for j, sid in enumerate(group):
             a, e = u.node_off[j], u.node_off[j + 1]
             ids = tid[a:e].clone()
             out[sid] = (ids, tracking.tracks_from_ids(ids, pos[a:e]) if want_tracks else None)
+
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        staged = stage(groups[0]) if groups else None
+        pending = None
+        for gi, group in enumerate(groups):
+            sub, u, ev = staged
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+                for t in vars(u).values():                     # tensors made on the copy stream, used on this one
+                    if torch.is_tensor(t):
+                        t.record_stream(torch.cuda.current_stream())
+            staged = stage(groups[gi + 1]) if gi + 1 < len(groups) else None
+            b = window_batch(u, window)
+            if b.n_windows == 0 or b.edge_index.size(1) == 0:
+                for sid, sc in zip(group, sub):
+                    out[sid] = (torch.full((sc.pose_feats.size(0),), -1, dtype=torch.long), [])
+                continue
+            scores = forward_scores(model, b, multimodal)
+            n = u.node_classes.numel()
+            e_out, e_in, mean = tracking.average_edge_scores(b.g_out, b.g_in, scores, n)
+            k_out, k_in, k_s = tracking.greedy_edges(e_out, e_in, mean, u.node_classes)
+            host = tracking.to_host(k_out, k_in, k_s, u.node_classes, u.scene_id.int())     # one D2H of the survivors
+            if pending is not None:
+                finish(*pending)
+            pending = (group, sub, u, pool.submit(tracking.hier_tracks_host_arrays, *host, len(sub)))
+        if pending is not None:
+            finish(*pending)
     return out

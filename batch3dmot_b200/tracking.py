@@ -135,23 +135,34 @@ def hier_tracks(e_out, e_in, score, node_classes):
     return tracks
 
 
-def hier_tracks_native(e_out, e_in, score, node_classes, scene_of_node=None, n_scenes=1):
-    """hier_tracks for the union of many scenes in ONE device->host transfer and one native loop
-    (libb3d b3d_hier_tracks_host). Returns (track_id [n] int64, per-scene numbering; track_pos [n] int64;
-    tracks_per_scene [n_scenes] int64) as CPU tensors."""
+def to_host(e_out, e_in, score, node_classes, scene_of_node=None):
+    """The surviving edges and the node tables as contiguous CPU tensors (the one device->host transfer of the
+    track assembly)."""
+    host = [t.detach().to("cpu").contiguous() for t in
+            (e_out.to(torch.int64), e_in.to(torch.int64), score.to(torch.float64), node_classes.to(torch.int64))]
+    host.append(scene_of_node.detach().to("cpu", torch.int32).contiguous() if scene_of_node is not None else None)
+    return host
+
+
+def hier_tracks_host_arrays(e_out, e_in, score, node_classes, scene_of_node, n_scenes=1):
+    """b3d_hier_tracks_host on CPU tensors (callable from a worker thread: ctypes releases the GIL)."""
     from . import _lib as L
     n = node_classes.numel()
-    host = [t.detach().to("cpu", non_blocking=False).contiguous() for t in
-            (e_out.to(torch.int64), e_in.to(torch.int64), score.to(torch.float64), node_classes.to(torch.int64))]
-    sc_of = scene_of_node.detach().to("cpu", torch.int32).contiguous() if scene_of_node is not None else None
     tid = torch.empty(n, dtype=torch.int64)
     pos = torch.empty(n, dtype=torch.int64)
     per = torch.empty(n_scenes, dtype=torch.int64)
     thr = THRESHOLDS.contiguous()
-    L.check(L.lib().b3d_hier_tracks_host(L.ptr(host[0]), L.ptr(host[1]), L.ptr(host[2]), host[0].numel(), L.ptr(host[3]),
-                                         L.ptr(sc_of), n, n_scenes, L.ptr(thr), thr.numel(), L.ptr(tid), L.ptr(pos),
+    L.check(L.lib().b3d_hier_tracks_host(L.ptr(e_out), L.ptr(e_in), L.ptr(score), e_out.numel(), L.ptr(node_classes),
+                                         L.ptr(scene_of_node), n, n_scenes, L.ptr(thr), thr.numel(), L.ptr(tid), L.ptr(pos),
                                          L.ptr(per)), "b3d_hier_tracks_host")
     return tid, pos, per
+
+
+def hier_tracks_native(e_out, e_in, score, node_classes, scene_of_node=None, n_scenes=1):
+    """hier_tracks for the union of many scenes in ONE device->host transfer and one native loop
+    (libb3d b3d_hier_tracks_host). Returns (track_id [n] int64, per-scene numbering; track_pos [n] int64;
+    tracks_per_scene [n_scenes] int64) as CPU tensors."""
+    return hier_tracks_host_arrays(*to_host(e_out, e_in, score, node_classes, scene_of_node), n_scenes)
 
 
 def tracks_from_ids(track_id, track_pos):

@@ -225,8 +225,8 @@ def extras(a, rank, world, dev, model, d, tm, E_global):
     rates = val_scene_rates(a.val_scenes)
     est = [40 * r * min(40.0, 1.1 * r) for r in rates]          # edge-count estimate known to every rank without generating
     mine = lpt_partition(est, world)[rank]
-    scenes = {i: synth.add_modalities(synth.scene_graph(seed=SEED + 5000 + i, T=40, frame_sizes=[rates[i]] * 40),
-                                      SEED + 5000 + i, raw=False) for i in mine}
+    scenes = {i: inference.pin_scene(synth.add_modalities(
+        synth.scene_graph(seed=SEED + 5000 + i, T=40, frame_sizes=[rates[i]] * 40), SEED + 5000 + i, raw=False)) for i in mine}
     lst = [scenes[i] for i in mine]
     model.eval()
     n_tracks = [0]
@@ -247,7 +247,7 @@ def extras(a, rank, world, dev, model, d, tm, E_global):
         dist.all_reduce(win_edges)
     x["batched_inference"] = {
         "workload": f"configs[3]: {a.val_scenes} val-shaped scenes x 36 sliding 5-frame windows, scene-sharded (LPT) over "
-                    f"{world} GPU(s): host->device copy of the scenes, window cut on device, forward, track assembly",
+                    f"{world} GPU(s): host->device copy of the (pinned) scenes, window cut on device, forward, track assembly",
         "scenes_per_s": a.val_scenes / float(dt.item()), "seconds": float(dt.item()), "scaling": "strong",
         "window_edges_approx": int(win_edges.item()), "tracks_rank0": n_tracks[0], "timed": "host wall clock, max over ranks"}
     model.train()
