@@ -108,19 +108,19 @@ class GNN(nn.Module):
         a_img = self._affine_attention(self.c2c_att, x_img)        # :148-149
         a_lid = self._affine_attention(self.l2l_att, x_lidar)      # :151-152
         a_rad = self._affine_attention(self.r2r_att, x_radar)      # :154-155
-        if ops.get_precision() == "bf16":
+        if ops.preprojected():
             # pre-projected form: the two 288-wide node-side blocks of att_edge_encoder.0 applied per node
             ae = [m for m in self.att_edge_encoder if isinstance(m, nn.Linear)]
             w0, sens = ae[0].weight, [(a_rad, None), (a_lid, None), (a_img, None)]
-            p_i = ops.fused_mlp(sens, [w0[:, :288]], [ae[0].bias], out_dtype=torch.bfloat16)    # [N,512]
-            p_j = ops.fused_mlp(sens, [w0[:, 288:576]], [None], out_dtype=torch.bfloat16)
-            e0 = e0.to(torch.bfloat16)         # edge-level tensors are kept in bf16 between kernels
+            p_i = ops.fused_mlp(sens, [w0[:, :288]], [ae[0].bias], out_dtype=ops.store_dtype())    # [N,512]
+            p_j = ops.fused_mlp(sens, [w0[:, 288:576]], [None], out_dtype=ops.store_dtype())
+            e0 = e0.to(ops.store_dtype())      # edge-level tensors are kept in bf16 between kernels (bf16 mode)
             if ops.att_edge_encoder_supported(e0, ae):
                 att = ops.att_edge_encoder_block(g, e0, p_i, p_j, w0[:, 576:], ae)      # two fused launches
             else:
                 att = ops.fused_mlp([(e0, None)], [w0[:, 576:]] + [m.weight for m in ae[1:]],
                                     [None] + [m.bias for m in ae[1:]], adds=[(p_i, dst), (p_j, src)],
-                                    out_dtype=torch.bfloat16)
+                                    out_dtype=ops.store_dtype())
         else:
             att_in = [(a_rad, dst), (a_lid, dst), (a_img, dst),    # x_sens_i :161
                       (a_rad, src), (a_lid, src), (a_img, src),    # x_sens_j
@@ -129,10 +129,10 @@ class GNN(nn.Module):
         x_sens = torch.cat([x_img, x_lidar, x_radar], dim=1)       # :172 (C7)
         x0 = ops.run_mlp(self.node_encoder, [(pose, None)])        # :174-176
         x, e = x0, e0
-        invs = self.message_passing.invariants_per_iteration(x0, self.depth) if ops.get_precision() == "bf16" \
+        invs = self.message_passing.invariants_per_iteration(x0, self.depth) if ops.preprojected() \
             else [None] * self.depth
         # att_edge_attr feeds every iteration: one depth-way gradient sum instead of depth-1 additions
-        atts = ops.fanout(att, self.depth) if ops.get_precision() == "bf16" else (att,) * self.depth
+        atts = ops.fanout(att, self.depth) if ops.preprojected() else (att,) * self.depth
         for i in range(self.depth):
             if i % 2 == 0 and self.apply_knn_update:
                 x = knn_attention_conv(self.knn_conv, x, data.node_timestamps)

@@ -139,6 +139,17 @@ def get_precision():
     return _PRECISION
 
 
+def preprojected():
+    """The node-side first-layer blocks are applied per NODE in the bf16 mode and in the tensor-core
+    1e-4 mode; the "exact" (FFMA) mode keeps the reference's per-edge concatenation."""
+    return _PRECISION == "bf16" or (_PRECISION == "fp32" and FEATURES["split_tc"])
+
+
+def store_dtype():
+    """Storage type of edge / node tensors between kernels in the pre-projected formulation."""
+    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+
+
 _weight_epoch = 0        # bumped by invalidate_weight_cache(); part of every derived-weight key
 
 

@@ -68,7 +68,7 @@ class CausalMessagePassing(nn.Module):
         srcs = [eu0.weight, eu0.bias, wf.weight, wf.bias, wp.weight, wp.bias, self.create_future_msgs[2].weight,
                 self.create_future_msgs[2].bias, self.create_past_msgs[2].weight, self.create_past_msgs[2].bias]
         w_cat, b_cat, w_inv, w_post = ops.derived_weights(("mp_stacks", id(self)), srcs, stacks)
-        p_inv = ops.fused_mlp([(x0, None)], [w_inv], [None], out_dtype=torch.bfloat16)  # [N, 2*Hm]
+        p_inv = ops.fused_mlp([(x0, None)], [w_inv], [None], out_dtype=ops.store_dtype())  # [N, 2*Hm]
         inv_all = torch.cat([p_inv.new_zeros(p_inv.size(0), 2 * h1), p_inv], 1)         # [N, 2*H1 + 2*Hm]
         return w_cat, b_cat, inv_all, (h1, hm), w_post
 
@@ -88,7 +88,7 @@ class CausalMessagePassing(nn.Module):
         if inv is None:
             inv = self.project_invariants(x0)
         w_cat, b_cat, inv_all, (h1, hm), w_post = inv
-        lowp = torch.bfloat16
+        lowp = ops.store_dtype()      # bf16 between kernels in the bf16 mode, fp32 in the tf32 x3 (1e-4) mode
         # one node-level GEMM per iteration for all four node-side blocks: [N, H1 | H1 | Hm | Hm]
         p_all = ops.fused_mlp([(x, None)], [w_cat], [b_cat], adds=[(inv_all, None)], out_dtype=lowp)
         p_i, p_j, p_f, p_p = ops.split_cols(p_all, (h1, h1, hm, hm))
@@ -149,7 +149,7 @@ class CausalMessagePassing(nn.Module):
         return x_new, e_out
 
     def forward_graph(self, x, g, e, x0, att=None, inv=None):
-        if ops.get_precision() == "bf16":
+        if ops.preprojected():
             return self.forward_preprojected(x, g, e, x0, att, inv)
         dst, src = g.by_dst, g.by_src
         feats = [(x, dst), (x, src), (e, None)] + ([(att, None)] if att is not None else [])  # :210
@@ -186,7 +186,7 @@ class PoseGNN(nn.Module):
         e = ops.run_mlp(self.edge_encoder, [(ops.edge_attr_rows(data.edge_attr), None)], out_dtype=lowp)   # :67
         x0 = ops.run_mlp(self.node_encoder, [(pose, None)])                          # :68 (C6: once)
         x, x_enc = x0, x0
-        invs = self.message_passing.invariants_per_iteration(x0, self.depth) if ops.get_precision() == "bf16" \
+        invs = self.message_passing.invariants_per_iteration(x0, self.depth) if ops.preprojected() \
             else [None] * self.depth
         for i in range(self.depth):
             if i % 2 == 0 and self.apply_knn_update:
