@@ -72,7 +72,7 @@ class Trainer:
     the flat buffers that the all-reduce and the Adam kernel operate on."""
 
     def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, batch_size=2,
-                 from_logits=False, loss="bce", focal_alpha=0.25, focal_gamma=2.0):
+                 from_logits=False, loss="bce", focal_alpha=0.25, focal_gamma=2.0, data_parallel=True):
         from . import ops
         self.ops = ops
         self.model = model
@@ -83,6 +83,8 @@ class Trainer:
         self.loss, self.focal = loss, (focal_alpha, focal_gamma)
         self.step_no = 0
         self._step_dev = None
+        # data_parallel=False: a rank-local trainer inside a multi-rank job (no gradient all-reduce, no loss re-weighting)
+        self.data_parallel = data_parallel
 
     def _loss(self, data, global_edges, fwd_kwargs):
         ops = self.ops
@@ -93,7 +95,7 @@ class Trainer:
         else:
             loss = ops.bce_loss(out, data.y, getattr(data, "edge_weights", None), batch_size=self.batch_size,
                                 from_logits=self.from_logits)
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        world = dist.get_world_size() if (self.data_parallel and dist.is_available() and dist.is_initialized()) else 1
         if global_edges is not None:
             loss = loss * (out.size(0) / float(global_edges))
         elif world > 1:
@@ -126,7 +128,8 @@ class Trainer:
             self.fp.zero_grad()
             loss = self._loss(data, global_edges, fwd_kwargs)
             loss.backward()
-        allreduce_sum_(self.fp.grad)
+        if self.data_parallel:
+            allreduce_sum_(self.fp.grad)
         self.step_no += 1
         if self._step_dev is not None:      # graph-capturable form: the step number lives on the device
             ops.adam_step_dev(self.fp.flat, self.fp.grad, self.m, self.v, self.lr, self.betas, self.eps, self.wd,

@@ -275,7 +275,7 @@ def extras(a, rank, world, dev, model, d, tm, E_global):
     ops.set_precision("fp32")
     torch.manual_seed(SEED)
     m32 = GNN(None, None, None).to(dev)
-    tr32 = Trainer(m32, batch_size=2)
+    tr32 = Trainer(m32, batch_size=2, data_parallel=False)        # rank-0-only extras: no collectives
     ms = tm.run(lambda: tr32.step(small, **mm_kwargs(small)), 3, 2, reduce=False)
     with torch.no_grad():
         msf = tm.run(lambda: m32(small, **mm_kwargs(small)), 3, 1, reduce=False)
@@ -287,7 +287,7 @@ def extras(a, rank, world, dev, model, d, tm, E_global):
     # ---- configs[0]: poses-only model, forward and forward+backward, 64 scenes and 1 scene
     torch.manual_seed(SEED)
     pm = PoseGNN().to(dev)
-    ptr_ = Trainer(pm, batch_size=2, from_logits=True)
+    ptr_ = Trainer(pm, batch_size=2, from_logits=True, data_parallel=False)
     one = to_dev(synth.add_labels(synth.scene_graph(seed=SEED), SEED), dev)
     one._b3d_graph = ops.Graph(one.edge_index, one.num_nodes)
     res = {}
@@ -310,7 +310,7 @@ def extras(a, rank, world, dev, model, d, tm, E_global):
     one_mm = to_dev(make_batch(0, 1), dev)
     torch.manual_seed(SEED)
     ms_ = GNN(None, None, None).to(dev)
-    trs = Trainer(ms_, batch_size=2)
+    trs = Trainer(ms_, batch_size=2, data_parallel=False)
     res = {}
     for name, dd in (("2_windows", two), ("1_scene", one_mm)):
         dd._b3d_graph = ops.Graph(dd.edge_index, dd.num_nodes)
@@ -382,7 +382,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     from batch3dmot_b200 import _lib, ops, build
     from batch3dmot_b200.clr_att_gnn import GNN
     from batch3dmot_b200.parallel import Trainer
