@@ -12,6 +12,7 @@
 // (tcgen05.mma is asynchronous; tcgen05.commit -> mbarrier frees the stage). Two CTAs per SM
 // overlap one CTA's epilogue with the other's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "b3d_common.cuh"
 #include "tc_common.cuh"
@@ -104,6 +105,7 @@ struct TcArgs {
   int nadd;
   const uint32_t* mask_bits;   // ReLU mask as sign bits: word [(col / 32) * M + row], bit col % 32
   uint32_t* bits_out;          // same layout, written for this layer's (post-activation) output
+  int stage_mask = 0;          // (TMA kernel only) addends staged through shared memory
 };
 
 template <int ACT>
@@ -141,23 +143,32 @@ __device__ __forceinline__ void epilogue_prefetch(const EP& a, long long row, in
     ld64B(reinterpret_cast<const __nv_bfloat16*>(a.out_mask) + row * a.ldm + cbase, pf.u);
     pf.flags |= 1;
   }
-  if (a.nadd > 0 && a.add[0].dtype == B3D_BF16) {
+  if (a.nadd > 0 && a.add[0].dtype == B3D_BF16 && !(a.stage_mask & 1)) {
     const SegDev& S = a.add[0];
     const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(S.ptr) + (long long)g0 * S.ld + cbase;
     if (pf.flags & 1) ld64B(ap, pf.v); else ld64B(ap, pf.u);
     pf.flags |= 2;
   }
-  if (a.nadd > 1 && a.add[1].dtype == B3D_BF16 && !(pf.flags & 1)) {
+  if (a.nadd > 1 && a.add[1].dtype == B3D_BF16 && !(pf.flags & 1) && !(a.stage_mask & 2)) {
     const SegDev& S = a.add[1];
     ld64B(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + (long long)g1 * S.ld + cbase, pf.v);
     pf.flags |= 4;
   }
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// sadd (optional): shared-memory address of THIS row inside the staged tile of addend t (0 = not staged); the
+// 16-byte chunk c of row r sits at chunk position c ^ (r & 7) (conflict-free for the row-per-lane reads).
 template <int ACT, class EP>
 __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int n0, int col0, const uint32_t (&r)[32],
                                                  const float* s_bias, bool plain, bool rz, int nlim,
-                                                 const EpiPrefetch* pf = nullptr) {
+                                                 const EpiPrefetch* pf = nullptr, const uint32_t* sadd = nullptr,
+                                                 int swz = 0) {
   // nlim: first global column this CTA must NOT write (min(Nout, end of its column block))
   using namespace tc;
     float o[32];
@@ -172,6 +183,19 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   }
   for (int t = 0; t < a.nadd; ++t) {   // node-side first-layer blocks, pre-projected per node
     const SegDev& S = a.add[t];
+    if (sadd && sadd[t]) {                // staged in shared memory by the addend producer warps
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = lds128(sadd[t] + (uint32_t)((((col0 >> 3) + q) ^ swz) << 4));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[8 * q + 2 * j] += __uint_as_float(w[j] << 16);
+          o[8 * q + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+      }
+      continue;
+    }
     if (pf && (pf->flags & (2 << t))) {   // already in registers
       const uint4* src = (t == 0 && !(pf->flags & 1)) ? pf->u : pf->v;
 #pragma unroll
@@ -730,7 +754,7 @@ static bool seg_tc_ok(const SegDev& S) {
 // persistent over row tiles; two TMEM accumulators let the epilogue of tile t overlap the MMAs of
 // tile t+1. No thread touches the operands: the staging cost of k_linear_tc disappears.
 constexpr int TMA_STAGES = 4;
-constexpr int TMA_THREADS = 320;   // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
+constexpr int TMA_THREADS = 384;   // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter), warps 10-11 addend rows
 constexpr int WG_THREADS = 192;
 
 // TMA tile::gather4: four rows r0..r3 of a 2D tensor (tensor map encoded with box {64 columns, 1 row}), 64 columns
@@ -765,6 +789,10 @@ struct TmaArgs {
   int nadd;
   const uint32_t* mask_bits;
   uint32_t* bits_out;
+  // Row-gathered bf16 addends staged through shared memory by two producer warps (cp.async of whole addend rows:
+  // coalesced 16-byte chunks, no registers held across the latency) instead of one 32-byte request per epilogue
+  // lane: bit t of stage_mask = addend t is staged; add_bufs buffers of add_slots tiles of add_tile_bytes each.
+  int stage_mask, add_bufs, add_slots, add_tile_bytes, stages;
 };
 
 template <int ACT>
@@ -779,18 +807,24 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
   const uint32_t pad = (1024u - (smem_u32(smem) & 1023u)) & 1023u;   // 128B-swizzled tiles need 1024-byte alignment
   const uint32_t sW = smem_u32(smem) + pad;
   const uint32_t sA = sW + a.nchunks * w_chunk;                 // both multiples of 1024
-  const uint32_t misc = a.nchunks * w_chunk + TMA_STAGES * TC_A_STAGE;
-  const uint32_t sBar = sW + misc;   // full[4] @0, empty[4] @32, accf[2] @64, acce[2] @80, wfull @96, tmem ptr @104
+  const int STG = a.stages;
+  const uint32_t add_buf_bytes = (uint32_t)(a.add_slots * a.add_tile_bytes);
+  const uint32_t sAdd = sA + STG * TC_A_STAGE;                  // staged addend tiles: [add_bufs][add_slots][128 rows][Nb bf16]
+  const uint32_t misc = a.nchunks * w_chunk + STG * TC_A_STAGE + a.add_bufs * add_buf_bytes;
+  // full[4] @0, empty[4] @32, accf[2] @64, acce[2] @80, wfull @96, tmem ptr @104, addf[2] @112, adde[2] @128
+  const uint32_t sBar = sW + misc;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + pad + misc + 104);
-  float* s_bias = reinterpret_cast<float*>(smem + pad + misc + 128);  // [256]
+  float* s_bias = reinterpret_cast<float*>(smem + pad + misc + 160);  // [256]
   const uint32_t ncols = 2 * (uint32_t)a.acc_stride;
 
   if (warp == 1) tmem_alloc(sBar + 104, ncols);
   if (tid == 0) {
-    for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(sBar + 8 * s, 1); mbar_init(sBar + 32 + 8 * s, 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(sBar + 8 * s, 1); mbar_init(sBar + 32 + 8 * s, 1); }
     mbar_init(sBar + 64, 1); mbar_init(sBar + 72, 1);      // accumulator full (tcgen05.commit)
     mbar_init(sBar + 80, 8); mbar_init(sBar + 88, 8);      // accumulator empty (8 epilogue warps)
     mbar_init(sBar + 96, 1);                                // weights resident
+    mbar_init(sBar + 112, 64); mbar_init(sBar + 120, 64);  // staged addends landed (64 producer threads, cp.async arrive)
+    mbar_init(sBar + 128, 8); mbar_init(sBar + 136, 8);    // staged addends consumed (8 epilogue warps)
     fence_mbar_init();
   }
   for (int i = tid; i < 256; i += TMA_THREADS) s_bias[i] = (a.bias && i < a.Nb && n0 + i < a.Nout) ? __ldg(a.bias + n0 + i) : 0.f;
@@ -822,9 +856,9 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
       for (int sg = 0; sg < a.nseg; ++sg) {
         const int sel = a.seg_gsel[sg];
         for (int c = 0; c < a.seg_chunks[sg]; ++c, ++it) {
-          const int s = it % TMA_STAGES;
+          const int s = it % STG;
           if (lane == 0) {
-            if (it >= TMA_STAGES) mbar_wait(sBar + 32 + 8 * s, ((it / TMA_STAGES) - 1) & 1);
+            if (it >= STG) mbar_wait(sBar + 32 + 8 * s, ((it / STG) - 1) & 1);
             mbar_expect_tx(sBar + 8 * s, TC_A_STAGE);
             if (sel < 0) tma_load_2d(sA + s * TC_A_STAGE, &maps.m[sg], c * 64, (int)(tile * TC_BM), sBar + 8 * s);
           }
@@ -847,8 +881,8 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem + (uint32_t)(acc * a.acc_stride);
         for (int c = 0; c < a.nchunks; ++c, ++it) {
-          const int s = it % TMA_STAGES;
-          mbar_wait(sBar + 8 * s, (it / TMA_STAGES) & 1);
+          const int s = it % STG;
+          mbar_wait(sBar + 8 * s, (it / STG) & 1);
           tc_fence_after_sync();
 #pragma unroll
           for (int j = 0; j < TC_BK / 16; ++j)
@@ -859,10 +893,64 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
         mma_commit(sBar + 64 + 8 * acc);      // accumulator ready for the epilogue
       }
     }
+  } else if (warp >= 10) {
+    // Addend producer warps: thread t copies the addend rows of tile rows t and t + 64 (16-byte cp.async chunks, the
+    // chunk index XOR-swizzled by the row so that the epilogue's row-per-lane reads are conflict-free). A warp's 32
+    // consecutive chunks of one row are one coalesced 512-byte request: 4 L1 wavefronts per row instead of the 16 of
+    // the epilogue's 32-byte-per-lane loads, and nothing waits on them but the mbarrier.
+    if (a.stage_mask) {
+      const int t64 = tid - 320;
+      const int chunks = (a.Nb * 2) >> 4;                 // 16-byte chunks per staged row (Nb % 64 == 0: multiple of 8)
+      int tcount = 0;
+      for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+        const int buf = tcount % a.add_bufs;
+        if (tcount >= a.add_bufs) mbar_wait(sBar + 128 + 8 * buf, ((tcount / a.add_bufs) - 1) & 1);
+        int slot = 0;
+        for (int t = 0; t < a.nadd; ++t) {
+          if (!((a.stage_mask >> t) & 1)) continue;
+          const SegDev& S = a.add[t];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int rr = t64 + 64 * h;
+            const long long row = tile * TC_BM + rr;
+            if (row < a.M) {
+              const long long g = S.idx ? (long long)__ldg(S.idx + row) : row;
+              const uint8_t* src = reinterpret_cast<const uint8_t*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + g * S.ld + n0);
+              const uint32_t dst = sAdd + buf * add_buf_bytes + slot * a.add_tile_bytes + (uint32_t)rr * (uint32_t)(a.Nb * 2);
+              for (int c = 0; c < chunks; ++c)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)((c ^ (rr & 7)) << 4)), "l"(src + c * 16)
+                             : "memory");
+            }
+          }
+          ++slot;
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sBar + 112 + 8 * buf) : "memory");
+      }
+    }
   } else {
     const int lq = warp & 3;                  // TMEM lane quarter this warp may access
     const bool plain = !a.out_mask && !a.mask_bits && !a.row_mask && !(a.flags & B3D_FLAG_ACCUMULATE);
     const int cb0 = ((warp - 2) >> 2) * 32;   // the two warps of a quarter interleave 32-column blocks
+    // staged addends: wait for this tile's buffer, address of this lane's row in each staged tile
+    uint32_t sadd[2] = {0u, 0u};
+    auto staged_begin = [&](int tcount) {
+      if (!a.stage_mask) return;
+      const int buf = tcount % a.add_bufs;
+      mbar_wait(sBar + 112 + 8 * buf, (tcount / a.add_bufs) & 1);
+      int slot = 0;
+      for (int t = 0; t < 2; ++t) {
+        sadd[t] = ((a.stage_mask >> t) & 1)
+                      ? sAdd + buf * add_buf_bytes + slot * a.add_tile_bytes + (uint32_t)(lq * 32 + lane) * (uint32_t)(a.Nb * 2)
+                      : 0u;
+        slot += (a.stage_mask >> t) & 1;
+      }
+    };
+    auto staged_end = [&](int tcount) {
+      if (!a.stage_mask) return;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sBar + 128 + 8 * (tcount % a.add_bufs));
+    };
+    const int swz = lane & 7;
     const int nlim = min(a.Nout, n0 + a.Nb);
     const long long lrow = lq * 32 + lane;
     // The global operands of a block (bf16 ReLU mask, row-gathered addends) are requested ONE BLOCK
@@ -887,7 +975,8 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
     // Measured (scripts/epi_probe.py): the look-ahead pays for the gathered addends (L2-resident node
     // tables: 437 -> 380 us on the 64->192 message layer) but not for the dense DRAM-streamed ReLU mask
     // (647 -> 700 us), which keeps the same-block prefetch.
-    if (a.out_mask || a.nadd == 0) {
+    const bool all_staged = a.nadd > 0 && a.stage_mask == (1 << a.nadd) - 1;
+    if (a.out_mask || a.nadd == 0 || all_staged) {
       int tcount = 0;
       for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
         const int acc = tcount & 1;
@@ -897,14 +986,16 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
         if (tcount) gather_rows(tile, cg0, cg1);
         mbar_wait(sBar + 64 + 8 * acc, (tcount >> 1) & 1);
         tc_fence_after_sync();
+        staged_begin(tcount);
         for (int col0 = cb0; col0 < a.Nb; col0 += 64) {
           uint32_t r[32];
           tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
           pfa.flags = 0;
           if (row_ok) epilogue_prefetch(a, row, cg0, cg1, n0 + col0, nlim, pfa);   // global latency overlaps the TMEM load
           tmem_ld_wait();
-          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa);
+          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa, sadd, swz);
         }
+        staged_end(tcount);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(sBar + 80 + 8 * acc);
@@ -923,6 +1014,7 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
       const bool rz = row_ok && a.row_mask && a.row_mask[row] == 0;
       mbar_wait(sBar + 64 + 8 * acc, (tcount >> 1) & 1);
       tc_fence_after_sync();
+      staged_begin(tcount);
       for (int col0 = cb0; col0 < a.Nb; col0 += 64, parity ^= 1) {
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
@@ -934,14 +1026,15 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
           pfb.flags = 0;
           if (p_ok) epilogue_prefetch(a, prow, same ? cg0 : ng0, same ? cg1 : ng1, pcol, nlim, pfb);
           tmem_ld_wait();
-          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa);
+          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa, sadd, swz);
         } else {
           pfa.flags = 0;
           if (p_ok) epilogue_prefetch(a, prow, same ? cg0 : ng0, same ? cg1 : ng1, pcol, nlim, pfa);
           tmem_ld_wait();
-          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfb);
+          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfb, sadd, swz);
         }
       }
+      staged_end(tcount);
       cg0 = ng0; cg1 = ng1; ng0 = fg0; ng1 = fg1;
       tc_fence_before_sync();
       __syncwarp();
@@ -1379,7 +1472,31 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
       return bad_arg("b3d_linear_tma: tensor map A");
   }
   if (make_tmap_bf16(&mW, Wr, Npad, Kpad, Kpad, Nb)) return bad_arg("b3d_linear_tma: tensor map W");
-  size_t smem = (size_t)a.nchunks * Nb * 128 + TMA_STAGES * TC_A_STAGE + 128 + 1024 + 1024;   // + alignment slack
+  // Staging plan for the row-gathered addends (see the producer warps 10-11): prefer double-buffered tiles; all
+  // addends if they fit, else the LAST one (the source-side rows: targets are sorted, so the first addend's rows
+  // repeat along a tile and are cheap to load from the epilogue). The operand ring shrinks to 2 stages for short K
+  // when that buys the second buffer.
+  a.stage_mask = 0; a.add_bufs = 1; a.add_slots = 0; a.add_tile_bytes = TC_BM * Nb * 2; a.stages = TMA_STAGES;
+  {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("B3D_STAGE_ADDENDS"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    bool ok = enabled && nadd > 0 && (Nb % 64) == 0 && (n_logical % Nb) == 0 && y_dtype == B3D_BF16;
+    for (int q = 0; q < nadd; ++q) ok = ok && a.add[q].dtype == B3D_BF16;
+    if (ok) {
+      const long long fixed = (long long)a.nchunks * Nb * 128 + 160 + 1024 + 1024 + 64, tile = a.add_tile_bytes;
+      const long long limit = 227 * 1024;
+      struct { int n, bufs, stages; } opts[] = {{nadd, 2, 4}, {1, 2, 4}, {nadd, 2, 2}, {1, 2, 2}, {nadd, 1, 4}, {1, 1, 4}};
+      for (auto& o : opts) {
+        if (o.stages == 2 && a.nchunks > 2) continue;
+        if (fixed + (long long)o.stages * TC_A_STAGE + (long long)o.n * o.bufs * tile > limit) continue;
+        a.add_slots = o.n; a.add_bufs = o.bufs; a.stages = o.stages;
+        a.stage_mask = o.n == nadd ? (1 << nadd) - 1 : 1 << (nadd - 1);
+        break;
+      }
+    }
+  }
+  size_t smem = (size_t)a.nchunks * Nb * 128 + (size_t)a.stages * TC_A_STAGE + (size_t)a.add_bufs * a.add_slots * a.add_tile_bytes +
+                160 + 1024 + 1024;   // + alignment slack
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_linear_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
