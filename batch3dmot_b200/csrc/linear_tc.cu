@@ -899,28 +899,33 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
     // consecutive chunks of one row are one coalesced 512-byte request: 4 L1 wavefronts per row instead of the 16 of
     // the epilogue's 32-byte-per-lane loads, and nothing waits on them but the mbarrier.
     if (a.stage_mask) {
-      const int t64 = tid - 320;
-      const int chunks = (a.Nb * 2) >> 4;                 // 16-byte chunks per staged row (Nb % 64 == 0: multiple of 8)
+      const int wp = warp - 10;                           // rows wp, wp + 2, ...: one row per warp instruction
+      const int chunks = (a.Nb * 2) >> 4;                 // 16-byte chunks per staged row (Nb % 64 == 0, <= 32)
       int tcount = 0;
       for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
         const int buf = tcount % a.add_bufs;
-        if (tcount >= a.add_bufs) mbar_wait(sBar + 128 + 8 * buf, ((tcount / a.add_bufs) - 1) & 1);
+        if (tcount >= a.add_bufs) {
+          if (lane == 0) mbar_wait(sBar + 128 + 8 * buf, ((tcount / a.add_bufs) - 1) & 1);
+          __syncwarp();
+        }
         int slot = 0;
         for (int t = 0; t < a.nadd; ++t) {
           if (!((a.stage_mask >> t) & 1)) continue;
           const SegDev& S = a.add[t];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int rr = t64 + 64 * h;
-            const long long row = tile * TC_BM + rr;
-            if (row < a.M) {
-              const long long g = S.idx ? (long long)__ldg(S.idx + row) : row;
-              const uint8_t* src = reinterpret_cast<const uint8_t*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + g * S.ld + n0);
-              const uint32_t dst = sAdd + buf * add_buf_bytes + slot * a.add_tile_bytes + (uint32_t)rr * (uint32_t)(a.Nb * 2);
-              for (int c = 0; c < chunks; ++c)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)((c ^ (rr & 7)) << 4)), "l"(src + c * 16)
-                             : "memory");
-            }
+          // source rows of this warp's 64 tile rows: lane l holds rows wp + 2 l and wp + 2 (l + 32)
+          long long r0 = tile * TC_BM + wp + 2 * lane, r1 = r0 + 64;
+          const int g0 = r0 < a.M ? (S.idx ? __ldg(S.idx + r0) : (int)r0) : -1;
+          const int g1 = r1 < a.M ? (S.idx ? __ldg(S.idx + r1) : (int)r1) : -1;
+          const uint32_t dst_t = sAdd + buf * add_buf_bytes + slot * a.add_tile_bytes;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + n0);
+          for (int j = 0; j < 64; ++j) {
+            const int g = __shfl_sync(0xffffffffu, j < 32 ? g0 : g1, j & 31);
+            const int rr = wp + 2 * j;
+            if (g >= 0 && lane < chunks)      // the warp's lanes copy consecutive 16-byte chunks of ONE row: coalesced
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                           ::"r"(dst_t + (uint32_t)rr * (uint32_t)(a.Nb * 2) + (uint32_t)((lane ^ (rr & 7)) << 4)),
+                             "l"(base + (long long)g * S.ld * 2 + lane * 16)
+                           : "memory");
           }
           ++slot;
         }
