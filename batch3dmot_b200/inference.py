@@ -173,25 +173,23 @@ def track_scenes(model, scenes, device, rank=0, world_size=1, multimodal=True, w
     """Scene-sharded inference + track assembly. Returns {scene_id: (track_ids [N] int64, tracks)}
     for the scenes owned by `rank`. Scenes are processed in chunks of at most `max_edges` scene edges (each
     edge sits in ~2.5 windows): per chunk one window cut, one forward, one track assembly. The chunks form a
-    three-stage pipeline: the H2D copies of chunk k+1 run on a copy stream while chunk k is in the model, and the
-    sequential clustering of chunk k-1 runs on a host thread (b3d_hier_tracks_host releases the GIL)."""
+    pipeline on the host side: the copies of chunk k+1 are submitted (asynchronously, from pinned scenes) while
+    chunk k is in the model, and the sequential clustering of chunk k-1 runs on a host thread
+    (b3d_hier_tracks_host releases the GIL)."""
     from concurrent.futures import ThreadPoolExecutor
     costs = [int(s.edge_index.size(1)) for s in scenes]
     mine = lpt_partition(costs, world_size)[rank]
-    groups = chunk_scenes(mine, costs, max_edges)
+    # at least ~4 chunks per rank (when the share is big enough to split) so that the three pipeline stages overlap
+    # also for small shares (many ranks, few scenes each)
+    share = sum(costs[i] for i in mine)
+    groups = chunk_scenes(mine, costs, min(max_edges, max(300_000, -(-share // 4))))
     out = {}
-    cuda = torch.device(device).type == "cuda"
-    copy_stream = torch.cuda.Stream(device=device) if cuda else None
 
     def stage(group):
+        # asynchronous copies from pinned scenes, enqueued on the compute stream behind the previous chunk's kernels:
+        # what overlaps is the HOST side (this chunk's Python / copy submission under the previous chunk's GPU work)
         sub = [scenes[i] for i in group]
-        if copy_stream is None:
-            return sub, collate_scenes(sub, device), None
-        with torch.cuda.stream(copy_stream):
-            u = collate_scenes(sub, device)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return sub, u, ev
+        return sub, collate_scenes(sub, device)
 
     def finish(group, sub, u, fut):
         tid, pos, _ = fut.result()
@@ -204,12 +202,7 @@ def track_scenes(model, scenes, device, rank=0, world_size=1, multimodal=True, w
         staged = stage(groups[0]) if groups else None
         pending = None
         for gi, group in enumerate(groups):
-            sub, u, ev = staged
-            if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)
-                for t in vars(u).values():                     # tensors made on the copy stream, used on this one
-                    if torch.is_tensor(t):
-                        t.record_stream(torch.cuda.current_stream())
+            sub, u = staged
             staged = stage(groups[gi + 1]) if gi + 1 < len(groups) else None
             b = window_batch(u, window)
             if b.n_windows == 0 or b.edge_index.size(1) == 0:

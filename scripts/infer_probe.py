@@ -49,7 +49,7 @@ for rep in range(2):
 # the pipelined public path (pinned scenes, copy stream, host clustering on a worker thread)
 for sc in scenes:
     inference.pin_scene(sc)
-for rep in range(3):
+for rep in range(6):
     t = sync()
     res = inference.track_scenes(model, scenes, dev, want_tracks=False)
     dt = sync() - t
