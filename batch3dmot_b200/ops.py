@@ -242,11 +242,14 @@ _chain_packs = {}
 #   gather_tma bf16 mode: the node-feature operands of the edge layers are row-gathered by the TMA unit
 #              (tile::gather4) straight into the tensor-core tile — the reference's un-projected cat[x_i, x_j, e, att]
 #              form — instead of arriving as epilogue addends of per-node pre-projections.
+#   edge_block the edge side of a message-passing iteration as ONE autograd node with an explicit backward
+#              (ops._MPEdgeBlockG): same kernels in the forward pass, a K-concatenated de' GEMM instead of two
+#              GEMMs + a 3-way sum kernel in the backward pass.
 #   chain      fused MLP chains / edge blocks (chain_tc.cu). Validated (tests/test_gpu_chain.py runs it whatever this
 #              switch says) but OFF in the model path: with one 128-row tile in flight per SM the fused kernel is
 #              bound by the same epilogue work as the per-layer kernels plus the layer-to-layer hand-over latency,
 #              and measured no faster (profiles/r2_chain_kernel.md), so the per-layer TMA kernels stay the default.
-_FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True, "gather_tma": False}
+_FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True, "gather_tma": False, "edge_block": True}
 
 
 def _read_features():
@@ -934,18 +937,26 @@ class _MPEdgeBlockG(torch.autograd.Function):
     blocks — the same gradients as the un-projected function's, at node-level instead of edge-level cost."""
 
     @staticmethod
-    def forward(ctx, g, x, x0, e, att, p_i, p_j, p_f, p_p, W0, b0, W1, b1, W2, b2, Wf, bf_, Wp, bp_, W0e, Wfe, Wpe):
+    def forward(ctx, g, gathered, x, x0, e, att, p_i, p_j, p_f, p_p, W0, b0, W1, b1, W2, b2, Wf, bf_, Wp, bp_, W0e, Wfe, Wpe):
         M, dev, bf = e.size(0), e.device, torch.bfloat16
         train = any(ctx.needs_input_grad)
         dst, src = g.by_dst.idx, g.by_src.idx
         bt = lambda n: new_relu_bits(M, n, dev) if train else None
         b_x1, b_x2, b_f, b_p = bt(W0.size(0)), bt(W1.size(0)), bt(Wf.size(0)), bt(Wp.size(0))
-        ins = [_it(x, dst), _it(x, src), _it(e)] + ([_it(att)] if att is not None else [])
-        x1 = linear_raw(ins, W0, b0, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_x1)
+        dense = [_it(e)] + ([_it(att)] if att is not None else [])
+        if gathered:      # node features row-gathered by the TMA unit into the operand tiles (un-projected first layers)
+            x1 = linear_raw([_it(x, dst), _it(x, src)] + dense, W0, b0, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_x1)
+        else:             # per-node pre-projections as row-gathered epilogue addends
+            x1 = linear_raw(dense, W0e, None, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_x1,
+                            adds=[(p_i, dst), (p_j, src)])
         x2 = linear_raw([_it(x1)], W1, b1, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_x2)
         e_new = linear_raw([_it(x2)], W2, b2, M, L.ACT_NONE, tc=True, out_dtype=bf)
-        h_f = linear_raw([_it(x, dst), _it(e_new), _it(x0, dst)], Wf, bf_, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_f)
-        h_p = linear_raw([_it(x, src), _it(e_new), _it(x0, src)], Wp, bp_, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_p)
+        if gathered:
+            h_f = linear_raw([_it(x, dst), _it(e_new), _it(x0, dst)], Wf, bf_, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_f)
+            h_p = linear_raw([_it(x, src), _it(e_new), _it(x0, src)], Wp, bp_, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_p)
+        else:
+            h_f = linear_raw([_it(e_new)], Wfe, None, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_f, adds=[(p_f, dst)])
+            h_p = linear_raw([_it(e_new)], Wpe, None, M, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=b_p, adds=[(p_p, src)])
         ctx.g, ctx.has_att = g, att is not None
         if train:
             ctx.save_for_backward(e, att if att is not None else e, x1, x2, e_new, b_x1, b_x2, W0e, W1, W2, Wfe, Wpe)
@@ -981,24 +992,29 @@ class _MPEdgeBlockG(torch.autograd.Function):
         dp_p = segment_sum_raw(dhp, g.by_src, out_dtype=bf)
         d_e = dA[:, :e.size(1)]
         d_att = dA[:, e.size(1):] if ctx.has_att else None
-        # inputs: g, x, x0, e, att, p_i, p_j, p_f, p_p, W0, b0, W1, b1, W2, b2, Wf, bf_, Wp, bp_, W0e, Wfe, Wpe
-        return (None, None, None, d_e, d_att, dp_i, dp_j, dp_f, dp_p, None, None, dW1, db1, dW2, db2, None, None, None,
+        # inputs: g, gathered, x, x0, e, att, p_i, p_j, p_f, p_p, W0, b0, W1, b1, W2, b2, Wf, bf_, Wp, bp_, W0e, Wfe, Wpe
+        return (None, None, None, None, d_e, d_att, dp_i, dp_j, dp_f, dp_p, None, None, dW1, db1, dW2, db2, None, None, None,
                 None, dW0e, dWfe, dWpe)
 
 
-def mp_edge_block_gathered_supported(x, e, att):
-    if not FEATURES["gather_tma"] or _PRECISION != "bf16" or e.size(0) < _TC_MIN_ROWS:
+def mp_edge_block_explicit_supported(x, e, att):
+    """The explicit edge block (one autograd node per iteration instead of five chains + two fan-outs): bf16 mode,
+    dense 16-byte aligned bf16 edge tensors. Its forward takes the TMA row gathers when FEATURES["gather_tma"] is on,
+    the per-node addends otherwise; its backward forms de' in ONE K-concatenated GEMM with the direct gradient as an
+    addend (no 3-way sum kernel, one launch instead of two)."""
+    if _PRECISION != "bf16" or e.size(0) < _TC_MIN_ROWS or not FEATURES["edge_block"]:
         return False
     ts = [x, e] + ([att] if att is not None else [])
-    return all(t.dtype == torch.bfloat16 and _al16(t) and t.size(1) % 8 == 0 and t.is_contiguous() for t in ts)
+    return all(t.dtype == torch.bfloat16 and _al16(t) and t.size(1) % 8 == 0 and t.is_contiguous() for t in ts) \
+        and e.size(1) % 64 == 0 and (att is None or att.size(1) % 64 == 0)
 
 
-def mp_edge_block_gathered(g, x, x0, e, att, p_i, p_j, p_f, p_p, eu, lf0, lp0, D, E_):
+def mp_edge_block_explicit(g, x, x0, e, att, p_i, p_j, p_f, p_p, eu, lf0, lp0, D, E_):
     """eu: the three nn.Linear of edge_update; lf0 / lp0: first layers of create_future_msgs / create_past_msgs.
-    Returns (e', h_f, bits_f, h_p, bits_p). The full first-layer weights and biases feed the forward only (this
-    block returns no gradient for them: the node-side blocks and biases get theirs through p_i .. p_p); the
+    Returns (e', h_f, bits_f, h_p, bits_p). The full first-layer weights and biases feed the (gathered) forward only
+    (this block returns no gradient for them: the node-side blocks and biases get theirs through p_i .. p_p); the
     edge-feature column blocks are passed again as views so that their gradients come back from this block."""
-    return _MPEdgeBlockG.apply(g, x, x0, e, att, p_i, p_j, p_f, p_p, eu[0].weight, eu[0].bias,
+    return _MPEdgeBlockG.apply(g, FEATURES["gather_tma"], x, x0, e, att, p_i, p_j, p_f, p_p, eu[0].weight, eu[0].bias,
                                eu[1].weight, eu[1].bias, eu[2].weight, eu[2].bias, lf0.weight, lf0.bias,
                                lp0.weight, lp0.bias, eu[0].weight[:, 2 * D:], lf0.weight[:, D:D + E_],
                                lp0.weight[:, D:D + E_])

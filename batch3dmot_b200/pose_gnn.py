@@ -100,11 +100,11 @@ class CausalMessagePassing(nn.Module):
             e = e.to(lowp)
         lf0, lp0 = self.create_future_msgs[0], self.create_past_msgs[0]
         xb = x if x.dtype == lowp else x.to(lowp)
-        if ops.mp_edge_block_gathered_supported(xb, e, att):
-            # node features row-gathered by the TMA unit into the edge tiles (the reference's cat[x_i, x_j, e, att]
-            # form in the forward pass; gradients still flow through the per-node pre-projections p_*)
+        if ops.mp_edge_block_explicit_supported(xb, e, att):
+            # one autograd node for the edge side of the iteration (explicit backward: ops._MPEdgeBlockG); with the
+            # gather_tma feature its forward gathers the node features by TMA (the reference's cat[x_i, x_j, e, att] form)
             x0b = x0 if x0.dtype == lowp else x0.detach().to(lowp)
-            e_out, h_f, bits_f, h_p, bits_p = ops.mp_edge_block_gathered(g, xb.detach(), x0b, e, att, p_i, p_j, p_f, p_p,
+            e_out, h_f, bits_f, h_p, bits_p = ops.mp_edge_block_explicit(g, xb.detach(), x0b, e, att, p_i, p_j, p_f, p_p,
                                                                          eu, lf0, lp0, D, E_)
             agg = []
             for h, bits, into, wpost in ((h_f, bits_f, src, w_post[0]), (h_p, bits_p, dst, w_post[1])):

@@ -81,6 +81,7 @@ def test_gathered_edge_block_matches_preprojected_path_and_oracle(multimodal):
     res = {}
     for on in (True, False):
         ops.FEATURES["gather_tma"] = on
+        ops.FEATURES["edge_block"] = on
         ops.invalidate_weight_cache()
         torch.manual_seed(5621)
         m = (GNN(None, None, None) if multimodal else PoseGNN()).to(DEV)

@@ -173,3 +173,29 @@ def test_fused_blocks_match_the_per_layer_kernels():
     assert rel_max(res[True][0], res[False][0]) < 1e-2
     for k, gv in res[False][1].items():
         assert fro(res[True][1][k], gv) < 3e-2, k
+
+
+def test_explicit_edge_block_matches_the_chain_of_autograd_nodes():
+    """ops._MPEdgeBlockG (one autograd node per iteration, de' formed by one K-concatenated GEMM with the direct
+    gradient as an addend) against the five fused_mlp chains + fan-out sums it replaces: identical forward values,
+    gradients equal up to the bf16 rounding of differently grouped sums."""
+    data = batch(2, True)
+    d = to_dev(data)
+    res = {}
+    old = ops.FEATURES["edge_block"]
+    try:
+        for on in (True, False):
+            ops.FEATURES["edge_block"] = on
+            ops.invalidate_weight_cache()
+            torch.manual_seed(5621)
+            m = GNN(None, None, None).to(DEV)
+            out, _ = m(d, **mm_kw(d))
+            ops.bce_loss(out, d.y, d.edge_weights, batch_size=2).backward()
+            res[on] = (out.detach().float().cpu(), {k: p.grad.detach().float().cpu() for k, p in m.named_parameters()
+                                                    if p.grad is not None})
+    finally:
+        ops.FEATURES["edge_block"] = old
+    assert torch.equal(res[True][0], res[False][0])          # same forward kernels, same operands
+    assert set(res[True][1]) == set(res[False][1])
+    for k, gv in res[False][1].items():
+        assert fro(res[True][1][k], gv) < 2e-2, k
