@@ -244,12 +244,13 @@ _chain_packs = {}
 #              form — instead of arriving as epilogue addends of per-node pre-projections.
 #   edge_block the edge side of a message-passing iteration as ONE autograd node with an explicit backward
 #              (ops._MPEdgeBlockG): same kernels in the forward pass, a K-concatenated de' GEMM instead of two
-#              GEMMs + a 3-way sum kernel in the backward pass.
+#              GEMMs + a 3-way sum kernel in the backward pass. Measured 110.3 ms/step against 107.2 ms (10 GB less
+#              memory): OFF.
 #   chain      fused MLP chains / edge blocks (chain_tc.cu). Validated (tests/test_gpu_chain.py runs it whatever this
 #              switch says) but OFF in the model path: with one 128-row tile in flight per SM the fused kernel is
 #              bound by the same epilogue work as the per-layer kernels plus the layer-to-layer hand-over latency,
 #              and measured no faster (profiles/r2_chain_kernel.md), so the per-layer TMA kernels stay the default.
-_FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True, "gather_tma": False, "edge_block": True}
+_FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True, "gather_tma": False, "edge_block": False}
 
 
 def _read_features():
