@@ -156,19 +156,12 @@ __device__ __forceinline__ void epilogue_prefetch(const EP& a, long long row, in
   }
 }
 
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-
-// sadd (optional): shared-memory address of THIS row inside the staged tile of addend t (0 = not staged); the
-// 16-byte chunk c of row r sits at chunk position c ^ (r & 7) (conflict-free for the row-per-lane reads).
+// Addends whose bit is set in a.stage_mask never reach the epilogue: the MMA warp adds their staged tiles to the
+// accumulator (k_linear_tma).
 template <int ACT, class EP>
 __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int n0, int col0, const uint32_t (&r)[32],
                                                  const float* s_bias, bool plain, bool rz, int nlim,
-                                                 const EpiPrefetch* pf = nullptr, const uint32_t* sadd = nullptr,
-                                                 int swz = 0) {
+                                                 const EpiPrefetch* pf = nullptr) {
   // nlim: first global column this CTA must NOT write (min(Nout, end of its column block))
   using namespace tc;
     float o[32];
@@ -183,19 +176,7 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
   }
   for (int t = 0; t < a.nadd; ++t) {   // node-side first-layer blocks, pre-projected per node
     const SegDev& S = a.add[t];
-    if (sadd && sadd[t]) {                // staged in shared memory by the addend producer warps
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 v = lds128(sadd[t] + (uint32_t)((((col0 >> 3) + q) ^ swz) << 4));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          o[8 * q + 2 * j] += __uint_as_float(w[j] << 16);
-          o[8 * q + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-        }
-      }
-      continue;
-    }
+    if ((a.stage_mask >> t) & 1) continue;   // already in the accumulator
     if (pf && (pf->flags & (2 << t))) {   // already in registers
       const uint4* src = (t == 0 && !(pf->flags & 1)) ? pf->u : pf->v;
 #pragma unroll
@@ -354,6 +335,60 @@ __device__ __forceinline__ void epilogue_block32(const EP& a, long long row, int
       }
     }
   }
+}
+
+// The common bf16 block of the persistent TMA kernel, with everything the generic block decides per element hoisted
+// out: a full, 32-byte aligned block of a bf16 output whose addends (if any) are already in the accumulator, no row
+// mask, no bf16 activation mask, no accumulate. ~4 instructions per element instead of ~11: integer max as ReLU
+// (exact for every non-NaN input, -0 included), the sign-bit word built with one subtract + one funnel shift per
+// element (x > 0 <=> the integer 0 - bits(x) is negative, for x >= 0), bias only when the layer has one.
+template <int ACT, bool BIAS, bool MASK, bool BITS>
+__device__ __forceinline__ void epilogue_fast32(const uint32_t (&r)[32], const float* sb, uint32_t* bits_out_word,
+                                                uint32_t mword, __nv_bfloat16* yrow) {
+  using namespace tc;
+  uint32_t o[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (BIAS) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + 4 * q);
+      o[4 * q + 0] = __float_as_uint(__uint_as_float(r[4 * q + 0]) + b4.x);
+      o[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + b4.y);
+      o[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + b4.z);
+      o[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + b4.w);
+    } else {
+      o[4 * q + 0] = r[4 * q + 0]; o[4 * q + 1] = r[4 * q + 1]; o[4 * q + 2] = r[4 * q + 2]; o[4 * q + 3] = r[4 * q + 3];
+    }
+  }
+  if (ACT == B3D_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = (uint32_t)max((int)o[j], 0);
+  }
+  if (BITS) {
+    uint32_t word = 0u;
+    if (ACT == B3D_ACT_RELU) {
+#pragma unroll
+      for (int j = 31; j >= 0; --j) word = __funnelshift_l(0u - o[j], word, 1);   // (word << 1) | (o[j] != 0)
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) word |= (__uint_as_float(o[j]) > 0.f) ? (1u << j) : 0u;
+    }
+    *bits_out_word = word;
+  }
+  if (MASK) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)   // test-bit-into-predicate + select: 2 instructions per element
+      asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.b32 p, t, 0;\n\tselp.b32 %0, %0, 0, p;\n\t}"
+          : "+r"(o[j]) : "r"(mword), "r"(1u << j));
+  }
+  uint4 pk[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    pk[q] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]), __uint_as_float(o[8 * q + 1])),
+                       pack_bf16x2(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3])),
+                       pack_bf16x2(__uint_as_float(o[8 * q + 4]), __uint_as_float(o[8 * q + 5])),
+                       pack_bf16x2(__uint_as_float(o[8 * q + 6]), __uint_as_float(o[8 * q + 7])));
+  stg256(yrow, pk[0], pk[1]);
+  stg256(yrow + 16, pk[2], pk[3]);
 }
 
 // split helpers. bf16 pair (weight-gradient kernel): v = hi + lo with hi = bf16(v), lo = bf16(v - hi).
@@ -754,7 +789,17 @@ static bool seg_tc_ok(const SegDev& S) {
 // persistent over row tiles; two TMEM accumulators let the epilogue of tile t overlap the MMAs of
 // tile t+1. No thread touches the operands: the staging cost of k_linear_tc disappears.
 constexpr int TMA_STAGES = 4;
-constexpr int TMA_THREADS = 384;   // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter), warps 10-11 addend rows
+constexpr uint32_t TMA_ID_BYTES = 512;
+// warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter), warps 10.. addend rows. Two builds of the
+// kernel: the general one (2 addend warps, 384 threads x 168 registers: generic epilogue with its look-ahead operand
+// registers) and the LEAN one for layers the host knows to need only the lean epilogue block (bf16 output, addends all
+// staged, sign-bit masks, no ragged column block): 4 addend warps, 448 threads x 128 registers (a scheduler's 16 K
+// registers hold 4 warps of 128).
+constexpr int TMA_FIRST_ADD_WARP = 10;
+template <bool LEAN> struct TmaCfg {
+  static constexpr int ADD_WARPS = LEAN ? 4 : 2;
+  static constexpr int THREADS = 32 * (TMA_FIRST_ADD_WARP + ADD_WARPS);
+};
 constexpr int WG_THREADS = 192;
 
 // TMA tile::gather4: four rows r0..r3 of a 2D tensor (tensor map encoded with box {64 columns, 1 row}), 64 columns
@@ -793,12 +838,103 @@ struct TmaArgs {
   // coalesced 16-byte chunks, no registers held across the latency) instead of one 32-byte request per epilogue
   // lane: bit t of stage_mask = addend t is staged; add_bufs buffers of add_slots tiles of add_tile_bytes each.
   int stage_mask, add_bufs, add_slots, add_tile_bytes, stages;
+  int fast_epi;   // lean epilogue block for plain bf16 layers (B3D_FAST_EPI=0 turns it off for A/B runs)
 };
 
+// One staged addend of one tile, this warp's RPW rows: every instruction copies R rows (lane = chunk c of row
+// j + sub); g0 / g1 hold the source rows of tile rows lane and lane + 32 of the warp's share. Fully unrolled, so that
+// the choice between g0 and g1, the row offsets and the row part of the swizzle are compile-time.
+template <int R, int RPW>
+__device__ __forceinline__ void add_rows(uint32_t dst, const uint8_t* base, uint32_t ldb, uint32_t g0, uint32_t g1, int sub,
+                                         int c, bool on) {
+  const uint32_t x0 = (uint32_t)((c ^ sub) & 7);
+#pragma unroll
+  for (int j = 0; j < RPW; j += R) {
+    const uint32_t gr = __shfl_sync(0xffffffffu, j < 32 ? g0 : g1, (j & 31) + sub);
+    const uint32_t swz = (x0 ^ (uint32_t)(j & 7)) << 4;     // (c ^ (j + sub)) & 7: j is a multiple of R > sub
+    if (on)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                   ::"r"(dst + (uint32_t)j * 128u + swz), "l"(base + (unsigned long long)gr * ldb)
+                   : "memory");
+  }
+}
+
+// Ragged last block of a lean-epilogue layer (fewer than 32 valid columns): the generic block, kept out of line (it
+// is ~2,500 instructions) and loading its own accumulator columns so that no register array crosses the call.
 template <int ACT>
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+__device__ __noinline__ void ragged_block(const TmaArgs& a, uint32_t taddr, long long row, int n0, int col0,
+                                          const float* s_bias, bool plain, int nlim) {
+  uint32_t r[32];
+  tc::tmem_ld32(taddr, r);
+  tc::tmem_ld_wait();
+  if (row < a.M) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, false, nlim, nullptr);
+}
+
+// Epilogue warp of k_linear_tma over this CTA's tiles, lean form (see epilogue_fast32). tm = TMEM address of this
+// warp's lane quarter.
+template <int ACT, bool BIAS, bool MASK, bool BITS, bool RAGGED>
+__device__ __forceinline__ void fast_tiles(const TmaArgs& a, uint32_t tm, uint32_t sBar, const float* s_bias, int n0, int nlim,
+                                           int cb0, long long lrow, int lane, bool plain) {
+  using namespace tc;
+  const long long M = a.M, ntiles = a.ntiles;
+  const int Nb = a.Nb, acc_stride = a.acc_stride, ldy = a.ldy;
+  const uint32_t* mask_bits = a.mask_bits;
+  uint32_t* bits_out = a.bits_out;
+  // sign-bit mask words of this lane's row, one per 32-column block of this warp (at most 4: Nb <= 256), loaded ONE
+  // TILE AHEAD: the words stream from DRAM (each is used once), and a block that waits for its own word pays a full
+  // DRAM latency with only two warps per scheduler to hide it
+  uint32_t mw[4] = {0u, 0u, 0u, 0u}, mwn[4] = {0u, 0u, 0u, 0u};
+  auto load_masks = [&](long long tile, uint32_t (&w)[4]) {
+    const long long row = tile * TC_BM + lrow;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int cbase = n0 + cb0 + 64 * b;
+      w[b] = (tile < ntiles && row < M && cb0 + 64 * b < Nb && cbase + 31 < nlim)
+                 ? __ldg(mask_bits + (long long)(cbase >> 5) * M + row) : 0u;
+    }
+  };
+  if (MASK) load_masks(blockIdx.x, mw);
+  int tcount = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    const int acc = tcount & 1;
+    const long long row = tile * TC_BM + lrow;
+    const bool row_ok = row < M;
+    __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(a.Y) + row * ldy + n0;
+    if (MASK) load_masks(tile + gridDim.x, mwn);
+    mbar_wait(sBar + 64 + 8 * acc, (tcount >> 1) & 1);
+    tc_fence_after_sync();
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int col0 = cb0 + 64 * b;
+      if (col0 >= Nb) break;
+      const int cbase = n0 + col0;
+      const uint32_t taddr = tm + (uint32_t)(acc * acc_stride + col0);
+      if (!RAGGED || cbase + 31 < nlim) {       // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+        if (row_ok)
+          epilogue_fast32<ACT, BIAS, MASK, BITS>(r, s_bias + col0, BITS ? bits_out + (long long)(cbase >> 5) * M + row : nullptr,
+                                                 mw[b], yrow + col0);
+      } else if (RAGGED) {
+        ragged_block<ACT>(a, taddr, row, n0, col0, s_bias, plain, nlim);
+      }
+    }
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sBar + 80 + 8 * acc);
+    if (MASK) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) mw[b] = mwn[b];
+    }
+  }
+}
+
+template <int ACT, bool LEAN>
+__global__ void __launch_bounds__(TmaCfg<LEAN>::THREADS, 1)
 k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUtensorMap mapW,
              const __grid_constant__ TmaArgs a) {
+  constexpr int TMA_THREADS = TmaCfg<LEAN>::THREADS, TMA_ADD_WARPS = TmaCfg<LEAN>::ADD_WARPS;
   extern __shared__ __align__(1024) uint8_t smem[];
   using namespace tc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -809,8 +945,12 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
   const uint32_t sA = sW + a.nchunks * w_chunk;                 // both multiples of 1024
   const int STG = a.stages;
   const uint32_t add_buf_bytes = (uint32_t)(a.add_slots * a.add_tile_bytes);
-  const uint32_t sAdd = sA + STG * TC_A_STAGE;                  // staged addend tiles: [add_bufs][add_slots][128 rows][Nb bf16]
-  const uint32_t misc = a.nchunks * w_chunk + STG * TC_A_STAGE + a.add_bufs * add_buf_bytes;
+  // staged addend tiles: [add_bufs][add_slots][Nb / 64 column groups][128 rows][64 bf16], every group a 128B-swizzled
+  // K-major operand tile (what TMA would write), followed by a 16 x 16 identity (the B operand of the addend MMAs)
+  const uint32_t sAdd = sA + STG * TC_A_STAGE;
+  const uint32_t sId = sAdd + a.add_bufs * add_buf_bytes;
+  const uint32_t id_bytes = a.stage_mask ? TMA_ID_BYTES : 0u;
+  const uint32_t misc = a.nchunks * w_chunk + STG * TC_A_STAGE + a.add_bufs * add_buf_bytes + id_bytes;
   // full[4] @0, empty[4] @32, accf[2] @64, acce[2] @80, wfull @96, tmem ptr @104, addf[2] @112, adde[2] @128
   const uint32_t sBar = sW + misc;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + pad + misc + 104);
@@ -823,9 +963,19 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
     mbar_init(sBar + 64, 1); mbar_init(sBar + 72, 1);      // accumulator full (tcgen05.commit)
     mbar_init(sBar + 80, 8); mbar_init(sBar + 88, 8);      // accumulator empty (8 epilogue warps)
     mbar_init(sBar + 96, 1);                                // weights resident
-    mbar_init(sBar + 112, 64); mbar_init(sBar + 120, 64);  // staged addends landed (64 producer threads, cp.async arrive)
-    mbar_init(sBar + 128, 8); mbar_init(sBar + 136, 8);    // staged addends consumed (8 epilogue warps)
+    mbar_init(sBar + 112, 32 * TMA_ADD_WARPS); mbar_init(sBar + 120, 32 * TMA_ADD_WARPS);  // staged addends landed (all producer threads)
+    mbar_init(sBar + 128, 1); mbar_init(sBar + 136, 1);    // staged addends consumed (tcgen05.commit)
     fence_mbar_init();
+  }
+  if (a.stage_mask) {
+    // B operand of the addend MMAs: a 16 x 16 bf16 identity (row n = output column n of a 16-column group, K index k),
+    // K-major without swizzle: offset(n, k) = (k / 8) * 256 + n * 16 + (k % 8) * 2  (LBO 256, SBO 128; 512 bytes).
+    for (int wi = tid; wi < (int)TMA_ID_BYTES / 4; wi += TMA_THREADS) {
+      const int n = (wi & 63) >> 2, k0 = (wi >> 6) * 8 + (wi & 3) * 2;
+      const uint32_t v = ((k0 == n) ? 0x3F80u : 0u) | ((k0 + 1 == n) ? 0x3F800000u : 0u);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sId + 4u * (uint32_t)wi), "r"(v) : "memory");
+    }
+    fence_proxy_async_smem();
   }
   for (int i = tid; i < 256; i += TMA_THREADS) s_bias[i] = (a.bias && i < a.Nb && n0 + i < a.Nout) ? __ldg(a.bias + n0 + i) : 0.f;
   tc_fence_before_sync();
@@ -873,6 +1023,8 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(TC_BM, (uint32_t)a.Nb, 0, 0);
+      const uint32_t idesc16 = make_idesc_bf16(TC_BM, 16u, 0, 0);
+      const uint64_t id_desc = make_smem_desc(sId, 256, 128);
       mbar_wait(sBar + 96, 0);
       int it = 0, tcount = 0;
       for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
@@ -890,72 +1042,91 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
                         make_smem_desc_sw128(sW + c * w_chunk + j * 32), idesc, (c | j) != 0);
           mma_commit(sBar + 32 + 8 * s);      // stage free once these MMAs have read it
         }
+        if (a.stage_mask) {
+          // Row-gathered addends: D[:, 16-column group] += staged tile[:, same group] * I. The rows were gathered by
+          // the producer warps 10-11 into operand-shaped tiles, so the tensor core (idle > 85 % of the time in these
+          // layers) does the additions and the epilogue never sees an addend: bf16 * 1.0 accumulated in fp32 is exact.
+          const int buf = tcount % a.add_bufs;
+          mbar_wait(sBar + 112 + 8 * buf, (tcount / a.add_bufs) & 1);
+          fence_proxy_async_smem();
+          tc_fence_after_sync();
+          for (int slot = 0; slot < a.add_slots; ++slot) {
+            const uint32_t base = sAdd + buf * add_buf_bytes + slot * a.add_tile_bytes;
+            for (int q = 0; q < (a.Nb >> 6); ++q) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                mma_bf16_ss(d_tmem + (uint32_t)(q * 64 + j * 16), make_smem_desc_sw128(base + q * TC_A_STAGE + j * 32),
+                            id_desc, idesc16, 1u);
+            }
+          }
+          mma_commit(sBar + 128 + 8 * buf);   // addend buffer free once these MMAs have read it
+        }
         mma_commit(sBar + 64 + 8 * acc);      // accumulator ready for the epilogue
       }
     }
-  } else if (warp >= 10) {
-    // Addend producer warps: thread t copies the addend rows of tile rows t and t + 64 (16-byte cp.async chunks, the
-    // chunk index XOR-swizzled by the row so that the epilogue's row-per-lane reads are conflict-free). A warp's 32
-    // consecutive chunks of one row are one coalesced 512-byte request: 4 L1 wavefronts per row instead of the 16 of
-    // the epilogue's 32-byte-per-lane loads, and nothing waits on them but the mbarrier.
+  } else if (warp >= TMA_FIRST_ADD_WARP) {
+    // Addend producer warps: a warp instruction copies whole addend rows — R = 32 / chunks rows per instruction, the
+    // lanes of a row = its consecutive 16-byte chunks (coalesced 256- or 512-byte requests, 2-4 L1 wavefronts per row,
+    // no registers held across the latency) — into tiles shaped like the TMA-written operand tiles: column group
+    // q = chunk / 8 of tile row rr at q * 16 KB + rr * 128, its chunk c at position (c ^ rr) & 7. The MMA warp consumes
+    // them. Completion is signalled by the copies themselves (cp.async.mbarrier.arrive.noinc), so the producers run as
+    // far ahead as the buffers allow. Rows past M copy source row 0 (never stored): the loop has no predicates, and
+    // the row indices of the next tile are loaded while this tile's copies are issued.
     if (a.stage_mask) {
-      const int wp = warp - 10;                           // rows wp, wp + 2, ...: one row per warp instruction
+      const int wp = warp - TMA_FIRST_ADD_WARP;
+      constexpr int RPW = TC_BM / TMA_ADD_WARPS;          // tile rows per producer warp (<= 64: two index registers)
       const int chunks = (a.Nb * 2) >> 4;                 // 16-byte chunks per staged row (Nb % 64 == 0, <= 32)
+      const int R = chunks <= 8 ? 4 : chunks <= 16 ? 2 : 1;   // rows per warp instruction
+      const int sub = lane / (32 / R);                    // this lane's row within the instruction
+      const int c = lane % (32 / R);                      // its chunk
+      const bool on = c < chunks;                         // (a 24-chunk row leaves 8 lanes idle)
+      const uint32_t c_off = (uint32_t)(c >> 3) * TC_A_STAGE;
+      auto load_idx = [&](long long tile, int t, uint32_t& g0, uint32_t& g1) {
+        const SegDev& S = a.add[t];
+        const long long r0 = tile * TC_BM + RPW * wp + lane, r1 = r0 + 32;
+        g0 = (tile < a.ntiles && r0 < a.M && lane < RPW) ? (S.idx ? (uint32_t)__ldg(S.idx + r0) : (uint32_t)r0) : 0u;
+        g1 = (tile < a.ntiles && r1 < a.M && lane + 32 < RPW) ? (S.idx ? (uint32_t)__ldg(S.idx + r1) : (uint32_t)r1) : 0u;
+      };
+      uint32_t g[2][2], gn[2][2];
+      for (int t = 0; t < 2; ++t) {
+        g[t][0] = g[t][1] = 0u;
+        if (t < a.nadd && ((a.stage_mask >> t) & 1)) load_idx(blockIdx.x, t, g[t][0], g[t][1]);
+      }
       int tcount = 0;
       for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
         const int buf = tcount % a.add_bufs;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          gn[t][0] = gn[t][1] = 0u;
+          if (t < a.nadd && ((a.stage_mask >> t) & 1)) load_idx(tile + gridDim.x, t, gn[t][0], gn[t][1]);
+        }
         if (tcount >= a.add_bufs) {
           if (lane == 0) mbar_wait(sBar + 128 + 8 * buf, ((tcount / a.add_bufs) - 1) & 1);
           __syncwarp();
         }
         int slot = 0;
-        for (int t = 0; t < a.nadd; ++t) {
-          if (!((a.stage_mask >> t) & 1)) continue;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (!(t < a.nadd && ((a.stage_mask >> t) & 1))) continue;
           const SegDev& S = a.add[t];
-          // source rows of this warp's 64 tile rows: lane l holds rows wp + 2 l and wp + 2 (l + 32)
-          long long r0 = tile * TC_BM + wp + 2 * lane, r1 = r0 + 64;
-          const int g0 = r0 < a.M ? (S.idx ? __ldg(S.idx + r0) : (int)r0) : -1;
-          const int g1 = r1 < a.M ? (S.idx ? __ldg(S.idx + r1) : (int)r1) : -1;
-          const uint32_t dst_t = sAdd + buf * add_buf_bytes + slot * a.add_tile_bytes;
-          const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + n0);
-          for (int j = 0; j < 64; ++j) {
-            const int g = __shfl_sync(0xffffffffu, j < 32 ? g0 : g1, j & 31);
-            const int rr = wp + 2 * j;
-            if (g >= 0 && lane < chunks)      // the warp's lanes copy consecutive 16-byte chunks of ONE row: coalesced
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                           ::"r"(dst_t + (uint32_t)rr * (uint32_t)(a.Nb * 2) + (uint32_t)((lane ^ (rr & 7)) << 4)),
-                             "l"(base + (long long)g * S.ld * 2 + lane * 16)
-                           : "memory");
-          }
+          const uint32_t dst_t = sAdd + buf * add_buf_bytes + slot * a.add_tile_bytes + c_off + (uint32_t)(RPW * wp + sub) * 128u;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + n0) + c * 16;
+          const uint32_t ldb = (uint32_t)S.ld * 2u;
+          const uint32_t g0 = g[t][0], g1 = g[t][1];
+          if (R == 1) add_rows<1, RPW>(dst_t, base, ldb, g0, g1, sub, c, on);
+          else if (R == 2) add_rows<2, RPW>(dst_t, base, ldb, g0, g1, sub, c, on);
+          else add_rows<4, RPW>(dst_t, base, ldb, g0, g1, sub, c, on);
           ++slot;
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sBar + 112 + 8 * buf) : "memory");
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { g[t][0] = gn[t][0]; g[t][1] = gn[t][1]; }
       }
     }
   } else {
     const int lq = warp & 3;                  // TMEM lane quarter this warp may access
     const bool plain = !a.out_mask && !a.mask_bits && !a.row_mask && !(a.flags & B3D_FLAG_ACCUMULATE);
     const int cb0 = ((warp - 2) >> 2) * 32;   // the two warps of a quarter interleave 32-column blocks
-    // staged addends: wait for this tile's buffer, address of this lane's row in each staged tile
-    uint32_t sadd[2] = {0u, 0u};
-    auto staged_begin = [&](int tcount) {
-      if (!a.stage_mask) return;
-      const int buf = tcount % a.add_bufs;
-      mbar_wait(sBar + 112 + 8 * buf, (tcount / a.add_bufs) & 1);
-      int slot = 0;
-      for (int t = 0; t < 2; ++t) {
-        sadd[t] = ((a.stage_mask >> t) & 1)
-                      ? sAdd + buf * add_buf_bytes + slot * a.add_tile_bytes + (uint32_t)(lq * 32 + lane) * (uint32_t)(a.Nb * 2)
-                      : 0u;
-        slot += (a.stage_mask >> t) & 1;
-      }
-    };
-    auto staged_end = [&](int tcount) {
-      if (!a.stage_mask) return;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sBar + 128 + 8 * (tcount % a.add_bufs));
-    };
-    const int swz = lane & 7;
     const int nlim = min(a.Nout, n0 + a.Nb);
     const long long lrow = lq * 32 + lane;
     // The global operands of a block (bf16 ReLU mask, row-gathered addends) are requested ONE BLOCK
@@ -981,7 +1152,26 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
     // tables: 437 -> 380 us on the 64->192 message layer) but not for the dense DRAM-streamed ReLU mask
     // (647 -> 700 us), which keeps the same-block prefetch.
     const bool all_staged = a.nadd > 0 && a.stage_mask == (1 << a.nadd) - 1;
-    if (a.out_mask || a.nadd == 0 || all_staged) {
+    const bool fast = LEAN || (a.fast_epi && ACT != B3D_ACT_SIGMOID && a.y_bf16 && !a.out_mask && !a.row_mask &&
+                      !(a.flags & B3D_FLAG_ACCUMULATE) && (a.nadd == 0 || all_staged) && (a.ldy & 15) == 0 && al32(a.Y) &&
+                      (n0 & 31) == 0);
+    if (fast) {
+      // bf16 layer whose addends (if any) are already in the accumulator: the lean block (epilogue_fast32),
+      // instantiated per (bias, sign-bit mask, sign-bit output) combination so that no per-block branch is left
+      const int sel = (a.bias ? 1 : 0) | (a.mask_bits ? 2 : 0) | (a.bits_out ? 4 : 0);
+      const uint32_t tm = tmem + ((uint32_t)(lq * 32) << 16);
+      switch (sel) {
+        case 0: fast_tiles<ACT, false, false, false, !LEAN>(a, tm, sBar, s_bias, n0, nlim, cb0, lrow, lane, plain); break;
+        case 1: fast_tiles<ACT, true, false, false, !LEAN>(a, tm, sBar, s_bias, n0, nlim, cb0, lrow, lane, plain); break;
+        case 2: fast_tiles<ACT, false, true, false, !LEAN>(a, tm, sBar, s_bias, n0, nlim, cb0, lrow, lane, plain); break;
+        case 3: fast_tiles<ACT, true, true, false, !LEAN>(a, tm, sBar, s_bias, n0, nlim, cb0, lrow, lane, plain); break;
+        case 4: fast_tiles<ACT, false, false, true, !LEAN>(a, tm, sBar, s_bias, n0, nlim, cb0, lrow, lane, plain); break;
+        case 5: fast_tiles<ACT, true, false, true, !LEAN>(a, tm, sBar, s_bias, n0, nlim, cb0, lrow, lane, plain); break;
+        case 6: fast_tiles<ACT, false, true, true, !LEAN>(a, tm, sBar, s_bias, n0, nlim, cb0, lrow, lane, plain); break;
+        default: fast_tiles<ACT, true, true, true, !LEAN>(a, tm, sBar, s_bias, n0, nlim, cb0, lrow, lane, plain); break;
+      }
+    } else if (LEAN) {
+    } else if (a.out_mask || a.nadd == 0 || all_staged) {
       int tcount = 0;
       for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
         const int acc = tcount & 1;
@@ -991,16 +1181,14 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
         if (tcount) gather_rows(tile, cg0, cg1);
         mbar_wait(sBar + 64 + 8 * acc, (tcount >> 1) & 1);
         tc_fence_after_sync();
-        staged_begin(tcount);
         for (int col0 = cb0; col0 < a.Nb; col0 += 64) {
           uint32_t r[32];
           tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
           pfa.flags = 0;
           if (row_ok) epilogue_prefetch(a, row, cg0, cg1, n0 + col0, nlim, pfa);   // global latency overlaps the TMEM load
           tmem_ld_wait();
-          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa, sadd, swz);
+          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa);
         }
-        staged_end(tcount);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(sBar + 80 + 8 * acc);
@@ -1019,7 +1207,6 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
       const bool rz = row_ok && a.row_mask && a.row_mask[row] == 0;
       mbar_wait(sBar + 64 + 8 * acc, (tcount >> 1) & 1);
       tc_fence_after_sync();
-      staged_begin(tcount);
       for (int col0 = cb0; col0 < a.Nb; col0 += 64, parity ^= 1) {
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.acc_stride + col0), r);
@@ -1031,15 +1218,14 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
           pfb.flags = 0;
           if (p_ok) epilogue_prefetch(a, prow, same ? cg0 : ng0, same ? cg1 : ng1, pcol, nlim, pfb);
           tmem_ld_wait();
-          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa, sadd, swz);
+          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfa);
         } else {
           pfa.flags = 0;
           if (p_ok) epilogue_prefetch(a, prow, same ? cg0 : ng0, same ? cg1 : ng1, pcol, nlim, pfa);
           tmem_ld_wait();
-          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfb, sadd, swz);
+          if (row_ok) epilogue_block32<ACT>(a, row, n0, col0, r, s_bias, plain, rz, nlim, &pfb);
         }
       }
-      staged_end(tcount);
       cg0 = ng0; cg1 = ng1; ng0 = fg0; ng1 = fg1;
       tc_fence_before_sync();
       __syncwarp();
@@ -1455,7 +1641,7 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   if (Nb > TC_NMAX) Nb = TC_NMAX;
   if (Nb > round_up(Npad, gran)) Nb = round_up(Npad, gran);
   if (Nb < gran) return bad_arg("b3d_linear_tma: K too large for a resident weight block");
-  const int ny = (Npad + Nb - 1) / Nb;
+  int ny = (Npad + Nb - 1) / Nb;
   Nb = round_up((Npad + ny - 1) / ny, gran);      // balance the column blocks
   a.Nb = Nb;
   a.acc_stride = (int)tmem_cols_for(Nb);
@@ -1476,37 +1662,70 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
     if (make_tmap_bf16(&maps.m[s], seg[src].ptr, rows, seg[src].width, seg[src].ld, seg[src].idx ? 1 : TC_BM))
       return bad_arg("b3d_linear_tma: tensor map A");
   }
-  if (make_tmap_bf16(&mW, Wr, Npad, Kpad, Kpad, Nb)) return bad_arg("b3d_linear_tma: tensor map W");
   // Staging plan for the row-gathered addends (see the producer warps 10-11): prefer double-buffered tiles; all
   // addends if they fit, else the LAST one (the source-side rows: targets are sorted, so the first addend's rows
   // repeat along a tile and are cheap to load from the epilogue). The operand ring shrinks to 2 stages for short K
   // when that buys the second buffer.
   a.stage_mask = 0; a.add_bufs = 1; a.add_slots = 0; a.add_tile_bytes = TC_BM * Nb * 2; a.stages = TMA_STAGES;
   {
-    static int enabled = -1;
+    static int enabled = -1, split = -1, fast = -1;
     if (enabled < 0) { const char* e = getenv("B3D_STAGE_ADDENDS"); enabled = (e && e[0] == '0') ? 0 : 1; }
-    bool ok = enabled && nadd > 0 && (Nb % 64) == 0 && (n_logical % Nb) == 0 && y_dtype == B3D_BF16;
+    if (split < 0) { const char* e = getenv("B3D_STAGE_SPLIT"); split = (e && e[0] == '0') ? 0 : 1; }
+    if (fast < 0) { const char* e = getenv("B3D_FAST_EPI"); fast = (e && e[0] == '0') ? 0 : 1; }
+    a.fast_epi = fast;
+    bool ok = enabled && nadd > 0 && y_dtype == B3D_BF16;
     for (int q = 0; q < nadd; ++q) ok = ok && a.add[q].dtype == B3D_BF16;
+    const long long limit = 227 * 1024;
+    auto fits = [&](int nb, int n, int bufs, int stages) {
+      return (long long)a.nchunks * nb * 128 + 160 + 1024 + 1024 + 64 + TMA_ID_BYTES + (long long)stages * TC_A_STAGE +
+                 (long long)n * bufs * TC_BM * nb * 2 <= limit;
+    };
+    // narrower column blocks when that lets EVERY addend be staged and double-buffered (the operand tile is then read
+    // once per column block, from L2 after the first): all addends in the accumulator = the lean epilogue
+    const int st_min = a.nchunks > 2 ? 4 : 2;
+    if (ok && split && (n_logical % 64) == 0 && (Nb % 64) == 0 && !fits(Nb, nadd, 2, st_min)) {
+      for (int nb = Nb - 64; nb >= 64; nb -= 64) {
+        if ((n_logical % nb) || !fits(nb, nadd, 2, st_min)) continue;
+        Nb = nb;
+        ny = n_logical / nb;
+        break;
+      }
+    }
+    a.Nb = Nb;
+    a.acc_stride = (int)tmem_cols_for(Nb);
+    a.add_tile_bytes = TC_BM * Nb * 2;
+    ok = ok && (Nb % 64) == 0 && (n_logical % Nb) == 0;
     if (ok) {
-      const long long fixed = (long long)a.nchunks * Nb * 128 + 160 + 1024 + 1024 + 64, tile = a.add_tile_bytes;
-      const long long limit = 227 * 1024;
-      struct { int n, bufs, stages; } opts[] = {{nadd, 2, 4}, {1, 2, 4}, {nadd, 2, 2}, {1, 2, 2}, {nadd, 1, 4}, {1, 1, 4}};
+      // all addends staged (lean epilogue) before a partial plan; double-buffered before single
+      struct { int n, bufs, stages; } opts[] = {{nadd, 2, 4}, {nadd, 2, 2}, {nadd, 1, 4}, {nadd, 1, 2},
+                                                {1, 2, 4}, {1, 2, 2}, {1, 1, 4}, {0, 0, 0}};
+      static int forced[3] = {-1, 0, 0};
+      if (forced[0] == -1) {
+        forced[0] = 0;
+        const char* e = getenv("B3D_STAGE_PLAN");       // "n,bufs,stages": experiments only
+        if (e && sscanf(e, "%d,%d,%d", &forced[0], &forced[1], &forced[2]) != 3) forced[0] = 0;
+      }
+      if (forced[0] > 0 && forced[0] <= nadd) opts[0] = {forced[0] == 2 ? nadd : 1, forced[1], forced[2]};
       for (auto& o : opts) {
+        if (o.n == 0) break;
         if (o.stages == 2 && a.nchunks > 2) continue;
-        if (fixed + (long long)o.stages * TC_A_STAGE + (long long)o.n * o.bufs * tile > limit) continue;
+        if (!fits(Nb, o.n, o.bufs, o.stages)) continue;
         a.add_slots = o.n; a.add_bufs = o.bufs; a.stages = o.stages;
         a.stage_mask = o.n == nadd ? (1 << nadd) - 1 : 1 << (nadd - 1);
         break;
       }
     }
   }
+  if (make_tmap_bf16(&mW, Wr, Npad, Kpad, Kpad, Nb)) return bad_arg("b3d_linear_tma: tensor map W");
   size_t smem = (size_t)a.nchunks * Nb * 128 + (size_t)a.stages * TC_A_STAGE + (size_t)a.add_bufs * a.add_slots * a.add_tile_bytes +
-                160 + 1024 + 1024;   // + alignment slack
+                (a.stage_mask ? TMA_ID_BYTES : 0) + 160 + 1024 + 1024;   // + alignment slack
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_linear_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_linear_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_linear_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail("k_linear_tma smem attr", e);
     attr_set = true;
   }
@@ -1522,9 +1741,15 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   if (gx > a.ntiles) gx = a.ntiles;
   dim3 grid((unsigned)gx, (unsigned)ny);
   cudaStream_t st = (cudaStream_t)stream;
-  if (act == B3D_ACT_RELU) k_linear_tma<1><<<grid, TMA_THREADS, smem, st>>>(maps, mW, a);
-  else if (act == B3D_ACT_SIGMOID) k_linear_tma<2><<<grid, TMA_THREADS, smem, st>>>(maps, mW, a);
-  else k_linear_tma<0><<<grid, TMA_THREADS, smem, st>>>(maps, mW, a);
+  // the LEAN build when every block of every CTA is a lean block (see TmaCfg)
+  const bool lean = a.fast_epi && act != B3D_ACT_SIGMOID && a.y_bf16 && !a.out_mask && !a.row_mask &&
+                    !(flags & B3D_FLAG_ACCUMULATE) && (nadd == 0 || a.stage_mask == (1 << nadd) - 1) && (ldy & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(Y) & 31) == 0 && (Nb & 31) == 0 && (n_logical % Nb) == 0;
+  if (lean && act == B3D_ACT_RELU) k_linear_tma<1, true><<<grid, TmaCfg<true>::THREADS, smem, st>>>(maps, mW, a);
+  else if (lean) k_linear_tma<0, true><<<grid, TmaCfg<true>::THREADS, smem, st>>>(maps, mW, a);
+  else if (act == B3D_ACT_RELU) k_linear_tma<1, false><<<grid, TmaCfg<false>::THREADS, smem, st>>>(maps, mW, a);
+  else if (act == B3D_ACT_SIGMOID) k_linear_tma<2, false><<<grid, TmaCfg<false>::THREADS, smem, st>>>(maps, mW, a);
+  else k_linear_tma<0, false><<<grid, TmaCfg<false>::THREADS, smem, st>>>(maps, mW, a);
   B3D_LAUNCH_CHECK("k_linear_tma");
   return 0;
 }

@@ -32,6 +32,26 @@ x64b = torch.randn(E, 64, device=dev).to(bf)
 cases["fwd [64|64]->256 + 2 gathered addends + relu + bits"] = lambda: ops.linear_raw(
     [(x64, None, None, 0), (x64b, None, None, 0)], W2, None, E, L.ACT_RELU, tc=True, out_dtype=bf,
     adds=[(pi, idx), (pj, src_idx)], bits_out=bits)
+# input-gradient layers of the backward pass with the producing layer's ReLU mask as sign bits
+bits256 = ops.new_relu_bits(E, 256, dev); bits256.random_(-2**31, 2**31 - 1)
+bits128 = ops.new_relu_bits(E, 128, dev); bits128.random_(-2**31, 2**31 - 1)
+W64 = torch.randn(64, 128, device=dev) * 0.05          # Linear(128 -> 64): dgrad 64 -> 128
+cases["dgrad 128->256 + sign-bit mask"] = lambda: ops.linear_raw([(x128, None, None, 0)], W, None, E, trans_w=True, mask_bits=bits256, tc=True, out_dtype=bf)
+cases["dgrad 64->128 + sign-bit mask"] = lambda: ops.linear_raw([(x64, None, None, 0)], W64, None, E, trans_w=True, mask_bits=bits128, tc=True, out_dtype=bf)
+cases["fwd 64->192 + gathered addend + relu + bits"] = lambda: ops.linear_raw([(x64, None, None, 0)], Wm, None, E, L.ACT_RELU, tc=True, out_dtype=bf, adds=[(p, idx)], bits_out=ops.new_relu_bits(E, 192, dev))
+# att_edge_encoder first layer: 64 -> 512, two gathered addends
+W5 = torch.randn(512, 64, device=dev) * 0.05
+qi, qj = torch.randn(N, 512, device=dev).to(bf), torch.randn(N, 512, device=dev).to(bf)
+bits512 = ops.new_relu_bits(E, 512, dev)
+cases["fwd 64->512 + 2 gathered addends + relu + bits"] = lambda: ops.linear_raw(
+    [(x64, None, None, 0)], W5, None, E, L.ACT_RELU, tc=True, out_dtype=bf, adds=[(qi, idx), (qj, src_idx)], bits_out=bits512)
+bias128 = torch.randn(128, device=dev)
+cases["plain fwd 256->128 + bias + bits"] = lambda: ops.linear_raw([(x256, None, None, 0)], W, bias128, E, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=bits128)
+cases["fwd 64->192 relu, no addend"] = lambda: ops.linear_raw([(x64, None, None, 0)], Wm, None, E, L.ACT_RELU, tc=True, out_dtype=bf)
+pd = torch.randn(E, 192, device=dev).to(bf)
+cases["fwd 64->192 relu + dense addend"] = lambda: ops.linear_raw([(x64, None, None, 0)], Wm, None, E, L.ACT_RELU, tc=True, out_dtype=bf, adds=[(pd, None)])
+cases["fwd 64->256 relu, no addend"] = lambda: ops.linear_raw([(x64, None, None, 0)], W2[:, :64].contiguous(), None, E, L.ACT_RELU, tc=True, out_dtype=bf)
+cases["fwd 64->128 relu, no addend"] = lambda: ops.linear_raw([(x64, None, None, 0)], W64.t().contiguous(), None, E, L.ACT_RELU, tc=True, out_dtype=bf)
 only = sys.argv[2] if len(sys.argv) > 2 else None
 if only:
     cases = {k: v for k, v in cases.items() if only in k}
