@@ -909,6 +909,7 @@ __device__ __forceinline__ void fast_tiles(const TmaArgs& a, uint32_t tm, uint32
       if (col0 >= Nb) break;
       const int cbase = n0 + col0;
       const uint32_t taddr = tm + (uint32_t)(acc * acc_stride + col0);
+      if (!RAGGED && cbase >= nlim) break;      // column block past the last output column (N % Nb != 0)
       if (!RAGGED || cbase + 31 < nlim) {       // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr, r);
@@ -1744,7 +1745,7 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   // the LEAN build when every block of every CTA is a lean block (see TmaCfg)
   const bool lean = a.fast_epi && act != B3D_ACT_SIGMOID && a.y_bf16 && !a.out_mask && !a.row_mask &&
                     !(flags & B3D_FLAG_ACCUMULATE) && (nadd == 0 || a.stage_mask == (1 << nadd) - 1) && (ldy & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(Y) & 31) == 0 && (Nb & 31) == 0 && (n_logical % Nb) == 0;
+                    (reinterpret_cast<uintptr_t>(Y) & 31) == 0 && (Nb & 31) == 0 && (n_logical & 31) == 0;
   if (lean && act == B3D_ACT_RELU) k_linear_tma<1, true><<<grid, TmaCfg<true>::THREADS, smem, st>>>(maps, mW, a);
   else if (lean) k_linear_tma<0, true><<<grid, TmaCfg<true>::THREADS, smem, st>>>(maps, mW, a);
   else if (act == B3D_ACT_RELU) k_linear_tma<1, false><<<grid, TmaCfg<false>::THREADS, smem, st>>>(maps, mW, a);
@@ -1757,7 +1758,7 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
 extern "C" size_t b3d_wgrad_tma_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {
   // worst case: one split per 512 rows is never exceeded by the plan below
   long long tiles = (long long)((Nout + TC_BM - 1) / TC_BM) * ((round_up(K, 64) / 64 + 3) / 4);
-  long long S = (148 + tiles - 1) / tiles;
+  long long S = (148 + tiles - 1) / tiles;   // upper bound of the launch plan's split count
   long long smax = (M + 1023) / 1024;
   if (S > smax) S = smax;
   if (S < 1) S = 1;
@@ -1786,7 +1787,7 @@ extern "C" int b3d_wgrad_tma(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t
   a.Ktot = K; a.Nout = Nout; a.M = M;
   a.ktiles = (a.ngroups_total + 3) / 4;
   long long tiles = (long long)((Nout + TC_BM - 1) / TC_BM) * a.ktiles;
-  long long S = (148 + tiles - 1) / tiles;
+  long long S = 148 / tiles;          // ONE wave: S * tiles <= 148 CTAs (rounding up put 150 CTAs on 148 SMs)
   long long smax = (M + 1023) / 1024;
   if (S > smax) S = smax;
   if (S < 1) S = 1;

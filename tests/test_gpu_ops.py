@@ -94,6 +94,29 @@ def test_segment_sum_empty_and_isolated():
     assert torch.equal(ops.gather_rows_raw(got.to(DEV), G.dst32).cpu(), got[ei[1]])
 
 
+@pytest.mark.parametrize("C", [64, 96, 192, 256, 512])
+@pytest.mark.parametrize("src_bf16", [True, False])
+def test_gather_rows_bf16_with_relu_masks(C, src_bf16):
+    """Backward of a bf16 segment sum: out[r] = src[idx[r]] (rounded to bf16), zeroed where the ReLU mask says so; the
+    mask as sign bits (B3D_BITS words) or as the bf16 activation itself; M not a multiple of the rows per warp."""
+    torch.manual_seed(C)
+    N, M = 333, 10007
+    src = torch.randn(N, C)
+    src = src.to(torch.bfloat16) if src_bf16 else src
+    idx = torch.randint(0, N, (M,), dtype=torch.int32)
+    act = torch.randn(M, C).to(torch.bfloat16)
+    keep = act > 0
+    words = (keep.reshape(M, C // 32, 32).to(torch.int64) << torch.arange(32)).sum(2).t().contiguous()
+    bits = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).to(DEV)
+    ref = src[idx.long()].to(torch.bfloat16)
+    got = ops.gather_rows_raw(src.to(DEV), idx.to(DEV), out_dtype=torch.bfloat16)
+    assert torch.equal(got.cpu(), ref)
+    got = ops.gather_rows_raw(src.to(DEV), idx.to(DEV), out_dtype=torch.bfloat16, relu_bits=bits)
+    assert torch.equal(got.cpu(), ref * keep)
+    got = ops.gather_rows_raw(src.to(DEV), idx.to(DEV), out_dtype=torch.bfloat16, relu_mask=act.to(DEV))
+    assert torch.equal(got.cpu(), ref * keep)
+
+
 # ------------------------------------------------------------------ dense layers
 @pytest.mark.parametrize("widths,n_out,gather", [((48, 48, 32), 96, True), ((96, 96, 64, 64), 256, True),
                                                 ((19,), 24, False), ((4,), 8, False), ((64,), 1, False),
