@@ -790,6 +790,7 @@ static bool seg_tc_ok(const SegDev& S) {
 // tile t+1. No thread touches the operands: the staging cost of k_linear_tc disappears.
 constexpr int TMA_STAGES = 4;
 constexpr uint32_t TMA_ID_BYTES = 512;
+constexpr int TMA_BAR_BYTES = 208;     // mbarriers + TMEM pointer of k_linear_tma (the bias follows)
 // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter), warps 10.. addend rows. Two builds of the
 // kernel: the general one (2 addend warps, 384 threads x 168 registers: generic epilogue with its look-ahead operand
 // registers) and the LEAN one for layers the host knows to need only the lean epilogue block (bf16 output, addends all
@@ -952,15 +953,18 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
   const uint32_t sId = sAdd + a.add_bufs * add_buf_bytes;
   const uint32_t id_bytes = a.stage_mask ? TMA_ID_BYTES : 0u;
   const uint32_t misc = a.nchunks * w_chunk + STG * TC_A_STAGE + a.add_bufs * add_buf_bytes + id_bytes;
-  // full[4] @0, empty[4] @32, accf[2] @64, acce[2] @80, wfull @96, tmem ptr @104, addf[2] @112, adde[2] @128
+  // full[0..3] @0, empty[0..3] @32, accf[2] @64, acce[2] @80, wfull @96, tmem ptr @104, addf[2] @112, adde[2] @128,
+  // full[4..7] @144, empty[4..7] @176 (operand rings of up to 8 stages), bias @TMA_BAR_BYTES
   const uint32_t sBar = sW + misc;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + pad + misc + 104);
-  float* s_bias = reinterpret_cast<float*>(smem + pad + misc + 160);  // [256]
+  float* s_bias = reinterpret_cast<float*>(smem + pad + misc + TMA_BAR_BYTES);  // [256]
+  auto bar_full = [&](int s) { return sBar + (uint32_t)(s < 4 ? 8 * s : 144 + 8 * (s - 4)); };
+  auto bar_empty = [&](int s) { return sBar + (uint32_t)(s < 4 ? 32 + 8 * s : 176 + 8 * (s - 4)); };
   const uint32_t ncols = 2 * (uint32_t)a.acc_stride;
 
   if (warp == 1) tmem_alloc(sBar + 104, ncols);
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(sBar + 8 * s, 1); mbar_init(sBar + 32 + 8 * s, 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     mbar_init(sBar + 64, 1); mbar_init(sBar + 72, 1);      // accumulator full (tcgen05.commit)
     mbar_init(sBar + 80, 8); mbar_init(sBar + 88, 8);      // accumulator empty (8 epilogue warps)
     mbar_init(sBar + 96, 1);                                // weights resident
@@ -1009,14 +1013,14 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
         for (int c = 0; c < a.seg_chunks[sg]; ++c, ++it) {
           const int s = it % STG;
           if (lane == 0) {
-            if (it >= STG) mbar_wait(sBar + 32 + 8 * s, ((it / STG) - 1) & 1);
-            mbar_expect_tx(sBar + 8 * s, TC_A_STAGE);
-            if (sel < 0) tma_load_2d(sA + s * TC_A_STAGE, &maps.m[sg], c * 64, (int)(tile * TC_BM), sBar + 8 * s);
+            if (it >= STG) mbar_wait(bar_empty(s), ((it / STG) - 1) & 1);
+            mbar_expect_tx(bar_full(s), TC_A_STAGE);
+            if (sel < 0) tma_load_2d(sA + s * TC_A_STAGE, &maps.m[sg], c * 64, (int)(tile * TC_BM), bar_full(s));
           }
           if (sel >= 0) {
             __syncwarp();      // the stage is free and its transaction count armed before any lane writes into it
             tma_gather4(sA + s * TC_A_STAGE + lane * 512, &maps.m[sg], c * 64, g[sel][0], g[sel][1], g[sel][2], g[sel][3],
-                        sBar + 8 * s);
+                        bar_full(s));
           }
         }
       }
@@ -1035,13 +1039,13 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
         const uint32_t d_tmem = tmem + (uint32_t)(acc * a.acc_stride);
         for (int c = 0; c < a.nchunks; ++c, ++it) {
           const int s = it % STG;
-          mbar_wait(sBar + 8 * s, (it / STG) & 1);
+          mbar_wait(bar_full(s), (it / STG) & 1);
           tc_fence_after_sync();
 #pragma unroll
           for (int j = 0; j < TC_BK / 16; ++j)
             mma_bf16_ss(d_tmem, make_smem_desc_sw128(sA + s * TC_A_STAGE + j * 32),
                         make_smem_desc_sw128(sW + c * w_chunk + j * 32), idesc, (c | j) != 0);
-          mma_commit(sBar + 32 + 8 * s);      // stage free once these MMAs have read it
+          mma_commit(bar_empty(s));      // stage free once these MMAs have read it
         }
         if (a.stage_mask) {
           // Row-gathered addends: D[:, 16-column group] += staged tile[:, same group] * I. The rows were gathered by
@@ -1638,12 +1642,31 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   // weight block resident in shared memory: Nb * Kpad * 2 <= 144 KB. Sign-bit words cover 32 columns,
   // so with bit masks every column block must start on a word boundary (granularity 32 instead of 16).
   const int gran = (relu_bits_out || mask_dtype == B3D_BITS) ? 32 : 16;
-  int Nb = (144 * 1024 / (Kpad * 2)) / gran * gran;
-  if (Nb > TC_NMAX) Nb = TC_NMAX;
-  if (Nb > round_up(Npad, gran)) Nb = round_up(Npad, gran);
+  auto plan_nb = [&](int budget_kb, int* ny_out) {
+    int nb = (budget_kb * 1024 / (Kpad * 2)) / gran * gran;
+    if (nb > TC_NMAX) nb = TC_NMAX;
+    if (nb > round_up(Npad, gran)) nb = round_up(Npad, gran);
+    if (nb < gran) { *ny_out = 0; return 0; }
+    const int y = (Npad + nb - 1) / nb;
+    *ny_out = y;
+    return round_up((Npad + y - 1) / y, gran);      // balance the column blocks
+  };
+  int ny = 0;
+  int Nb = plan_nb(144, &ny);
+  // Long-K layers (K >= 384): a 192 KB weight block with a 2-stage operand ring when that means fewer column blocks,
+  // i.e. fewer passes over the [M, K] operand (512 -> 384: 2 instead of 3; 384 -> 256: 1 instead of 2).
+  int wide_stages = 0;
+  {
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("B3D_TMA_WIDE"); wide = (e && e[0] == '1') ? 1 : 0; }   // measured slower: opt-in
+    int ny2 = 0;
+    const int nb2 = wide ? plan_nb(192, &ny2) : 0;
+    if (nb2 && ny2 < ny && nadd == 0 &&
+        (long long)(Kpad / TC_BK) * nb2 * 128 + 2 * TC_A_STAGE + TMA_BAR_BYTES + 1024 + 1024 + 64 <= 227 * 1024) {
+      Nb = nb2; ny = ny2; wide_stages = 2;
+    }
+  }
   if (Nb < gran) return bad_arg("b3d_linear_tma: K too large for a resident weight block");
-  int ny = (Npad + Nb - 1) / Nb;
-  Nb = round_up((Npad + ny - 1) / ny, gran);      // balance the column blocks
   a.Nb = Nb;
   a.acc_stride = (int)tmem_cols_for(Nb);
   a.ntiles = ceil_div(M, TC_BM);
@@ -1667,7 +1690,8 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   // addends if they fit, else the LAST one (the source-side rows: targets are sorted, so the first addend's rows
   // repeat along a tile and are cheap to load from the epilogue). The operand ring shrinks to 2 stages for short K
   // when that buys the second buffer.
-  a.stage_mask = 0; a.add_bufs = 1; a.add_slots = 0; a.add_tile_bytes = TC_BM * Nb * 2; a.stages = TMA_STAGES;
+  a.stage_mask = 0; a.add_bufs = 1; a.add_slots = 0; a.add_tile_bytes = TC_BM * Nb * 2;
+  a.stages = wide_stages ? wide_stages : TMA_STAGES;
   {
     static int enabled = -1, split = -1, fast = -1;
     if (enabled < 0) { const char* e = getenv("B3D_STAGE_ADDENDS"); enabled = (e && e[0] == '0') ? 0 : 1; }
@@ -1678,7 +1702,7 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
     for (int q = 0; q < nadd; ++q) ok = ok && a.add[q].dtype == B3D_BF16;
     const long long limit = 227 * 1024;
     auto fits = [&](int nb, int n, int bufs, int stages) {
-      return (long long)a.nchunks * nb * 128 + 160 + 1024 + 1024 + 64 + TMA_ID_BYTES + (long long)stages * TC_A_STAGE +
+      return (long long)a.nchunks * nb * 128 + TMA_BAR_BYTES + 1024 + 1024 + 64 + TMA_ID_BYTES + (long long)stages * TC_A_STAGE +
                  (long long)n * bufs * TC_BM * nb * 2 <= limit;
     };
     // narrower column blocks when that lets EVERY addend be staged and double-buffered (the operand tile is then read
@@ -1718,8 +1742,20 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
     }
   }
   if (make_tmap_bf16(&mW, Wr, Npad, Kpad, Kpad, Nb)) return bad_arg("b3d_linear_tma: tensor map W");
-  size_t smem = (size_t)a.nchunks * Nb * 128 + (size_t)a.stages * TC_A_STAGE + (size_t)a.add_bufs * a.add_slots * a.add_tile_bytes +
-                (a.stage_mask ? TMA_ID_BYTES : 0) + 160 + 1024 + 1024;   // + alignment slack
+  // the operand ring takes what is left, up to 8 stages: the ring is the bytes in flight per SM, and a long-K tile
+  // (512 -> 384: 128 KB of operand per tile visit) is bound by ring size / TMA latency, not by L2 or HBM bandwidth
+  const size_t rest = (size_t)a.nchunks * Nb * 128 + (size_t)a.add_bufs * a.add_slots * a.add_tile_bytes +
+                      (a.stage_mask ? TMA_ID_BYTES : 0) + TMA_BAR_BYTES + 1024 + 1024;   // + alignment slack
+  {
+    static int deep = -1;
+    if (deep < 0) { const char* e = getenv("B3D_TMA_DEEP"); deep = (e && e[0] == '0') ? 0 : 1; }
+    if (deep && !wide_stages && a.nchunks >= 4) {      // short-K layers measured no faster / slower with a deeper ring
+      int st = (int)((227 * 1024 - (long long)rest) / TC_A_STAGE);
+      if (st > 8) st = 8;
+      if (st > a.stages) a.stages = st;
+    }
+  }
+  size_t smem = rest + (size_t)a.stages * TC_A_STAGE;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_linear_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -52,6 +52,15 @@ pd = torch.randn(E, 192, device=dev).to(bf)
 cases["fwd 64->192 relu + dense addend"] = lambda: ops.linear_raw([(x64, None, None, 0)], Wm, None, E, L.ACT_RELU, tc=True, out_dtype=bf, adds=[(pd, None)])
 cases["fwd 64->256 relu, no addend"] = lambda: ops.linear_raw([(x64, None, None, 0)], W2[:, :64].contiguous(), None, E, L.ACT_RELU, tc=True, out_dtype=bf)
 cases["fwd 64->128 relu, no addend"] = lambda: ops.linear_raw([(x64, None, None, 0)], W64.t().contiguous(), None, E, L.ACT_RELU, tc=True, out_dtype=bf)
+# att_edge_encoder body: long-K layers (column blocks of a resident weight block)
+x512 = torch.randn(E, 512, device=dev).to(bf)
+x384 = torch.randn(E, 384, device=dev).to(bf)
+W384 = torch.randn(384, 512, device=dev) * 0.05
+W256 = torch.randn(256, 384, device=dev) * 0.05
+b384 = torch.randn(384, device=dev)
+cases["wide fwd 512->384 + bias + bits"] = lambda: ops.linear_raw([(x512, None, None, 0)], W384, b384, E, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=ops.new_relu_bits(E, 384, dev))
+cases["wide dgrad 384->512 + sign-bit mask"] = lambda: ops.linear_raw([(x384, None, None, 0)], W384, None, E, trans_w=True, mask_bits=bits512, tc=True, out_dtype=bf)
+cases["wide fwd 384->256 + bits"] = lambda: ops.linear_raw([(x384, None, None, 0)], W256, None, E, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=bits256)
 only = sys.argv[2] if len(sys.argv) > 2 else None
 if only:
     cases = {k: v for k, v in cases.items() if only in k}
