@@ -31,6 +31,7 @@ class ChainLayer(C.Structure):
 
 
 ACT_MASKBITS = 3
+NARROW_INPUT_RELU = 0x100      # flag of b3d_narrow_mlp_*'s final_act (include/b3d.h)
 CHAIN_MAX_LAYERS = 6
 
 _SIGS = {

@@ -23,8 +23,8 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 template <int D0_, int D1_, int D2_, int D3_, int D4_>
 struct Chain {
   static constexpr int D0 = D0_, D1 = D1_, D2 = D2_, D3 = D3_, D4 = D4_;
-  static constexpr int NL = D4_ > 0 ? 4 : 3;
-  static constexpr int DL = D4_ > 0 ? D4_ : D3_;
+  static constexpr int NL = D4_ > 0 ? 4 : (D3_ > 0 ? 3 : 2);
+  static constexpr int DL = D4_ > 0 ? D4_ : (D3_ > 0 ? D3_ : D2_);
   // parameter layout in shared memory and in the per-CTA gradient partials
   static constexpr int W0 = 0, W1 = W0 + D1 * D0, W2 = W1 + D2 * D1, W3 = W2 + D3 * D2;
   static constexpr int B0 = W3 + D4 * D3, B1 = B0 + D1, B2 = B1 + D2, B3 = B2 + D3;
@@ -211,23 +211,39 @@ __global__ void __launch_bounds__(NM_THREADS, 2) k_narrow_fwd(const void* __rest
   __shared__ __align__(16) float P[C::NSMEM];
   nm_load_params<C>(P, w);
   __syncthreads();
+  const int act = final_act & 0xFF;
+  const bool in_relu = (final_act & B3D_NARROW_INPUT_RELU) != 0;
+  constexpr int D3S = C::D3 > 0 ? C::D3 : 1;
   for (long long r = (long long)blockIdx.x * NM_THREADS + threadIdx.x; r < M; r += (long long)gridDim.x * NM_THREADS) {
-    float x[C::D0], h1[C::D1], h2[C::D2], h3[C::D3];
+    float x[C::D0], h1[C::D1], h2[C::D2];
     nm_load_row<C::D0>(X, x_dtype, r, ldx, x);
-    nm_layer<C::D0, C::D1, true>(P + C::T0, P + C::B0, x, h1);
-    nm_layer<C::D1, C::D2, true>(P + C::T1, P + C::B1, h1, h2);
-    if constexpr (C::NL == 3) {
-      nm_layer<C::D2, C::D3, false>(P + C::T2, P + C::B2, h2, h3);
-      if (final_act == B3D_ACT_SIGMOID) {
+    if (in_relu) {
 #pragma unroll
-        for (int j = 0; j < C::D3; ++j) h3[j] = 1.f / (1.f + expf(-h3[j]));
+      for (int k = 0; k < C::D0; ++k) x[k] = fmaxf(x[k], 0.f);
+    }
+    nm_layer<C::D0, C::D1, true>(P + C::T0, P + C::B0, x, h1);
+    if constexpr (C::NL == 2) {
+      nm_layer<C::D1, C::D2, false>(P + C::T1, P + C::B1, h1, h2);
+      if (act == B3D_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < C::D2; ++j) h2[j] = fmaxf(h2[j], 0.f);
       }
-      nm_store_row<C::D3>(Y, y_dtype, r, ldy, h3);
+      nm_store_row<C::D2>(Y, y_dtype, r, ldy, h2);
+    } else if constexpr (C::NL == 3) {
+      float h3[D3S];
+      nm_layer<C::D1, C::D2, true>(P + C::T1, P + C::B1, h1, h2);
+      nm_layer<C::D2, D3S, false>(P + C::T2, P + C::B2, h2, h3);
+      if (act == B3D_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < D3S; ++j) h3[j] = 1.f / (1.f + expf(-h3[j]));
+      }
+      nm_store_row<D3S>(Y, y_dtype, r, ldy, h3);
     } else {
-      float h4[C::D4 > 0 ? C::D4 : 1];
-      nm_layer<C::D2, C::D3, true>(P + C::T2, P + C::B2, h2, h3);
-      nm_layer<C::D3, (C::D4 > 0 ? C::D4 : 1), false>(P + C::T3, P + C::B3, h3, h4);
-      if (final_act == B3D_ACT_SIGMOID) {
+      float h3[D3S], h4[C::D4 > 0 ? C::D4 : 1];
+      nm_layer<C::D1, C::D2, true>(P + C::T1, P + C::B1, h1, h2);
+      nm_layer<C::D2, D3S, true>(P + C::T2, P + C::B2, h2, h3);
+      nm_layer<D3S, (C::D4 > 0 ? C::D4 : 1), false>(P + C::T3, P + C::B3, h3, h4);
+      if (act == B3D_ACT_SIGMOID) {
 #pragma unroll
         for (int j = 0; j < C::D4; ++j) h4[j] = 1.f / (1.f + expf(-h4[j]));
       }
@@ -310,16 +326,19 @@ k_narrow_bwd(const void* __restrict__ X, int x_dtype, int ldx, long long M, cons
   constexpr int D4S = C::D4 > 0 ? C::D4 : 1;
   nm_load_params<C>(P, w);
 
-  float aw0[nm_ept(C::D0, C::D1)], aw1[nm_ept(C::D1, C::D2)], aw2[nm_ept(C::D2, C::D3)], aw3[nm_ept(C::D3, D4S)];
+  constexpr int D3S = C::D3 > 0 ? C::D3 : 1;
+  const int act = final_act & 0xFF;
+  const bool in_relu = (final_act & B3D_NARROW_INPUT_RELU) != 0;
+  float aw0[nm_ept(C::D0, C::D1)], aw1[nm_ept(C::D1, C::D2)], aw2[nm_ept(C::D2, D3S)], aw3[nm_ept(D3S, D4S)];
   float ab0 = 0.f, ab1 = 0.f, ab2 = 0.f, ab3 = 0.f;
 #pragma unroll
   for (int i = 0; i < nm_ept(C::D0, C::D1); ++i) aw0[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < nm_ept(C::D1, C::D2); ++i) aw1[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < nm_ept(C::D2, C::D3); ++i) aw2[i] = 0.f;
+  for (int i = 0; i < nm_ept(C::D2, D3S); ++i) aw2[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < nm_ept(C::D3, D4S); ++i) aw3[i] = 0.f;
+  for (int i = 0; i < nm_ept(D3S, D4S); ++i) aw3[i] = 0.f;
   __syncthreads();
 
   const long long ntiles = (M + NM_THREADS - 1) / NM_THREADS;
@@ -329,12 +348,18 @@ k_narrow_bwd(const void* __restrict__ X, int x_dtype, int ldx, long long M, cons
     float x[C::D0], h1[C::D1], h2[C::D2];
     if (ok) {
       nm_load_row<C::D0>(X, x_dtype, r, ldx, x);
+      if (in_relu) {
+#pragma unroll
+        for (int k = 0; k < C::D0; ++k) x[k] = fmaxf(x[k], 0.f);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < C::D0; ++k) x[k] = 0.f;
     }
     nm_layer<C::D0, C::D1, true>(P + C::T0, P + C::B0, x, h1);
-    nm_layer<C::D1, C::D2, true>(P + C::T1, P + C::B1, h1, h2);
+    // layer 1 is the last (linear, or ReLU when asked) layer of a 2-layer chain, a hidden ReLU layer otherwise
+    if constexpr (C::NL == 2) nm_layer<C::D1, C::D2, false>(P + C::T1, P + C::B1, h1, h2);
+    else nm_layer<C::D1, C::D2, true>(P + C::T1, P + C::B1, h1, h2);
     float g[DLAST];   // gradient of the chain's last pre-activation
     if (ok) {
       nm_load_row<DLAST>(dY, dy_dtype, r, lddy, g);
@@ -343,38 +368,49 @@ k_narrow_bwd(const void* __restrict__ X, int x_dtype, int ldx, long long M, cons
       for (int j = 0; j < DLAST; ++j) g[j] = 0.f;
     }
     float g2[C::D2];  // gradient of layer 1's pre-activation (set below)
-    if constexpr (C::NL == 3) {
-      // 3-layer chains (the edge encoders) end linear: the host rejects a final activation for them
-      nm_stage<C::D2, C::D3>(S, g, h2);
-      __syncthreads();
-      nm_accum<C::D2, C::D3>(S, aw2, ab2);
-      __syncthreads();
-      nm_layer_t<C::D2, C::D3>(P + C::W2, S, g2);
-      nm_relu_mask<C::D2>(g2, h2);
-    } else {
-      float h3[C::D3];
-      nm_layer<C::D2, C::D3, true>(P + C::T2, P + C::B2, h2, h3);
-      if (final_act == B3D_ACT_SIGMOID) {
-        float z[D4S];
-        nm_layer<C::D3, D4S, false>(P + C::T3, P + C::B3, h3, z);
+    if constexpr (C::NL == 2) {
 #pragma unroll
-        for (int j = 0; j < D4S; ++j) {
-          const float s = 1.f / (1.f + expf(-z[j]));
-          g[j] *= s * (1.f - s);
+      for (int j = 0; j < C::D2; ++j) g2[j] = (act == B3D_ACT_RELU && !(h2[j] > 0.f)) ? 0.f : g[j];
+    } else if constexpr (C::NL == 3) {
+      if (act == B3D_ACT_SIGMOID) {
+        float z[D3S];
+        nm_layer<C::D2, D3S, false>(P + C::T2, P + C::B2, h2, z);
+#pragma unroll
+        for (int j = 0; j < D3S; ++j) {
+          const float sg = 1.f / (1.f + expf(-z[j]));
+          g[j] *= sg * (1.f - sg);
         }
       }
-      nm_stage<C::D3, D4S>(S, g, h3);
+      nm_stage<C::D2, D3S>(S, g, h2);
       __syncthreads();
-      nm_accum<C::D3, D4S>(S, aw3, ab3);
+      nm_accum<C::D2, D3S>(S, aw2, ab2);
       __syncthreads();
-      float g3[C::D3];
-      nm_layer_t<C::D3, D4S>(P + C::W3, S, g3);
-      nm_relu_mask<C::D3>(g3, h3);
-      nm_stage<C::D2, C::D3>(S, g3, h2);
+      nm_layer_t<C::D2, D3S>(P + C::W2, S, g2);
+      nm_relu_mask<C::D2>(g2, h2);
+    } else {
+      float h3[D3S];
+      nm_layer<C::D2, D3S, true>(P + C::T2, P + C::B2, h2, h3);
+      if (act == B3D_ACT_SIGMOID) {
+        float z[D4S];
+        nm_layer<D3S, D4S, false>(P + C::T3, P + C::B3, h3, z);
+#pragma unroll
+        for (int j = 0; j < D4S; ++j) {
+          const float sg = 1.f / (1.f + expf(-z[j]));
+          g[j] *= sg * (1.f - sg);
+        }
+      }
+      nm_stage<D3S, D4S>(S, g, h3);
       __syncthreads();
-      nm_accum<C::D2, C::D3>(S, aw2, ab2);
+      nm_accum<D3S, D4S>(S, aw3, ab3);
       __syncthreads();
-      nm_layer_t<C::D2, C::D3>(P + C::W2, S, g2);
+      float g3[D3S];
+      nm_layer_t<D3S, D4S>(P + C::W3, S, g3);
+      nm_relu_mask<D3S>(g3, h3);
+      nm_stage<C::D2, D3S>(S, g3, h2);
+      __syncthreads();
+      nm_accum<C::D2, D3S>(S, aw2, ab2);
+      __syncthreads();
+      nm_layer_t<C::D2, D3S>(P + C::W2, S, g2);
       nm_relu_mask<C::D2>(g2, h2);
     }
     nm_stage<C::D1, C::D2>(S, g2, h1);
@@ -391,14 +427,15 @@ k_narrow_bwd(const void* __restrict__ X, int x_dtype, int ldx, long long M, cons
     if (dX != nullptr && ok) {
       float gx[C::D0];
       nm_layer_t<C::D0, C::D1>(P + C::W0, S, gx);
+      if (in_relu) nm_relu_mask<C::D0>(gx, x);      // x holds relu(input): > 0 exactly where the input was
       nm_store_row<C::D0>(dX, dx_dtype, r, lddx, gx);
     }
   }
   float* part = partials + (long long)blockIdx.x * C::NPAD;
   nm_write_partial<C::D0, C::D1>(part, C::W0, C::B0, aw0, ab0);
   nm_write_partial<C::D1, C::D2>(part, C::W1, C::B1, aw1, ab1);
-  nm_write_partial<C::D2, C::D3>(part, C::W2, C::B2, aw2, ab2);
-  if constexpr (C::NL == 4) nm_write_partial<C::D3, D4S>(part, C::W3, C::B3, aw3, ab3);
+  if constexpr (C::NL >= 3) nm_write_partial<C::D2, D3S>(part, C::W2, C::B2, aw2, ab2);
+  if constexpr (C::NL == 4) nm_write_partial<D3S, D4S>(part, C::W3, C::B3, aw3, ab3);
 }
 
 // fixed-order sum of the per-CTA partials, scattered into the per-layer gradient tensors
@@ -421,15 +458,28 @@ using ChainEncPose = Chain<4, 8, 16, 32, 0>;
 using ChainClsMM = Chain<64, 32, 16, 8, 1>;
 using ChainClsPose = Chain<32, 16, 8, 4, 1>;
 
+using ChainClsTail = Chain<32, 16, 8, 1, 0>;    // 64 -> 32 of the classifier runs as a tensor-core layer in front of it
+using ChainEncHead = Chain<4, 16, 32, 0, 0>;    // 32 -> 64 of the edge encoder runs as a tensor-core layer behind it
+
 static int chain_id(int nl, const int32_t* d) {
   auto eq = [&](int n, int a, int b, int c, int e, int f) {
-    return nl == n && d[0] == a && d[1] == b && d[2] == c && d[3] == e && (n == 3 || d[4] == f);
+    return nl == n && d[0] == a && d[1] == b && d[2] == c && (n < 3 || d[3] == e) && (n < 4 || d[4] == f);
   };
   if (eq(3, 4, 16, 32, 64, 0)) return 0;
   if (eq(3, 4, 8, 16, 32, 0)) return 1;
   if (eq(4, 64, 32, 16, 8, 1)) return 2;
   if (eq(4, 32, 16, 8, 4, 1)) return 3;
+  if (eq(3, 32, 16, 8, 1, 0)) return 4;
+  if (eq(2, 4, 16, 32, 0, 0)) return 5;
   return -1;
+}
+
+// final_act = activation of the last layer (low byte) | B3D_NARROW_INPUT_RELU: Sigmoid on chains of >= 3 layers, ReLU
+// on 2-layer chains (the chain is then the head of a longer nn.Sequential)
+static bool act_ok(int nl, int final_act) {
+  const int act = final_act & 0xFF;
+  if (final_act & ~(0xFF | B3D_NARROW_INPUT_RELU)) return false;
+  return act == B3D_ACT_NONE || (act == B3D_ACT_SIGMOID && nl >= 3) || (act == B3D_ACT_RELU && nl == 2);
 }
 
 static int sm_count() {
@@ -499,7 +549,9 @@ static int npad_of(int id) {
     case 0: return ChainEncMM::NPAD;
     case 1: return ChainEncPose::NPAD;
     case 2: return ChainClsMM::NPAD;
-    default: return ChainClsPose::NPAD;
+    case 3: return ChainClsPose::NPAD;
+    case 4: return ChainClsTail::NPAD;
+    default: return ChainEncHead::NPAD;
   }
 }
 
@@ -508,17 +560,16 @@ static int npad_of(int id) {
 using namespace b3d;
 
 extern "C" int b3d_narrow_mlp_supported(int32_t nl, const int32_t* dims) {
-  return dims && (nl == 3 || nl == 4) && chain_id(nl, dims) >= 0;
+  return dims && nl >= 2 && nl <= 4 && chain_id(nl, dims) >= 0;
 }
 
 extern "C" int b3d_narrow_mlp_fwd(const void* X, int32_t x_dtype, int32_t ldx, int64_t M, int32_t nl,
                                   const int32_t* dims, const float* const* W, const float* const* b,
                                   int32_t final_act, void* Y, int32_t y_dtype, int32_t ldy, void* stream) {
-  if (!X || !Y || !dims || !W || M < 0 || (nl != 3 && nl != 4)) return bad_arg("b3d_narrow_mlp_fwd");
+  if (!X || !Y || !dims || !W || M < 0 || nl < 2 || nl > 4) return bad_arg("b3d_narrow_mlp_fwd");
   const int id = chain_id(nl, dims);
   if (id < 0) return bad_arg("b3d_narrow_mlp_fwd: unsupported layer widths");
-  if (final_act != B3D_ACT_NONE && !(final_act == B3D_ACT_SIGMOID && nl == 4))
-    return bad_arg("b3d_narrow_mlp_fwd: final_act (Sigmoid is supported on the 4-layer classifier chains only)");
+  if (!act_ok(nl, final_act)) return bad_arg("b3d_narrow_mlp_fwd: final_act (Sigmoid: >= 3 layers, ReLU: 2 layers)");
   if (!row_aligned(X, x_dtype, ldx, dims[0]) || !row_aligned(Y, y_dtype, ldy, dims[nl]))
     return bad_arg("b3d_narrow_mlp_fwd: rows must be 16-byte aligned");
   if (M == 0) return 0;
@@ -533,12 +584,14 @@ extern "C" int b3d_narrow_mlp_fwd(const void* X, int32_t x_dtype, int32_t ldx, i
     case 0: return launch_fwd<ChainEncMM>(X, x_dtype, ldx, M, w, final_act, Y, y_dtype, ldy, st);
     case 1: return launch_fwd<ChainEncPose>(X, x_dtype, ldx, M, w, final_act, Y, y_dtype, ldy, st);
     case 2: return launch_fwd<ChainClsMM>(X, x_dtype, ldx, M, w, final_act, Y, y_dtype, ldy, st);
-    default: return launch_fwd<ChainClsPose>(X, x_dtype, ldx, M, w, final_act, Y, y_dtype, ldy, st);
+    case 3: return launch_fwd<ChainClsPose>(X, x_dtype, ldx, M, w, final_act, Y, y_dtype, ldy, st);
+    case 4: return launch_fwd<ChainClsTail>(X, x_dtype, ldx, M, w, final_act, Y, y_dtype, ldy, st);
+    default: return launch_fwd<ChainEncHead>(X, x_dtype, ldx, M, w, final_act, Y, y_dtype, ldy, st);
   }
 }
 
 extern "C" size_t b3d_narrow_mlp_bwd_workspace_bytes(int64_t M, int32_t nl, const int32_t* dims) {
-  if (!dims || (nl != 3 && nl != 4)) return 0;
+  if (!dims || nl < 2 || nl > 4) return 0;
   const int id = chain_id(nl, dims);
   if (id < 0) return 0;
   return (size_t)bwd_grid(M) * npad_of(id) * sizeof(float);
@@ -549,11 +602,10 @@ extern "C" int b3d_narrow_mlp_bwd(const void* X, int32_t x_dtype, int32_t ldx, i
                                   int32_t final_act, const void* dY, int32_t dy_dtype, int32_t lddy, void* dX,
                                   int32_t dx_dtype, int32_t lddx, float* const* dW, float* const* db,
                                   int32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!X || !dY || !dims || !W || M <= 0 || (nl != 3 && nl != 4) || !workspace) return bad_arg("b3d_narrow_mlp_bwd");
+  if (!X || !dY || !dims || !W || M <= 0 || nl < 2 || nl > 4 || !workspace) return bad_arg("b3d_narrow_mlp_bwd");
   const int id = chain_id(nl, dims);
   if (id < 0) return bad_arg("b3d_narrow_mlp_bwd: unsupported layer widths");
-  if (final_act != B3D_ACT_NONE && !(final_act == B3D_ACT_SIGMOID && nl == 4))
-    return bad_arg("b3d_narrow_mlp_bwd: final_act (Sigmoid is supported on the 4-layer classifier chains only)");
+  if (!act_ok(nl, final_act)) return bad_arg("b3d_narrow_mlp_bwd: final_act (Sigmoid: >= 3 layers, ReLU: 2 layers)");
   if (workspace_bytes < b3d_narrow_mlp_bwd_workspace_bytes(M, nl, dims)) return bad_arg("b3d_narrow_mlp_bwd: workspace");
   if (!row_aligned(X, x_dtype, ldx, dims[0]) || !row_aligned(dY, dy_dtype, lddy, dims[nl]) ||
       (dX && !row_aligned(dX, dx_dtype, lddx, dims[0])))
@@ -570,6 +622,8 @@ extern "C" int b3d_narrow_mlp_bwd(const void* X, int32_t x_dtype, int32_t ldx, i
     case 0: return launch_bwd<ChainEncMM>(X, x_dtype, ldx, M, w, final_act, dY, dy_dtype, lddy, dX, dx_dtype, lddx, dW, db, flags, part, st);
     case 1: return launch_bwd<ChainEncPose>(X, x_dtype, ldx, M, w, final_act, dY, dy_dtype, lddy, dX, dx_dtype, lddx, dW, db, flags, part, st);
     case 2: return launch_bwd<ChainClsMM>(X, x_dtype, ldx, M, w, final_act, dY, dy_dtype, lddy, dX, dx_dtype, lddx, dW, db, flags, part, st);
-    default: return launch_bwd<ChainClsPose>(X, x_dtype, ldx, M, w, final_act, dY, dy_dtype, lddy, dX, dx_dtype, lddx, dW, db, flags, part, st);
+    case 3: return launch_bwd<ChainClsPose>(X, x_dtype, ldx, M, w, final_act, dY, dy_dtype, lddy, dX, dx_dtype, lddx, dW, db, flags, part, st);
+    case 4: return launch_bwd<ChainClsTail>(X, x_dtype, ldx, M, w, final_act, dY, dy_dtype, lddy, dX, dx_dtype, lddx, dW, db, flags, part, st);
+    default: return launch_bwd<ChainEncHead>(X, x_dtype, ldx, M, w, final_act, dY, dy_dtype, lddy, dX, dx_dtype, lddx, dW, db, flags, part, st);
   }
 }

@@ -246,11 +246,14 @@ _chain_packs = {}
 #              (ops._MPEdgeBlockG): same kernels in the forward pass, a K-concatenated de' GEMM instead of two
 #              GEMMs + a 3-way sum kernel in the backward pass. Measured 110.3 ms/step against 107.2 ms (10 GB less
 #              memory): OFF.
+#   narrow_split bf16 mode: the widest layer of the two narrow chains (classifier 64 -> 32, edge encoder 32 -> 64) as a
+#              tensor-core layer, the rest in the narrow kernel (_narrow_split). ON.
 #   chain      fused MLP chains / edge blocks (chain_tc.cu). Validated (tests/test_gpu_chain.py runs it whatever this
 #              switch says) but OFF in the model path: with one 128-row tile in flight per SM the fused kernel is
 #              bound by the same epilogue work as the per-layer kernels plus the layer-to-layer hand-over latency,
 #              and measured no faster (profiles/r2_chain_kernel.md), so the per-layer TMA kernels stay the default.
-_FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True, "gather_tma": False, "edge_block": False}
+_FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True, "gather_tma": False, "edge_block": False,
+                     "narrow_split": True}
 
 
 def _read_features():
@@ -1110,7 +1113,7 @@ class _NarrowMLP(torch.autograd.Function):
     direction (narrow_mlp.cu): hidden activations never leave registers; backward recomputes them."""
 
     @staticmethod
-    def forward(ctx, nl, final_act, out_dtype, x, *params):
+    def forward(ctx, nl, final_act, out_dtype, in_relu, x, *params):
         Ws = [w.contiguous() for w in params[0::2]]
         bs = [b.contiguous() if b is not None else None for b in params[1::2]]
         if x.dtype != torch.float64:           # float64 rows (edge_attr as stored) are cast inside the kernel
@@ -1118,7 +1121,8 @@ class _NarrowMLP(torch.autograd.Function):
         dims = [Ws[0].size(1)] + [w.size(0) for w in Ws]
         M = x.size(0)
         y = torch.empty((M, dims[-1]), dtype=out_dtype, device=x.device)
-        ctx.nl, ctx.act, ctx.dims, ctx.has_bias = nl, _ACT[final_act], dims, [b is not None for b in bs]
+        ctx.nl, ctx.dims, ctx.has_bias = nl, dims, [b is not None for b in bs]
+        ctx.act = _ACT[final_act] | (L.NARROW_INPUT_RELU if in_relu else 0)
         if M > 0:
             L.check(L.lib().b3d_narrow_mlp_fwd(L.ptr(x), _DT[x.dtype], x.stride(0), M, nl, L.int_array(dims),
                                                L.ptr_array(Ws), L.ptr_array(bs), ctx.act, L.ptr(y), _DT[y.dtype],
@@ -1136,12 +1140,14 @@ class _NarrowMLP(torch.autograd.Function):
         if not dy.is_contiguous():
             dy = dy.contiguous()
         M = x.size(0)
-        dX = torch.empty_like(x) if ctx.needs_input_grad[3] else None
+        dX = torch.empty_like(x) if ctx.needs_input_grad[4] else None
         dWs = [torch.empty_like(w) for w in Ws]
         dbs = [torch.empty_like(b) if b is not None else None for b in bs]
         if M == 0:
             for t in dWs + [d for d in dbs if d is not None]:
                 t.zero_()
+            if dX is not None:
+                dX.zero_()
         else:
             lib = L.lib()
             d32 = L.int_array(dims)
@@ -1155,7 +1161,47 @@ class _NarrowMLP(torch.autograd.Function):
         flat = []
         for dw, db in zip(dWs, dbs):
             flat += [dw, db]
-        return (None, None, None, dX, *flat)
+        return (None, None, None, None, dX, *flat)
+
+
+def _narrow_dims_ok(x, dims):
+    if x.dim() == 2 and x.dtype == torch.float64 and x.stride(1) == 1 and not x.requires_grad and \
+            x.data_ptr() % 16 == 0 and x.stride(0) % 2 == 0:
+        pass                                   # float64 input rows: loaded as double2, cast in registers
+    elif x.dim() != 2 or x.dtype not in (torch.float32, torch.bfloat16) or x.stride(1) != 1 or not _al16(x):
+        return False
+    return x.size(1) == dims[0] and bool(L.lib().b3d_narrow_mlp_supported(len(dims) - 1, L.int_array(dims)))
+
+
+def _narrow_split(inputs, weights, biases, final_act, row_mask, adds, out_dtype, premasked):
+    """bf16 mode: the widest layer of a narrow chain as a tensor-core layer, the rest as the narrow kernel —
+    classifier 64 -> 32 | ReLU, 32 -> 16 -> 8 -> 1 [Sigmoid] (clr_att_gnn.py:49-57) and edge encoder
+    4 -> 16 -> 32, ReLU | 32 -> 64 (clr_att_gnn.py:35-41): three quarters of either chain's multiply-adds leave the
+    FFMA pipe (narrow_mlp.cu ran at 24 TFLOP/s: 7 % of the step), at the price of one bf16 [rows, 32] round trip.
+    Returns None when the chain is not one of the two."""
+    if _PRECISION != "bf16" or not FEATURES["narrow_split"] or len(inputs) != 1 or inputs[0][1] is not None \
+            or row_mask is not None or adds or premasked:
+        return None
+    x = inputs[0][0]
+    dims = [weights[0].size(1)] + [w.size(0) for w in weights]
+    if x.size(0) < _TC_MIN_ROWS:
+        return None
+    bf = torch.bfloat16
+    if dims == [64, 32, 16, 8, 1] and final_act in (None, "sigmoid") and x.dtype == bf and _al16(x) and x.stride(1) == 1:
+        z0 = _FusedMLP.apply(1, None, None, (None,), (), bf, False, weights[0], biases[0], x)
+        if not _narrow_dims_ok(z0, dims[1:]):
+            return None
+        flat = []
+        for w, b in zip(weights[1:], biases[1:]):
+            flat += [w, b]
+        return _NarrowMLP.apply(3, final_act, out_dtype or torch.float32, True, z0, *flat)
+    if dims == [4, 16, 32, 64] and final_act is None and _narrow_dims_ok(x, dims[:3]):
+        flat = []
+        for w, b in zip(weights[:2], biases[:2]):
+            flat += [w, b]
+        h = _NarrowMLP.apply(2, "relu", bf, False, x, *flat)
+        return _FusedMLP.apply(1, None, None, (None,), (), out_dtype, False, weights[2], biases[2], h)
+    return None
 
 
 def _narrow_ok(inputs, weights, final_act, row_mask, adds, premasked):
@@ -1163,14 +1209,8 @@ def _narrow_ok(inputs, weights, final_act, row_mask, adds, premasked):
         return False
     if final_act not in (None, "sigmoid") or len(weights) not in (3, 4) or (final_act and len(weights) != 4):
         return False
-    x = inputs[0][0]
-    if x.dim() == 2 and x.dtype == torch.float64 and x.stride(1) == 1 and not x.requires_grad and \
-            x.data_ptr() % 16 == 0 and x.stride(0) % 2 == 0:
-        pass                                   # float64 input rows: loaded as double2, cast in registers
-    elif x.dim() != 2 or x.dtype not in (torch.float32, torch.bfloat16) or x.stride(1) != 1 or not _al16(x):
-        return False
     dims = [weights[0].size(1)] + [w.size(0) for w in weights]
-    return x.size(1) == dims[0] and bool(L.lib().b3d_narrow_mlp_supported(len(weights), L.int_array(dims)))
+    return _narrow_dims_ok(inputs[0][0], dims)
 
 
 def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=(), out_dtype=None, premasked=False):
@@ -1183,8 +1223,11 @@ def fused_mlp(inputs, weights, biases, final_act=None, row_mask=None, adds=(), o
     flat = []
     for w, b in zip(weights, biases):
         flat += [w, b]
+    y = _narrow_split(inputs, weights, biases, final_act, row_mask, adds, out_dtype, premasked)
+    if y is not None:
+        return y
     if _narrow_ok(inputs, weights, final_act, row_mask, adds, premasked):
-        return _NarrowMLP.apply(len(weights), final_act, out_dtype or torch.float32, xs[0], *flat)
+        return _NarrowMLP.apply(len(weights), final_act, out_dtype or torch.float32, False, xs[0], *flat)
     return _FusedMLP.apply(len(weights), final_act, row_mask, nidx, tuple(ni for _, ni in adds), out_dtype,
                            premasked, *flat, *xs, *[t for t, _ in adds])
 

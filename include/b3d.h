@@ -37,6 +37,7 @@ extern "C" {
 enum { B3D_MASK_NONE = 0, B3D_MASK_RELU = 1, B3D_MASK_SIGMOID = 2 };
 enum { B3D_ACT_NONE = 0, B3D_ACT_RELU = 1, B3D_ACT_SIGMOID = 2,
        B3D_ACT_MASKBITS = 3 };      /* b3d_chain_run only: multiply by a ReLU mask given as sign bits (backward chains) */
+enum { B3D_NARROW_INPUT_RELU = 0x100 };   /* flag of b3d_narrow_mlp_*'s final_act, see there */
 enum { B3D_FLAG_ACCUMULATE = 1,     /* out += result instead of out = result */
        B3D_FLAG_OUT_BF16 = 2,       /* b3d_segment_sum: `out` is really __nv_bfloat16* (bf16 source, no accumulate) */
        B3D_FLAG_SPLIT = 4 };        /* the tensor-core arithmetic of the 1e-4 parity mode. b3d_linear_tc: "tf32 x3" — every fp32
@@ -202,9 +203,13 @@ int b3d_wgrad_tc(const b3d_seg_t* dy /*host*/, const b3d_seg_t* segs /*host*/, i
  * pose_gnn.py:45-53): Linear/ReLU/.../Linear[/Sigmoid] with every width <= 64. One thread per row,
  * parameters in shared memory, hidden activations in registers: HBM sees X and Y only. fp32
  * arithmetic; X / Y / dY / dX may be stored as B3D_F32 or B3D_BF16.
- * dims: host int32[nl+1] = in, hidden..., out (nl = 3 or 4 Linear layers). W / b / dW / db: HOST
+ * dims: host int32[nl+1] = in, hidden..., out (nl = 2, 3 or 4 Linear layers). W / b / dW / db: HOST
  * arrays of nl DEVICE pointers to contiguous nn.Linear parameters ([out,in] row-major; b[l], dW[l],
- * db[l] may be null). final_act: B3D_ACT_NONE, or B3D_ACT_SIGMOID on the 4-layer chains.
+ * db[l] may be null). final_act: activation after the LAST layer — B3D_ACT_NONE, B3D_ACT_SIGMOID (chains of
+ * >= 3 layers) or B3D_ACT_RELU (2-layer chains) — optionally OR-ed with B3D_NARROW_INPUT_RELU (the chain
+ * starts with a ReLU on its input rows; dX is masked accordingly). The last two serve the bf16 mode, where the
+ * widest layer of a chain runs as a tensor-core layer in front of (classifier: 64->32 | ReLU,32->16->8->1) or
+ * behind (edge encoder: 4->16->32,ReLU | 32->64) the narrow rest.
  * Backward recomputes the hidden activations, so only X is needed; dX may be null. Weight gradients
  * are reduced per CTA in registers and summed over CTAs in fixed order (deterministic). */
 int b3d_narrow_mlp_supported(int32_t nl, const int32_t* dims /*host*/);

@@ -409,3 +409,63 @@ def test_narrow_mlp_bf16_storage():
     grads_ref = torch.autograd.grad(enc(a), list(enc.parameters()), g16.float())
     for g, r in zip(grads, grads_ref):
         assert rel_err(g, r) < 1e-4
+
+
+@pytest.mark.parametrize("M", [1, 255, 1000, 70001])
+def test_narrow_mlp_partial_chains(M):
+    """The narrow remainders of the bf16 mode's split chains (ops._narrow_split), fp32 arithmetic against torch
+    autograd: ReLU -> 32 -> 16 -> 8 -> 1 -> Sigmoid (a ReLU on the chain INPUT, dX masked by it) and
+    4 -> 16 -> 32 -> ReLU (a 2-layer chain ending in a ReLU)."""
+    torch.manual_seed(M)
+    for dims, in_relu, final in (((32, 16, 8, 1), True, "sigmoid"), ((32, 16, 8, 1), True, None), ((4, 16, 32), False, "relu"),
+                                 ((4, 16, 32), False, None)):
+        seq = _torch_chain(dims, final == "sigmoid").double()
+        x = torch.randn(M, dims[0]).double().requires_grad_(True)
+        h = torch.relu(x) if in_relu else x
+        y_ref = seq(h)
+        if final == "relu":
+            y_ref = torch.relu(y_ref)
+        gy = torch.randn_like(y_ref)
+        y_ref.backward(gy)
+        lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
+        params = []
+        for m in lin:
+            params += [m.weight.detach().float().to(DEV).requires_grad_(True), m.bias.detach().float().to(DEV).requires_grad_(True)]
+        xd = x.detach().float().to(DEV).requires_grad_(True)
+        y = ops._NarrowMLP.apply(len(lin), final, torch.float32, in_relu, xd, *params)
+        assert rel_err(y, y_ref) < 1e-5
+        y.backward(gy.float().to(DEV))
+        assert rel_err(xd.grad, x.grad) < 1e-4
+        for m, (w, b) in zip(lin, zip(params[0::2], params[1::2])):
+            assert rel_err(w.grad, m.weight.grad) < 1e-4 and rel_err(b.grad, m.bias.grad) < 1e-4
+
+
+def test_narrow_chains_split_in_bf16_mode():
+    """bf16 mode: classifier 64 -> 32 and edge encoder 32 -> 64 run as tensor-core layers, the rest in the narrow
+    kernel; outputs and gradients against torch fp32 on the same (bf16-representable) inputs within the bf16 tolerance."""
+    torch.manual_seed(11)
+    M = 20000
+    ops.set_precision("bf16")
+    try:
+        for dims, sig in (((64, 32, 16, 8, 1), True), ((4, 16, 32, 64), False)):
+            seq = _torch_chain(dims, sig).to(DEV)
+            x = torch.randn(M, dims[0], device=DEV)
+            x = x.to(torch.bfloat16) if dims[0] == 64 else x.double()
+            xr = x.float().requires_grad_(True)
+            y_ref = seq(xr)
+            gy = torch.randn_like(y_ref)
+            gref = torch.autograd.grad(y_ref, [xr] + list(seq.parameters()), gy)
+            xin = x.clone().requires_grad_(dims[0] == 64)
+            before = L.launch_count()
+            y = ops.run_mlp(seq, [(ops.edge_attr_rows(xin) if dims[0] == 4 else xin, None)],
+                            final_act="sigmoid" if sig else None, out_dtype=torch.float32 if sig else torch.bfloat16)
+            assert L.launch_count() - before == 3, "pack + tensor-core layer + narrow kernel"
+            assert rel_err(y, y_ref) < 2e-2
+            got = torch.autograd.grad(y, ([xin] if dims[0] == 64 else []) + list(seq.parameters()), gy.to(y.dtype))
+            # Frobenius norms: a hidden unit within bf16 rounding of zero can land on the other side of its ReLU, which
+            # changes single rows of dX by a large fraction (seen: one element at 0.26 of the maximum)
+            for g, r in zip(got, gref[0 if dims[0] == 64 else 1:]):
+                assert float((g.double() - r.double()).norm() / r.double().norm()) < 2e-2
+    finally:
+        ops.set_precision("exact")
+        ops.invalidate_weight_cache()
