@@ -61,6 +61,10 @@ b384 = torch.randn(384, device=dev)
 cases["wide fwd 512->384 + bias + bits"] = lambda: ops.linear_raw([(x512, None, None, 0)], W384, b384, E, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=ops.new_relu_bits(E, 384, dev))
 cases["wide dgrad 384->512 + sign-bit mask"] = lambda: ops.linear_raw([(x384, None, None, 0)], W384, None, E, trans_w=True, mask_bits=bits512, tc=True, out_dtype=bf)
 cases["wide fwd 384->256 + bits"] = lambda: ops.linear_raw([(x384, None, None, 0)], W256, None, E, L.ACT_RELU, tc=True, out_dtype=bf, bits_out=bits256)
+out384 = torch.empty(E, 384, device=dev, dtype=bf)
+cases["wide fwd 512->384 + bias (bench roofline launch, E rows)"] = lambda: ops.linear_raw([(x512, None, None, 0)], W384, b384, E, L.ACT_RELU, tc=True, out=out384)
+Er = 489812
+cases["wide fwd 512->384 + bias (bench roofline launch, 489,812 rows)"] = lambda: ops.linear_raw([(x512[:Er], None, None, 0)], W384, b384, Er, L.ACT_RELU, tc=True, out=out384[:Er])
 only = sys.argv[2] if len(sys.argv) > 2 else None
 if only:
     cases = {k: v for k, v in cases.items() if only in k}
