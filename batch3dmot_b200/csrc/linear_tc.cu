@@ -840,6 +840,7 @@ struct TmaArgs {
   // lane: bit t of stage_mask = addend t is staged; add_bufs buffers of add_slots tiles of add_tile_bytes each.
   int stage_mask, add_bufs, add_slots, add_tile_bytes, stages;
   int fast_epi;   // lean epilogue block for plain bf16 layers (B3D_FAST_EPI=0 turns it off for A/B runs)
+  int cluster;    // > 1: the column-block CTAs of a row tile form a thread-block cluster and share its operand loads
 };
 
 // One staged addend of one tile, this warp's RPW rows: every instruction copies R rows (lane = chunk c of row
@@ -964,7 +965,8 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
 
   if (warp == 1) tmem_alloc(sBar + 104, ncols);
   if (tid == 0) {
-    for (int s = 0; s < 8; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    // cluster mode: a stage is free once the MMAs of EVERY CTA of the cluster have read it (multicast commits)
+    for (int s = 0; s < 8; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), (uint32_t)a.cluster); }
     mbar_init(sBar + 64, 1); mbar_init(sBar + 72, 1);      // accumulator full (tcgen05.commit)
     mbar_init(sBar + 80, 8); mbar_init(sBar + 88, 8);      // accumulator empty (8 epilogue warps)
     mbar_init(sBar + 96, 1);                                // weights resident
@@ -984,12 +986,18 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
   }
   for (int i = tid; i < 256; i += TMA_THREADS) s_bias[i] = (a.bias && i < a.Nb && n0 + i < a.Nout) ? __ldg(a.bias + n0 + i) : 0.f;
   tc_fence_before_sync();
-  __syncthreads();
+  if (a.cluster > 1) cluster_sync_all();      // peers' barriers are initialised before any remote arrival / multicast
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *s_tmem;
+  const uint16_t cmask = (uint16_t)((1u << a.cluster) - 1u);
+  const int crank = a.cluster > 1 ? (int)cluster_ctarank() : 0;
 
   if (warp == 0) {
-    // Producer warp. Dense segments: lane 0 issues one {64 x 128} box per chunk. Row-gathered segments (the
+    // Producer warp. Dense segments: lane 0 issues one {64 x 128} box per chunk. Cluster mode (the column-block CTAs
+    // of a row tile, which all read the same [128, K] operand): every CTA arms its own barrier for every chunk, the
+    // chunks are issued round-robin by the CTAs of the cluster and MULTICAST into all of them — the operand crosses the
+    // L2 -> SM fabric once per row tile instead of once per column block. Row-gathered segments (the
     // reference's x[edge_index] operands, pose_gnn.py:180 / clr_att_gnn.py:284): every lane owns 4 rows of the tile
     // and issues one tile::gather4 per chunk for them, so the gather runs in the TMA unit (no registers, no L1
     // wavefronts, hundreds of rows in flight) instead of in the epilogue.
@@ -1015,7 +1023,11 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
           if (lane == 0) {
             if (it >= STG) mbar_wait(bar_empty(s), ((it / STG) - 1) & 1);
             mbar_expect_tx(bar_full(s), TC_A_STAGE);
-            if (sel < 0) tma_load_2d(sA + s * TC_A_STAGE, &maps.m[sg], c * 64, (int)(tile * TC_BM), bar_full(s));
+            if (sel < 0) {
+              if (a.cluster <= 1) tma_load_2d(sA + s * TC_A_STAGE, &maps.m[sg], c * 64, (int)(tile * TC_BM), bar_full(s));
+              else if (it % a.cluster == crank)
+                tma_load_2d_mc(sA + s * TC_A_STAGE, &maps.m[sg], c * 64, (int)(tile * TC_BM), bar_full(s), cmask);
+            }
           }
           if (sel >= 0) {
             __syncwarp();      // the stage is free and its transaction count armed before any lane writes into it
@@ -1045,7 +1057,8 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
           for (int j = 0; j < TC_BK / 16; ++j)
             mma_bf16_ss(d_tmem, make_smem_desc_sw128(sA + s * TC_A_STAGE + j * 32),
                         make_smem_desc_sw128(sW + c * w_chunk + j * 32), idesc, (c | j) != 0);
-          mma_commit(bar_empty(s));      // stage free once these MMAs have read it
+          if (a.cluster > 1) mma_commit_mc(bar_empty(s), cmask);
+          else mma_commit(bar_empty(s));      // stage free once these MMAs have read it
         }
         if (a.stage_mask) {
           // Row-gathered addends: D[:, 16-column group] += staged tile[:, same group] * I. The rows were gathered by
@@ -1239,7 +1252,8 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
     }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (a.cluster > 1) cluster_sync_all();      // no CTA leaves while a peer may still write into it or arrive on its barriers
+  else __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, ncols);
 }
 
@@ -1776,17 +1790,52 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
   long long gx = n_sm / ny;
   if (gx < 1) gx = 1;
   if (gx > a.ntiles) gx = a.ntiles;
-  dim3 grid((unsigned)gx, (unsigned)ny);
   cudaStream_t st = (cudaStream_t)stream;
   // the LEAN build when every block of every CTA is a lean block (see TmaCfg)
   const bool lean = a.fast_epi && act != B3D_ACT_SIGMOID && a.y_bf16 && !a.out_mask && !a.row_mask &&
                     !(flags & B3D_FLAG_ACCUMULATE) && (nadd == 0 || a.stage_mask == (1 << nadd) - 1) && (ldy & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(Y) & 31) == 0 && (Nb & 31) == 0 && (n_logical & 31) == 0;
-  if (lean && act == B3D_ACT_RELU) k_linear_tma<1, true><<<grid, TmaCfg<true>::THREADS, smem, st>>>(maps, mW, a);
-  else if (lean) k_linear_tma<0, true><<<grid, TmaCfg<true>::THREADS, smem, st>>>(maps, mW, a);
-  else if (act == B3D_ACT_RELU) k_linear_tma<1, false><<<grid, TmaCfg<false>::THREADS, smem, st>>>(maps, mW, a);
-  else if (act == B3D_ACT_SIGMOID) k_linear_tma<2, false><<<grid, TmaCfg<false>::THREADS, smem, st>>>(maps, mW, a);
-  else k_linear_tma<0, false><<<grid, TmaCfg<false>::THREADS, smem, st>>>(maps, mW, a);
+  const void* fn = lean ? (act == B3D_ACT_RELU ? (const void*)k_linear_tma<1, true> : (const void*)k_linear_tma<0, true>)
+                        : (act == B3D_ACT_RELU ? (const void*)k_linear_tma<1, false>
+                           : act == B3D_ACT_SIGMOID ? (const void*)k_linear_tma<2, false> : (const void*)k_linear_tma<0, false>);
+  const unsigned threads = lean ? TmaCfg<true>::THREADS : TmaCfg<false>::THREADS;
+  // Cluster mode: the ny column-block CTAs of a row tile as one thread-block cluster sharing the operand loads (TMA
+  // multicast). All clusters must be resident together (the tile loop is a static partition over the clusters).
+  a.cluster = 1;
+  {
+    static int want = -1;
+    // measured SLOWER than independent CTAs (512 -> 384: 1,217 vs 1,033 us; profiles/r2_lean_epilogue.md): opt-in
+    if (want < 0) { const char* e = getenv("B3D_TMA_CLUSTER"); want = (e && e[0] == '1') ? 1 : 0; }
+    bool dense = true;
+    for (int sg = 0; sg < nseg; ++sg) dense = dense && a.seg_gsel[sg] < 0;
+    if (want && ny >= 2 && ny <= 8 && dense) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)gx, (unsigned)ny);
+      cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)ny; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) == cudaSuccess && ncl >= 1) {
+        if (gx > ncl) gx = ncl;
+        cfg.gridDim = dim3((unsigned)gx, (unsigned)ny);
+        a.cluster = ny;
+        void* args[] = {(void*)&maps, (void*)&mW, (void*)&a};
+        cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+        if (e != cudaSuccess) return fail("k_linear_tma cluster launch", e);
+        B3D_LAUNCH_CHECK("k_linear_tma");
+        return 0;
+      }
+      (void)cudaGetLastError();
+    }
+  }
+  dim3 grid((unsigned)gx, (unsigned)ny);
+  void* args[] = {(void*)&maps, (void*)&mW, (void*)&a};
+  cudaError_t le = cudaLaunchKernel(fn, grid, dim3(threads), args, smem, st);
+  if (le != cudaSuccess) return fail("k_linear_tma launch", le);
   B3D_LAUNCH_CHECK("k_linear_tma");
   return 0;
 }

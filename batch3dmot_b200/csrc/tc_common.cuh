@@ -190,6 +190,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// Cluster variants: the same box delivered to the same shared-memory offset of every CTA in cta_mask (each CTA's
+// mbarrier at the same offset receives the bytes), and a tcgen05.commit that arrives on every CTA's barrier.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major operand tile written by TMA with 128-byte swizzle: rows of 128 B, 8-row groups of 1024 B.
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
