@@ -248,12 +248,13 @@ _chain_packs = {}
 #              memory): OFF.
 #   narrow_split bf16 mode: the widest layer of the two narrow chains (classifier 64 -> 32, edge encoder 32 -> 64) as a
 #              tensor-core layer, the rest in the narrow kernel (_narrow_split). ON.
+#   bf16_inputs bf16 mode: dense fp32 inputs of a tensor-core chain are rounded to bf16 once (not per tile). ON.
 #   chain      fused MLP chains / edge blocks (chain_tc.cu). Validated (tests/test_gpu_chain.py runs it whatever this
 #              switch says) but OFF in the model path: with one 128-row tile in flight per SM the fused kernel is
 #              bound by the same epilogue work as the per-layer kernels plus the layer-to-layer hand-over latency,
 #              and measured no faster (profiles/r2_chain_kernel.md), so the per-layer TMA kernels stay the default.
 _FEATURE_DEFAULTS = {"chain": False, "split_tc": True, "window_knn": True, "gather_tma": False, "edge_block": False,
-                     "narrow_split": True}
+                     "narrow_split": True, "bf16_inputs": True}
 
 
 def _read_features():
@@ -710,6 +711,13 @@ class _FusedMLP(torch.autograd.Function):
             and all(w.size(0) % 8 == 0 and w.size(1) % 8 == 0 and w.size(0) >= 16 and w.size(1) >= 32 for w in Ws)
         if not tc:
             adds = [(t.float(), i) for t, i in adds]
+        if tc and FEATURES["bf16_inputs"] and any(x.dtype == torch.float32 and ni is None for x, ni in zip(xs, nidx)):
+            # dense fp32 inputs of a bf16 chain (the raw sensor features of the fc_*_encoder layers): rounded to bf16
+            # ONCE here — exactly what the thread-staged kernel does per tile while staging — so that the layer and its
+            # weight gradient run on the TMA-fed kernels (k_wgrad_tc on fp32 rows ran at ~1 TB/s)
+            xs = [x.to(torch.bfloat16) if (x.dtype == torch.float32 and ni is None and x.size(1) % 8 == 0) else x
+                  for x, ni in zip(xs, nidx)]
+            items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
         if not tc and any(x.dtype != torch.float32 for x in xs):      # fp32 kernels take fp32 operands
             xs = [x.float() for x in xs]
             items = [(x, ni.idx if ni is not None else None, None, 0) for x, ni in zip(xs, nidx)]
