@@ -840,13 +840,14 @@ struct TmaArgs {
   // lane: bit t of stage_mask = addend t is staged; add_bufs buffers of add_slots tiles of add_tile_bytes each.
   int stage_mask, add_bufs, add_slots, add_tile_bytes, stages;
   int fast_epi;   // lean epilogue block for plain bf16 layers (B3D_FAST_EPI=0 turns it off for A/B runs)
+  int add_ca;     // addend row copies through L1 (cp.async.ca) instead of L2 only (.cg)
   int cluster;    // > 1: the column-block CTAs of a row tile form a thread-block cluster and share its operand loads
 };
 
 // One staged addend of one tile, this warp's RPW rows: every instruction copies R rows (lane = chunk c of row
 // j + sub); g0 / g1 hold the source rows of tile rows lane and lane + 32 of the warp's share. Fully unrolled, so that
 // the choice between g0 and g1, the row offsets and the row part of the swizzle are compile-time.
-template <int R, int RPW>
+template <int R, int RPW, bool CA>
 __device__ __forceinline__ void add_rows(uint32_t dst, const uint8_t* base, uint32_t ldb, uint32_t g0, uint32_t g1, int sub,
                                          int c, bool on) {
   const uint32_t x0 = (uint32_t)((c ^ sub) & 7);
@@ -854,10 +855,18 @@ __device__ __forceinline__ void add_rows(uint32_t dst, const uint8_t* base, uint
   for (int j = 0; j < RPW; j += R) {
     const uint32_t gr = __shfl_sync(0xffffffffu, j < 32 ? g0 : g1, (j & 31) + sub);
     const uint32_t swz = (x0 ^ (uint32_t)(j & 7)) << 4;     // (c ^ (j + sub)) & 7: j is a multiple of R > sub
-    if (on)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                   ::"r"(dst + (uint32_t)j * 128u + swz), "l"(base + (unsigned long long)gr * ldb)
-                   : "memory");
+    // .ca (opt-in): target-sorted edges repeat the same addend row ~60 times in a row (one node's in-edges), so those
+    // copies could hit L1 instead of crossing the L2 -> SM fabric again — measured 2-6 % SLOWER than .cg
+    if (on) {
+      if (CA)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
+                     ::"r"(dst + (uint32_t)j * 128u + swz), "l"(base + (unsigned long long)gr * ldb)
+                     : "memory");
+      else
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                     ::"r"(dst + (uint32_t)j * 128u + swz), "l"(base + (unsigned long long)gr * ldb)
+                     : "memory");
+    }
   }
 }
 
@@ -1131,9 +1140,15 @@ k_linear_tma(const __grid_constant__ TmaMaps maps, const __grid_constant__ CUten
           const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<const __nv_bfloat16*>(S.ptr) + n0) + c * 16;
           const uint32_t ldb = (uint32_t)S.ld * 2u;
           const uint32_t g0 = g[t][0], g1 = g[t][1];
-          if (R == 1) add_rows<1, RPW>(dst_t, base, ldb, g0, g1, sub, c, on);
-          else if (R == 2) add_rows<2, RPW>(dst_t, base, ldb, g0, g1, sub, c, on);
-          else add_rows<4, RPW>(dst_t, base, ldb, g0, g1, sub, c, on);
+          if (a.add_ca) {
+            if (R == 1) add_rows<1, RPW, true>(dst_t, base, ldb, g0, g1, sub, c, on);
+            else if (R == 2) add_rows<2, RPW, true>(dst_t, base, ldb, g0, g1, sub, c, on);
+            else add_rows<4, RPW, true>(dst_t, base, ldb, g0, g1, sub, c, on);
+          } else {
+            if (R == 1) add_rows<1, RPW, false>(dst_t, base, ldb, g0, g1, sub, c, on);
+            else if (R == 2) add_rows<2, RPW, false>(dst_t, base, ldb, g0, g1, sub, c, on);
+            else add_rows<4, RPW, false>(dst_t, base, ldb, g0, g1, sub, c, on);
+          }
           ++slot;
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sBar + 112 + 8 * buf) : "memory");
@@ -1712,6 +1727,7 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
     if (split < 0) { const char* e = getenv("B3D_STAGE_SPLIT"); split = (e && e[0] == '0') ? 0 : 1; }
     if (fast < 0) { const char* e = getenv("B3D_FAST_EPI"); fast = (e && e[0] == '0') ? 0 : 1; }
     a.fast_epi = fast;
+    { static int ca = -1; if (ca < 0) { const char* e = getenv("B3D_ADD_CA"); ca = (e && e[0] == '1') ? 1 : 0; } a.add_ca = ca; }   // measured 2-6 % slower: opt-in
     bool ok = enabled && nadd > 0 && y_dtype == B3D_BF16;
     for (int q = 0; q < nadd; ++q) ok = ok && a.add[q].dtype == B3D_BF16;
     const long long limit = 227 * 1024;
