@@ -600,8 +600,24 @@ __device__ __forceinline__ void stage_piece(uint32_t dst, const void* p, int dty
   }
 }
 
+// The register half of stage_piece for fp32 sources: the stores (asm volatile, memory clobber) keep the compiler from
+// moving a later piece's loads above them, so a loop of stage_piece calls pays one global-load latency PER PIECE
+// (12 per 64-row chunk: ~14 us per chunk, 1 TB/s). The staging loops below load all pieces of a batch first.
+__device__ __forceinline__ void store_piece_f32(uint32_t dst, const float4& v0, const float4& v1, uint32_t lo_off) {
+  using namespace tc;
+  if (lo_off) {
+    uint32_t h[4], l[4];
+    split_pack2(v0.x, v0.y, h[0], l[0]); split_pack2(v0.z, v0.w, h[1], l[1]);
+    split_pack2(v1.x, v1.y, h[2], l[2]); split_pack2(v1.z, v1.w, h[3], l[3]);
+    st_shared_v4(dst, h[0], h[1], h[2], h[3]);
+    st_shared_v4(dst + lo_off, l[0], l[1], l[2], l[3]);
+  } else {
+    st_shared_v4(dst, pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+  }
+}
+
 template <bool SPLIT>
-__global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, SPLIT ? 1 : 2) k_wgrad_tc(const WgTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   using namespace tc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -647,13 +663,25 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
     {
       const int ng = gq & 15;
       const int n = n0 + ng * 8;
+      const bool f32 = a.dy.dtype != B3D_BF16;
+      float4 va[4][2];
+      int kind[4];      // 0: zeros, 1: fp32 piece in registers, 2: done (bf16 cp.async / ragged tail)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int i = (gq >> 4) * 4 + j;
         const long long r = rbase + i * 8 + rl;
         const uint32_t dst = sA + s * NI * TC_A_STAGE + ng * 1024 + i * 128 + rl * 16;
+        kind[j] = 0;
         if (r < r1 && n + 7 < a.Nout) {
-          stage_piece(dst, seg_addr(a.dy, r, n), a.dy.dtype, a_lo);
+          if (f32) {
+            const float4* p = reinterpret_cast<const float4*>(seg_addr(a.dy, r, n));
+            va[j][0] = __ldg(p);
+            va[j][1] = __ldg(p + 1);
+            kind[j] = 1;
+          } else {
+            stage_piece(dst, seg_addr(a.dy, r, n), a.dy.dtype, a_lo);
+            kind[j] = 2;
+          }
         } else if (r < r1 && n < a.Nout) {   // ragged tail of Nout (not a multiple of 8): scalar
           float t[8];
 #pragma unroll
@@ -662,16 +690,18 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
                        ? (a.dy.dtype == B3D_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.dy.ptr)[r * a.dy.ld + n + q])
                                                  : a.dy.ptr[r * a.dy.ld + n + q])
                        : 0.f;
-          if (SPLIT) {
-            uint32_t h[4], l[4];
+          va[j][0] = make_float4(t[0], t[1], t[2], t[3]);
+          va[j][1] = make_float4(t[4], t[5], t[6], t[7]);
+          kind[j] = 1;
+        }
+      }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) split_pack2(t[2 * q], t[2 * q + 1], h[q], l[q]);
-            st_shared_v4(dst, h[0], h[1], h[2], h[3]);
-            st_shared_v4(dst + a_lo, l[0], l[1], l[2], l[3]);
-          } else {
-            st_shared_v4(dst, pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
-          }
-        } else {
+      for (int j = 0; j < 4; ++j) {
+        const int i = (gq >> 4) * 4 + j;
+        const uint32_t dst = sA + s * NI * TC_A_STAGE + ng * 1024 + i * 128 + rl * 16;
+        if (kind[j] == 1) {
+          store_piece_f32(dst, va[j][0], va[j][1], a_lo);
+        } else if (kind[j] == 0) {
           st_shared_v4(dst, 0u, 0u, 0u, 0u);
           if (SPLIT) st_shared_v4(dst + a_lo, 0u, 0u, 0u, 0u);
         }
@@ -681,17 +711,39 @@ __global__ void __launch_bounds__(TC_THREADS) k_wgrad_tc(const WgTcArgs a) {
     if (gq < Nk / 8) {
       const int ent = s_tab[k0 / 8 + gq];
       const bool ones = (ent < 0) && (k0 + gq * 8 == a.Ktot);
+      const bool f32 = ent >= 0 && a.seg[ent >> 24].dtype != B3D_BF16;
+      float4 vb[8][2];
+      long long gr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {       // row indices of a gathered segment first (their own latency)
+        const long long r = rbase + i * 8 + rl;
+        gr[i] = r;
+        if (ent >= 0 && r < r1 && a.seg[ent >> 24].idx) gr[i] = (long long)__ldg(a.seg[ent >> 24].idx + r);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long long r = rbase + i * 8 + rl;
         const uint32_t dst = sB + s * NI * b_stage + gq * 1024 + i * 128 + rl * 16;
         if (ent >= 0 && r < r1) {
           const SegDev& S = a.seg[ent >> 24];
-          const long long gr = S.idx ? (long long)__ldg(S.idx + r) : r;
-          stage_piece(dst, seg_addr(S, gr, ent & 0xFFFFFF), S.dtype, b_lo);
+          if (f32) {
+            const float4* p = reinterpret_cast<const float4*>(seg_addr(S, gr[i], ent & 0xFFFFFF));
+            vb[i][0] = __ldg(p);
+            vb[i][1] = __ldg(p + 1);
+          } else {
+            stage_piece(dst, seg_addr(S, gr[i], ent & 0xFFFFFF), S.dtype, b_lo);
+          }
         } else {
           st_shared_v4(dst, (ones && r < r1) ? 0x00003F80u : 0u, 0u, 0u, 0u);   // bf16(1.0) in element 0
           if (SPLIT) st_shared_v4(dst + b_lo, 0u, 0u, 0u, 0u);
+        }
+      }
+      if (f32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long r = rbase + i * 8 + rl;
+          const uint32_t dst = sB + s * NI * b_stage + gq * 1024 + i * 128 + rl * 16;
+          if (r < r1) store_piece_f32(dst, vb[i][0], vb[i][1], b_lo);
         }
       }
     }
