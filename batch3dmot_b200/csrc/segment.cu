@@ -57,19 +57,31 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) k_segment_sum(
   }
 }
 
-template <bool VEC>
+// fp32 rows; MASK: zero where the fp32 ReLU activation `mask` (same shape as out) is <= 0 (backward of an fp32
+// segment sum whose source was a ReLU output: gather + mask in one pass)
+template <bool VEC, bool MASK>
 __global__ void __launch_bounds__(SEG_WARPS * 32) k_gather_rows(
     const float* __restrict__ src, int ld, const int32_t* __restrict__ idx, long long M, int C,
-    float* __restrict__ out, int ldo) {
+    float* __restrict__ out, int ldo, const float* __restrict__ mask, int ldm) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5);
   if (r >= M) return;
   const long long g = __ldg(idx + r);
   if (VEC) {
-    for (int c = lane * 4; c < C; c += 128)
-      *reinterpret_cast<float4*>(out + r * ldo + c) = __ldg(reinterpret_cast<const float4*>(src + g * ld + c));
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(src + g * ld + c));
+      if (MASK) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mask + r * ldm + c));
+        v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(out + r * ldo + c) = v;
+    }
   } else {
-    for (int c = lane; c < C; c += 32) out[r * ldo + c] = __ldg(src + g * ld + c);
+    for (int c = lane; c < C; c += 32) {
+      float v = __ldg(src + g * ld + c);
+      if (MASK) v = __ldg(mask + r * ldm + c) > 0.f ? v : 0.f;
+      out[r * ldo + c] = v;
+    }
   }
 }
 
@@ -306,12 +318,18 @@ extern "C" int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* 
     B3D_LAUNCH_CHECK("k_gather_rows_bf16");
     return 0;
   }
-  if (relu_mask || src_dtype == B3D_BF16) return bad_arg("b3d_gather_rows: relu_mask / bf16 source need bf16 output");
+  if (src_dtype == B3D_BF16) return bad_arg("b3d_gather_rows: a bf16 source needs bf16 output");
+  if (relu_mask && mask_dtype != B3D_F32) return bad_arg("b3d_gather_rows: fp32 output takes an fp32 relu_mask");
   float* out = reinterpret_cast<float*>(out_v);
-  bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out);
+  const float* mk = reinterpret_cast<const float*>(relu_mask);
+  bool vec = (C % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && al16(src) && al16(out) &&
+             (!mk || ((ld_mask % 4 == 0) && al16(mk)));
   unsigned grid = (unsigned)ceil_div(M, SEG_WARPS);
-  if (vec) k_gather_rows<true><<<grid, SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(src, ld_src, idx, M, C, out, ld_out);
-  else k_gather_rows<false><<<grid, SEG_WARPS * 32, 0, (cudaStream_t)stream>>>(src, ld_src, idx, M, C, out, ld_out);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec && mk) k_gather_rows<true, true><<<grid, SEG_WARPS * 32, 0, st>>>(src, ld_src, idx, M, C, out, ld_out, mk, ld_mask);
+  else if (vec) k_gather_rows<true, false><<<grid, SEG_WARPS * 32, 0, st>>>(src, ld_src, idx, M, C, out, ld_out, nullptr, 0);
+  else if (mk) k_gather_rows<false, true><<<grid, SEG_WARPS * 32, 0, st>>>(src, ld_src, idx, M, C, out, ld_out, mk, ld_mask);
+  else k_gather_rows<false, false><<<grid, SEG_WARPS * 32, 0, st>>>(src, ld_src, idx, M, C, out, ld_out, nullptr, 0);
   B3D_LAUNCH_CHECK("k_gather_rows");
   return 0;
 }

@@ -565,9 +565,13 @@ def gather_rows_raw(src, idx32, out_dtype=torch.float32, relu_mask=None, relu_bi
                                         L.stream()),
                 "b3d_gather_rows")
         return out
+    mdt = L.BF16
+    if fused_mask is None and relu_mask is not None and out_dtype == torch.float32 and relu_mask.dtype == torch.float32 \
+            and relu_mask.dim() == 2 and relu_mask.stride(1) == 1 and relu_mask.shape == out.shape:
+        fused_mask, mdt = relu_mask, L.F32          # fp32 gather + fp32 ReLU mask in one pass (1e-4 modes)
     L.check(L.lib().b3d_gather_rows(L.ptr(src), src.stride(0), L.ptr(idx32), M, src.size(1), L.ptr(out),
                                     _DT[out_dtype], out.stride(0), L.ptr(fused_mask),
-                                    fused_mask.stride(0) if fused_mask is not None else 0, L.BF16, _DT[src.dtype],
+                                    fused_mask.stride(0) if fused_mask is not None else 0, mdt, _DT[src.dtype],
                                     L.stream()),
             "b3d_gather_rows")
     if relu_mask is not None and fused_mask is None:

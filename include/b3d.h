@@ -111,7 +111,7 @@ int b3d_segment_sum(const void* src, int32_t src_dtype, int32_t ld_src, const in
  * were ReLU outputs, so the gathered gradient is zeroed where relu_mask <= 0. */
 int b3d_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t M, int32_t C,
                     void* out, int32_t out_dtype, int32_t ld_out, const void* relu_mask, int32_t ld_mask,
-                    int32_t mask_dtype /* B3D_BF16 or B3D_BITS */, int32_t src_dtype /* B3D_F32, or B3D_BF16
+                    int32_t mask_dtype /* bf16 output: B3D_BF16 or B3D_BITS; fp32 output: B3D_F32 */, int32_t src_dtype /* B3D_F32, or B3D_BF16
                     (src is really __nv_bfloat16*, ld in elements; bf16 output only) */, void* stream);
 
 /* out[M,C] = sum_k ins[k][M,C] (n <= 8 dense fp32/bf16 inputs of equal width C % 8 == 0, each with its

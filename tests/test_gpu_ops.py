@@ -94,6 +94,19 @@ def test_segment_sum_empty_and_isolated():
     assert torch.equal(ops.gather_rows_raw(got.to(DEV), G.dst32).cpu(), got[ei[1]])
 
 
+@pytest.mark.parametrize("C", [7, 64, 192])
+def test_gather_rows_fp32_with_relu_mask(C):
+    """fp32 gather with the fp32 ReLU activation as mask (backward of an fp32 segment sum) in one pass."""
+    torch.manual_seed(C)
+    N, M = 333, 10007
+    src, act = torch.randn(N, C), torch.randn(M, C)
+    idx = torch.randint(0, N, (M,), dtype=torch.int32)
+    before = L.launch_count()
+    got = ops.gather_rows_raw(src.to(DEV), idx.to(DEV), relu_mask=act.to(DEV))
+    assert L.launch_count() - before == 1
+    assert torch.equal(got.cpu(), src[idx.long()] * (act > 0))
+
+
 @pytest.mark.parametrize("C", [64, 96, 192, 256, 512])
 @pytest.mark.parametrize("src_bf16", [True, False])
 def test_gather_rows_bf16_with_relu_masks(C, src_bf16):
