@@ -11,6 +11,13 @@
 // Pipeline (both kernels): 256 threads stage chunk c+1 while the tensor core works on chunk c
 // (tcgen05.mma is asynchronous; tcgen05.commit -> mbarrier frees the stage). Two CTAs per SM
 // overlap one CTA's epilogue with the other's main loop.
+//
+//   b3d_linear_tma / b3d_wgrad_tma (second half of the file): the TMA-fed persistent kernels that run the dense bf16
+//                   layers of the bf16 mode — operand tiles by cp.async.bulk.tensor (128-byte swizzle), the weight
+//                   block resident in shared memory, double-buffered TMEM accumulators; row-gathered bf16 addends are
+//                   staged by producer warps (cp.async) into operand-shaped tiles and added to the accumulator by
+//                   identity MMAs; lean epilogue block for bf16 outputs; see the comment above k_linear_tma.
+//   SPLIT variants of the thread-staged kernels: the 1e-4 mode (tf32 x3 layers, split-bf16 weight gradients).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -833,10 +840,12 @@ static bool seg_tc_ok(const SegDev& S) {
 }
 
 // ------------------------------------------------------------------ TMA-fed persistent forward / dgrad
-// Dense bf16 operands only (1-2 row-major segments, widths multiples of 64 except the last):
-//   warp 0 : TMA producer  (cp.async.bulk.tensor 2D boxes {64 cols, 128 rows}, 128B swizzle)
-//   warp 1 : MMA issuer    (tcgen05.mma, operands straight from the TMA-written tiles)
-//   warps 2-9: epilogue    (TMEM -> registers -> bias/adds/act/masks -> global)
+// Dense bf16 operands (1-6 row-major segments, each padded to whole 64-column chunks in the packed weights; row-gathered
+// segments by TMA tile::gather4 are supported but off in the model path):
+//   warp 0 : TMA producer  (cp.async.bulk.tensor 2D boxes {64 cols, 128 rows}, 128B swizzle, 4-8 stage ring)
+//   warp 1 : MMA issuer    (tcgen05.mma, operands straight from the TMA-written tiles; identity MMAs for staged addends)
+//   warps 2-9: epilogue    (TMEM -> registers -> [bias / un-staged addends] / act / masks -> global; lean or generic block)
+//   warps 10..: addend producers (cp.async of whole addend rows into operand-shaped tiles)
 // The weight block [Nb, K] stays resident in shared memory for the CTA's lifetime; CTAs are
 // persistent over row tiles; two TMEM accumulators let the epilogue of tile t overlap the MMAs of
 // tile t+1. No thread touches the operands: the staging cost of k_linear_tc disappears.
