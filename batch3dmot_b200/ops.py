@@ -244,8 +244,8 @@ _chain_packs = {}
 #              form — instead of arriving as epilogue addends of per-node pre-projections.
 #   edge_block the edge side of a message-passing iteration as ONE autograd node with an explicit backward
 #              (ops._MPEdgeBlockG): same kernels in the forward pass, a K-concatenated de' GEMM instead of two
-#              GEMMs + a 3-way sum kernel in the backward pass. Measured 110.3 ms/step against 107.2 ms (10 GB less
-#              memory): OFF.
+#              GEMMs + a 3-way sum kernel in the backward pass. Same speed as the default (86.2 vs 86.1 ms/step), 10 GB
+#              less memory at 64 scenes: OFF (nothing to gain in time).
 #   narrow_split bf16 mode: the widest layer of the two narrow chains (classifier 64 -> 32, edge encoder 32 -> 64) as a
 #              tensor-core layer, the rest in the narrow kernel (_narrow_split). ON.
 #   bf16_inputs bf16 mode: dense fp32 inputs of a tensor-core chain are rounded to bf16 once (not per tile). ON.
@@ -991,8 +991,12 @@ class _MPEdgeBlockG(torch.autograd.Function):
         dhf, dhp = z(dhf, nm), z(dhp, nm)
         # de' = cat[dh_f, dh_p] . [Wf_e ; Wp_e] + (direct gradient of e'), then the masked chain back to cat[e, att]
         w_fp = torch.cat([Wfe, Wpe], 0)
+        # the direct gradient arrives as a column slice of the next block's [E, 128] input gradient: a dense addend
+        # with its own row stride, no copy
+        if de is not None and not (de.dim() == 2 and de.stride(1) == 1 and de.dtype == bf and _al16(de) and de.stride(0) % 8 == 0):
+            de = de.to(bf).contiguous()
         dz2 = linear_raw([_it(dhf), _it(dhp)], w_fp, None, M, trans_w=True, tc=True, out_dtype=bf,
-                         adds=[(de.contiguous(), None)] if de is not None else None)
+                         adds=[(de, None)] if de is not None else None)
         dz1 = linear_raw([_it(dz2)], W2, None, M, trans_w=True, mask_bits=b_x2, tc=True, out_dtype=bf)
         dz0 = linear_raw([_it(dz1)], W1, None, M, trans_w=True, mask_bits=b_x1, tc=True, out_dtype=bf)
         dA = linear_raw([_it(dz0)], W0e, None, M, trans_w=True, tc=True, out_dtype=bf)
