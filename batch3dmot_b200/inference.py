@@ -130,6 +130,38 @@ def forward_scores(model, b, multimodal=True):
     return out.reshape(-1).float()
 
 
+def capture_forward(model, b, multimodal=True, warmup=2):
+    """The inference forward of the batch graph `b` captured in a CUDA graph; returns `replay() -> scores [E]` (a static
+    buffer, overwritten by every replay). For the launch-bound regime — one scene graph or a few window graphs per call
+    (BASELINE configs[0]: a poses-only forward is ~150 short kernels for 61 k edges), where Python / ctypes dispatch
+    costs several times the kernels. Shapes and addresses are static: new inputs of the SAME graph structure are copied
+    into b's tensors in place (`b.pose_feats.copy_(...)`); a different edge_index needs a new capture. The weight packs
+    are re-made inside the graph from the live parameters at every replay, so in-place weight updates
+    (optimizer.step(), load_state_dict) are followed."""
+    from . import ops
+    if getattr(b, "_b3d_graph", None) is None:
+        b._b3d_graph = ops.Graph(b.edge_index, b.pose_feats.size(0))
+    dev = b.pose_feats.device
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(warmup):                  # allocator pools, lazily built tables (degree blocks), module caches
+            forward_scores(model, b, multimodal)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    ops.invalidate_weight_cache()                # packs / stacked weights are produced inside the graph
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        scores = forward_scores(model, b, multimodal)
+    ops.invalidate_weight_cache()                # nothing allocated from the graph's pool stays in a cache
+
+    def replay():
+        graph.replay()
+        return scores
+    replay.graph, replay.scores = graph, scores
+    return replay
+
+
 def infer_scene_scores(model, scenes, device, multimodal=True, window=5):
     """One forward over every window of every given scene. Returns, per scene, the list of
     (global_node_id, edge_index, scores) triples that tracking.assign_track_ids consumes

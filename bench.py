@@ -57,10 +57,11 @@ def parse():
     return ap.parse_args()
 
 
-def make_batch(rank, scenes, raw=False):
+def make_batch(rank, scenes, raw=False, ids=None):
+    """`scenes` scene graphs of rank `rank` (seeds SEED + 1000 rank + i), or the scenes `ids` of rank 0's batch."""
     from batch3dmot_b200 import synth
     gs = []
-    for i in range(scenes):
+    for i in (range(scenes) if ids is None else ids):
         s = SEED + 1000 * rank + i
         gs.append(synth.add_labels(synth.add_modalities(synth.scene_graph(seed=s), s, raw=raw), s))
     return synth.collate(gs)
@@ -209,7 +210,7 @@ def val_scene_rates(n, seed=SEED):
     return r.clamp(5, 300).round().long().tolist()
 
 
-def extras(a, rank, world, dev, model, d, tm, E_global):
+def extras(a, rank, world, dev, model, d, tm, E_global, trainer, headline):
     """The other BASELINE configs and regimes, as extra keys of the JSON line."""
     import torch.distributed as dist
     from batch3dmot_b200 import _lib, ops, synth, inference
@@ -252,6 +253,29 @@ def extras(a, rank, world, dev, model, d, tm, E_global):
         "window_edges_approx": int(win_edges.item()), "tracks_rank0": n_tracks[0], "timed": "host wall clock, max over ranks"}
     model.train()
     del scenes, lst
+
+    # ---- configs[4] as STRONG scaling: the SAME global batch (rank 0's `--scenes` scene graphs of the headline) split
+    # over the ranks by scene (contiguous shares), one gradient all-reduce per step; at 1 GPU this is the headline itself
+    if world == 1:
+        x["strong_scaling_training"] = dict(headline, global_scenes=a.scenes, scenes_per_gpu=a.scenes, note="= the headline step")
+    else:
+        per = -(-a.scenes // world)
+        ids = list(range(rank * per, min(a.scenes, (rank + 1) * per)))
+        if ids:
+            ds = to_dev(make_batch(0, 0, ids=ids), dev)
+            ds._b3d_graph = ops.Graph(ds.edge_index, ds.num_nodes)
+            Es = ds.edge_index.size(1)
+        else:
+            ds, Es = None, 0
+        et = torch.tensor([Es], dtype=torch.int64, device=dev)
+        dist.all_reduce(et)
+        Eg = int(et.item())
+        if (world - 1) * per < a.scenes:      # every rank owns at least one scene (same decision on every rank)
+            ms_s = tm.run(lambda: trainer.step(ds, global_edges=Eg, **mm_kwargs(ds)), max(3, a.steps // 2), 2)
+            x["strong_scaling_training"] = {"global_scenes": a.scenes, "scenes_per_gpu": per, "edges_per_step": Eg,
+                                            "ms_per_step": ms_s, "edges_per_s": Eg / ms_s * 1e3, "scaling": "strong",
+                                            "timed": "CUDA events, max over ranks"}
+        del ds
     if rank != 0:
         return x
 
@@ -298,6 +322,14 @@ def extras(a, rank, world, dev, model, d, tm, E_global):
             msf = tm.run(lambda: pm(dd), 5, 2, reduce=False)
         res[name] = {"edges": Ed, "fwd_bwd_edges_per_s": Ed / ms * 1e3, "forward_edges_per_s": Ed / msf * 1e3,
                      "ms_per_step": ms}
+        if name == "1_scene":        # configs[0] proper: one scene graph per call is launch-bound -> CUDA-graph replay
+            try:
+                rp = inference.capture_forward(pm, dd, multimodal=False)
+                msg = tm.run(rp, 20, 3, reduce=False)
+                res[name].update(cuda_graph_forward_us=msg * 1e3, cuda_graph_forward_edges_per_s=Ed / msg * 1e3)
+                del rp
+            except Exception as ex:                  # noqa: BLE001 - reported, not fatal for the headline
+                res[name]["cuda_graph_error"] = repr(ex)[:200]
     x["pose_model"] = dict(res, workload="configs[0]: poses-only PoseGNN, random init, fwd + BCE-with-logits + bwd + Adam")
     del pm, ptr_
 
@@ -571,7 +603,8 @@ def main():
                              "note": "inference forward of the same batch under torch.no_grad()"},
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30}
     if not a.no_extras:
-        line.update(extras(a, rank, world, dev, model, d, tm, E_global))
+        line.update(extras(a, rank, world, dev, model, d, tm, E_global, trainer,
+                           {"edges_per_step": E_global, "ms_per_step": ms_per_step, "edges_per_s": value}))
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, cms, cE, thr, kind, how = cpu_reference_run(1, 1, a.cpu_scenes)
         line["cpu_baseline"] = {"value": v, "unit": "edges/s", "cores": thr, "kind": kind,

@@ -248,3 +248,44 @@ def test_cuda_graph_of_the_training_step_replays_the_eager_trajectory(precision)
     finally:
         ops.set_precision("fp32")
         ops.invalidate_weight_cache()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("multimodal", [False, True])
+def test_cuda_graph_of_the_inference_forward_equals_eager_and_follows_inputs_and_weights(multimodal):
+    """inference.capture_forward (BASELINE configs[0]: one scene graph per call is launch-bound): the replayed scores are
+    bit-identical to the eager forward, follow in-place input updates of the same graph structure and in-place weight
+    updates (the packs are re-made inside the graph), and leave nothing from the graph's pool in the weight caches."""
+    from batch3dmot_b200 import inference
+    from batch3dmot_b200.clr_att_gnn import GNN
+    from batch3dmot_b200.pose_gnn import PoseGNN
+    sc = synth.add_modalities(synth.scene_graph(seed=21, T=10, nodes_per_frame=40), 21, raw=False)
+    d = to_dev(sc)
+    ops.set_precision("bf16")
+    try:
+        torch.manual_seed(5621)
+        model = (GNN(None, None, None) if multimodal else PoseGNN()).to(DEV).eval()
+        with torch.no_grad():          # positive biases: no dead ReLU layer under the default init (the scores must move)
+            for n, p in model.named_parameters():
+                if n.endswith("bias"):
+                    p.abs_().add_(0.05)
+        eager = inference.forward_scores(model, d, multimodal).clone()
+        assert float(eager.std()) > 0
+        replay = inference.capture_forward(model, d, multimodal)
+        assert torch.equal(replay(), eager)
+        assert torch.equal(inference.forward_scores(model, d, multimodal), eager)      # eager path intact after the capture
+        g = torch.Generator().manual_seed(3)
+        d.pose_feats.copy_(torch.randn(d.pose_feats.shape, generator=g).to(DEV))        # new inputs, same structure
+        d.edge_attr.copy_(torch.randn(d.edge_attr.shape, generator=g).to(DEV).to(d.edge_attr.dtype))
+        want = inference.forward_scores(model, d, multimodal).clone()
+        assert not torch.equal(want, eager)
+        assert torch.equal(replay(), want)
+        with torch.no_grad():                                                             # in-place weight update
+            for p in model.parameters():
+                p.mul_(1.01)
+        want2 = inference.forward_scores(model, d, multimodal).clone()
+        assert not torch.equal(want2, want)
+        assert torch.equal(replay(), want2)
+    finally:
+        ops.set_precision("fp32")
+        ops.invalidate_weight_cache()
