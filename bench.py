@@ -275,6 +275,21 @@ def extras(a, rank, world, dev, model, d, tm, E_global, trainer, headline):
             x["strong_scaling_training"] = {"global_scenes": a.scenes, "scenes_per_gpu": per, "edges_per_step": Eg,
                                             "ms_per_step": ms_s, "edges_per_s": Eg / ms_s * 1e3, "scaling": "strong",
                                             "timed": "CUDA events, max over ranks"}
+            # the same step as a CUDA graph per rank (Trainer.capture: kernels + the NCCL all-reduce + Adam captured): with
+            # few scenes per GPU the eager step is bound by the host-side dispatch of its ~490 launches, not by the GPU
+            if os.environ.get("B3D_BENCH_GRAPH", "1") == "1":
+                ok = torch.ones(1, device=dev)
+                try:
+                    replay = trainer.capture(ds, global_edges=Eg, **mm_kwargs(ds))
+                except Exception as ex:                      # noqa: BLE001 - reported, not fatal for the headline
+                    ok.zero_()
+                    x["strong_scaling_training"]["cuda_graph_error"] = repr(ex)[:200]
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # replay only when every rank holds a graph (collective inside)
+                if float(ok.item()) > 0:
+                    ms_g = tm.run(replay, max(3, a.steps // 2), 2)
+                    x["strong_scaling_training"].update(cuda_graph_ms_per_step=ms_g, cuda_graph_edges_per_s=Eg / ms_g * 1e3)
+                    del replay
+                trainer._step_dev = None
         del ds
     if rank != 0:
         return x
