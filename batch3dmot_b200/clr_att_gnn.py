@@ -115,10 +115,13 @@ class GNN(nn.Module):
             p_i = ops.fused_mlp(sens, [w0[:, :288]], [ae[0].bias], out_dtype=ops.store_dtype())    # [N,512]
             p_j = ops.fused_mlp(sens, [w0[:, 288:576]], [None], out_dtype=ops.store_dtype())
             e0 = e0.to(ops.store_dtype())      # edge-level tensors are kept in bf16 between kernels (bf16 mode)
-            if ops.att_edge_encoder_supported(e0, ae):
-                att = ops.att_edge_encoder_block(g, e0, p_i, p_j, w0[:, 576:], ae)      # two fused launches
+            # e0 feeds att_edge_encoder and the first message-passing iteration: one two-way gradient sum kernel
+            # instead of autograd's strided elementwise addition
+            e0, e0_att = ops.fanout(e0, 2)
+            if ops.att_edge_encoder_supported(e0_att, ae):
+                att = ops.att_edge_encoder_block(g, e0_att, p_i, p_j, w0[:, 576:], ae)      # two fused launches
             else:
-                att = ops.fused_mlp([(e0, None)], [w0[:, 576:]] + [m.weight for m in ae[1:]],
+                att = ops.fused_mlp([(e0_att, None)], [w0[:, 576:]] + [m.weight for m in ae[1:]],
                                     [None] + [m.bias for m in ae[1:]], adds=[(p_i, dst), (p_j, src)],
                                     out_dtype=ops.store_dtype())
         else:

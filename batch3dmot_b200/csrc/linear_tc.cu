@@ -803,14 +803,27 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 1 : 2) k_wgrad_tc(const Wg
   if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
-__global__ void k_wgrad_tc_reduce(const float* __restrict__ part, int S, int Nout, int Ktot,
-                                  float* __restrict__ dW, int lddw, float* __restrict__ db, int accumulate) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// Fixed-order sum of the S split partials. A block owns 32 consecutive output elements; its 8 warps take the partials
+// p = w, w + 8, ... (each load a coalesced 128-byte line), the eight sums meet in shared memory and are added in warp
+// order: deterministic, and S / 8 dependent loads per thread instead of S (the launches were latency-bound: a
+// [128, 201] gradient with S = 125 is 100 blocks of threads walking 125 strided loads each).
+constexpr int WG_RED_WARPS = 8;
+__global__ void __launch_bounds__(32 * WG_RED_WARPS)
+k_wgrad_tc_reduce(const float* __restrict__ part, int S, int Nout, int Ktot,
+                  float* __restrict__ dW, int lddw, float* __restrict__ db, int accumulate) {
+  __shared__ float sm[WG_RED_WARPS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + lane;
   const int Kw = Ktot + 1;
   const long long tot = (long long)Nout * Kw;
-  if (i >= tot) return;
   float s = 0.f;
-  for (int p = 0; p < S; ++p) s += part[(long long)p * tot + i];   // fixed order: deterministic
+  if (i < tot)
+    for (int p = w; p < S; p += WG_RED_WARPS) s += __ldg(part + (long long)p * tot + i);
+  sm[w][lane] = s;
+  __syncthreads();
+  if (w != 0 || i >= tot) return;
+#pragma unroll
+  for (int q = 1; q < WG_RED_WARPS; ++q) s += sm[q][lane];
   const int n = (int)(i / Kw), k = (int)(i % Kw);
   if (k < Ktot) {
     float* o = dW + (long long)n * lddw + k;
@@ -1643,7 +1656,7 @@ extern "C" int b3d_wgrad_tc(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t 
   else k_wgrad_tc<false><<<grid, TC_THREADS, smem, st>>>(a);
   B3D_LAUNCH_CHECK("k_wgrad_tc");
   long long tot = (long long)Nout * (K + 1);
-  k_wgrad_tc_reduce<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(a.part, S, Nout, K, dW, lddw, db,
+  k_wgrad_tc_reduce<<<(unsigned)ceil_div(tot, 32), 32 * WG_RED_WARPS, 0, st>>>(a.part, S, Nout, K, dW, lddw, db,
                                                                   (flags & B3D_FLAG_ACCUMULATE) ? 1 : 0);
   B3D_LAUNCH_CHECK("k_wgrad_tc_reduce");
   return 0;
@@ -1978,7 +1991,7 @@ extern "C" int b3d_wgrad_tma(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t
   k_wgrad_tma<<<grid, WG_THREADS, smem, st>>>(mDY, mA0, mA1, a);
   B3D_LAUNCH_CHECK("k_wgrad_tma");
   long long tot = (long long)Nout * (K + 1);
-  k_wgrad_tc_reduce<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(a.part, (int)S, Nout, K, dW, lddw, db,
+  k_wgrad_tc_reduce<<<(unsigned)ceil_div(tot, 32), 32 * WG_RED_WARPS, 0, st>>>(a.part, (int)S, Nout, K, dW, lddw, db,
                                                                   (flags & B3D_FLAG_ACCUMULATE) ? 1 : 0);
   B3D_LAUNCH_CHECK("k_wgrad_tc_reduce");
   return 0;
