@@ -291,6 +291,36 @@ def extras(a, rank, world, dev, model, d, tm, E_global, trainer, headline):
                     del replay
                 trainer._step_dev = None
         del ds
+        # the reference's OWN batch on every rank (cl_config.yaml:99: 2 window graphs), data parallel: ~490 launches of a
+        # few microseconds + one 5.28 MB all-reduce per step; eager (host-dispatch bound) and as a CUDA graph per rank
+        sd = SEED + 31 * rank
+        wins = synth.windows(synth.add_labels(synth.add_modalities(synth.scene_graph(seed=sd), sd, raw=False), sd), 5)[:2]
+        for w in wins:
+            synth.add_labels(w, sd)
+        dw = to_dev(synth.collate(wins), dev)
+        dw._b3d_graph = ops.Graph(dw.edge_index, dw.num_nodes)
+        et = torch.tensor([dw.edge_index.size(1)], dtype=torch.int64, device=dev)
+        dist.all_reduce(et)
+        Ew = int(et.item())
+        kww = mm_kwargs(dw)
+        ms_e = tm.run(lambda: trainer.step(dw, global_edges=Ew, **kww), 10, 3)
+        res = {"windows_per_gpu": 2, "edges_per_step": Ew, "us_per_step": ms_e * 1e3, "edges_per_s": Ew / ms_e * 1e3,
+               "scaling": "weak"}
+        if os.environ.get("B3D_BENCH_GRAPH", "1") == "1":
+            ok = torch.ones(1, device=dev)
+            try:
+                replay = trainer.capture(dw, global_edges=Ew, **kww)
+            except Exception as ex:                          # noqa: BLE001
+                ok.zero_()
+                res["cuda_graph_error"] = repr(ex)[:200]
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) > 0:
+                ms_g = tm.run(replay, 20, 3)
+                res.update(cuda_graph_us_per_step=ms_g * 1e3, cuda_graph_edges_per_s=Ew / ms_g * 1e3)
+                del replay
+            trainer._step_dev = None
+        x["small_batch_data_parallel"] = res
+        del dw
     if rank != 0:
         return x
 
@@ -355,11 +385,15 @@ def extras(a, rank, world, dev, model, d, tm, E_global, trainer, headline):
         synth.add_labels(w, SEED)
     two = to_dev(synth.collate(wins), dev)
     one_mm = to_dev(make_batch(0, 1), dev)
+    all_w = synth.windows(synth.add_labels(synth.add_modalities(synth.scene_graph(seed=SEED), SEED, raw=False), SEED), 5)
+    for w in all_w:
+        synth.add_labels(w, SEED)
+    scene_w = to_dev(synth.collate(all_w), dev)          # SURVEY 8d config 5 large-batch variant: all windows of one scene
     torch.manual_seed(SEED)
     ms_ = GNN(None, None, None).to(dev)
     trs = Trainer(ms_, batch_size=2, data_parallel=False)
     res = {}
-    for name, dd in (("2_windows", two), ("1_scene", one_mm)):
+    for name, dd in (("2_windows", two), ("1_scene", one_mm), ("all_windows_of_1_scene", scene_w)):
         dd._b3d_graph = ops.Graph(dd.edge_index, dd.num_nodes)
         Ed = dd.edge_index.size(1)
         kwd = mm_kwargs(dd)
