@@ -876,6 +876,7 @@ template <bool LEAN> struct TmaCfg {
   static constexpr int THREADS = 32 * (TMA_FIRST_ADD_WARP + ADD_WARPS);
 };
 constexpr int WG_THREADS = 192;
+constexpr int WG_MIN_ROWS = 256;       // fewest rows a split of k_wgrad_tma takes (bounds the number of partials)
 
 // TMA tile::gather4: four rows r0..r3 of a 2D tensor (tensor map encoded with box {64 columns, 1 row}), 64 columns
 // from column c0, land in four consecutive 128-byte rows at dst with the same address-based 128B swizzle as a
@@ -1931,10 +1932,10 @@ extern "C" int b3d_linear_tma(const b3d_seg_t* segs, int32_t nseg, const void* W
 }
 
 extern "C" size_t b3d_wgrad_tma_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {
-  // worst case: one split per 512 rows is never exceeded by the plan below
+  // worst case: one split per 256 rows is never exceeded by the plan below
   long long tiles = (long long)((Nout + TC_BM - 1) / TC_BM) * ((round_up(K, 64) / 64 + 3) / 4);
   long long S = (148 + tiles - 1) / tiles;   // upper bound of the launch plan's split count
-  long long smax = (M + 1023) / 1024;
+  long long smax = (M + WG_MIN_ROWS - 1) / WG_MIN_ROWS;
   if (S > smax) S = smax;
   if (S < 1) S = 1;
   return sizeof(float) * (size_t)S * Nout * (K + 1) + 256;
@@ -1963,7 +1964,9 @@ extern "C" int b3d_wgrad_tma(const b3d_seg_t* dy, const b3d_seg_t* segs, int32_t
   a.ktiles = (a.ngroups_total + 3) / 4;
   long long tiles = (long long)((Nout + TC_BM - 1) / TC_BM) * a.ktiles;
   long long S = 148 / tiles;          // ONE wave: S * tiles <= 148 CTAs (rounding up put 150 CTAs on 148 SMs)
-  long long smax = (M + 1023) / 1024;
+  // at least 4 chunks of 64 rows per CTA. (1,024 rows per CTA left a 9,629-row launch — the reference's own 2-window
+  // training batch — on 9 CTAs walking 16 chunks each: 19.6 us per launch, 25 % of that step.)
+  long long smax = (M + WG_MIN_ROWS - 1) / WG_MIN_ROWS;
   if (S > smax) S = smax;
   if (S < 1) S = 1;
   long long rps = ((M + S - 1) / S + 63) / 64 * 64;
