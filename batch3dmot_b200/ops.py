@@ -163,6 +163,41 @@ def invalidate_weight_cache():
     _chain_packs.clear()
 
 
+# Weight gradients straight into .grad. Inside `with grads_into_params():` (parallel.Trainer wraps its loss.backward()
+# in it once the flat gradient buffer exists) the weight-gradient kernels of _FusedMLP ACCUMULATE into the .grad of a leaf
+# parameter — or into the matching row / column window of it when the layer's weight is a slice view of a parameter —
+# and autograd receives no gradient for that input: no fresh dW tensor, no AccumulateGrad addition per use of a shared
+# weight (6 iterations x ~16 tensors), no zero-filled full-size gradient per sliced block. Same additions in the same
+# order as autograd's accumulation, so the result is unchanged. Off by default: torch.autograd.grad(), hooks and
+# .grad = None flows keep autograd's own semantics.
+_GRAD_SINK = False
+
+
+class grads_into_params:
+    def __enter__(self):
+        global _GRAD_SINK
+        self.prev, _GRAD_SINK = _GRAD_SINK, True
+
+    def __exit__(self, *a):
+        global _GRAD_SINK
+        _GRAD_SINK = self.prev
+
+
+def _grad_target(w):
+    """The fp32 window of a leaf parameter's .grad that corresponds to `w` (the parameter itself or a view of it)."""
+    if not _GRAD_SINK or w is None or w.dtype != torch.float32:
+        return None
+    base = w._base if w._base is not None else w
+    if not (base.is_leaf and base.requires_grad):      # (.grad of a non-leaf tensor must not even be looked at)
+        return None
+    g = base.grad
+    if g is None or g.dtype != torch.float32 or g.device != w.device or g.shape != base.shape or g.stride() != base.stride():
+        return None
+    if w is base:
+        return g
+    return torch.as_strided(g, w.size(), w.stride(), g.storage_offset() + w.storage_offset() - base.storage_offset())
+
+
 _USE_TMA = True          # dense bf16 operands go through the TMA-fed persistent kernel
 _USE_BITS = True         # bf16 chains keep ReLU masks as sign bits (B3D_BITS) for the backward pass
 
@@ -776,7 +811,7 @@ class _FusedMLP(torch.autograd.Function):
         ctx.add_nidx = add_nidx
         ctx.has_bias = [b is not None for b in bs]
         ctx.bits = bits
-        ctx.save_for_backward(*Ws, *[t if t is not None else acts[-1] for t in acts], *xs)
+        ctx.save_for_backward(*Ws, *[t if t is not None else acts[-1] for t in acts], *xs, *[b for b in bs if b is not None])
         if premasked:      # the consumer (segment_sum) needs the output's sign bits for its own backward
             out_bits = bits[-1] if bits[-1] is not None else acts[-1].new_zeros(0, dtype=torch.int32)
             ctx.mark_non_differentiable(out_bits)
@@ -803,6 +838,8 @@ class _FusedMLP(torch.autograd.Function):
         nx = len(nidx)
         need_x = ctx.needs_input_grad[7 + 2 * nl:7 + 2 * nl + nx]
         need_add = ctx.needs_input_grad[7 + 2 * nl + nx:]
+        b_saved = list(xs[nx:])
+        bs = [b_saved.pop(0) if hb else None for hb in ctx.has_bias]
         xs = xs[:nx]
         dxs = [None] * nx
         dadds = [None] * len(ctx.add_nidx)
@@ -837,8 +874,14 @@ class _FusedMLP(torch.autograd.Function):
                         g = segment_sum_raw(dz_item[0], ni, out_dtype=ctx.add_dtypes[t]) if ni is not None else dz_item[0]
                         dadds[t] = g if g.dtype == ctx.add_dtypes[t] else g.to(ctx.add_dtypes[t])
             if ctx.needs_input_grad[7 + 2 * l]:
-                dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc_arg)
-                grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)
+                tW = _grad_target(W)
+                tb = _grad_target(bs[l]) if ctx.has_bias[l] else None
+                if tW is not None and (not ctx.has_bias[l] or tb is not None):
+                    # grads_into_params: accumulated into the parameters' .grad by the kernel, nothing for autograd
+                    wgrad_raw(dz_item, a_items, M, n_out, K, dW=tW, db=tb, accumulate=True, want_bias=ctx.has_bias[l], tc=tc_arg)
+                else:
+                    dW, db = wgrad_raw(dz_item, a_items, M, n_out, K, want_bias=ctx.has_bias[l], tc=tc_arg)
+                    grads[2 * l], grads[2 * l + 1] = dW, (db if ctx.has_bias[l] else None)
             if l > 0:
                 if pre_dz is not None:
                     dz = pre_dz[l - 1]

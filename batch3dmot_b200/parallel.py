@@ -127,7 +127,8 @@ class Trainer:
         else:
             self.fp.zero_grad()
             loss = self._loss(data, global_edges, fwd_kwargs)
-            loss.backward()
+            with ops.grads_into_params():      # weight-gradient kernels accumulate straight into the flat buffer
+                loss.backward()
         if self.data_parallel:
             allreduce_sum_(self.fp.grad)
         self.step_no += 1

@@ -289,3 +289,48 @@ def test_cuda_graph_of_the_inference_forward_equals_eager_and_follows_inputs_and
     finally:
         ops.set_precision("fp32")
         ops.invalidate_weight_cache()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_weight_gradients_accumulated_into_param_grads_equal_autograd(precision):
+    """ops.grads_into_params (what Trainer wraps its backward in): the weight-gradient kernels accumulate into .grad of
+    leaf parameters and of slice views of them; every parameter gradient equals plain autograd accumulation bit for bit
+    from zeroed gradients (same additions, same order), and within fp32 rounding on top of non-zero gradients."""
+    from batch3dmot_b200.clr_att_gnn import GNN
+    sc = synth.add_labels(synth.add_modalities(synth.scene_graph(seed=31, T=8, nodes_per_frame=40), 31, raw=False), 31)
+    d = to_dev(sc)
+    kw = dict(x_img=d.x_img, pointnet_out=d.pointnet_out, radarnet_out=d.radarnet_out, lidar_mask=d.m_lidar,
+              radar_mask=d.m_radar)
+    ops.set_precision(precision)
+    try:
+        torch.manual_seed(5621)
+        model = GNN(None, None, None).to(DEV)
+
+        def run(sink, passes):
+            for p in model.parameters():
+                p.grad = torch.zeros_like(p) if p.requires_grad else None
+            for _ in range(passes):
+                out, _ = model(d, **kw)
+                loss = ops.bce_loss(out, d.y, d.edge_weights, batch_size=2)
+                if sink:
+                    with ops.grads_into_params():
+                        loss.backward()
+                else:
+                    loss.backward()
+            return {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        for passes in (1, 2):
+            want, got = run(False, passes), run(True, passes)
+            assert want.keys() == got.keys()
+            used = 0
+            for n in want:
+                if passes == 1:
+                    assert torch.equal(want[n], got[n]), (n, float((want[n] - got[n]).abs().max()))
+                else:       # autograd sums the uses of a shared weight BEFORE adding them to a non-zero .grad: fp32 rounding
+                    assert float((want[n] - got[n]).abs().max()) <= 1e-5 * float(want[n].abs().max()) + 1e-12, n
+                used += int(want[n].abs().sum() > 0)
+            assert used > 40
+        assert not ops._GRAD_SINK
+    finally:
+        ops.set_precision("fp32")
+        ops.invalidate_weight_cache()
