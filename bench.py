@@ -595,8 +595,8 @@ def main():
         ach = Er * (512 + 384) * 2 / t / 1e9
         roof = {"kernel": "k_linear_tma<relu> (TMA-fed tcgen05 bf16; att_edge_encoder layer 2, [E,512]x[512,384])", "bound": "hbm",
                 "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": 848_617_984,   # dram read+write bytes per launch (502,058,240 + 346,559,744), ncu --set full, same shape
-                "traffic_source": "profiles/r1_roofline_kernel.md (algorithmic bytes: E*(512+384)*2 = 877,743,104)",
+                "traffic": 849_700_000,   # dram read + write bytes per launch (502.1 MB + 347.6 MB), ncu --set full of the lean build, same shape
+                "traffic_source": "profiles/r2_roofline_kernel.md, r2_lean_epilogue.md last table row (algorithmic bytes: E*(512+384)*2 = 877,743,104)",
                 "peak_source": src + " HBM copy bandwidth (burst); kernel timed alone with CUDA events",
                 "rows": Er, "us_per_launch": t * 1e6,
                 "tensor_view": {"achieved_tflops": ach_t, "peak_tflops": tf_burst, "frac": ach_t / tf_burst}}
