@@ -149,3 +149,34 @@ def test_focal_loss_oracle_reduces_to_bce():
     w = torch.rand(500) + 0.5
     assert abs(float(R.focal_loss(p, y, w, gamma=0.0, alpha=0.5)) - 0.5 * float(R.bce_loss(p, y, w))) < 1e-6
     assert float(R.focal_loss(p, y, w, gamma=2.0, alpha=0.5)) < float(R.focal_loss(p, y, w, gamma=0.0, alpha=0.5))
+
+
+def test_grad_target_windows_alias_the_parameter_gradient():
+    """ops._grad_target (CPU: pure tensor bookkeeping): inside ops.grads_into_params() a leaf parameter maps to its .grad,
+    a row / column slice view of it to the same window of .grad (also when the parameter and its gradient are views of
+    flat buffers, as parallel.FlatParams lays them out); everything else maps to None."""
+    import torch
+    from batch3dmot_b200 import ops
+    flat, gflat = torch.zeros(100 + 6 * 10), torch.zeros(100 + 6 * 10)
+    p = torch.nn.Parameter(torch.randn(6, 10))
+    p.data = flat[100:160].view(6, 10)
+    assert ops._grad_target(p) is None                      # switch off
+    with ops.grads_into_params():
+        assert ops._grad_target(p) is None                  # no .grad yet
+        p.grad = gflat[100:160].view(6, 10)
+        assert ops._grad_target(p) is p.grad
+        for view in (p[:, 3:7], p[2:5], p[1:4, 2:9], p[:, 4:]):
+            t = ops._grad_target(view)
+            assert t.shape == view.shape and t.stride() == view.stride()
+            t.fill_(1.0)
+            mark = torch.zeros_like(p.data)
+            torch.as_strided(mark, view.size(), view.stride(), view.storage_offset() - p.storage_offset()).fill_(1.0)
+            assert torch.equal(p.grad, mark)
+            p.grad.zero_()
+        assert ops._grad_target(p.detach().clone()) is None                    # not a leaf that requires grad
+        assert ops._grad_target(torch.cat([p[:, :2], p[:, 5:]], 1)) is None      # derived (non-leaf, non-view)
+        assert ops._grad_target(p.double()) is None
+        q = torch.nn.Parameter(torch.randn(4, 4))
+        q.grad = torch.zeros(4, 4).t()                                          # gradient laid out differently
+        assert ops._grad_target(q) is None
+    assert not ops._GRAD_SINK
