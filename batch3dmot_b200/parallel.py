@@ -6,6 +6,8 @@ same-category nodes inside a window), so:
     (1,319,697 floats = 5.28 MB for the multimodal model), then the same Adam step on every rank.
 The reference trains the GNN on a single device (train.py:45); its only DDP precedent is the
 encoder trainer (training/train_resnet_ae_ddp.py:125-175)."""
+from types import SimpleNamespace
+
 import torch
 import torch.distributed as dist
 
@@ -83,6 +85,7 @@ class Trainer:
         self.loss, self.focal = loss, (focal_alpha, focal_gamma)
         self.step_no = 0
         self._step_dev = None
+        self._loss_scale = None      # device scalar multiplied into the loss (BucketedTrainer: mean over the REAL edges)
         # data_parallel=False: a rank-local trainer inside a multi-rank job (no gradient all-reduce, no loss re-weighting)
         self.data_parallel = data_parallel
 
@@ -100,6 +103,8 @@ class Trainer:
             loss = loss * (out.size(0) / float(global_edges))
         elif world > 1:
             loss = loss / world          # SUM all-reduce of per-rank mean losses -> mean over ranks (DDP convention)
+        if self._loss_scale is not None:
+            loss = loss * self._loss_scale
         return loss
 
     def _first_step(self, data, global_edges, fwd_kwargs):
@@ -170,3 +175,130 @@ class Trainer:
             return loss
         replay.graph = graph
         return replay
+
+
+def _bucket(n, floor):
+    """Smallest size >= n on a ladder with 8 steps per octave (and steps of at least `floor`): padding stays below
+    12.5 %, and a stream of batches of similar size maps onto a handful of sizes."""
+    n = max(int(n), 1)
+    q = max(floor, 1 << max(0, n.bit_length() - 4))
+    return -(-n // q) * q
+
+
+class BucketedTrainer:
+    """`Trainer.step` for a STREAM of small batches of varying size at CUDA-graph speed.
+
+    The reference trains on 2 window graphs per step (cl_config.yaml:99; ~10 k edges, a different graph every step): a
+    step is ~490 kernels of a few microseconds, so the eager step is bound by host dispatch (14 ms against 3.7 ms of GPU
+    work). A CUDA graph needs static shapes, so every batch is padded to a size bucket — dummy nodes without features
+    and dummy edges on the last dummy node with loss weight 0, i.e. zero gradient — and the whole step of each bucket
+    (CSR build from the copied edge_index, forward, loss, backward, all-reduce, Adam) is captured once and replayed
+    for every later batch of that bucket. Real nodes and edges see exactly the unpadded arithmetic (padding only
+    appends rows; the mean of the loss is rescaled by a device scalar); weight gradients differ from the unpadded
+    step by fp32 summation order only.
+
+    batch: the attributes `Trainer.step` reads (pose_feats, edge_index, edge_attr, y, edge_weights[, node_timestamps])
+    plus, for the multimodal model, the keyword tensors x_img, pointnet_out, radarnet_out, lidar_mask, radar_mask.
+    The k-NN attention update must be off (the reference's default): dummy nodes would join the last frame."""
+
+    NODE_KEYS = ("pose_feats", "node_timestamps")
+    EDGE_KEYS = ("edge_attr", "y", "edge_weights")
+
+    def __init__(self, trainer, max_graphs=64):
+        assert not getattr(trainer.model, "apply_knn_update", False), "padding is not defined for the k-NN attention update"
+        self.tr, self.max_graphs = trainer, max_graphs
+        self.graphs = {}                 # (N_pad, E_pad) -> (CUDAGraph, static data, static kwargs, scale, loss)
+        self.pool = None
+        self.captures = 0
+
+    def _static(self, data, kw, n_pad, e_pad):
+        dev = data.pose_feats.device
+        s = SimpleNamespace(num_nodes=n_pad)
+        for k in self.NODE_KEYS:
+            if hasattr(data, k):
+                t = getattr(data, k)
+                setattr(s, k, torch.zeros((n_pad,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev))
+        for k in self.EDGE_KEYS:
+            t = getattr(data, k)
+            setattr(s, k, torch.zeros((e_pad,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev))
+        s.edge_index = torch.full((2, e_pad), n_pad - 1, dtype=torch.int64, device=dev)
+        skw = {k: torch.zeros((n_pad,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for k, t in kw.items()}
+        return s, skw
+
+    @staticmethod
+    def _fill(s, skw, data, kw, n, e):
+        n_pad, e_pad = s.num_nodes, s.edge_index.size(1)
+        for k in BucketedTrainer.NODE_KEYS:
+            if hasattr(s, k):
+                t = getattr(s, k)
+                t[:n].copy_(getattr(data, k), non_blocking=True)
+                if n < n_pad:
+                    t[n:].zero_() if k != "node_timestamps" else t[n:].fill_(int(2 ** 30))   # a frame of their own
+        for k in BucketedTrainer.EDGE_KEYS:
+            t = getattr(s, k)
+            t[:e].copy_(getattr(data, k), non_blocking=True)
+            if e < e_pad:
+                t[e:].zero_()                                   # weight 0: no loss, no gradient from the padding
+        s.edge_index[:, :e].copy_(data.edge_index, non_blocking=True)
+        if e < e_pad:
+            s.edge_index[:, e:].fill_(n_pad - 1)                # dummy edges sit on the last dummy node
+        for k, t in skw.items():
+            t[:n].copy_(kw[k], non_blocking=True)
+            if n < n_pad:
+                t[n:].zero_()
+
+    def _one_step(self, s, skw, scale):
+        from . import ops
+        s._b3d_graph = ops.Graph(s.edge_index, s.num_nodes)     # CSR / CSC of THIS batch's edges: part of the graph
+        self.tr._loss_scale = scale
+        try:
+            return self.tr.step(s, **skw)
+        finally:
+            self.tr._loss_scale = None
+
+    def step(self, data, **kw):
+        tr = self.tr
+        if tr.fp is None:                                        # the first step decides which parameters train (eager)
+            return tr.step(data, **kw)
+        n, e = data.pose_feats.size(0), data.edge_index.size(1)
+        key = (_bucket(n + 1, 64), _bucket(e, 512))
+        ent = self.graphs.get(key)
+        if ent is None:
+            if len(self.graphs) >= self.max_graphs:
+                return tr.step(data, **kw)                       # bucket table full: plain eager step
+            ent = self._capture(key, data, kw, n, e)
+        graph, s, skw, scale, loss = ent
+        self._fill(s, skw, data, kw, n, e)
+        scale.fill_(s.edge_index.size(1) / max(e, 1))            # mean over the real edges
+        graph.replay()
+        tr.step_no += 1
+        return loss
+
+    def _capture(self, key, data, kw, n, e):
+        tr = self.tr
+        dev = data.pose_feats.device
+        s, skw = self._static(data, kw, *key)
+        self._fill(s, skw, data, kw, n, e)
+        scale = torch.full((1,), key[1] / max(e, 1), dtype=torch.float32, device=dev)
+        if tr._step_dev is None:
+            tr._step_dev = torch.full((1,), tr.step_no, dtype=torch.int32, device=dev)
+        # the warm-up steps below are real optimiser steps on this batch: take them back afterwards
+        saved = (tr.fp.flat.clone(), tr.m.clone(), tr.v.clone(), tr.step_no)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._one_step(s, skw, scale)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()           # one pool for all buckets: they never replay concurrently
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self.pool):
+            loss = self._one_step(s, skw, scale)
+        tr.fp.flat.copy_(saved[0]); tr.m.copy_(saved[1]); tr.v.copy_(saved[2])
+        tr.step_no = saved[3]
+        tr._step_dev.fill_(tr.step_no)
+        self.captures += 1
+        ent = self.graphs[key] = (graph, s, skw, scale, loss)
+        return ent

@@ -411,6 +411,33 @@ def extras(a, rank, world, dev, model, d, tm, E_global, trainer, headline):
         except Exception as ex:                      # noqa: BLE001 - reported, not fatal for the headline
             res[name]["cuda_graph_error"] = repr(ex)[:200]
         trs._step_dev = None
+    # a STREAM of different 2-window batches (what train.py's DataLoader delivers): eager Trainer.step against
+    # parallel.BucketedTrainer (batches padded to size buckets, one captured CUDA graph per bucket, replayed)
+    try:
+        from batch3dmot_b200.parallel import BucketedTrainer
+        stream = []
+        for sd in (SEED + 1, SEED + 2):
+            ws = synth.windows(synth.add_labels(synth.add_modalities(synth.scene_graph(seed=sd), sd, raw=False), sd), 5)
+            for w in ws:
+                synth.add_labels(w, sd)
+            stream += [to_dev(synth.collate(ws[i:i + 2]), dev) for i in range(0, 24, 2)]
+        e_stream = sum(b.edge_index.size(1) for b in stream)
+
+        def run_stream(step):
+            for b in stream:
+                step(b, **mm_kwargs(b))
+        ms_eager = tm.run(lambda: run_stream(trs.step), 1, 1, reduce=False)
+        bt = BucketedTrainer(trs)
+        run_stream(bt.step)                                  # first pass: captures one graph per size bucket
+        ms_b = tm.run(lambda: run_stream(bt.step), 2, 1, reduce=False)
+        res["stream_of_2_window_batches"] = {
+            "batches": len(stream), "edges": e_stream, "size_buckets": bt.captures,
+            "eager_us_per_step": ms_eager * 1e3 / len(stream), "bucketed_graph_us_per_step": ms_b * 1e3 / len(stream),
+            "eager_edges_per_s": e_stream / ms_eager * 1e3, "bucketed_graph_edges_per_s": e_stream / ms_b * 1e3}
+        del bt, stream
+    except Exception as ex:                                  # noqa: BLE001 - reported, not fatal for the headline
+        res["stream_of_2_window_batches"] = {"error": repr(ex)[:200]}
+    trs._step_dev = None
     x["small_batch"] = dict(res, workload="configs[4]: multimodal training step at the reference's batch (2 window graphs) and at 1 scene")
     del ms_, trs
 
