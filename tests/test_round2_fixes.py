@@ -357,6 +357,7 @@ def test_bucketed_trainer_replays_padded_graphs_and_tracks_the_eager_trainer(pre
     try:
         torch.manual_seed(5621)
         m1 = GNN(None, None, None).to(DEV)
+        init = {n: p.detach().clone() for n, p in m1.named_parameters()}
         t1 = Trainer(m1, lr=1e-3)
         eager = [float(t1.step(d, **kwf(d))) for d in batches]
         torch.manual_seed(5621)
@@ -366,12 +367,16 @@ def test_bucketed_trainer_replays_padded_graphs_and_tracks_the_eager_trainer(pre
         assert 1 <= bt.captures < len(batches) - 1                # first step eager, later batches share buckets
         for a, b in zip(eager, got):
             assert abs(a - b) <= 2e-3 * abs(a), (eager, got)
-        # parameters in the Frobenius norm: Adam turns the fp32 summation-order noise of a near-zero gradient entry into
-        # an O(lr) difference of that entry (measured: 3e-4 on single entries after 10 steps at lr 1e-3), so single
-        # entries are not comparable, tensors are
+        # parameters: per tensor, the difference of the two runs against the distance the tensor MOVED in 10 steps
+        # (Frobenius norms). Adam turns the summation-order noise of a near-zero gradient entry into an O(lr) difference
+        # of that entry, and in the bf16 mode a last-bit difference of a weight moves bf16 roundings downstream
+        # (measured: 0.9 % of the movement for message_passing.create_past_msgs.2.weight in the bf16 mode); a wrong
+        # loss scale or a gradient leaking from the padding would be O(100 %)
+        lim = 0.25 if precision == "bf16" else 0.1
         for (n, a), b in zip(m1.named_parameters(), m2.parameters()):
             a, b = a.detach(), b.detach()
-            assert float((a - b).norm()) <= 2e-3 * float(a.norm()) + 1e-7, (n, float((a - b).norm()), float(a.norm()))
+            moved = float((a - init[n]).norm())
+            assert float((a - b).norm()) <= lim * moved + 1e-6, (n, float((a - b).norm()), moved)
         assert bt.tr.step_no == t1.step_no == len(batches)
     finally:
         ops.set_precision("fp32")
