@@ -180,3 +180,39 @@ def test_grad_target_windows_alias_the_parameter_gradient():
         q.grad = torch.zeros(4, 4).t()                                          # gradient laid out differently
         assert ops._grad_target(q) is None
     assert not ops._GRAD_SINK
+
+
+def test_bucketed_trainer_size_ladder_and_padding_layout():
+    """parallel._bucket / BucketedTrainer._static / _fill on CPU tensors: sizes land on a ladder with at most 12.5 %
+    padding (plus the floor), padded rows are zero, dummy edges sit on the last dummy node with weight 0, dummy nodes get
+    a frame of their own, and a smaller batch re-using the buffers leaves nothing of the previous one behind."""
+    import torch
+    from types import SimpleNamespace
+    from batch3dmot_b200.parallel import BucketedTrainer, _bucket
+    for n in (1, 63, 64, 65, 500, 513, 9629, 61561, 146961, 3925343):
+        b = _bucket(n, 512)
+        assert b >= n and b % 512 == 0 and (b - n) <= max(512, n // 8) and _bucket(b, 512) == b
+    assert len({_bucket(n, 512) for n in range(8193, 16385)}) == 8          # 8 sizes per octave
+
+    def batch(n, e, seed):
+        g = torch.Generator().manual_seed(seed)
+        return SimpleNamespace(pose_feats=torch.randn(n, 19, generator=g), node_timestamps=torch.randint(0, 5, (n,), generator=g),
+                               edge_attr=torch.randn(e, 4, generator=g).double(), y=torch.randint(0, 2, (e,), generator=g),
+                               edge_weights=torch.rand(e, generator=g), edge_index=torch.randint(0, n, (2, e), generator=g))
+    d1, d2 = batch(100, 700, 1), batch(90, 650, 2)
+    kw1 = {"x_img": torch.randn(100, 96), "lidar_mask": torch.ones(100, dtype=torch.bool)}
+    kw2 = {"x_img": torch.randn(90, 96), "lidar_mask": torch.ones(90, dtype=torch.bool)}
+    bt = BucketedTrainer.__new__(BucketedTrainer)
+    n_pad, e_pad = _bucket(101, 64), _bucket(700, 512)
+    assert (n_pad, e_pad) == (_bucket(91, 64), _bucket(650, 512)) == (128, 1024)
+    s, skw = bt._static(d1, kw1, n_pad, e_pad)
+    for d, kw, n, e in ((d1, kw1, 100, 700), (d2, kw2, 90, 650)):
+        BucketedTrainer._fill(s, skw, d, kw, n, e)
+        assert torch.equal(s.pose_feats[:n], d.pose_feats) and float(s.pose_feats[n:].abs().sum()) == 0
+        assert torch.equal(s.edge_index[:, :e], d.edge_index) and bool((s.edge_index[:, e:] == n_pad - 1).all())
+        assert torch.equal(s.edge_weights[:e], d.edge_weights) and float(s.edge_weights[e:].abs().sum()) == 0
+        assert torch.equal(s.edge_attr[:e], d.edge_attr) and s.edge_attr.dtype == torch.float64
+        assert torch.equal(s.y[:e], d.y) and int(s.y[e:].abs().sum()) == 0
+        assert torch.equal(s.node_timestamps[:n], d.node_timestamps) and bool((s.node_timestamps[n:] > 10 ** 6).all())
+        assert torch.equal(skw["x_img"][:n], kw["x_img"]) and float(skw["x_img"][n:].abs().sum()) == 0
+        assert bool(skw["lidar_mask"][:n].all()) and not bool(skw["lidar_mask"][n:].any())
